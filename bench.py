@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the RKHS SE(3) registration inner loop on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPUs
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic 3000 x 3000-point RGB-D pairs, fixed
+ell = 0.10, exactly 100 inner iterations per pair (stop tests off) -- as a batch of `--pairs` independent
+pairs per GPU per step (default 2 x #SMs).  One step = align() of the whole batch.
+  value  = pairs / device time of the align kernel (CUDA events on the library's stream), clouds resident in HBM
+  e2e    = pairs / wall time of: upload of every pair from pinned host memory (cvo_b200_set_pair: H2D + on-device
+           Morton sort/pack) + cvo_b200_align + the poses coming back to the host (+ NCCL all-gather of the poses
+           when N > 1), through the C ABI the reference's frontends would call.
+Multi-GPU: one process per GPU (torchrun), pairs are independent => weak scaling, no data-path collective;
+the only exchange is one all-gather of the 4x4 poses per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 3000
+FIXED_ELL = 0.10
+FIXED_ITERS = 100
+METRIC = "frame-pairs/sec (3k x 3k pts, fixed ell=0.10, 100 inner iters)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_iteration(n, m):
+    """32 B per point, K1 and K2 each read both clouds once: 64 (N+M) + 96 B."""
+    return 64 * (n + m) + 96
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_params(capi_mod):
+    p = capi_mod.default_params("cvo")
+    p.ell_policy, p.ell_init, p.fixed_iters = 2, FIXED_ELL, FIXED_ITERS  # ELL_FIXED
+    return p
+
+
+def cpu_reference_run(n_pairs, seed0, threads=None):
+    """Times the reference algorithm's CPU restatement (oracle) on `n_pairs` pairs of the workload, one after
+    another, all host threads per pair (the reference's execution model, tbb::parallel_for over rows).
+    Prefers oracle/_ref (ball query = the reference's own nanoflann kd-tree, as in src/cvo.cpp:110-125)."""
+    from cvo_rgbd_b200 import synth
+    from oracle import cvo_oracle as O
+    variant = "port"
+    try:
+        O.load("ref")
+        variant = "ref"
+    except Exception:
+        O.load("port")
+    if threads:
+        O.set_num_threads(threads, variant)
+    p = O.default_params("cvo")
+    p.ell_policy, p.ell_init, p.fixed_iters = O.ELL_FIXED, FIXED_ELL, FIXED_ITERS
+    pairs = [synth.config_pair(2, seed0 + i) for i in range(n_pairs)]
+    t0 = time.perf_counter()
+    for pr in pairs:
+        O.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], p)
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, pairs=n_pairs, pairs_per_s=n_pairs / dt, cores=O.num_threads(variant),
+                backend=O.backend(variant))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_pairs = args.cpu_pairs
+    for _ in range(args.warmup):
+        cpu_reference_run(1, 0)
+    times = []
+    for s in range(args.steps):
+        r = cpu_reference_run(sample_pairs, 1 + s * sample_pairs)
+        times.append(r["seconds"])
+    ms = 1e3 * float(np.mean(times))
+    value = sample_pairs / (ms / 1e3)
+    sample = "%d cfg-2 pairs per step (3000x3000, fixed ell %.2f, %d iters), sequential, all host threads per pair; %s" % (
+        sample_pairs, FIXED_ELL, FIXED_ITERS, r["backend"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 3000x3000 synthetic RGB-D pair, fixed ell=0.10, 100 inner iterations",
+                       "pairs_per_step": sample_pairs, "points": [N_POINTS, N_POINTS]},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (default 2 x #SMs)")
+    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
+    ap.add_argument("--cluster", type=int, default=0, help="CTAs per pair (0 = automatic)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    from cvo_rgbd_b200 import build, capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm)")
+    build.build_library()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    probe = capi.Context(local_rank, 64, 1)
+    num_sms = probe.num_sms
+    probe.close()
+    P = args.pairs if args.pairs > 0 else 2 * num_sms
+    ctx = capi.Context(local_rank, max_points=N_POINTS + 72, max_slots=P)
+    if args.cluster:
+        ctx.set_cluster_size(args.cluster)
+    params = make_params(capi)
+
+    # synthetic workload: P distinct seeded pairs per rank, staged in PINNED host memory
+    pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
+    hx, hfx, hy, hfy = pin((P, N_POINTS, 3)), pin((P, N_POINTS, 5)), pin((P, N_POINTS, 3)), pin((P, N_POINTS, 5))
+    for s in range(P):
+        pr = synth.config_pair(2, rank * P + s)
+        hx[s], hfx[s], hy[s], hfy[s] = pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"]
+    slots = np.arange(P, dtype=np.int32)
+    h2d_bytes = int(hx.nbytes + hfx.nbytes + hy.nbytes + hfy.nbytes)
+    d2h_bytes = int(P * (16 * 4 + 16 * 4 + 4 + 4 + 200))  # poses + state records read back per step
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    gathered = torch.empty((world, P, 16), dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def upload_all():
+        for s in range(P):
+            rc = ctx.set_pair_raw(s, hx[s], hfx[s], hy[s], hfy[s])
+            if rc != 0:
+                raise RuntimeError("set_pair failed: %d" % rc)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_poses(res):
+        if dist is None:
+            return
+        mine = torch.from_numpy(res["transform"].reshape(P, 16)).cuda(non_blocking=True)
+        dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))  # the single collective: 64 B per pair
+        torch.cuda.synchronize()
+
+    # ---------------- resident arm: clouds already in HBM ----------------
+    upload_all()
+    ctx.sync()
+    for _ in range(args.warmup):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.align(slots, params)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    kernel_ms, total_iters = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        res = ctx.align(slots, params)
+        kernel_ms.append(ctx.last_kernel_ms)
+        total_iters += ctx.last_total_iterations
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop()
+    dev_s = float(np.sum(kernel_ms)) / 1e3
+
+    # ---------------- end-to-end arm: host buffers -> poses on the host ----------------
+    for _ in range(min(args.warmup, 2)):
+        upload_all()
+        gather_poses(ctx.align(slots, params))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload_all()
+        res = ctx.align(slots, params)
+        gather_poses(res)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = ctx.kernel_launches - launches0 - launches
+
+    if dist is not None:
+        t = torch.tensor([dev_s, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, wall_resident = [float(x) for x in t.tolist()]
+    pairs_total = P * world * args.steps
+    value = pairs_total / dev_s
+    e2e_value = pairs_total / e2e_s
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        iters_per_launch = total_iters / args.steps
+        alg_bytes = algorithmic_bytes_per_iteration(N_POINTS, N_POINTS) * iters_per_launch
+        launch_s = float(np.mean(kernel_ms)) / 1e3
+        achieved = alg_bytes / launch_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "align_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        sm_mhz = clocks["sm_mhz"] or 1965.0
+        pass_evals = 2.0 * N_POINTS * N_POINTS * iters_per_launch  # two all-pairs passes per iteration
+        issue_roof = num_sms * 128 * sm_mhz * 1e6 / 7.0  # 7 FP32 issue slots per candidate pair
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 3000x3000 synthetic RGB-D pairs, fixed ell=0.10, 100 inner iterations per pair",
+                       "pairs_per_gpu_per_step": P, "points": [N_POINTS, N_POINTS], "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
+                       "ctas_per_pair": ctx.last_cluster_size, "clusters": ctx.last_num_clusters,
+                       "l2": "256 MiB device memset between timed steps (flush)", "timing": "CUDA events on the library stream around the align kernel"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "launches_per_step": e2e_launches / args.steps},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "BASELINE.json asks for HBM GB/s, but with A never materialised the kernel is FP32-issue-bound (SURVEY.md 8d): see issue_roof",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "cvo_b200::align_kernel", "kernel_ms": 1e3 * launch_s},
+            "issue_roof": {"pair_evals_per_s": pass_evals / launch_s, "roof_pair_evals_per_s": issue_roof,
+                           "frac_nm_equivalent": pass_evals / launch_s / issue_roof,
+                           "note": "N*M-equivalent candidate pairs per second vs 148 SM x 128 lanes x f_SM / 7 slots; tile-box culling skips most of them"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args.cpu_pairs, 10_000)
+            line["cpu_baseline"] = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                                    "sample": "%d cfg-2 pairs, sequential, all host threads per pair, %.1f s; %s" % (
+                                        r["pairs"], r["seconds"], r["backend"])}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,42 @@
+"""Builds libcvo_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "csrc", "cvo_api.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "cvo_kernels.cuh"),
+        os.path.join(_HERE, "..", "include", "cvo_b200.h")]
+OUT = os.path.join(_HERE, "libcvo_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build_library(force=False, verbose=False):
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc]
+    if os.path.exists("/usr/bin/g++"):  # the image exports CXX=/opt/gcc/bin/g++; use the distro host compiler
+        cmd += ["-ccbin", "/usr/bin/g++"]
+    cmd += NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+def build_frontend_example():
+    """Compiles examples/frontend_example.cpp (C++ host classes above the C ABI) against the in-tree library."""
+    root = os.path.dirname(_HERE)
+    src = os.path.join(root, "examples", "frontend_example.cpp")
+    out = os.path.join(root, "examples", "frontend_example")
+    deps = [src, os.path.join(root, "include", "cvo_b200_frontend.hpp"), os.path.join(root, "include", "cvo_b200.h"), OUT]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + _HERE, "-lcvo_b200",
+                    "-Wl,-rpath,$ORIGIN/../cvo_rgbd_b200"], check=True)
+    return out
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,515 @@
+// cvo_api.cu -- host side of libcvo_b200.so: context, buffers, launches, the C ABI of include/cvo_b200.h.
+// No torch, no CPU fallback: every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cvo_kernels.cuh"
+
+using namespace cvo_b200;
+
+struct cvo_b200_ctx {
+    int device = 0;
+    int max_points = 0;
+    int max_slots = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // raw staging (stream-ordered reuse): two clouds of xyz (n x 3) and feat (n x 5)
+    float* d_raw_xyz = nullptr;
+    float* d_raw_feat = nullptr;
+    // packed clouds: [slot][2][max_points]
+    float4* d_pk_g = nullptr;
+    float4* d_pk_f = nullptr;
+
+    struct Slot {
+        int n[2] = {0, 0};
+        int fixed_buf = 0;  // which of the two buffers currently holds the fixed cloud
+        bool bound = false;
+    };
+    std::vector<Slot> slots;
+
+    PairDev* d_pairs = nullptr;
+    PairState* d_states = nullptr;
+    PairDev* h_pairs = nullptr;     // pinned
+    PairState* h_states = nullptr;  // pinned
+    int* d_counter = nullptr;
+    cvo_b200_iter_rec* d_trace = nullptr;
+    cvo_b200_iter_rec* h_trace = nullptr;  // pinned
+    int trace_cap = 0;
+    double* d_inner = nullptr;
+    PackJob* d_jobs = nullptr;  // descriptors of the pack launch in flight (stream-ordered reuse)
+    double* h_inner = nullptr;  // pinned
+
+    float last_ms = 0.f;
+    long long launches = 0;
+    int last_G = 0, last_nclusters = 0, force_G = 0;
+    long long last_total_iters = 0;
+    int sort_points = 1;
+    size_t pack_smem_max = 0;
+    std::string err;
+};
+
+namespace {
+
+constexpr int kTraceCap = 4096;
+
+bool cuda_ok(cvo_b200_ctx* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    if (ctx) ctx->err = buf;
+    return false;
+}
+#define CK(call)                                                        \
+    do {                                                                \
+        if (!cuda_ok(ctx, (call), #call)) return CVO_B200_ERR_CUDA;     \
+    } while (0)
+
+int fail_arg(cvo_b200_ctx* ctx, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return CVO_B200_ERR_ARG;
+}
+
+float4* slot_g(cvo_b200_ctx* ctx, int slot, int buf) {
+    return ctx->d_pk_g + ((size_t)slot * 2 + buf) * ctx->max_points;
+}
+float4* slot_f(cvo_b200_ctx* ctx, int slot, int buf) {
+    return ctx->d_pk_f + ((size_t)slot * 2 + buf) * ctx->max_points;
+}
+
+// Host-side constants in the reference's own arithmetic (src/cvo.cpp:102-103, src/adaptive_cvo.cpp:100-101).
+KParams make_kparams(const cvo_b200_params* p, bool for_inner_product) {
+    KParams k;
+    memset(&k, 0, sizeof(k));
+    k.mode = p->mode;
+    k.ell_policy = p->ell_policy;
+    k.max_iter = p->max_iter;
+    k.fixed_iters = p->fixed_iters;
+    k.ell_min = p->ell_min;
+    k.s2 = p->sigma * p->sigma;
+    k.cs2 = p->c_sigma * p->c_sigma;
+    k.sp_thres = p->sp_thres;
+    float c_gate;
+    if (for_inner_product) {  // src/adaptive_cvo.cpp:391-392
+        k.log_ratio = logf(p->sp_thres / p->sigma / p->sigma);
+        c_gate = p->sp_thres;
+    } else {
+        k.log_ratio = logf(p->sp_thres / k.s2);
+        c_gate = (p->mode == CVO_B200_MODE_ACVO) ? p->c_sp_thres : p->sp_thres;
+    }
+    k.d2c_thres = (float)(-2.0 * p->c_ell * p->c_ell * logf(c_gate / p->c_sigma / p->c_sigma));
+    k.inv2cl2 = (float)(1.0 / (2.0 * (double)p->c_ell * (double)p->c_ell));
+    k.inv_c = 1 / p->c;
+    k.inv_d = 1 / p->d;
+    k.min_step = p->min_step;
+    k.max_step = p->max_step;
+    k.eps = p->eps;
+    k.eps_2 = p->eps_2;
+    k.dl_step = p->dl_step;
+    return k;
+}
+
+int upload_cloud(cvo_b200_ctx* ctx, int which, const float* xyz, const float* feat, int n) {
+    float* dx = ctx->d_raw_xyz + (size_t)which * ctx->max_points * 3;
+    float* df = ctx->d_raw_feat + (size_t)which * ctx->max_points * 5;
+    CK(cudaMemcpyAsync(dx, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(df, feat, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, ctx->stream));
+    return CVO_B200_OK;
+}
+
+int launch_pack(cvo_b200_ctx* ctx, const PackJob* jobs_host, int njobs, PackJob* d_jobs_scratch) {
+    int nmax = 0;
+    for (int i = 0; i < njobs; ++i) nmax = jobs_host[i].n > nmax ? jobs_host[i].n : nmax;
+    int npad = 1;
+    while (npad < nmax) npad <<= 1;
+    const size_t smem = (size_t)npad * sizeof(unsigned long long);
+    if (smem > ctx->pack_smem_max) return fail_arg(ctx, "cloud too large for the single-CTA sort");
+    CK(cudaMemcpyAsync(d_jobs_scratch, jobs_host, sizeof(PackJob) * njobs, cudaMemcpyHostToDevice, ctx->stream));
+    pack_sort_kernel<<<njobs, kPackThreads, smem, ctx->stream>>>(d_jobs_scratch, ctx->sort_points);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return CVO_B200_OK;
+}
+
+int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
+    if (ctx->force_G > 0) return ctx->force_G;
+    int G = 1;
+    while (G < 16 && (long long)n_pairs * G * 2 <= ctx->num_sms) G *= 2;
+    return G;
+}
+
+template <typename KernelT, typename ArgT>
+int launch_cluster_kernel(cvo_b200_ctx* ctx, KernelT kernel, const ArgT& args, int G, int want_clusters,
+                          int* nclusters_out) {
+    const size_t smem = sizeof(Smem);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (G > 8) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cfg.gridDim = dim3(G, 1, 1);
+    int max_clusters = 0;
+    CK(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    if (max_clusters < 1) {
+        ctx->err = "cluster size not schedulable on this device";
+        return CVO_B200_ERR_CUDA;
+    }
+    int ncl = want_clusters < max_clusters ? want_clusters : max_clusters;
+    if (ncl < 1) ncl = 1;
+    cfg.gridDim = dim3(ncl * G, 1, 1);
+    CK(cudaLaunchKernelEx(&cfg, kernel, args));
+    ctx->launches += 1;
+    if (nclusters_out) *nclusters_out = ncl;
+    return CVO_B200_OK;
+}
+
+PairDev make_pair_dev(cvo_b200_ctx* ctx, int slot) {
+    const cvo_b200_ctx::Slot& s = ctx->slots[slot];
+    PairDev pd;
+    const int fb = s.fixed_buf, mb = 1 - s.fixed_buf;
+    pd.x.g = slot_g(ctx, slot, fb);
+    pd.x.f = slot_f(ctx, slot, fb);
+    pd.x.n = s.n[fb];
+    pd.x.pad = 0;
+    pd.y.g = slot_g(ctx, slot, mb);
+    pd.y.f = slot_f(ctx, slot, mb);
+    pd.y.n = s.n[mb];
+    pd.y.pad = 0;
+    return pd;
+}
+
+int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, float* RT_io,
+              float* ell_io, float* transform, float* prev_transform, int* iters, int* status,
+              cvo_b200_iter_rec* trace, int trace_cap, int* trace_len) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!slots || !p || n_pairs <= 0 || n_pairs > ctx->max_slots) return fail_arg(ctx, "bad align arguments");
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n_pairs; ++i) {
+        const int s = slots[i];
+        if (s < 0 || s >= ctx->max_slots || !ctx->slots[s].bound) return fail_arg(ctx, "slot not bound");
+        ctx->h_pairs[i] = make_pair_dev(ctx, s);
+        PairState& st = ctx->h_states[i];
+        memset(&st, 0, sizeof(st));
+        if (RT_io) {
+            memcpy(st.R, RT_io + (size_t)i * 12, sizeof(float) * 9);
+            memcpy(st.T, RT_io + (size_t)i * 12 + 9, sizeof(float) * 3);
+        } else {
+            st.R[0] = st.R[4] = st.R[8] = 1.f;
+        }
+        st.ell = ell_io ? ell_io[i] : p->ell_init;
+        st.ell_max = p->ell_max;
+    }
+    AlignArgs args;
+    args.pairs = ctx->d_pairs;
+    args.states = ctx->d_states;
+    args.n_pairs = n_pairs;
+    args.counter = ctx->d_counter;
+    args.trace = nullptr;
+    args.trace_cap = 0;
+    if (trace && trace_cap > 0) {
+        args.trace = ctx->d_trace;
+        args.trace_cap = trace_cap < ctx->trace_cap ? trace_cap : ctx->trace_cap;
+    }
+    args.kp = make_kparams(p, false);
+    CK(cudaMemcpyAsync(ctx->d_pairs, ctx->h_pairs, sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_states, ctx->h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    int G = choose_cluster(ctx, n_pairs);
+    int ncl = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = launch_cluster_kernel(ctx, align_kernel, args, G, n_pairs, &ncl);
+    if (rc != CVO_B200_OK && G > 8 && ctx->force_G == 0) {  // 16-CTA clusters are opt-in; fall back to portable 8
+        G = 8;
+        rc = launch_cluster_kernel(ctx, align_kernel, args, G, n_pairs, &ncl);
+    }
+    if (rc != CVO_B200_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_states, ctx->d_states, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (args.trace)
+        CK(cudaMemcpyAsync(ctx->h_trace, ctx->d_trace, sizeof(cvo_b200_iter_rec) * args.trace_cap,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    ctx->last_G = G;
+    ctx->last_nclusters = ncl;
+    long long total = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const PairState& st = ctx->h_states[i];
+        total += st.n_run;
+        if (RT_io) {
+            memcpy(RT_io + (size_t)i * 12, st.R, sizeof(float) * 9);
+            memcpy(RT_io + (size_t)i * 12 + 9, st.T, sizeof(float) * 3);
+        }
+        if (ell_io) ell_io[i] = st.ell;
+        if (transform) memcpy(transform + (size_t)i * 16, st.tf, sizeof(float) * 16);
+        if (prev_transform) memcpy(prev_transform + (size_t)i * 16, st.prev_tf, sizeof(float) * 16);
+        if (iters) iters[i] = st.iters;
+        if (status) status[i] = st.status;
+    }
+    ctx->last_total_iters = total;
+    if (args.trace) {
+        const int n = ctx->h_states[0].n_run < args.trace_cap ? ctx->h_states[0].n_run : args.trace_cap;
+        memcpy(trace, ctx->h_trace, sizeof(cvo_b200_iter_rec) * n);
+    }
+    if (trace_len) *trace_len = ctx->h_states[0].n_run;
+    return CVO_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void cvo_b200_default_params_cvo(cvo_b200_params* p) {  // src/cvo.cpp:18-48
+    memset(p, 0, sizeof(*p));
+    p->mode = CVO_B200_MODE_CVO;
+    p->ell_policy = CVO_B200_ELL_SCHEDULE;
+    p->ell_init = 0.15f;
+    p->ell_min = 0.0391f;
+    p->ell_max = 0.15f;
+    p->dl_step = 0.3;
+    p->sigma = 0.1f;
+    p->sp_thres = 8e-3f;
+    p->c = 7.0f;
+    p->d = 7.0f;
+    p->c_ell = 200.f;
+    p->c_sigma = 1.f;
+    p->c_sp_thres = 8e-3f;
+    p->max_iter = 2000;
+    p->min_step = (float)(2 * 1.0e-1);
+    p->max_step = 0.8f;
+    p->eps = (float)(5 * 1.0e-5);
+    p->eps_2 = 1.0e-5f;
+    p->fixed_iters = 0;
+}
+
+void cvo_b200_default_params_acvo(cvo_b200_params* p) {  // src/adaptive_cvo.cpp:18-50
+    cvo_b200_default_params_cvo(p);
+    p->mode = CVO_B200_MODE_ACVO;
+    p->ell_policy = CVO_B200_ELL_ADAPTIVE;
+    p->ell_init = 0.1f;
+    p->sp_thres = 8.315e-3f;
+    p->c_ell = 0.5f;
+    p->c_sp_thres = 8.315e-3f;
+}
+
+int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slots) {
+    if (!out || max_points <= 0 || max_slots <= 0) return CVO_B200_ERR_ARG;
+    *out = nullptr;
+    cvo_b200_ctx* ctx = new cvo_b200_ctx();
+    ctx->device = device;
+    ctx->max_points = (max_points + 31) / 32 * 32;
+    ctx->max_slots = max_slots;
+    ctx->slots.resize(max_slots);
+    ctx->trace_cap = kTraceCap;
+    cudaError_t e;
+#define CKC(call)                                                                   \
+    do {                                                                            \
+        e = (call);                                                                 \
+        if (e != cudaSuccess) {                                                     \
+            fprintf(stderr, "cvo_b200_create: %s: %s\n", #call, cudaGetErrorString(e)); \
+            cvo_b200_destroy(ctx);                                                  \
+            return CVO_B200_ERR_CUDA;                                               \
+        }                                                                           \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fprintf(stderr, "cvo_b200_create: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
+                prop.major, prop.minor);
+        cvo_b200_destroy(ctx);
+        return CVO_B200_ERR_CUDA;
+    }
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&ctx->ev0));
+    CKC(cudaEventCreate(&ctx->ev1));
+    const size_t mp = ctx->max_points;
+    CKC(cudaMalloc(&ctx->d_raw_xyz, sizeof(float) * 3 * mp * 2));
+    CKC(cudaMalloc(&ctx->d_raw_feat, sizeof(float) * 5 * mp * 2));
+    CKC(cudaMalloc(&ctx->d_pk_g, sizeof(float4) * mp * 2 * max_slots));
+    CKC(cudaMalloc(&ctx->d_pk_f, sizeof(float4) * mp * 2 * max_slots));
+    CKC(cudaMalloc(&ctx->d_pairs, sizeof(PairDev) * max_slots));
+    CKC(cudaMalloc(&ctx->d_states, sizeof(PairState) * max_slots));
+    CKC(cudaMallocHost(&ctx->h_pairs, sizeof(PairDev) * max_slots));
+    CKC(cudaMallocHost(&ctx->h_states, sizeof(PairState) * max_slots));
+    CKC(cudaMalloc(&ctx->d_counter, sizeof(int)));
+    CKC(cudaMalloc(&ctx->d_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
+    CKC(cudaMallocHost(&ctx->h_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
+    CKC(cudaMalloc(&ctx->d_inner, sizeof(double) * 2));
+    CKC(cudaMalloc(&ctx->d_jobs, sizeof(PackJob) * 2));
+    CKC(cudaMallocHost(&ctx->h_inner, sizeof(double) * 2));
+    ctx->pack_smem_max = 128 * 1024;
+    CKC(cudaFuncSetAttribute(pack_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pack_smem_max));
+    if ((size_t)ctx->max_points * sizeof(unsigned long long) > ctx->pack_smem_max) {
+        fprintf(stderr, "cvo_b200_create: max_points %d exceeds the single-CTA sort capacity (16384)\n", max_points);
+        cvo_b200_destroy(ctx);
+        return CVO_B200_ERR_ARG;
+    }
+    const char* env = getenv("CVO_B200_NO_SORT");
+    if (env && env[0] == '1') ctx->sort_points = 0;
+#undef CKC
+    *out = ctx;
+    return CVO_B200_OK;
+}
+
+void cvo_b200_destroy(cvo_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_raw_xyz);
+    cudaFree(ctx->d_raw_feat);
+    cudaFree(ctx->d_pk_g);
+    cudaFree(ctx->d_pk_f);
+    cudaFree(ctx->d_pairs);
+    cudaFree(ctx->d_states);
+    cudaFreeHost(ctx->h_pairs);
+    cudaFreeHost(ctx->h_states);
+    cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_trace);
+    cudaFreeHost(ctx->h_trace);
+    cudaFree(ctx->d_inner);
+    cudaFree(ctx->d_jobs);
+    cudaFreeHost(ctx->h_inner);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cvo_b200_last_error(const cvo_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const float* fixed_feat, int n_fixed,
+                      const float* moving_xyz, const float* moving_feat, int n_moving) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
+    if (!fixed_xyz || !fixed_feat || !moving_xyz || !moving_feat) return fail_arg(ctx, "null cloud pointer");
+    if (n_fixed <= 0 || n_moving <= 0) {
+        ctx->err = "empty cloud";
+        return CVO_B200_ERR_EMPTY;
+    }
+    if (n_fixed > ctx->max_points || n_moving > ctx->max_points) return fail_arg(ctx, "cloud larger than max_points");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_cloud(ctx, 0, fixed_xyz, fixed_feat, n_fixed);
+    if (rc) return rc;
+    rc = upload_cloud(ctx, 1, moving_xyz, moving_feat, n_moving);
+    if (rc) return rc;
+    cvo_b200_ctx::Slot& s = ctx->slots[slot];
+    s.fixed_buf = 0;
+    s.n[0] = n_fixed;
+    s.n[1] = n_moving;
+    s.bound = true;
+    PackJob jobs[2];
+    const size_t mp = ctx->max_points;
+    jobs[0] = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0), n_fixed, 0};
+    jobs[1] = {ctx->d_raw_xyz + mp * 3, ctx->d_raw_feat + mp * 5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1), n_moving, 0};
+    return launch_pack(ctx, jobs, 2, ctx->d_jobs);
+}
+
+int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots || !ctx->slots[slot].bound) return fail_arg(ctx, "slot not bound");
+    if (!xyz || !feat) return fail_arg(ctx, "null cloud pointer");
+    if (n <= 0) {
+        ctx->err = "empty cloud";
+        return CVO_B200_ERR_EMPTY;
+    }
+    if (n > ctx->max_points) return fail_arg(ctx, "cloud larger than max_points");
+    CK(cudaSetDevice(ctx->device));
+    cvo_b200_ctx::Slot& s = ctx->slots[slot];
+    s.fixed_buf = 1 - s.fixed_buf;  // moving becomes fixed (src/cvo.cpp:417)
+    const int mb = 1 - s.fixed_buf;
+    int rc = upload_cloud(ctx, 0, xyz, feat, n);
+    if (rc) return rc;
+    s.n[mb] = n;
+    PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), n, 0};
+    return launch_pack(ctx, &job, 1, ctx->d_jobs);
+}
+
+int cvo_b200_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, float* RT_io,
+                   float* ell_io, float* transform, float* prev_transform, int* iters, int* status) {
+    return run_align(ctx, slots, n_pairs, p, RT_io, ell_io, transform, prev_transform, iters, status, nullptr, 0,
+                     nullptr);
+}
+
+int cvo_b200_align_trace(cvo_b200_ctx* ctx, int slot, const cvo_b200_params* p, float* RT_io, float* ell_io,
+                         float* transform, float* prev_transform, int* iters, int* status,
+                         cvo_b200_iter_rec* trace, int trace_cap, int* trace_len) {
+    return run_align(ctx, &slot, 1, p, RT_io, ell_io, transform, prev_transform, iters, status, trace, trace_cap,
+                     trace_len);
+}
+
+int cvo_b200_eval(cvo_b200_ctx* ctx, int slot, const float* R, const float* T, float ell, const cvo_b200_params* p,
+                  cvo_b200_iter_rec* out) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!R || !T || !p || !out) return fail_arg(ctx, "null pointer");
+    cvo_b200_params q = *p;
+    q.fixed_iters = 1;
+    float RT[12];
+    memcpy(RT, R, sizeof(float) * 9);
+    memcpy(RT + 9, T, sizeof(float) * 3);
+    float ell_io = ell;
+    int len = 0;
+    return run_align(ctx, &slot, 1, &q, RT, &ell_io, nullptr, nullptr, nullptr, nullptr, out, 1, &len);
+}
+
+int cvo_b200_inner_product(cvo_b200_ctx* ctx, int slot, float ell, const cvo_b200_params* p, float* value,
+                           double* sum_a, long long* nnz) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots || !ctx->slots[slot].bound) return fail_arg(ctx, "slot not bound");
+    if (!p) return fail_arg(ctx, "null params");
+    CK(cudaSetDevice(ctx->device));
+    InnerArgs args;
+    args.pair = make_pair_dev(ctx, slot);
+    args.kp = make_kparams(p, true);
+    args.ell = ell;
+    args.out = ctx->d_inner;
+    int G = ctx->force_G > 0 ? ctx->force_G : 8;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = launch_cluster_kernel(ctx, inner_product_kernel, args, G, 1, nullptr);
+    if (rc != CVO_B200_OK) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_inner, ctx->d_inner, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    const double s = ctx->h_inner[0], c = ctx->h_inner[1];
+    if (sum_a) *sum_a = s;
+    if (nnz) *nnz = (long long)c;
+    if (value) *value = (float)(s / c);  // src/adaptive_cvo.cpp:438
+    return CVO_B200_OK;
+}
+
+int cvo_b200_sync(cvo_b200_ctx* ctx) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CVO_B200_OK;
+}
+
+float cvo_b200_last_kernel_ms(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+long long cvo_b200_kernel_launches(const cvo_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int cvo_b200_last_cluster_size(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_G : 0; }
+int cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_nclusters : 0; }
+int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16)) return fail_arg(ctx, "cluster size must be 0,1,2,4,8,16");
+    ctx->force_G = g;
+    return CVO_B200_OK;
+}
+long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_total_iters : 0; }
+int cvo_b200_num_sms(const cvo_b200_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+}  // extern "C"

@@ -1,0 +1,926 @@
+// cvo_kernels.cuh -- sm_100a kernels for the RKHS SE(3) registration inner loop.
+//
+// One persistent kernel runs the reference's whole align() loop
+// (cpp/rkhs_registration/src/cvo.cpp:361-420, src/adaptive_cvo.cpp:490-555) on the device:
+// a thread-block CLUSTER of G CTAs owns one frame pair at a time and iterates
+//     transform_pcd -> se_kernel -> compute_flow -> compute_step_size -> Exp_SEK3 update
+// without host round trips.  The sparse affinity matrix A (inc/cvo.hpp:92) is never stored:
+// both all-pairs passes (flow, step coefficients) re-derive it tile by tile in shared memory
+// with an on-the-fly ell-ball cutoff; tile pairs whose bounding boxes are farther apart than
+// the ball radius are culled (clouds are Morton-sorted at upload), which is this design's
+// replacement for the reference's nanoflann kd-tree (thirdparty/nanoflann.hpp).
+// Cross-CTA reductions go through distributed shared memory + cluster barriers.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cvo_b200.h"
+
+namespace cvo_b200 {
+
+namespace cg = cooperative_groups;
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTile = 32;
+constexpr int kRowChunk = 2048;
+constexpr int kColChunk = 2048;
+constexpr int kRowTiles = kRowChunk / kTile;
+constexpr int kColTiles = kColChunk / kTile;
+constexpr int kMaxCluster = 16;
+constexpr int kNumAcc = 16;
+constexpr int kListCap = kRowTiles * kColTiles;
+constexpr int kListBlocks = kListCap / 32;
+constexpr int kFlowOff = 4;  // sm.sum[0..3] = B,C,D,E ; sm.sum[kFlowOff + ACC_*] = flow totals
+constexpr float kRowSentinel = 1.0e30f;
+constexpr float kColSentinel = -1.0e30f;
+
+enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INNER = 4 };
+
+// accumulator slots of the flow exchange
+enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZXX = 9, ACC_SXX = 10,
+       ACC_NNZYY = 11, ACC_SYY = 12, ACC_FLOW_COUNT = 13 };
+static_assert(ACC_FLOW_COUNT <= kNumAcc, "flow accumulators must fit the exchange buffers");
+
+struct CloudDev {
+    const float4* g;  // {x, y, z, f0}
+    const float4* f;  // {f1, f2, f3, f4}
+    int n;
+    int pad;
+};
+
+struct PairDev {
+    CloudDev x;  // fixed  (cloud_x)
+    CloudDev y;  // moving (cloud_y), original positions
+};
+
+struct PairState {
+    float R[9];
+    float T[3];
+    float ell;
+    float ell_max;
+    int iters;
+    int status;
+    int n_run;
+    int pad;
+    float tf[16];
+    float prev_tf[16];
+};
+
+// cvo_b200_params + constants precomputed on the host in the reference's own arithmetic
+struct KParams {
+    int mode, ell_policy;
+    int max_iter, fixed_iters;
+    float ell_min;
+    float s2;          // sigma*sigma
+    float cs2;         // c_sigma*c_sigma
+    float sp_thres;
+    float log_ratio;   // logf(sp_thres/s2)            (src/cvo.cpp:102; log on a float is f32)
+    float d2c_thres;   // colour gate                   (src/cvo.cpp:103 / src/adaptive_cvo.cpp:101)
+    float inv2cl2;     // 1/(2 c_ell^2)
+    float inv_c, inv_d;
+    float min_step, max_step, eps, eps_2;
+    double dl_step;
+};
+
+struct IterConsts {
+    float tf[12];  // transform: rows of R^T, then -R^T T   (src/cvo.cpp:83-87)
+    float d2_thres, d2c_thres, inv2l2, inv_ell3;
+    float omega[3], v[3];
+    float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
+    float temp_coef, m2t, p2t;
+};
+
+struct Smem {
+    float4 rowG[kRowChunk];
+    float4 rowF[kRowChunk];
+    float4 colG[kColChunk];
+    float4 colF[kColChunk];
+    float rowBox[kRowTiles][8];
+    float colBox[kColTiles][8];
+    uint32_t list[kListCap];
+    int listBlockCount[kListBlocks];
+    int listBlockBase[kListBlocks];
+    int list_n;
+    int next_pair;
+    int done;
+    int k;
+    double red[kWarps][kNumAcc];
+    double xchg[2][kMaxCluster][kNumAcc];
+    double sum[kFlowOff + kNumAcc];
+    IterConsts ic;
+    PairState st;
+};
+
+struct AlignArgs {
+    const PairDev* pairs;
+    PairState* states;
+    int n_pairs;
+    int* counter;
+    cvo_b200_iter_rec* trace;  // records of pair 0 only (align_trace / eval), or nullptr
+    int trace_cap;
+    KParams kp;
+};
+
+struct InnerArgs {
+    PairDev pair;
+    KParams kp;
+    float ell;
+    double* out;  // [0] = sum_a, [1] = nnz
+};
+
+struct PackJob {
+    const float* xyz;   // n x 3
+    const float* feat;  // n x 5
+    float4* out_g;
+    float4* out_f;
+    int n;
+    int pad;
+};
+
+// --------------------------------------------------------------------------------------------
+// small helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// y = R^T p - R^T T with the fma chain documented in DESIGN.md (membership-critical)
+__device__ __forceinline__ void apply_tf(const float* tf, float& x, float& y, float& z) {
+    const float px = x, py = y, pz = z;
+    x = __fadd_rn(__fmaf_rn(tf[2], pz, __fmaf_rn(tf[1], py, __fmul_rn(tf[0], px))), tf[9]);
+    y = __fadd_rn(__fmaf_rn(tf[5], pz, __fmaf_rn(tf[4], py, __fmul_rn(tf[3], px))), tf[10]);
+    z = __fadd_rn(__fmaf_rn(tf[8], pz, __fmaf_rn(tf[7], py, __fmul_rn(tf[6], px))), tf[11]);
+}
+
+// squared distance exactly as nanoflann's L2 tail loop under fp-contract (thirdparty/nanoflann.hpp:402-406)
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ void mat3_mul(const float* a, const float* b, float* r) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r[i * 3 + j] = __fadd_rn(__fadd_rn(__fmul_rn(a[i * 3], b[j]), __fmul_rn(a[i * 3 + 1], b[3 + j])),
+                                     __fmul_rn(a[i * 3 + 2], b[6 + j]));
+}
+__device__ __forceinline__ void mat3_vec(const float* a, const float* v, float* r) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        r[i] = __fadd_rn(__fadd_rn(__fmul_rn(a[i * 3], v[0]), __fmul_rn(a[i * 3 + 1], v[1])), __fmul_rn(a[i * 3 + 2], v[2]));
+}
+__device__ __forceinline__ void skew3(const float* w, float* M) {  // src/LieGroup.cpp:20-27
+    M[0] = 0.f;   M[1] = -w[2]; M[2] = w[1];
+    M[3] = w[2];  M[4] = 0.f;   M[5] = -w[0];
+    M[6] = -w[1]; M[7] = w[0];  M[8] = 0.f;
+}
+__device__ __forceinline__ float dot3f(const float* a, const float* b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+}
+
+// --------------------------------------------------------------------------------------------
+// scalar epilogue pieces (one thread per CTA; every CTA of a cluster computes the same values)
+// --------------------------------------------------------------------------------------------
+
+// update_tf (src/cvo.cpp:83-87) + thresholds of se_kernel (src/cvo.cpp:102-103)
+__device__ void prepare_iter(Smem& sm, const KParams& kp, float d2c_thres) {
+    IterConsts& ic = sm.ic;
+    const float* R = sm.st.R;
+    const float* T = sm.st.T;
+    float nRt[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            ic.tf[i * 3 + j] = R[j * 3 + i];
+            nRt[i * 3 + j] = -R[j * 3 + i];
+        }
+    mat3_vec(nRt, T, &ic.tf[9]);
+    const double l = (double)sm.st.ell;
+    ic.d2_thres = (float)(-2.0 * l * l * (double)kp.log_ratio);
+    ic.d2c_thres = d2c_thres;
+    ic.inv2l2 = (float)(1.0 / (2.0 * l * l));
+    const float ell3 = __fmul_rn(__fmul_rn(sm.st.ell, sm.st.ell), sm.st.ell);  // src/adaptive_cvo.cpp:171
+    ic.inv_ell3 = 1.0f / ell3;
+}
+
+// tail of compute_flow (src/cvo.cpp:208-209) + the per-iteration constants of compute_step_size (:215-241)
+__device__ void finalize_flow(Smem& sm) {
+    IterConsts& ic = sm.ic;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        ic.omega[t] = (float)sm.sum[kFlowOff + ACC_W0 + t];
+        ic.v[t] = (float)sm.sum[kFlowOff + ACC_V0 + t];
+    }
+    float W[9];
+    skew3(ic.omega, W);
+    mat3_mul(W, W, ic.W2);
+    mat3_mul(ic.W2, W, ic.W3);
+    mat3_mul(ic.W3, W, ic.W4);
+    mat3_vec(W, ic.v, ic.Wv);
+    mat3_vec(ic.W2, ic.v, ic.W2v);
+    mat3_vec(ic.W3, ic.v, ic.W3v);
+    const double l = (double)sm.st.ell;
+    ic.temp_coef = (float)(1.0 / (2.0 * l * l));  // src/cvo.cpp:241
+    ic.m2t = (float)(-2.0 * (double)ic.temp_coef);
+    ic.p2t = (float)(2.0 * (double)ic.temp_coef);
+}
+
+// poly_solver + root selection (src/cvo.cpp:53-69,291-307): smallest positive real root of
+// 4E t^3 + 3D t^2 + 2C t + B, f64 closed form on the f32-normalised coefficients.
+__device__ float step_from_coeffs(double B, double C, double D, double E, float min_step, float max_step) {
+    const float p0 = (float)(4.0 * (double)(float)E);
+    const float p1 = (float)(3.0 * (double)(float)D);
+    const float p2 = (float)(2.0 * (double)(float)C);
+    const float p3 = (float)B;
+    const float a2f = p1 / p0, a1f = p2 / p0, a0f = p3 / p0;
+    const float kNone = 3.402823466e+38f;
+    float best = kNone;
+    if (isfinite(a2f) && isfinite(a1f) && isfinite(a0f)) {
+        const double a2 = a2f, a1 = a1f, a0 = a0f;
+        const double q = (3.0 * a1 - a2 * a2) * (1.0 / 9.0);
+        const double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) * (1.0 / 54.0);
+        const double disc = q * q * q + r * r;
+        double roots[3];
+        int n = 0;
+        const double shift = a2 * (1.0 / 3.0);
+        if (disc > 0.0) {
+            const double sd = sqrt(disc);
+            roots[n++] = cbrt(r + sd) + cbrt(r - sd) - shift;
+        } else if (disc == 0.0) {
+            const double s = cbrt(r);
+            roots[n++] = 2.0 * s - shift;
+            roots[n++] = -s - shift;
+        } else {
+            double cth = r / sqrt(-q * q * q);
+            cth = fmin(1.0, fmax(-1.0, cth));
+            const double th = acos(cth);
+            const double m = 2.0 * sqrt(-q);
+            const double kTwoPi = 6.283185307179586476925286766559;
+            roots[n++] = m * cos(th * (1.0 / 3.0)) - shift;
+            roots[n++] = m * cos((th + kTwoPi) * (1.0 / 3.0)) - shift;
+            roots[n++] = m * cos((th + 2.0 * kTwoPi) * (1.0 / 3.0)) - shift;
+        }
+        for (int i = 0; i < n; ++i) {
+            double x = roots[i];
+            for (int it = 0; it < 3; ++it) {
+                const double f = ((x + a2) * x + a1) * x + a0;
+                const double fp = (3.0 * x + 2.0 * a2) * x + a1;
+                if (fp == 0.0 || !isfinite(f)) break;
+                const double xn = x - f / fp;
+                if (!isfinite(xn)) break;
+                x = xn;
+            }
+            const float xr = (float)x;
+            if (xr > 0.f && xr < best) best = xr;
+        }
+    }
+    float step = (best == kNone) ? min_step : best;
+    return step > max_step ? max_step : step;
+}
+
+// Exp_SEK3 with K = 1 (src/LieGroup.cpp:159-186), including the small-angle quirk (Jl = I)
+__device__ void exp_sek3(const float* w, const float* v, float dt, float* dR, float* dT) {
+    const float theta = sqrtf(dot3f(w, w));
+    float Jl[9];
+    if (theta < 1e-6f) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dR[i] = Jl[i] = (i % 4 == 0) ? 1.f : 0.f;
+    } else {
+        float A[9], A2[9];
+        skew3(w, A);
+        mat3_mul(A, A, A2);
+        const float theta2 = theta * theta;
+        const float st = sinf(dt * theta), ct = cosf(dt * theta);
+        const float omc = (1.f - ct) / theta2;
+        const float sa = st / theta;
+        const float sj = (dt * theta - st) / (theta2 * theta);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const float I = (i % 4 == 0) ? 1.f : 0.f;
+            dR[i] = __fadd_rn(__fadd_rn(I, __fmul_rn(sa, A[i])), __fmul_rn(omc, A2[i]));
+            Jl[i] = __fadd_rn(__fadd_rn(__fmul_rn(dt, I), __fmul_rn(omc, A[i])), __fmul_rn(sj, A2[i]));
+        }
+    }
+    mat3_vec(Jl, v, dT);
+}
+
+// Body of align() after compute_step_size (src/cvo.cpp:379-410, src/adaptive_cvo.cpp:508-545)
+__device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_rec* rec) {
+    IterConsts& ic = sm.ic;
+    PairState& st = sm.st;
+    const double B = sm.sum[0], C = sm.sum[1], D = sm.sum[2], E = sm.sum[3];
+    const float step = step_from_coeffs(B, C, D, E, kp.min_step, kp.max_step);
+    const bool stops = !(kp.fixed_iters > 0);
+    const float ell_used = st.ell;
+    bool stop = false;
+    int status = CVO_B200_STATUS_MAX_ITER;
+    const float w2 = dot3f(ic.omega, ic.omega), v2 = dot3f(ic.v, ic.v);
+    if (!(isfinite(w2) && isfinite(v2))) {
+        stop = true;
+        status = CVO_B200_STATUS_NAN;
+    }
+    if (!stop && stops) {
+        bool small;
+        if (kp.mode == CVO_B200_MODE_ACVO) {  // src/adaptive_cvo.cpp:509, norms in f64
+            const double dw = sqrt((double)ic.omega[0] * ic.omega[0] + (double)ic.omega[1] * ic.omega[1] +
+                                   (double)ic.omega[2] * ic.omega[2]);
+            const double dv = sqrt((double)ic.v[0] * ic.v[0] + (double)ic.v[1] * ic.v[1] + (double)ic.v[2] * ic.v[2]);
+            small = dw < (double)kp.eps && dv < (double)kp.eps;
+        } else {  // src/cvo.cpp:380
+            small = sqrtf(w2) < kp.eps && sqrtf(v2) < kp.eps;
+        }
+        if (small) {
+            stop = true;
+            status = CVO_B200_STATUS_CONVERGED_TWIST;
+        }
+    }
+    if (!stop) {
+        float dR[9], dT[3], RdT[3], Rn[9];
+        exp_sek3(ic.omega, ic.v, step, dR, dT);  // src/cvo.cpp:391
+        mat3_vec(st.R, dT, RdT);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) st.T[t] = __fadd_rn(RdT[t], st.T[t]);  // :398
+        mat3_mul(st.R, dR, Rn);                                             // :399
+#pragma unroll
+        for (int t = 0; t < 9; ++t) st.R[t] = Rn[t];
+        if (stops) {
+            // dist_se3 (src/cvo.cpp:71-81): ||logm(Exp(step*[w^ v;0 0]))||_F in closed form
+            const float theta = sqrtf(w2);
+            const float dist = (theta < 1e-6f) ? sqrtf(v2) : step * sqrtf(2.f * w2 + v2);
+            if (dist < kp.eps_2) {  // :402
+                stop = true;
+                status = CVO_B200_STATUS_CONVERGED_UPDATE;
+            }
+        }
+    }
+    double dl = 0.0;
+    if (kp.mode == CVO_B200_MODE_ACVO) {  // src/adaptive_cvo.cpp:271
+        const double num = -2.0 * sm.sum[kFlowOff + ACC_DLXY] + sm.sum[kFlowOff + ACC_SXX] + sm.sum[kFlowOff + ACC_SYY];
+        const long long den = (long long)sm.sum[kFlowOff + ACC_NNZXX] + (long long)sm.sum[kFlowOff + ACC_NNZYY] -
+                              2 * (long long)sm.sum[kFlowOff + ACC_NNZ];
+        dl = num / (double)den;
+    }
+    if (!stop) {
+        if (kp.ell_policy == CVO_B200_ELL_SCHEDULE) {  // src/cvo.cpp:408-410
+            st.ell = (k > 2) ? 0.10f : st.ell;
+            st.ell = (k > 9) ? 0.06f : st.ell;
+            st.ell = (k > 19) ? 0.03f : st.ell;
+        } else if (kp.ell_policy == CVO_B200_ELL_ADAPTIVE) {  // src/adaptive_cvo.cpp:538-545
+            st.ell = (float)((double)st.ell + kp.dl_step * dl);
+            if (st.ell >= st.ell_max) {
+                st.ell = (float)((double)st.ell_max * 0.7);
+                st.ell_max = (float)((double)st.ell_max * 0.7);
+            }
+            st.ell = (st.ell < kp.ell_min) ? kp.ell_min : st.ell;
+        }
+    }
+    st.n_run = k + 1;
+    if (stop) {
+        st.iters = k;
+        st.status = status;
+        sm.done = 1;
+    }
+    if (rec) {
+        rec->ell = ell_used;
+        rec->step = step;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            rec->omega[t] = ic.omega[t];
+            rec->v[t] = ic.v[t];
+            rec->T[t] = st.T[t];
+        }
+        rec->B = B; rec->C = C; rec->D = D; rec->E = E;
+        rec->sum_a = sm.sum[kFlowOff + ACC_SUMA];
+        rec->dl = dl;
+        rec->nnz = (long long)sm.sum[kFlowOff + ACC_NNZ];
+        rec->nnz_xx = (long long)sm.sum[kFlowOff + ACC_NNZXX];
+        rec->nnz_yy = (long long)sm.sum[kFlowOff + ACC_NNZYY];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) rec->R[t] = st.R[t];
+    }
+}
+
+__device__ void write_tf44(const float* tf12, float* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) out[i * 4 + j] = tf12[i * 3 + j];
+        out[i * 4 + 3] = tf12[9 + i];
+    }
+    out[12] = out[13] = out[14] = 0.f;
+    out[15] = 1.f;
+}
+
+// --------------------------------------------------------------------------------------------
+// tile staging
+// --------------------------------------------------------------------------------------------
+
+// Stages `ntiles` 32-point tiles starting at point `base` of a packed cloud into shared memory,
+// applying the rigid transform on the way (this is transform_pcd, src/cvo.cpp:310-315: the
+// transformed cloud never exists in HBM) and reducing one bounding box per tile.
+__device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float (*box)[8], const CloudDev& c, int base,
+                                            int ntiles, bool tf, const float* tf12, float sentinel) {
+    const int lane = threadIdx.x & 31;
+    const float inf = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
+        const int p = base + i;
+        const bool valid = p < c.n;
+        float4 g, f;
+        if (valid) {
+            g = __ldg(c.g + p);
+            f = __ldg(c.f + p);
+            if (tf) apply_tf(tf12, g.x, g.y, g.z);
+        } else {
+            g = make_float4(sentinel, sentinel, sentinel, 0.f);
+            f = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        sg[i] = g;
+        sf[i] = f;
+        const float lx = warp_min(valid ? g.x : inf), ly = warp_min(valid ? g.y : inf), lz = warp_min(valid ? g.z : inf);
+        const float hx = warp_max(valid ? g.x : -inf), hy = warp_max(valid ? g.y : -inf), hz = warp_max(valid ? g.z : -inf);
+        if (lane == 0) {
+            float* b = box[i >> 5];
+            b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz;
+        }
+    }
+}
+
+// Deterministic list of (row tile, col tile) pairs whose boxes are within the ball radius.
+__device__ __forceinline__ void build_tile_list(Smem& sm, int nrt, int nct, float d2_thres) {
+    const int lane = threadIdx.x & 31;
+    const int npairs = nrt * nct;
+    const int nblocks = (npairs + 31) >> 5;
+    const float thr = d2_thres * 1.0001f;  // boxes are conservative; keep rounding on the safe side
+    uint32_t live_bits[kListBlocks / kWarps];
+    int nb = 0;
+    for (int blk = threadIdx.x >> 5; blk < nblocks; blk += kWarps, ++nb) {
+        const int p = blk * 32 + lane;
+        bool live = false;
+        if (p < npairs) {
+            const int rt = p / nct, ct = p - rt * nct;
+            const float* a = sm.rowBox[rt];
+            const float* b = sm.colBox[ct];
+            const float gx = fmaxf(0.f, fmaxf(a[0] - b[3], b[0] - a[3]));
+            const float gy = fmaxf(0.f, fmaxf(a[1] - b[4], b[1] - a[4]));
+            const float gz = fmaxf(0.f, fmaxf(a[2] - b[5], b[2] - a[5]));
+            live = (gx * gx + gy * gy + gz * gz) <= thr;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        live_bits[nb] = m;
+        if (lane == 0) sm.listBlockCount[blk] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of <= 128 block counts by one warp
+        int carry = 0;
+        for (int b0 = 0; b0 < nblocks; b0 += 32) {
+            const int b = b0 + lane;
+            const int c = (b < nblocks) ? sm.listBlockCount[b] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b < nblocks) sm.listBlockBase[b] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) sm.list_n = carry;
+    }
+    __syncthreads();
+    nb = 0;
+    for (int blk = threadIdx.x >> 5; blk < nblocks; blk += kWarps, ++nb) {
+        const uint32_t m = live_bits[nb];
+        if ((m >> lane) & 1u) {
+            const int p = blk * 32 + lane;
+            const int rt = p / nct, ct = p - rt * nct;
+            sm.list[sm.listBlockBase[blk] + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)rt << 16) | (uint32_t)ct;
+        }
+    }
+    __syncthreads();
+}
+
+// --------------------------------------------------------------------------------------------
+// per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xg,
+                                             const float4& xf, const float4& yg, const float4& yf, float d2,
+                                             float& a) {
+    const float e0 = xg.w - yg.w, e1 = xf.x - yf.x, e2 = xf.y - yf.y, e3 = xf.z - yf.z, e4 = xf.w - yf.w;
+    float d2c = __fmul_rn(e0, e0);
+    d2c = __fadd_rn(d2c, __fmul_rn(e1, e1));
+    d2c = __fadd_rn(d2c, __fmul_rn(e2, e2));
+    d2c = __fadd_rn(d2c, __fmul_rn(e3, e3));
+    d2c = __fadd_rn(d2c, __fmul_rn(e4, e4));
+    if (!(d2c < ic.d2c_thres)) return false;
+    const float k = __fmul_rn(kp.s2, expf(-__fmul_rn(d2, ic.inv2l2)));      // src/cvo.cpp:149
+    const float ck = __fmul_rn(kp.cs2, expf(-__fmul_rn(d2c, kp.inv2cl2)));  // :150
+    a = __fmul_rn(ck, k);                                                   // :151
+    return a > kp.sp_thres;                                                 // :152
+}
+
+// One (row tile, col tile) entry: lane = one row; 32 candidate columns.
+template <int KIND>
+__device__ __forceinline__ void process_entry(const Smem& sm, const KParams& kp, int rt, int ct, int lane,
+                                              int row_global, int yy_row_min, double* acc) {
+    const IterConsts& ic = sm.ic;
+    const float4 xg = sm.rowG[rt * kTile + lane];
+    const float4* cgp = sm.colG + ct * kTile;
+    const float4* cfp = sm.colF + ct * kTile;
+    const float thr = ic.d2_thres;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int jj = 0; jj < kTile; ++jj) {
+        const float4 c = cgp[jj];
+        const float d2 = dist2(c.x - xg.x, c.y - xg.y, c.z - xg.z);
+        mask |= (d2 < thr) ? (1u << jj) : 0u;  // strict <, thirdparty/nanoflann.hpp:249-253
+    }
+    if (__ballot_sync(0xffffffffu, mask != 0) == 0) return;
+    const float4 xf = sm.rowF[rt * kTile + lane];
+
+    if (KIND == PASS_FLOW) {
+        float po0 = 0.f, po1 = 0.f, po2 = 0.f, pv0 = 0.f, pv1 = 0.f, pv2 = 0.f, psum = 0.f, pdl = 0.f;
+        int cnt = 0;
+        while (mask) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 yg = cgp[jj];
+            const float4 yf = cfp[jj];
+            const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
+            const float d2 = dist2(dx, dy, dz);
+            float a;
+            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
+                const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
+                const float cy = xg.z * yg.x - xg.x * yg.z;
+                const float cz = xg.x * yg.y - xg.y * yg.x;
+                const float ac = kp.inv_c * a, ad = kp.inv_d * a;  // (1/c*Ai), (1/d*Ai), :197-198
+                po0 = fmaf(ac, cx, po0); po1 = fmaf(ac, cy, po1); po2 = fmaf(ac, cz, po2);
+                pv0 = fmaf(ad, dx, pv0); pv1 = fmaf(ad, dy, pv1); pv2 = fmaf(ad, dz, pv2);
+                psum += a;
+                pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, pdl);  // src/adaptive_cvo.cpp:202,228
+                ++cnt;
+            }
+        }
+        if (cnt) {
+            acc[ACC_W0] += (double)po0; acc[ACC_W0 + 1] += (double)po1; acc[ACC_W0 + 2] += (double)po2;
+            acc[ACC_V0] += (double)pv0; acc[ACC_V0 + 1] += (double)pv1; acc[ACC_V0 + 2] += (double)pv2;
+            acc[ACC_SUMA] += (double)psum;
+            acc[ACC_NNZ] += (double)cnt;
+            acc[ACC_DLXY] += (double)pdl;
+        }
+    } else if (KIND == PASS_XX || KIND == PASS_YY || KIND == PASS_INNER) {
+        float ps = 0.f, psum = 0.f;
+        int cnt = 0;
+        while (mask) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 yg = cgp[jj];
+            const float4 yf = cfp[jj];
+            const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;
+            const float d2 = dist2(dx, dy, dz);
+            float a;
+            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
+                ps = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, ps);  // src/adaptive_cvo.cpp:210,231 / :256,259
+                psum += a;
+                ++cnt;
+            }
+        }
+        if (cnt) {
+            if (KIND == PASS_XX) {
+                acc[ACC_NNZXX] += (double)cnt;
+                acc[ACC_SXX] += (double)ps;
+            } else if (KIND == PASS_YY) {
+                acc[ACC_NNZYY] += (double)cnt;
+                // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223)
+                if (row_global >= yy_row_min) acc[ACC_SYY] += (double)ps;
+            } else {
+                acc[0] += (double)psum;
+                acc[1] += (double)cnt;
+            }
+        }
+    } else {  // PASS_STEP: src/cvo.cpp:249-289
+        double Bi = 0.0, Ci = 0.0, Di = 0.0, Ei = 0.0;
+        bool any = false;
+        while (mask) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 yg = cgp[jj];
+            const float4 yf = cfp[jj];
+            const float rx = xg.x - yg.x, ry = xg.y - yg.y, rz = xg.z - yg.z;  // diff_xy, :260
+            const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
+            float a;
+            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
+                // xi*z+v ... xi^4*z+xi^3*v for this moving point (src/cvo.cpp:226-238)
+                const float* w = ic.omega;
+                const float z1x = (w[1] * yg.z - w[2] * yg.y) + ic.v[0];
+                const float z1y = (w[2] * yg.x - w[0] * yg.z) + ic.v[1];
+                const float z1z = (w[0] * yg.y - w[1] * yg.x) + ic.v[2];
+                const float z2x = ((ic.W2[0] * yg.x + ic.W2[1] * yg.y) + ic.W2[2] * yg.z) + ic.Wv[0];
+                const float z2y = ((ic.W2[3] * yg.x + ic.W2[4] * yg.y) + ic.W2[5] * yg.z) + ic.Wv[1];
+                const float z2z = ((ic.W2[6] * yg.x + ic.W2[7] * yg.y) + ic.W2[8] * yg.z) + ic.Wv[2];
+                const float z3x = ((ic.W3[0] * yg.x + ic.W3[1] * yg.y) + ic.W3[2] * yg.z) + ic.W2v[0];
+                const float z3y = ((ic.W3[3] * yg.x + ic.W3[4] * yg.y) + ic.W3[5] * yg.z) + ic.W2v[1];
+                const float z3z = ((ic.W3[6] * yg.x + ic.W3[7] * yg.y) + ic.W3[8] * yg.z) + ic.W2v[2];
+                const float z4x = ((ic.W4[0] * yg.x + ic.W4[1] * yg.y) + ic.W4[2] * yg.z) + ic.W3v[0];
+                const float z4y = ((ic.W4[3] * yg.x + ic.W4[4] * yg.y) + ic.W4[5] * yg.z) + ic.W3v[1];
+                const float z4z = ((ic.W4[6] * yg.x + ic.W4[7] * yg.y) + ic.W4[8] * yg.z) + ic.W3v[2];
+                const float nrm = (z1x * z1x + z1y * z1y) + z1z * z1z;                          // normxiz2
+                const float pdt = -((z1x * z2x + z1y * z2y) + z1z * z2z);                       // xiz_dot_xi2z
+                const float ecn = ((z2x * z2x + z2y * z2y) + z2z * z2z) + 2.f * ((z1x * z3x + z1y * z3y) + z1z * z3z);
+                const float beta = ((ic.m2t * z1x) * rx + (ic.m2t * z1y) * ry) + (ic.m2t * z1z) * rz;           // :262
+                const float gamma = -ic.temp_coef * (nrm + (((2.f * z2x) * rx + (2.f * z2y) * ry) + (2.f * z2z) * rz));  // :264
+                const float delta = ic.p2t * (pdt + (((-z3x) * rx + (-z3y) * ry) + (-z3z) * rz));              // :267
+                const float epsil = -ic.temp_coef * (ecn + (((2.f * z4x) * rx + (2.f * z4y) * ry) + (2.f * z4z) * rz));  // :270
+                const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
+                Bi += (double)(a * beta);                                                                       // :275
+                Ci += ad * (gd + (double)(beta * beta) / 2.0);                                                  // :276
+                Di += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) / 6.0);               // :277
+                Ei += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
+                            (1.0 / 24.0) * bd * bd * bd * bd);                                                  // :278-279
+                any = true;
+            }
+        }
+        if (any) {
+            acc[0] += Bi; acc[1] += Ci; acc[2] += Di; acc[3] += Ei;
+        }
+    }
+}
+
+// One all-pairs pass of `rows` x `cols` restricted to this CTA's share of the row tiles.
+template <int KIND>
+__device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
+                         bool col_tf, int rank, int G, int yy_row_min, double* acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total_rt = (rows.n + kTile - 1) / kTile;
+    const int t_begin = (int)(((long long)total_rt * rank) / G);
+    const int t_end = (int)(((long long)total_rt * (rank + 1)) / G);
+    const int total_ct = (cols.n + kTile - 1) / kTile;
+    for (int tb = t_begin; tb < t_end; tb += kRowTiles) {
+        const int nrt = min(kRowTiles, t_end - tb);
+        __syncthreads();  // previous users of rowG / colG are done
+        stage_tiles(sm.rowG, sm.rowF, sm.rowBox, rows, tb * kTile, nrt, row_tf, sm.ic.tf, kRowSentinel);
+        for (int cb = 0; cb < total_ct; cb += kColTiles) {
+            const int nct = min(kColTiles, total_ct - cb);
+            if (cb > 0) __syncthreads();
+            stage_tiles(sm.colG, sm.colF, sm.colBox, cols, cb * kTile, nct, col_tf, sm.ic.tf, kColSentinel);
+            __syncthreads();
+            build_tile_list(sm, nrt, nct, sm.ic.d2_thres);
+            const int n = sm.list_n;
+            for (int e = warp; e < n; e += kWarps) {
+                const uint32_t ent = sm.list[e];
+                const int rt = (int)(ent >> 16), ct = (int)(ent & 0xffffu);
+                process_entry<KIND>(sm, kp, rt, ct, lane, (tb + rt) * kTile + lane, yy_row_min, acc);
+            }
+        }
+    }
+}
+
+// Block reduction + all-gather of the per-CTA partial sums through distributed shared memory;
+// every CTA of the cluster ends with identical totals in sm.sum[dst_off ...].
+template <int NV>
+__device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& cluster, const double* acc, int buf,
+                                                  int dst_off) {
+    constexpr int nv = NV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+#pragma unroll
+    for (int i = 0; i < nv; ++i) {
+        const double s = warp_sum(acc[i]);
+        if (lane == 0) sm.red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += sm.red[w][threadIdx.x];
+        for (int r = 0; r < G; ++r) {
+            double* dst = cluster.map_shared_rank(&sm.xchg[buf][rank][threadIdx.x], r);
+            *dst = s;
+        }
+    }
+    cluster.sync();
+    if (threadIdx.x < nv) {
+        double s = 0.0;
+        for (int r = 0; r < G; ++r) s += sm.xchg[buf][r][threadIdx.x];
+        sm.sum[dst_off + threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// --------------------------------------------------------------------------------------------
+// the persistent align kernel
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    const KParams& kp = args.kp;
+    const bool acvo = kp.mode == CVO_B200_MODE_ACVO;
+    const int max_iter = kp.fixed_iters > 0 ? kp.fixed_iters : kp.max_iter;
+
+    while (true) {
+        if (rank == 0 && threadIdx.x == 0) {
+            const int idx = atomicAdd(args.counter, 1);
+            for (int r = 0; r < G; ++r) *cluster.map_shared_rank(&sm.next_pair, r) = idx;
+        }
+        cluster.sync();
+        const int pi = sm.next_pair;
+        if (pi >= args.n_pairs) break;
+        const PairDev pair = args.pairs[pi];
+        if (threadIdx.x == 0) {
+            sm.st = args.states[pi];
+            sm.st.iters = max_iter;
+            sm.st.status = CVO_B200_STATUS_MAX_ITER;
+            sm.st.n_run = 0;
+            sm.done = 0;
+        }
+        __syncthreads();
+
+        for (int k = 0; k < max_iter; ++k) {
+            if (threadIdx.x == 0) prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
+            __syncthreads();
+            double acc[kNumAcc];
+#pragma unroll
+            for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+            // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
+            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, acc);
+            if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
+                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, acc);
+                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, acc);
+            }
+            cluster_allreduce<ACC_FLOW_COUNT>(sm, cluster, acc, 0, kFlowOff);
+            if (threadIdx.x == 0) finalize_flow(sm);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = 0.0;
+            // compute_step_size (src/cvo.cpp:377)
+            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, acc);
+            cluster_allreduce<4>(sm, cluster, acc, 1, 0);
+            if (threadIdx.x == 0) {
+                // remember the transform used by this iteration: it is what the reference multiplies
+                // into accum_transform when the loop exits here (quirk Q3, src/cvo.cpp:413-414)
+                write_tf44(sm.ic.tf, sm.st.prev_tf);
+                cvo_b200_iter_rec* rec = nullptr;
+                if (args.trace && pi == 0 && rank == 0 && k < args.trace_cap) rec = args.trace + k;
+                update_state(sm, kp, k, rec);
+            }
+            __syncthreads();
+            if (sm.done) break;
+        }
+        if (threadIdx.x == 0 && rank == 0) {
+            prepare_iter(sm, kp, kp.d2c_thres);  // final update_tf(), src/cvo.cpp:415
+            write_tf44(sm.ic.tf, sm.st.tf);
+            args.states[pi] = sm.st;
+        }
+        __syncthreads();
+    }
+}
+
+// acvo::function_inner_product (src/adaptive_cvo.cpp:385-439): untransformed clouds, colour gate from sp_thres.
+__global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sm.st.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+        sm.st.T[0] = sm.st.T[1] = sm.st.T[2] = 0.f;
+        sm.st.ell = args.ell;
+        prepare_iter(sm, args.kp, args.kp.d2c_thres);
+    }
+    __syncthreads();
+    double acc[kNumAcc];
+#pragma unroll
+    for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
+    run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0, acc);
+    cluster_allreduce<2>(sm, cluster, acc, 0, 0);
+    if (rank == 0 && threadIdx.x == 0) {
+        args.out[0] = sm.sum[0];
+        args.out[1] = sm.sum[1];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// upload-time packing: Morton sort + 32-byte rows  (replaces the tail of set_pcd, src/cvo.cpp:343-356)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+constexpr int kPackThreads = 1024;
+
+// One CTA per cloud: bounding box -> 30-bit Morton key -> bitonic sort of (key, index) in shared
+// memory -> gather into {x,y,z,f0} / {f1..f4} rows.  Ties break on the original index, so the
+// packed order is a pure function of the input.
+__global__ void __launch_bounds__(kPackThreads, 1) pack_sort_kernel(const PackJob* jobs, int sort_points) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    __shared__ float sbox[6][32];
+    __shared__ float bb[6];
+    const PackJob job = jobs[blockIdx.x];
+    const int n = job.n;
+    if (n <= 0) return;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int i = threadIdx.x; i < n; i += kPackThreads) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = job.xyz[3 * i + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float l = warp_min(lo[a]), h = warp_max(hi[a]);
+        if (lane == 0) {
+            sbox[a][warp] = l;
+            sbox[3 + a][warp] = h;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float l = warp_min(sbox[a][lane]), h = warp_max(sbox[3 + a][lane]);
+            if (lane == 0) {
+                bb[a] = l;
+                bb[3 + a] = h;
+            }
+        }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ext = bb[3 + a] - bb[a];
+        scale[a] = ext > 0.f ? 1023.999f / ext : 0.f;
+    }
+    for (int i = threadIdx.x; i < npad; i += kPackThreads) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            uint32_t code = 0;
+            if (sort_points) {
+                const uint32_t qx = (uint32_t)((job.xyz[3 * i + 0] - bb[0]) * scale[0]);
+                const uint32_t qy = (uint32_t)((job.xyz[3 * i + 1] - bb[1]) * scale[1]);
+                const uint32_t qz = (uint32_t)((job.xyz[3 * i + 2] - bb[2]) * scale[2]);
+                code = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
+            }
+            key = ((unsigned long long)code << 32) | (unsigned long long)(uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    if (sort_points) {
+        for (int k = 2; k <= npad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (npad >> 1); t += kPackThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int p = i | j;
+                    const unsigned long long a = keys[i], b = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[p] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += kPackThreads) {
+        const int src = (int)(uint32_t)(keys[i] & 0xffffffffull);
+        const float* p = job.xyz + 3 * src;
+        const float* f = job.feat + 5 * src;
+        job.out_g[i] = make_float4(p[0], p[1], p[2], f[0]);
+        job.out_f[i] = make_float4(f[1], f[2], f[3], f[4]);
+    }
+}
+
+}  // namespace cvo_b200

@@ -1,0 +1,94 @@
+"""Python mirror of the reference's two frontends above the C ABI (same names, members and quirks as
+include/cvo_b200_frontend.hpp; reference: cpp/rkhs_registration/include/cvo.hpp:101-107,171-192 and
+include/adaptive_cvo.hpp:108-114,169-195).  Used by the tests and the benchmark driver; PyTorch-free.
+
+Inputs are the OUTPUT contract of the reference's image front-end (pcd_generator, out of scope):
+xyz N x 3 and features N x 5 (row-major)."""
+import numpy as np
+
+from . import capi
+
+
+class _Registration:
+    _KIND = "cvo"
+
+    def __init__(self, device=0, max_points=16384, ctx=None, slot=0, scratch_slot=1):
+        self._own = ctx is None
+        self._ctx = capi.Context(device, max_points, 2) if ctx is None else ctx
+        self._slot, self._scratch = slot, scratch_slot
+        self.params = capi.default_params(self._KIND)
+        # public members of the reference classes (inc/cvo.hpp:103-107)
+        self.init = False
+        self.iter = 0
+        self.transform = np.eye(4, dtype=np.float32)
+        self.prev_transform = np.eye(4, dtype=np.float32)
+        self.accum_transform = np.eye(4, dtype=np.float32)
+        # private state that carries across pairs (quirk Q4): R, T, and ell for cvo
+        self._RT = np.concatenate([np.eye(3).reshape(9), np.zeros(3)]).astype(np.float32)
+        self._ell = float(self.params.ell_init)
+        self._first = None
+        self._bound = False
+        self._have_moving = False
+        self.status = 0
+
+    def close(self):
+        if self._own:
+            self._ctx.close()
+
+    @property
+    def ell(self):
+        return self._ell
+
+    def set_pcd(self, xyz, feat):
+        """set_pcd (src/cvo.cpp:319-357): the first call stores the fixed cloud, later calls bind a moving cloud."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        feat = np.ascontiguousarray(feat, np.float32)
+        if not self.init:
+            self._first = (xyz, feat)
+            self.init = True
+            return
+        if not self._bound:
+            self._ctx.set_pair(self._slot, self._first[0], self._first[1], xyz, feat)
+            self._bound = True
+        else:
+            self._ctx.push_frame(self._slot, xyz, feat)  # fixed <- moving (src/cvo.cpp:417) + new moving cloud
+        if self._KIND == "acvo":  # src/adaptive_cvo.cpp:476-478
+            self._ell = float(self.params.ell_init)
+        self._have_moving = True
+
+    def align(self):
+        """align (src/cvo.cpp:361-420)."""
+        if not self._have_moving:
+            raise RuntimeError("align() called before a moving cloud was set")
+        r = self._ctx.align([self._slot], self.params, RT=self._RT[None], ell=np.array([self._ell], np.float32))
+        self._RT, self._ell = r["RT"][0], float(r["ell"][0])
+        self.status = int(r["status"][0])
+        if self.status != capi.STATUS_MAX_ITER:  # Q5: iter only assigned on early exit
+            self.iter = int(r["iters"][0])
+        self.prev_transform = r["prev_transform"][0]                       # Q3 (src/cvo.cpp:413)
+        self.accum_transform = self.accum_transform @ self.prev_transform  # :414
+        self.transform = r["transform"][0]                                 # :415
+        self._have_moving = False
+
+    def run_cvo(self, xyz, feat):
+        """run_cvo (src/cvo.cpp:422-435)."""
+        if not self.init:
+            self.set_pcd(xyz, feat)
+        else:
+            self.set_pcd(xyz, feat)
+            self.align()
+
+
+class cvo(_Registration):
+    """cvo::cvo"""
+    _KIND = "cvo"
+
+
+class acvo(_Registration):
+    """acvo::acvo"""
+    _KIND = "acvo"
+
+    def function_inner_product(self, cloud_a, cloud_b):
+        """acvo::function_inner_product (src/adaptive_cvo.cpp:385-439); clouds are (xyz, feat) tuples."""
+        self._ctx.set_pair(self._scratch, cloud_a[0], cloud_a[1], cloud_b[0], cloud_b[1])
+        return self._ctx.inner_product(self._scratch, self._ell, self.params)["value"]

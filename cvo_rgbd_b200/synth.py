@@ -3,7 +3,7 @@
 The reference selects ~3000 high-gradient pixels per frame (num_want,
 src/pcd_generator.cpp:22) and back-projects them with the TUM fr1 intrinsics
 (src/pcd_generator.cpp:251-257).  We imitate that output contract -- N x 3 xyz f32
-plus N x 5 features f32 -- with a "desk-like" scene: three planes and six boxes,
+plus N x 5 features f32 -- with a "desk-like" scene: three planes and three boxes,
 points drawn along edges / texture lines, depth 0.7-2.0 m inside the fr1 frustum.
 Feature flavours follow src/pcd_generator.cpp:336-381:
   "cvo"  (feature type 1): raw BGR in [0,255] + raw gradients
@@ -24,13 +24,13 @@ def _rect(origin, e1, e2):
 def _scene(rng):
     """Rectangles (origin, edge1, edge2) + albedo; fixed layout jittered by the seed."""
     rects = []
-    # desk/floor y = 0.35, back wall z = 1.9, side wall x = -0.8 (camera looks along +z, y down)
-    rects.append(_rect([-0.8, 0.35, 0.74], [1.6, 0, 0], [0, 0, 1.16]))
-    rects.append(_rect([-0.8, -0.75, 1.9], [1.6, 0, 0], [0, 1.10, 0]))
-    rects.append(_rect([-0.8, -0.75, 0.74], [0, 0, 1.16], [0, 1.10, 0]))
-    for _ in range(6):  # boxes standing on the desk: top, front and one side face
+    # desk y = 0.35, back wall z = 1.7, side wall x = -0.7 (camera looks along +z, y down)
+    rects.append(_rect([-0.7, 0.35, 0.80], [1.4, 0, 0], [0, 0, 0.90]))
+    rects.append(_rect([-0.7, -0.45, 1.7], [1.4, 0, 0], [0, 0.80, 0]))
+    rects.append(_rect([-0.7, -0.45, 0.80], [0, 0, 0.90], [0, 0.80, 0]))
+    for _ in range(3):  # boxes standing on the desk: top, front and one side face
         sx, sy, sz = rng.uniform(0.10, 0.30), rng.uniform(0.08, 0.30), rng.uniform(0.10, 0.25)
-        cx, cz = rng.uniform(-0.6, 0.6 - sx), rng.uniform(0.95, 1.7 - sz)
+        cx, cz = rng.uniform(-0.55, 0.55 - sx), rng.uniform(0.95, 1.6 - sz)
         y0 = 0.35 - sy
         rects.append(_rect([cx, y0, cz], [sx, 0, 0], [0, 0, sz]))          # top
         rects.append(_rect([cx, y0, cz], [sx, 0, 0], [0, sy, 0]))          # front (faces camera)
@@ -47,7 +47,7 @@ def _segments(rects, rng):
         corners = [o, o + e1, o + e1 + e2, o + e2]
         for a in range(4):
             p0.append(corners[a]); p1.append(corners[(a + 1) % 4]); rid.append(k)
-        n_tex = 10 if k < 3 else 4
+        n_tex = 1
         for _ in range(n_tex):
             a, b = rng.uniform(0, 1, 2), rng.uniform(0, 1, 2)
             p0.append(o + a[0] * e1 + a[1] * e2); p1.append(o + b[0] * e1 + b[1] * e2); rid.append(k)
@@ -88,7 +88,7 @@ def _draw(n, p0, p1, rid, albedo_bgr, rng, flavour):
         ok = (z > Z_MIN) & (z < Z_MAX) & (u >= 0) & (u < W) & (vv >= 0) & (vv < H)
         pts = np.concatenate([pts, q[ok]]); ids = np.concatenate([ids, rid[s][ok]])
     pts, ids = pts[:n], ids[:n]
-    bgr = np.clip(albedo_bgr[ids] + rng.normal(0, 8.0, size=(n, 3)), 0, 255)
+    bgr = np.clip(albedo_bgr[ids] + rng.normal(0, 6.0, size=(n, 3)), 0, 255)
     grad = rng.normal(0, 20.0, size=(n, 2))
     if flavour == "cvo":
         feat = np.concatenate([bgr, grad], axis=1)

@@ -1,0 +1,160 @@
+/*
+ * include/cvo_b200.h -- C ABI of libcvo_b200.so: the B200-native (sm_100a) replacement for the
+ * RKHS SE(3) registration inner loop of MaaniGhaffari/cvo-rgbd.
+ *
+ * The reference has no plugin / FFI layer: the hot path is four PRIVATE member functions
+ *     transform_pcd -> se_kernel -> compute_flow -> compute_step_size
+ * called only from align() of cvo::cvo / acvo::acvo
+ * (cpp/rkhs_registration/src/cvo.cpp:361-420, src/adaptive_cvo.cpp:490-555).  This ABI sits directly
+ * underneath align(): the C++ frontends in include/cvo_b200_frontend.hpp keep the reference's public
+ * surface (init, iter, transform, prev_transform, accum_transform, set_pcd, align, run_cvo,
+ * function_inner_product; inc/cvo.hpp:101-107,171-192, inc/adaptive_cvo.hpp:108-114,169-195) and
+ * forward to these entry points.  Plain pointers and sizes only; no C++ / torch types; nothing throws.
+ *
+ * All pointers are HOST pointers unless a name ends in _dev.  Matrices are row-major.
+ * One ctx = one GPU = one caller thread (like one cvo object, which is not thread-safe either).
+ * There is no CPU fallback: every entry point fails with CVO_B200_ERR_CUDA if the device is unusable.
+ */
+#ifndef CVO_B200_H
+#define CVO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvo_b200_ctx cvo_b200_ctx;
+
+enum { CVO_B200_OK = 0,
+       CVO_B200_ERR_ARG = -1,     /* bad slot / size / NULL pointer                     */
+       CVO_B200_ERR_CUDA = -2,    /* CUDA runtime error; see cvo_b200_last_error()      */
+       CVO_B200_ERR_EMPTY = -3 }; /* empty cloud (the reference asserts in nanoflann,
+                                     thirdparty/KDTreeVectorOfVectorsAdaptor.h:61)      */
+
+enum { CVO_B200_MODE_CVO = 0,     /* cvo::compute_flow   (src/cvo.cpp:164-210)          */
+       CVO_B200_MODE_ACVO = 1 };  /* acvo::compute_flow  (src/adaptive_cvo.cpp:154-272) */
+
+enum { CVO_B200_ELL_SCHEDULE = 0, /* src/cvo.cpp:408-410                                */
+       CVO_B200_ELL_ADAPTIVE = 1, /* src/adaptive_cvo.cpp:538-545                       */
+       CVO_B200_ELL_FIXED = 2 };  /* benchmark configs 2 and 5                          */
+
+/* per-pair exit status of align() */
+enum { CVO_B200_STATUS_MAX_ITER = 0,        /* loop cap hit (src/cvo.cpp:366)           */
+       CVO_B200_STATUS_CONVERGED_TWIST = 1, /* |omega|<eps && |v|<eps (src/cvo.cpp:380) */
+       CVO_B200_STATUS_CONVERGED_UPDATE = 2,/* dist_se3(dR,dT)<eps_2 (src/cvo.cpp:402)  */
+       CVO_B200_STATUS_NAN = 3 };           /* non-finite twist                         */
+
+/* Every constructor initialiser of the two reference classes
+ * (src/cvo.cpp:18-48, src/adaptive_cvo.cpp:18-50). */
+typedef struct cvo_b200_params {
+    int    mode;        /* CVO_B200_MODE_*                                       */
+    int    ell_policy;  /* CVO_B200_ELL_*                                        */
+    float  ell_init;    /* cvo 0.15 (src/cvo.cpp:25), acvo 0.1 (adaptive:25)     */
+    float  ell_min;     /* acvo 0.0391                                           */
+    float  ell_max;     /* acvo 0.15, re-armed per pair (adaptive:477)           */
+    double dl_step;     /* acvo 0.3                                              */
+    float  sigma;       /* 0.1                                                   */
+    float  sp_thres;    /* cvo 8e-3, acvo 8.315e-3                               */
+    float  c;           /* 7                                                     */
+    float  d;           /* 7                                                     */
+    float  c_ell;       /* cvo 200, acvo 0.5                                     */
+    float  c_sigma;     /* 1                                                     */
+    float  c_sp_thres;  /* acvo 8.315e-3 (cvo gates colour with sp_thres)        */
+    int    max_iter;    /* 2000                                                  */
+    float  min_step;    /* 0.2                                                   */
+    float  max_step;    /* 0.8                                                   */
+    float  eps;         /* 5e-5                                                  */
+    float  eps_2;       /* 1e-5                                                  */
+    int    fixed_iters; /* >0: run exactly this many iterations, stop tests off  */
+} cvo_b200_params;
+
+/* One outer iteration's observables (level-1 / level-2 parity hooks).  The reference keeps
+ * these in private members: omega, v (inc/cvo.hpp:93-94), step (:88), B..E (src/cvo.cpp:242-245),
+ * A.nonZeros(), dl (inc/adaptive_cvo.hpp:77). */
+typedef struct cvo_b200_iter_rec {
+    float     ell;
+    float     step;
+    float     omega[3];
+    float     v[3];
+    double    B, C, D, E;
+    double    sum_a;
+    double    dl;
+    long long nnz, nnz_xx, nnz_yy;
+    float     R[9];   /* state after this iteration's update */
+    float     T[3];
+} cvo_b200_iter_rec;
+
+void cvo_b200_default_params_cvo(cvo_b200_params* p);   /* == cvo::cvo()   src/cvo.cpp:18-48          */
+void cvo_b200_default_params_acvo(cvo_b200_params* p);  /* == acvo::acvo() src/adaptive_cvo.cpp:18-50 */
+
+/* Creates a context on `device` with `max_slots` frame-pair slots of up to `max_points` points per
+ * cloud.  All device buffers are owned by the ctx. */
+int  cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slots);
+void cvo_b200_destroy(cvo_b200_ctx* ctx);
+const char* cvo_b200_last_error(const cvo_b200_ctx* ctx);
+
+/* Replaces the tail of set_pcd() (src/cvo.cpp:343-356): binds the two clouds of a frame pair to a slot.
+ * xyz: n x 3 f32 (cloud_t, inc/data_type.h:30); feat: n x 5 f32 ROW-major (the reference's
+ * point_cloud::features is column-major, inc/data_type.h:64 -- callers pass .transpose() or rows).
+ * The data is copied (caller keeps ownership), spatially sorted and packed on the device.
+ * Enqueues on the ctx stream and returns; pageable host buffers may be reused on return, pinned ones
+ * after cvo_b200_sync(). */
+int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot,
+                      const float* fixed_xyz, const float* fixed_feat, int n_fixed,
+                      const float* moving_xyz, const float* moving_feat, int n_moving);
+
+/* Replaces `ptr_fixed_pcd = std::move(ptr_moving_pcd)` (src/cvo.cpp:417) + the next set_pcd():
+ * the slot's moving cloud becomes its fixed cloud (pointer swap on the device) and a new moving cloud
+ * is uploaded, so a sequence uploads each frame once. */
+int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n);
+
+/* One pass of transform_pcd + se_kernel + compute_flow + compute_step_size at a given state
+ * (src/cvo.cpp:368-377) without updating anything: fills one record (R,T echo the input). */
+int cvo_b200_eval(cvo_b200_ctx* ctx, int slot, const float* R, const float* T, float ell,
+                  const cvo_b200_params* p, cvo_b200_iter_rec* out);
+
+/* Replaces align() (src/cvo.cpp:361-420, src/adaptive_cvo.cpp:490-555) for `n_pairs` slots at once; the
+ * whole iteration (flow, step size, cubic, Exp_SEK3, stop tests, ell policy) runs on the device.
+ *  RT_io        n_pairs x 12 (R row-major, then T): in = carried-in state (quirk Q4 warm start),
+ *               out = state at loop exit.  NULL: start from identity, result not returned.
+ *  ell_io       n_pairs: in/out length-scale (cvo never re-arms ell between pairs); NULL: params->ell_init.
+ *  transform    n_pairs x 16: `transform` after align(), i.e. [R^T, -R^T T] of the final state (src/cvo.cpp:415)
+ *  prev_transform  n_pairs x 16 or NULL: the one-update-stale transform that the reference multiplies
+ *               into accum_transform (quirk Q3, src/cvo.cpp:413-414)
+ *  iters        n_pairs: k at exit (max_iter when the cap was hit);  status: CVO_B200_STATUS_*
+ * Synchronous: returns when results are in the host arrays. */
+int cvo_b200_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p,
+                   float* RT_io, float* ell_io, float* transform, float* prev_transform,
+                   int* iters, int* status);
+
+/* Same as cvo_b200_align for ONE slot, additionally returning the first `trace_cap` iteration records
+ * (level-2 parity).  *trace_len receives the number of iterations executed. */
+int cvo_b200_align_trace(cvo_b200_ctx* ctx, int slot, const cvo_b200_params* p,
+                         float* RT_io, float* ell_io, float* transform, float* prev_transform,
+                         int* iters, int* status,
+                         cvo_b200_iter_rec* trace, int trace_cap, int* trace_len);
+
+/* Replaces acvo::function_inner_product(cloud_a, cloud_b) (src/adaptive_cvo.cpp:385-439) with
+ * cloud_a = the slot's fixed cloud and cloud_b = its moving cloud, both UNtransformed, at length-scale
+ * `ell`.  *value = float(sum_a/nnz) as the reference returns; the parts are returned too. */
+int cvo_b200_inner_product(cvo_b200_ctx* ctx, int slot, float ell, const cvo_b200_params* p,
+                           float* value, double* sum_a, long long* nnz);
+
+/* Blocks until everything enqueued on the ctx stream has finished. */
+int cvo_b200_sync(cvo_b200_ctx* ctx);
+
+/* Measurement hooks (bench.py): device time of the kernels of the last align / eval call measured
+ * with CUDA events on the ctx stream, kernels launched so far, and the launch geometry last used. */
+float     cvo_b200_last_kernel_ms(const cvo_b200_ctx* ctx);
+long long cvo_b200_kernel_launches(const cvo_b200_ctx* ctx);
+int       cvo_b200_last_cluster_size(const cvo_b200_ctx* ctx);
+int       cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx);
+/* Overrides the CTAs-per-pair choice (1,2,4,8,16); 0 = automatic. */
+int       cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int ctas_per_pair);
+/* Sum over the pairs of the last align call of iterations executed (work accounting for the roofline). */
+long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
+int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

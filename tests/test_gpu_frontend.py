@@ -1,0 +1,75 @@
+"""GPU tests of the host frontends (Python mirror and the compiled C++ header) against the oracle driven the
+way the reference's driver drives its classes (src/cvo_main.cpp:36-66): a warm-started sequence of frames."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import pose_diff
+from cvo_rgbd_b200 import frontend, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sequence(kind, n_frames=4, n=1200):
+    """Frames of one scene seen from a slowly moving camera: frame 0 is the fixed cloud of seed 900, frame k >= 1 the
+    moving cloud of the same seed with the inter-frame motion scaled by 0.6 k (same scene, same rng stream)."""
+    first = synth.make_pair(900, n, n, kind)
+    frames = [(first["x_pos"], first["x_feat"])]
+    for k in range(1, n_frames):
+        pr = synth.make_pair(900, n, n, kind, motion_scale=0.6 * k)
+        frames.append((pr["y_pos"], pr["y_feat"]))
+    return frames
+
+
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_sequence_matches_oracle_driven_like_the_reference_driver(oracle, kind):
+    frames = _sequence(kind)
+    reg = (frontend.cvo if kind == "cvo" else frontend.acvo)(max_points=2048)
+    op = oracle.default_params(kind)
+    R, T, ell = np.eye(3, dtype=np.float32), np.zeros(3, np.float32), float(op.ell_init)
+    accum = np.eye(4)
+    try:
+        for k, (xyz, feat) in enumerate(frames):
+            reg.run_cvo(xyz, feat)
+            if k == 0:
+                assert reg.init and np.array_equal(reg.accum_transform, np.eye(4, dtype=np.float32))
+                continue
+            fx, ff = frames[k - 1]
+            if kind == "acvo":
+                ell = float(op.ell_init)  # re-armed per pair (src/adaptive_cvo.cpp:476)
+            o = oracle.align(fx, ff, xyz, feat, op, R=R, T=T, ell=ell)  # Q4: R, T (and cvo's ell) carry over
+            R, T, ell = o["R"], o["T"], o["ell"]
+            accum = accum @ o["prev_transform"].astype(np.float64)  # Q3
+            rot, tr = pose_diff(reg.transform, o["transform"])
+            assert rot < 1e-4 and tr < 1e-4, (k, rot, tr)
+            rot, tr = pose_diff(reg.accum_transform, accum)
+            assert rot < 2e-4 * k and tr < 2e-4 * k
+            assert abs(reg.ell - ell) < 1e-3
+    finally:
+        reg.close()
+
+
+def test_acvo_function_inner_product(oracle):
+    pr = synth.make_pair(950, 1500, 1400, "acvo")
+    reg = frontend.acvo(max_points=2048)
+    try:
+        got = reg.function_inner_product((pr["x_pos"], pr["x_feat"]), (pr["y_pos"], pr["y_feat"]))
+        want = oracle.inner_product(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], 0.1,
+                                    oracle.default_params("acvo"))["value"]
+        assert abs(got - want) < 1e-5 * want
+    finally:
+        reg.close()
+
+
+def test_compiled_cpp_frontend_example_recovers_known_motion():
+    exe = os.path.join(ROOT, "examples", "frontend_example")
+    if not os.path.exists(exe):
+        from cvo_rgbd_b200 import build
+        build.build_library()
+        build.build_frontend_example()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout

@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/cvo_b200.h) against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures, and -- at full size -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): final SE(3) pose within 1e-4 rad / 1e-4 m per pair; inner-product
+function value within 1e-5 relative.  Single-evaluation quantities are compared much tighter (1e-5 relative;
+counts exact up to a 2-pair slack for ulp-level boundary flips)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import pose_diff, rel_err
+from cvo_rgbd_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+R0 = synth._rotvec_to_R(np.array([0.01, -0.02, 0.015])).astype(np.float32)
+T0 = np.array([0.01, 0.005, -0.02], np.float32)
+POSE_ROT_TOL, POSE_TRANS_TOL, VALUE_REL_TOL = 1e-4, 1e-4, 1e-5
+
+
+def _set(ctx, slot, pr):
+    ctx.set_pair(slot, pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"])
+
+
+def _check_eval(g, o, acvo):
+    assert abs(g["nnz"] - o["nnz"]) <= 2
+    assert rel_err(g["sum_a"], o["sum_a"]) < 1e-5
+    scale_w = max(np.abs(o["omega"]).max(), 1e-30)
+    scale_v = max(np.abs(o["v"]).max(), 1e-30)
+    assert np.abs(g["omega"] - o["omega"]).max() < 1e-5 * scale_w + 2e-4 * abs(g["nnz"] - o["nnz"])
+    assert np.abs(g["v"] - o["v"]).max() < 1e-5 * scale_v + 2e-4 * abs(g["nnz"] - o["nnz"])
+    if g["nnz"] == o["nnz"]:
+        for k in ("B", "C", "D", "E"):
+            assert rel_err(g[k], o[k]) < 1e-5, k
+        assert abs(g["step"] - o["step"]) < 1e-5 * max(1.0, o["step"])
+    if acvo:
+        assert abs(g["nnz_xx"] - o["nnz_xx"]) <= 2 and abs(g["nnz_yy"] - o["nnz_yy"]) <= 2
+        if (g["nnz"], g["nnz_xx"], g["nnz_yy"]) == (o["nnz"], o["nnz_xx"], o["nnz_yy"]):
+            assert rel_err(g["dl"], o["dl"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind,seed,n,m", [("cvo", 1000, 500, 500), ("cvo", 51, 777, 1234), ("cvo", 52, 33, 2100),
+                                            ("cvo", 2000, 3000, 3000), ("acvo", 3000, 3000, 3000),
+                                            ("acvo", 53, 900, 650), ("acvo", 54, 600, 1000), ("cvo", 55, 1, 1),
+                                            ("cvo", 56, 31, 32), ("acvo", 57, 2049, 2050)])
+def test_level1_single_evaluation_matches_oracle(gpu_ctx, oracle, kind, seed, n, m):
+    """One pass of transform_pcd + se_kernel + compute_flow + compute_step_size (src/cvo.cpp:368-377)."""
+    pr = synth.make_pair(seed, n, m, kind)
+    _set(gpu_ctx, 0, pr)
+    gp, op = capi.default_params(kind), oracle.default_params(kind)
+    for ell in (0.15, 0.1, 0.05):
+        g = gpu_ctx.eval(0, R0, T0, ell, gp)
+        o = oracle.evaluate(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], R0, T0, ell, op)
+        _check_eval(g, o, kind == "acvo")
+
+
+def test_level1_result_is_independent_of_cluster_size(gpu_ctx):
+    pr = synth.make_pair(61, 2500, 2700, "acvo")
+    _set(gpu_ctx, 0, pr)
+    gp = capi.default_params("acvo")
+    base = None
+    try:
+        for g in (1, 2, 4, 8, 16):
+            gpu_ctx.set_cluster_size(g)
+            r = gpu_ctx.eval(0, R0, T0, 0.1, gp)
+            assert gpu_ctx.last_cluster_size in (g, 8)
+            if base is None:
+                base = r
+            assert (r["nnz"], r["nnz_xx"], r["nnz_yy"]) == (base["nnz"], base["nnz_xx"], base["nnz_yy"])
+            for k in ("omega", "v", "B", "C", "D", "E", "dl"):
+                assert rel_err(r[k], base[k]) < 1e-6, (g, k)
+    finally:
+        gpu_ctx.set_cluster_size(0)
+
+
+def test_level2_fixed_iterations_trajectory(gpu_ctx, oracle):
+    """BASELINE config 2 shape at reduced size: fixed ell, exactly K iterations, stop tests off."""
+    pr = synth.make_pair(62, 1500, 1500, "cvo")
+    _set(gpu_ctx, 0, pr)
+    gp, op = capi.default_params("cvo"), oracle.default_params("cvo")
+    for p in (gp, op):
+        p.ell_policy, p.ell_init, p.fixed_iters = capi.ELL_FIXED, 0.10, 30
+    g = gpu_ctx.align_trace(0, gp)
+    o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], op, trace_cap=64)
+    assert g["n_iterations_run"] == o["n_iterations_run"] == 30
+    for k in range(8):  # early iterations agree tightly; later ones only through the pose (chaotic line search)
+        assert abs(g["trace"][k]["nnz"] - o["trace"][k]["nnz"]) <= 2
+        assert np.abs(g["trace"][k]["omega"] - o["trace"][k]["omega"]).max() < 1e-4 * np.abs(o["trace"][k]["omega"]).max() + 1e-6
+        assert abs(g["trace"][k]["step"] - o["trace"][k]["step"]) < 1e-3 * o["trace"][k]["step"] + 1e-6
+    rot, tr = pose_diff(g["transform"], o["transform"])
+    assert rot < POSE_ROT_TOL and tr < POSE_TRANS_TOL
+
+
+@pytest.mark.parametrize("kind,cfg", [("cvo", 1), ("cvo", 2), ("acvo", 3)])
+def test_level3_converged_align_matches_oracle_pose(gpu_ctx, oracle, kind, cfg):
+    """BASELINE configs 1-3 with the stock schedules: final 4x4 within 1e-4 rad / 1e-4 m."""
+    pr = synth.config_pair(cfg)
+    _set(gpu_ctx, 0, pr)
+    g = gpu_ctx.align_trace(0, capi.default_params(kind), trace_cap=4)
+    o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], oracle.default_params(kind))
+    rot, tr = pose_diff(g["transform"], o["transform"])
+    assert rot < POSE_ROT_TOL and tr < POSE_TRANS_TOL, (rot, tr, g["iters"], o["iters"])
+    assert g["status"] in (capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE)
+    assert abs(g["iters"] - o["iters"]) <= max(15, o["iters"] // 3)  # stop tests fire on 1e-5-sized quantities
+    rot_gt, tr_gt = pose_diff(g["transform"], pr["T_gt"])
+    assert rot_gt < 1e-2 and tr_gt < 1e-2
+    # transform = [R^T, -R^T T] of the returned state (src/cvo.cpp:83-87,415); prev_transform is the stale one (Q3)
+    assert np.allclose(g["transform"][:3, :3], g["R"].T, atol=1e-6)
+    assert np.allclose(g["transform"][:3, 3], -g["R"].T @ g["T"], atol=1e-6)
+
+
+def test_real_data_pair_and_golden_fixtures(gpu_ctx):
+    gold = json.load(open(os.path.join(GOLD, "golden.json")))
+    for name, case in gold.items():
+        if name.startswith("syn_"):
+            pr = synth.make_pair(case["seed"], case["n"], case["m"], case["kind"])
+            R, T = R0, T0
+        else:
+            pr = dict(np.load(os.path.join(GOLD, "real_pair.npz")))
+            R, T = np.eye(3), np.zeros(3)
+        _set(gpu_ctx, 1, pr)
+        gp = capi.default_params(case["kind"])
+        for ell, want in case["eval"].items():
+            want = {k: (np.array(v) if isinstance(v, list) else v) for k, v in want.items()}
+            _check_eval(gpu_ctx.eval(1, R, T, float(ell), gp), want, case["kind"] == "acvo")
+        g = gpu_ctx.align(np.array([1]), gp)
+        rot, tr = pose_diff(g["transform"][0], np.array(case["align"]["transform"]))
+        assert rot < POSE_ROT_TOL and tr < POSE_TRANS_TOL, (name, rot, tr)
+        if "inner_product" in case:
+            ip = gpu_ctx.inner_product(1, 0.1, gp)
+            assert abs(ip["nnz"] - case["inner_product"]["nnz"]) <= 2
+            assert rel_err(ip["value"], case["inner_product"]["value"]) < VALUE_REL_TOL
+
+
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_inner_product_value(gpu_ctx, oracle, kind):
+    """acvo::function_inner_product (src/adaptive_cvo.cpp:385-439), function value within 1e-5 relative."""
+    pr = synth.make_pair(63, 2800, 3100, kind)
+    _set(gpu_ctx, 0, pr)
+    for ell in (0.15, 0.1, 0.0391):
+        g = gpu_ctx.inner_product(0, ell, capi.default_params(kind))
+        o = oracle.inner_product(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], ell, oracle.default_params(kind))
+        assert abs(g["nnz"] - o["nnz"]) <= 2
+        assert rel_err(g["value"], o["value"]) < VALUE_REL_TOL and rel_err(g["sum_a"], o["sum_a"]) < 1e-4
+
+
+def test_batch_of_pairs_equals_one_by_one_and_warm_start_state_round_trips(gpu_ctx):
+    prs = [synth.config_pair(4, i) for i in range(6)]
+    for s, pr in enumerate(prs):
+        _set(gpu_ctx, s, pr)
+    gp = capi.default_params("cvo")
+    gp.fixed_iters = 12
+    RT = np.tile(np.concatenate([np.eye(3).reshape(9), np.zeros(3)]).astype(np.float32), (6, 1))
+    ell = np.full(6, 0.15, np.float32)
+    batch = gpu_ctx.align(np.arange(6), gp, RT=RT, ell=ell)
+    for s in range(6):
+        one = gpu_ctx.align(np.array([s]), gp, RT=RT[s:s + 1], ell=ell[s:s + 1])
+        assert np.array_equal(one["transform"][0], batch["transform"][s])
+        assert np.array_equal(one["RT"][0], batch["RT"][s]) and one["ell"][0] == batch["ell"][s]
+    # quirk Q4: R, T (and ell for cvo) carry into the next call; continuing 12+12 equals 24 in one go
+    cont = gpu_ctx.align(np.arange(6), gp, RT=batch["RT"], ell=batch["ell"])
+    gp.fixed_iters = 24
+    full = gpu_ctx.align(np.arange(6), gp, RT=RT, ell=ell)
+    for s in range(6):
+        rot, tr = pose_diff(cont["transform"][s], full["transform"][s])
+        assert rot < 1e-6 and tr < 1e-6
+
+
+def test_permutation_and_rigid_motion_properties_at_full_size(gpu_ctx):
+    """Size-independent properties at BASELINE's 10 000-point stress size (config 5)."""
+    pr = synth.config_pair(5)
+    gp = capi.default_params("cvo")
+    _set(gpu_ctx, 0, pr)
+    a = gpu_ctx.eval(0, np.eye(3), np.zeros(3), 0.1, gp)
+    assert a["nnz"] > 100000
+    # (1) point order does not matter (only the f32 summation order changes)
+    rng = np.random.default_rng(0)
+    px, py = rng.permutation(10000), rng.permutation(10000)
+    gpu_ctx.set_pair(1, pr["x_pos"][px], pr["x_feat"][px], pr["y_pos"][py], pr["y_feat"][py])
+    b = gpu_ctx.eval(1, np.eye(3), np.zeros(3), 0.1, gp)
+    assert a["nnz"] == b["nnz"]
+    for k in ("omega", "v", "B", "C", "D", "E", "sum_a"):
+        assert rel_err(a[k], b[k]) < 1e-6, k
+    # (2) B equals 2t (c |omega|^2 + d |v|^2) analytically (first-order optimality of the line search)
+    t = 1.0 / (2 * 0.1 ** 2)
+    assert rel_err(a["B"], 2 * t * (7 * (a["omega"] ** 2).sum() + 7 * (a["v"] ** 2).sum())) < 1e-4
+    # (3) evaluating at state (R, T) equals evaluating at identity on the pre-transformed moving cloud
+    y_tf = ((pr["y_pos"].astype(np.float64) - T0) @ R0.astype(np.float64)).astype(np.float32)
+    gpu_ctx.set_pair(1, pr["x_pos"], pr["x_feat"], y_tf, pr["y_feat"])
+    c = gpu_ctx.eval(1, np.eye(3), np.zeros(3), 0.1, gp)
+    d = gpu_ctx.eval(0, R0, T0, 0.1, gp)
+    assert abs(c["nnz"] - d["nnz"]) <= max(8, d["nnz"] // 20000)
+    assert rel_err(c["omega"], d["omega"]) < 2e-4 and rel_err(c["v"], d["v"]) < 2e-4
+
+
+def test_full_size_config5_eval_matches_oracle(gpu_ctx, oracle):
+    pr = synth.config_pair(5)
+    _set(gpu_ctx, 0, pr)
+    g = gpu_ctx.eval(0, R0, T0, 0.1, capi.default_params("cvo"))
+    o = oracle.evaluate(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], R0, T0, 0.1, oracle.default_params("cvo"))
+    _check_eval(g, o, False)
+
+
+def test_push_frame_promotes_moving_to_fixed(gpu_ctx, oracle):
+    """src/cvo.cpp:417: after align() the moving cloud becomes the fixed cloud of the next pair."""
+    a, b = synth.make_pair(71, 900, 1000, "cvo"), synth.make_pair(72, 800, 1100, "cvo")
+    _set(gpu_ctx, 2, a)
+    gpu_ctx.push_frame(2, b["y_pos"], b["y_feat"])  # pair is now (a.moving, b.moving)
+    gp, op = capi.default_params("cvo"), oracle.default_params("cvo")
+    g = gpu_ctx.eval(2, np.eye(3), np.zeros(3), 0.15, gp)
+    o = oracle.evaluate(a["y_pos"], a["y_feat"], b["y_pos"], b["y_feat"], np.eye(3), np.zeros(3), 0.15, op)
+    _check_eval(g, o, False)
+
+
+def test_no_overlap_pair_falls_back_to_min_step_and_stops(gpu_ctx):
+    """A empty => omega = v = 0 and E = 0 => NaN roots => min_step (quirk Q7), stop-1 at k = 0."""
+    pr = synth.make_pair(73, 400, 400, "cvo")
+    far = pr["y_pos"] + np.array([50, 0, 0], np.float32)
+    gpu_ctx.set_pair(0, pr["x_pos"], pr["x_feat"], far, pr["y_feat"])
+    gp = capi.default_params("cvo")
+    e = gpu_ctx.eval(0, np.eye(3), np.zeros(3), 0.15, gp)
+    assert e["nnz"] == 0 and e["step"] == pytest.approx(0.2) and not e["omega"].any() and not e["v"].any()
+    r = gpu_ctx.align(np.array([0]), gp)
+    assert r["iters"][0] == 0 and r["status"][0] == capi.STATUS_CONVERGED_TWIST
+    assert np.allclose(r["transform"][0], np.eye(4))
+
+
+def test_error_paths(gpu_ctx):
+    pr = synth.make_pair(74, 64, 64, "cvo")
+    lib, h = capi.load(), gpu_ctx._h
+    fp = lambda a: a.ctypes.data_as(capi.C.POINTER(capi.C.c_float))  # noqa: E731
+    x, f = pr["x_pos"], pr["x_feat"]
+    assert lib.cvo_b200_set_pair(h, 0, fp(x), fp(f), 0, fp(x), fp(f), 64) == capi.ERR_EMPTY
+    assert lib.cvo_b200_set_pair(h, 10 ** 6, fp(x), fp(f), 64, fp(x), fp(f), 64) == capi.ERR_ARG
+    assert lib.cvo_b200_set_pair(h, 0, None, fp(f), 64, fp(x), fp(f), 64) == capi.ERR_ARG
+    assert lib.cvo_b200_set_pair(h, 0, fp(x), fp(f), 64, fp(x), fp(f), 10 ** 7) == capi.ERR_ARG
+    assert b"max_points" in lib.cvo_b200_last_error(h)
+    with pytest.raises(capi.CvoB200Error):
+        gpu_ctx.align(np.array([63]), capi.default_params("cvo"))  # slot never bound
