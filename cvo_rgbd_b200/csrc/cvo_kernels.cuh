@@ -47,6 +47,7 @@ static_assert(ACC_FLOW_COUNT <= kNumAcc, "flow accumulators must fit the exchang
 struct CloudDev {
     const float4* g;  // {x, y, z, f0}
     const float4* f;  // {f1, f2, f3, f4}
+    const int* idx;   // original (pre-sort) index of every packed point
     int n;
     int pad;
 };
@@ -98,6 +99,7 @@ struct Smem {
     float4 rowF[kRowChunk];
     float4 colG[kColChunk];
     float4 colF[kColChunk];
+    int rowOrig[kRowChunk];  // original row indices (PASS_YY only: quirk Q1 is defined on them)
     float rowBox[kRowTiles][8];
     float colBox[kColTiles][8];
     uint32_t list[kListCap];
@@ -136,6 +138,7 @@ struct PackJob {
     const float* feat;  // n x 5
     float4* out_g;
     float4* out_f;
+    int* out_idx;
     int n;
     int pad;
 };
@@ -538,7 +541,7 @@ __device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams
 // One (row tile, col tile) entry: lane = one row; 32 candidate columns.
 template <int KIND>
 __device__ __forceinline__ void process_entry(const Smem& sm, const KParams& kp, int rt, int ct, int lane,
-                                              int row_global, int yy_row_min, double* acc) {
+                                              int row_orig, int yy_row_min, double* acc) {
     const IterConsts& ic = sm.ic;
     const float4 xg = sm.rowG[rt * kTile + lane];
     const float4* cgp = sm.colG + ct * kTile;
@@ -608,7 +611,7 @@ __device__ __forceinline__ void process_entry(const Smem& sm, const KParams& kp,
             } else if (KIND == PASS_YY) {
                 acc[ACC_NNZYY] += (double)cnt;
                 // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223)
-                if (row_global >= yy_row_min) acc[ACC_SYY] += (double)ps;
+                if (row_orig >= yy_row_min) acc[ACC_SYY] += (double)ps;
             } else {
                 acc[0] += (double)psum;
                 acc[1] += (double)cnt;
@@ -675,6 +678,12 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
         const int nrt = min(kRowTiles, t_end - tb);
         __syncthreads();  // previous users of rowG / colG are done
         stage_tiles(sm.rowG, sm.rowF, sm.rowBox, rows, tb * kTile, nrt, row_tf, sm.ic.tf, kRowSentinel);
+        if (KIND == PASS_YY) {
+            for (int i = threadIdx.x; i < nrt * kTile; i += kThreads) {
+                const int p = tb * kTile + i;
+                sm.rowOrig[i] = p < rows.n ? __ldg(rows.idx + p) : -1;
+            }
+        }
         for (int cb = 0; cb < total_ct; cb += kColTiles) {
             const int nct = min(kColTiles, total_ct - cb);
             if (cb > 0) __syncthreads();
@@ -685,7 +694,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
             for (int e = warp; e < n; e += kWarps) {
                 const uint32_t ent = sm.list[e];
                 const int rt = (int)(ent >> 16), ct = (int)(ent & 0xffffu);
-                process_entry<KIND>(sm, kp, rt, ct, lane, (tb + rt) * kTile + lane, yy_row_min, acc);
+                process_entry<KIND>(sm, kp, rt, ct, lane, KIND == PASS_YY ? sm.rowOrig[rt * kTile + lane] : 0, yy_row_min, acc);
             }
         }
     }
@@ -920,6 +929,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_sort_kernel(const PackJo
         const float* f = job.feat + 5 * src;
         job.out_g[i] = make_float4(p[0], p[1], p[2], f[0]);
         job.out_f[i] = make_float4(f[1], f[2], f[3], f[4]);
+        job.out_idx[i] = src;
     }
 }
 

