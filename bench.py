@@ -169,7 +169,7 @@ def main():
         return run_reference_arm(args)
 
     import torch
-    from cvo_rgbd_b200 import build, capi, synth
+    from cvo_rgbd_b200 import build, capi, sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,13 +197,12 @@ def main():
     pin = lambda shape: torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()  # noqa: E731
     hx, hfx, hy, hfy = pin((P, N_POINTS, 3)), pin((P, N_POINTS, 5)), pin((P, N_POINTS, 3)), pin((P, N_POINTS, 5))
     for s in range(P):
-        pr = synth.config_pair(2, rank * P + s)
+        pr = synth.config_pair(2, rank + s * world)  # pair p -> rank p mod world (sharding.shard_pairs)
         hx[s], hfx[s], hy[s], hfy[s] = pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"]
     slots = np.arange(P, dtype=np.int32)
     h2d_bytes = int(hx.nbytes + hfx.nbytes + hy.nbytes + hfy.nbytes)
     d2h_bytes = int(P * (16 * 4 + 16 * 4 + 4 + 4 + 200))  # poses + state records read back per step
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    gathered = torch.empty((world, P, 16), dtype=torch.float32, device="cuda") if world > 1 else None
 
     def upload_all():
         for s in range(P):
@@ -218,10 +217,10 @@ def main():
 
     def gather_poses(res):
         if dist is None:
-            return
-        mine = torch.from_numpy(res["transform"].reshape(P, 16)).cuda(non_blocking=True)
-        dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))  # the single collective: 64 B per pair
-        torch.cuda.synchronize()
+            return res["transform"]
+        # the single collective of the path: one NCCL all-gather of the 4x4 poses (68 B per pair)
+        poses, _ = sharding.gather_poses(res["transform"], res["iters"], P * world, device="cuda")
+        return poses
 
     # ---------------- resident arm: clouds already in HBM ----------------
     upload_all()

@@ -25,14 +25,14 @@ namespace cg = cooperative_groups;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 32;
-constexpr int kRowChunk = 2048;
-constexpr int kColChunk = 2048;
-constexpr int kRowTiles = kRowChunk / kTile;
+constexpr int kColChunk = 3072;                 // moving-cloud points resident in shared memory per pass
 constexpr int kColTiles = kColChunk / kTile;
 constexpr int kMaxCluster = 16;
 constexpr int kNumAcc = 16;
-constexpr int kListCap = kRowTiles * kColTiles;
-constexpr int kListBlocks = kListCap / 32;
+constexpr int kMaxUnits = 256;                  // work units (row tile x column segment) per scheduling round
+constexpr int kUnitAcc = 9;                     // widest per-unit partial record (flow: omega, v, sum, nnz, dl)
+constexpr int kQueueCap = 32 + kTile * kTile;   // leftovers (< 32) + one full tile pair
+static_assert(kColChunk <= (1 << 12), "queue entries pack row:5 | col:12 bits");
 constexpr int kFlowOff = 4;  // sm.sum[0..3] = B,C,D,E ; sm.sum[kFlowOff + ACC_*] = flow totals
 constexpr float kRowSentinel = 1.0e30f;
 constexpr float kColSentinel = -1.0e30f;
@@ -94,27 +94,33 @@ struct IterConsts {
     float temp_coef, m2t, p2t;
 };
 
+// Private scratch of one warp: the row tile it currently owns and its survivor queue.
+struct WarpScratch {
+    float4 rowG[kTile];
+    float4 rowF[kTile];
+    int rowOrig[kTile];          // original row indices (PASS_YY only: quirk Q1 is defined on them)
+    uint32_t queue[kQueueCap];   // in-ball (row, col) pairs waiting for the survivor body
+};
+
 struct Smem {
-    float4 rowG[kRowChunk];
-    float4 rowF[kRowChunk];
     float4 colG[kColChunk];
     float4 colF[kColChunk];
-    int rowOrig[kRowChunk];  // original row indices (PASS_YY only: quirk Q1 is defined on them)
-    float rowBox[kRowTiles][8];
     float colBox[kColTiles][8];
-    uint32_t list[kListCap];
-    int listBlockCount[kListBlocks];
-    int listBlockBase[kListBlocks];
-    int list_n;
+    WarpScratch ws[kWarps];
+    double unitPart[kMaxUnits][kUnitAcc];  // one fixed slot per work unit => scheduling-independent sums
+    double blockTot[kNumAcc];
+    double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
+    int next_unit;
     int next_pair;
     int done;
     int k;
-    double red[kWarps][kNumAcc];
     double xchg[2][kMaxCluster][kNumAcc];
     double sum[kFlowOff + kNumAcc];
     IterConsts ic;
     PairState st;
 };
+
+static_assert(sizeof(Smem) <= 227 * 1024, "Smem must fit the 227 KB per-CTA shared memory of sm_100");
 
 struct AlignArgs {
     const PairDev* pairs;
@@ -465,60 +471,6 @@ __device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float (*box)
     }
 }
 
-// Deterministic list of (row tile, col tile) pairs whose boxes are within the ball radius.
-__device__ __forceinline__ void build_tile_list(Smem& sm, int nrt, int nct, float d2_thres) {
-    const int lane = threadIdx.x & 31;
-    const int npairs = nrt * nct;
-    const int nblocks = (npairs + 31) >> 5;
-    const float thr = d2_thres * 1.0001f;  // boxes are conservative; keep rounding on the safe side
-    uint32_t live_bits[kListBlocks / kWarps];
-    int nb = 0;
-    for (int blk = threadIdx.x >> 5; blk < nblocks; blk += kWarps, ++nb) {
-        const int p = blk * 32 + lane;
-        bool live = false;
-        if (p < npairs) {
-            const int rt = p / nct, ct = p - rt * nct;
-            const float* a = sm.rowBox[rt];
-            const float* b = sm.colBox[ct];
-            const float gx = fmaxf(0.f, fmaxf(a[0] - b[3], b[0] - a[3]));
-            const float gy = fmaxf(0.f, fmaxf(a[1] - b[4], b[1] - a[4]));
-            const float gz = fmaxf(0.f, fmaxf(a[2] - b[5], b[2] - a[5]));
-            live = (gx * gx + gy * gy + gz * gz) <= thr;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, live);
-        live_bits[nb] = m;
-        if (lane == 0) sm.listBlockCount[blk] = __popc(m);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // exclusive scan of <= 128 block counts by one warp
-        int carry = 0;
-        for (int b0 = 0; b0 < nblocks; b0 += 32) {
-            const int b = b0 + lane;
-            const int c = (b < nblocks) ? sm.listBlockCount[b] : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (b < nblocks) sm.listBlockBase[b] = carry + incl - c;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) sm.list_n = carry;
-    }
-    __syncthreads();
-    nb = 0;
-    for (int blk = threadIdx.x >> 5; blk < nblocks; blk += kWarps, ++nb) {
-        const uint32_t m = live_bits[nb];
-        if ((m >> lane) & 1u) {
-            const int p = blk * 32 + lane;
-            const int rt = p / nct, ct = p - rt * nct;
-            sm.list[sm.listBlockBase[blk] + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)rt << 16) | (uint32_t)ct;
-        }
-    }
-    __syncthreads();
-}
-
 // --------------------------------------------------------------------------------------------
 // per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
 // --------------------------------------------------------------------------------------------
@@ -538,15 +490,103 @@ __device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams
     return a > kp.sp_thres;                                                 // :152
 }
 
-// One (row tile, col tile) entry: lane = one row; 32 candidate columns.
+// Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
+// src/cvo.cpp:197-198); promoted to f64 when the unit is finished (src/cvo.cpp:202-203).
+struct FlowPartial {
+    float po0, po1, po2, pv0, pv1, pv2, psum, pdl;
+    int cnt;
+};
+
+// Survivor body: one (row, col) pair that passed the ell-ball test.  All 32 lanes of a warp work on 32 different
+// pairs popped from the warp's queue, so the expensive part runs at full lane utilisation.
 template <int KIND>
-__device__ __forceinline__ void process_entry(const Smem& sm, const KParams& kp, int rt, int ct, int lane,
-                                              int row_orig, int yy_row_min, double* acc) {
+__device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent,
+                                              int yy_row_min, FlowPartial& fp, double* acc) {
     const IterConsts& ic = sm.ic;
-    const float4 xg = sm.rowG[rt * kTile + lane];
+    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
+    const float4 xg = ws.rowG[row];
+    const float4 xf = ws.rowF[row];
+    const float4 yg = sm.colG[col];
+    const float4 yf = sm.colF[col];
+    const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
+    const float d2 = dist2(dx, dy, dz);
+    float a;
+    if (!kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) return;
+    if (KIND == PASS_FLOW) {
+        const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
+        const float cy = xg.z * yg.x - xg.x * yg.z;
+        const float cz = xg.x * yg.y - xg.y * yg.x;
+        const float ac = kp.inv_c * a, ad = kp.inv_d * a;  // (1/c*Ai), (1/d*Ai), :197-198
+        fp.po0 = fmaf(ac, cx, fp.po0); fp.po1 = fmaf(ac, cy, fp.po1); fp.po2 = fmaf(ac, cz, fp.po2);
+        fp.pv0 = fmaf(ad, dx, fp.pv0); fp.pv1 = fmaf(ad, dy, fp.pv1); fp.pv2 = fmaf(ad, dz, fp.pv2);
+        fp.psum += a;
+        fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:202,228
+        ++fp.cnt;
+    } else if (KIND == PASS_XX || KIND == PASS_INNER) {
+        fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:210,231
+        fp.psum += a;
+        ++fp.cnt;
+    } else if (KIND == PASS_YY) {
+        // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223); :256,259 otherwise
+        if (ws.rowOrig[row] >= yy_row_min) fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);
+        ++fp.cnt;
+    } else {  // PASS_STEP: src/cvo.cpp:249-289
+        const float rx = -dx, ry = -dy, rz = -dz;  // diff_xy = x - y, :260
+        // xi*z+v, xi^2*z+xi*v, ... (src/cvo.cpp:226-234) through z_{k+1} = omega x z_k  (= Omega^k y + Omega^(k-1) v)
+        const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+        const float z1x = (w1 * yg.z - w2 * yg.y) + ic.v[0];
+        const float z1y = (w2 * yg.x - w0 * yg.z) + ic.v[1];
+        const float z1z = (w0 * yg.y - w1 * yg.x) + ic.v[2];
+        const float z2x = w1 * z1z - w2 * z1y, z2y = w2 * z1x - w0 * z1z, z2z = w0 * z1y - w1 * z1x;
+        const float z3x = w1 * z2z - w2 * z2y, z3y = w2 * z2x - w0 * z2z, z3z = w0 * z2y - w1 * z2x;
+        const float z4x = w1 * z3z - w2 * z3y, z4y = w2 * z3x - w0 * z3z, z4z = w0 * z3y - w1 * z3x;
+        const float nrm = (z1x * z1x + z1y * z1y) + z1z * z1z;                                      // normxiz2, :235
+        const float pdt = -((z1x * z2x + z1y * z2y) + z1z * z2z);                                   // xiz_dot_xi2z, :236
+        const float ecn = ((z2x * z2x + z2y * z2y) + z2z * z2z) + 2.f * ((z1x * z3x + z1y * z3y) + z1z * z3z);  // :237
+        const float beta = ic.m2t * ((z1x * rx + z1y * ry) + z1z * rz);                             // :262
+        const float gamma = -ic.temp_coef * (nrm + 2.f * ((z2x * rx + z2y * ry) + z2z * rz));       // :264
+        const float delta = ic.p2t * (pdt - ((z3x * rx + z3y * ry) + z3z * rz));                    // :267
+        const float epsil = -ic.temp_coef * (ecn + 2.f * ((z4x * rx + z4y * ry) + z4z * rz));       // :270
+        const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
+        acc[0] += (double)(a * beta);                                                                // :275
+        acc[1] += ad * (gd + (double)(beta * beta) * 0.5);                                           // :276
+        acc[2] += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0));  // :277
+        acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
+                        (1.0 / 24.0) * (bd * bd) * (bd * bd));                                       // :278-279
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void flush_partial(FlowPartial& fp, double* acc) {
+    if (KIND == PASS_STEP) return;
+    if (fp.cnt) {
+        if (KIND == PASS_FLOW) {
+            acc[ACC_W0] += (double)fp.po0; acc[ACC_W0 + 1] += (double)fp.po1; acc[ACC_W0 + 2] += (double)fp.po2;
+            acc[ACC_V0] += (double)fp.pv0; acc[ACC_V0 + 1] += (double)fp.pv1; acc[ACC_V0 + 2] += (double)fp.pv2;
+            acc[ACC_SUMA] += (double)fp.psum;
+            acc[ACC_NNZ] += (double)fp.cnt;
+            acc[ACC_DLXY] += (double)fp.pdl;
+        } else if (KIND == PASS_XX || KIND == PASS_YY) {  // {nnz, sum} land in ACC_NNZXX.. / ACC_NNZYY.. later
+            acc[0] += (double)fp.cnt;
+            acc[1] += (double)fp.pdl;
+        } else {  // PASS_INNER
+            acc[0] += (double)fp.psum;
+            acc[1] += (double)fp.cnt;
+        }
+    }
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
+    fp.cnt = 0;
+}
+
+// One (row tile, col tile) pair.  Phase 1 (all lanes busy): lane = one row, 32 candidate columns, strict
+// ell-ball test -> 32-bit hit mask.  Phase 2: the hits of all lanes are compacted into the warp's queue
+// (row, col) and popped 32 at a time, so the kernel-value / flow / step arithmetic runs on full warps.
+template <int KIND>
+__device__ __forceinline__ void process_tile_pair(const Smem& sm, WarpScratch& ws, const KParams& kp, const float4& xg,
+                                                  int ct, int lane, int& qn, int yy_row_min, FlowPartial& fp,
+                                                  double* acc) {
     const float4* cgp = sm.colG + ct * kTile;
-    const float4* cfp = sm.colF + ct * kTile;
-    const float thr = ic.d2_thres;
+    const float thr = sm.ic.d2_thres;
     uint32_t mask = 0;
 #pragma unroll
     for (int jj = 0; jj < kTile; ++jj) {
@@ -555,179 +595,177 @@ __device__ __forceinline__ void process_entry(const Smem& sm, const KParams& kp,
         mask |= (d2 < thr) ? (1u << jj) : 0u;  // strict <, thirdparty/nanoflann.hpp:249-253
     }
     if (__ballot_sync(0xffffffffu, mask != 0) == 0) return;
-    const float4 xf = sm.rowF[rt * kTile + lane];
+    uint32_t* q = ws.queue;
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = qn + incl - cnt;
+    const uint32_t base = ((uint32_t)lane << 12) | (uint32_t)(ct * kTile);
+    while (mask) {
+        const int jj = __ffs(mask) - 1;
+        mask &= mask - 1;
+        q[pos++] = base + (uint32_t)jj;
+    }
+    qn += total;
+    __syncwarp();
+    while (qn >= 32) {
+        qn -= 32;
+        survivor_body<KIND>(sm, ws, kp, q[qn + lane], yy_row_min, fp, acc);
+    }
+    __syncwarp();
+}
 
-    if (KIND == PASS_FLOW) {
-        float po0 = 0.f, po1 = 0.f, po2 = 0.f, pv0 = 0.f, pv1 = 0.f, pv2 = 0.f, psum = 0.f, pdl = 0.f;
-        int cnt = 0;
-        while (mask) {
-            const int jj = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 yg = cgp[jj];
-            const float4 yf = cfp[jj];
-            const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
-            const float d2 = dist2(dx, dy, dz);
-            float a;
-            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
-                const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
-                const float cy = xg.z * yg.x - xg.x * yg.z;
-                const float cz = xg.x * yg.y - xg.y * yg.x;
-                const float ac = kp.inv_c * a, ad = kp.inv_d * a;  // (1/c*Ai), (1/d*Ai), :197-198
-                po0 = fmaf(ac, cx, po0); po1 = fmaf(ac, cy, po1); po2 = fmaf(ac, cz, po2);
-                pv0 = fmaf(ad, dx, pv0); pv1 = fmaf(ad, dy, pv1); pv2 = fmaf(ad, dz, pv2);
-                psum += a;
-                pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, pdl);  // src/adaptive_cvo.cpp:202,228
-                ++cnt;
-            }
+template <int KIND> struct PassTraits;
+template <> struct PassTraits<PASS_FLOW>  { static constexpr int NV = 9; };
+template <> struct PassTraits<PASS_XX>    { static constexpr int NV = 2; };
+template <> struct PassTraits<PASS_YY>    { static constexpr int NV = 2; };
+template <> struct PassTraits<PASS_STEP>  { static constexpr int NV = 4; };
+template <> struct PassTraits<PASS_INNER> { static constexpr int NV = 2; };
+
+// One work unit = one 32-row tile against one segment of the staged column tiles, done by ONE warp with no
+// block-level synchronisation.  The unit's totals go to its own slot, so the block sum does not depend on
+// which warp ran which unit (bit-deterministic under dynamic scheduling).
+template <int KIND>
+__device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, int tile,
+                                             int ct_begin, int ct_end, int slot, bool first_chunk, int yy_row_min) {
+    constexpr int NV = PassTraits<KIND>::NV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = sm.ws[warp];
+    const float inf = __int_as_float(0x7f800000);
+    // stage the row tile: registers for the mask phase, warp-private shared memory for the survivor body
+    const int p = tile * kTile + lane;
+    const bool valid = p < rows.n;
+    float4 xg, xf;
+    if (valid) {
+        xg = __ldg(rows.g + p);
+        xf = __ldg(rows.f + p);
+        if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
+    } else {
+        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
+        xf = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();  // the previous unit's body reads are done
+    ws.rowG[lane] = xg;
+    ws.rowF[lane] = xf;
+    if (KIND == PASS_YY) ws.rowOrig[lane] = valid ? __ldg(rows.idx + p) : -1;
+    const float lx = warp_min(valid ? xg.x : inf), ly = warp_min(valid ? xg.y : inf), lz = warp_min(valid ? xg.z : inf);
+    const float hx = warp_max(valid ? xg.x : -inf), hy = warp_max(valid ? xg.y : -inf), hz = warp_max(valid ? xg.z : -inf);
+    __syncwarp();
+
+    FlowPartial fp;
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
+    fp.cnt = 0;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    const float thr = sm.ic.d2_thres * 1.0001f;  // boxes are conservative; keep rounding on the safe side
+    int qn = 0;                                  // pairs waiting in this warp's queue (warp-uniform)
+    for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
+        const int ct = c0 + lane;
+        bool live = false;
+        if (ct < ct_end) {  // lane tests one column-tile box against the row-tile box
+            const float* b = sm.colBox[ct];
+            const float gx = fmaxf(0.f, fmaxf(lx - b[3], b[0] - hx));
+            const float gy = fmaxf(0.f, fmaxf(ly - b[4], b[1] - hy));
+            const float gz = fmaxf(0.f, fmaxf(lz - b[5], b[2] - hz));
+            live = (gx * gx + gy * gy + gz * gz) <= thr;
         }
-        if (cnt) {
-            acc[ACC_W0] += (double)po0; acc[ACC_W0 + 1] += (double)po1; acc[ACC_W0 + 2] += (double)po2;
-            acc[ACC_V0] += (double)pv0; acc[ACC_V0 + 1] += (double)pv1; acc[ACC_V0 + 2] += (double)pv2;
-            acc[ACC_SUMA] += (double)psum;
-            acc[ACC_NNZ] += (double)cnt;
-            acc[ACC_DLXY] += (double)pdl;
+        uint32_t lm = __ballot_sync(0xffffffffu, live);
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            process_tile_pair<KIND>(sm, ws, kp, xg, c0 + j, lane, qn, yy_row_min, fp, acc);
         }
-    } else if (KIND == PASS_XX || KIND == PASS_YY || KIND == PASS_INNER) {
-        float ps = 0.f, psum = 0.f;
-        int cnt = 0;
-        while (mask) {
-            const int jj = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 yg = cgp[jj];
-            const float4 yf = cfp[jj];
-            const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;
-            const float d2 = dist2(dx, dy, dz);
-            float a;
-            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
-                ps = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, ps);  // src/adaptive_cvo.cpp:210,231 / :256,259
-                psum += a;
-                ++cnt;
-            }
-        }
-        if (cnt) {
-            if (KIND == PASS_XX) {
-                acc[ACC_NNZXX] += (double)cnt;
-                acc[ACC_SXX] += (double)ps;
-            } else if (KIND == PASS_YY) {
-                acc[ACC_NNZYY] += (double)cnt;
-                // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223)
-                if (row_orig >= yy_row_min) acc[ACC_SYY] += (double)ps;
-            } else {
-                acc[0] += (double)psum;
-                acc[1] += (double)cnt;
-            }
-        }
-    } else {  // PASS_STEP: src/cvo.cpp:249-289
-        double Bi = 0.0, Ci = 0.0, Di = 0.0, Ei = 0.0;
-        bool any = false;
-        while (mask) {
-            const int jj = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 yg = cgp[jj];
-            const float4 yf = cfp[jj];
-            const float rx = xg.x - yg.x, ry = xg.y - yg.y, rz = xg.z - yg.z;  // diff_xy, :260
-            const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
-            float a;
-            if (kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) {
-                // xi*z+v ... xi^4*z+xi^3*v for this moving point (src/cvo.cpp:226-238)
-                const float* w = ic.omega;
-                const float z1x = (w[1] * yg.z - w[2] * yg.y) + ic.v[0];
-                const float z1y = (w[2] * yg.x - w[0] * yg.z) + ic.v[1];
-                const float z1z = (w[0] * yg.y - w[1] * yg.x) + ic.v[2];
-                const float z2x = ((ic.W2[0] * yg.x + ic.W2[1] * yg.y) + ic.W2[2] * yg.z) + ic.Wv[0];
-                const float z2y = ((ic.W2[3] * yg.x + ic.W2[4] * yg.y) + ic.W2[5] * yg.z) + ic.Wv[1];
-                const float z2z = ((ic.W2[6] * yg.x + ic.W2[7] * yg.y) + ic.W2[8] * yg.z) + ic.Wv[2];
-                const float z3x = ((ic.W3[0] * yg.x + ic.W3[1] * yg.y) + ic.W3[2] * yg.z) + ic.W2v[0];
-                const float z3y = ((ic.W3[3] * yg.x + ic.W3[4] * yg.y) + ic.W3[5] * yg.z) + ic.W2v[1];
-                const float z3z = ((ic.W3[6] * yg.x + ic.W3[7] * yg.y) + ic.W3[8] * yg.z) + ic.W2v[2];
-                const float z4x = ((ic.W4[0] * yg.x + ic.W4[1] * yg.y) + ic.W4[2] * yg.z) + ic.W3v[0];
-                const float z4y = ((ic.W4[3] * yg.x + ic.W4[4] * yg.y) + ic.W4[5] * yg.z) + ic.W3v[1];
-                const float z4z = ((ic.W4[6] * yg.x + ic.W4[7] * yg.y) + ic.W4[8] * yg.z) + ic.W3v[2];
-                const float nrm = (z1x * z1x + z1y * z1y) + z1z * z1z;                          // normxiz2
-                const float pdt = -((z1x * z2x + z1y * z2y) + z1z * z2z);                       // xiz_dot_xi2z
-                const float ecn = ((z2x * z2x + z2y * z2y) + z2z * z2z) + 2.f * ((z1x * z3x + z1y * z3y) + z1z * z3z);
-                const float beta = ((ic.m2t * z1x) * rx + (ic.m2t * z1y) * ry) + (ic.m2t * z1z) * rz;           // :262
-                const float gamma = -ic.temp_coef * (nrm + (((2.f * z2x) * rx + (2.f * z2y) * ry) + (2.f * z2z) * rz));  // :264
-                const float delta = ic.p2t * (pdt + (((-z3x) * rx + (-z3y) * ry) + (-z3z) * rz));              // :267
-                const float epsil = -ic.temp_coef * (ecn + (((2.f * z4x) * rx + (2.f * z4y) * ry) + (2.f * z4z) * rz));  // :270
-                const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
-                Bi += (double)(a * beta);                                                                       // :275
-                Ci += ad * (gd + (double)(beta * beta) / 2.0);                                                  // :276
-                Di += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) / 6.0);               // :277
-                Ei += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
-                            (1.0 / 24.0) * bd * bd * bd * bd);                                                  // :278-279
-                any = true;
-            }
-        }
-        if (any) {
-            acc[0] += Bi; acc[1] += Ci; acc[2] += Di; acc[3] += Ei;
+    }
+    if (qn > 0) {  // drain the tail of the queue
+        if (lane < qn) survivor_body<KIND>(sm, ws, kp, ws.queue[lane], yy_row_min, fp, acc);
+        __syncwarp();
+    }
+    flush_partial<KIND>(fp, acc);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double t = warp_sum(acc[i]);
+        if (lane == 0) {
+            if (first_chunk) sm.unitPart[slot][i] = t;
+            else sm.unitPart[slot][i] += t;
         }
     }
 }
 
-// One all-pairs pass of `rows` x `cols` restricted to this CTA's share of the row tiles.
+// One all-pairs pass of `rows` x `cols` restricted to this CTA's share of the row tiles.  The column cloud is
+// staged (and transformed) once per chunk; warps then pull work units from a shared counter.  On return
+// sm.blockTot[0 .. NV) holds this CTA's totals (valid for threads after the final barrier).
 template <int KIND>
 __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
-                         bool col_tf, int rank, int G, int yy_row_min, double* acc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                         bool col_tf, int rank, int G, int yy_row_min) {
+    constexpr int NV = PassTraits<KIND>::NV;
+    const int lane = threadIdx.x & 31;
     const int total_rt = (rows.n + kTile - 1) / kTile;
     const int t_begin = (int)(((long long)total_rt * rank) / G);
     const int t_end = (int)(((long long)total_rt * (rank + 1)) / G);
+    const int my_tiles = t_end - t_begin;
     const int total_ct = (cols.n + kTile - 1) / kTile;
-    for (int tb = t_begin; tb < t_end; tb += kRowTiles) {
-        const int nrt = min(kRowTiles, t_end - tb);
-        __syncthreads();  // previous users of rowG / colG are done
-        stage_tiles(sm.rowG, sm.rowF, sm.rowBox, rows, tb * kTile, nrt, row_tf, sm.ic.tf, kRowSentinel);
-        if (KIND == PASS_YY) {
-            for (int i = threadIdx.x; i < nrt * kTile; i += kThreads) {
-                const int p = tb * kTile + i;
-                sm.rowOrig[i] = p < rows.n ? __ldg(rows.idx + p) : -1;
-            }
-        }
+    // split every row tile's column range into S segments so that there are >= ~4 units per warp
+    int S = 1;
+    if (my_tiles > 0) {
+        S = (4 * kWarps + my_tiles - 1) / my_tiles;
+        const int s_max = max(1, min(total_ct, kColTiles) / 8);
+        S = max(1, min(min(S, s_max), kMaxUnits));
+    }
+    const int tiles_per_round = max(1, kMaxUnits / S);
+    if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
+    for (int rb = 0; rb < my_tiles; rb += tiles_per_round) {
+        const int ntile = min(tiles_per_round, my_tiles - rb);
+        const int nunits = ntile * S;
         for (int cb = 0; cb < total_ct; cb += kColTiles) {
             const int nct = min(kColTiles, total_ct - cb);
-            if (cb > 0) __syncthreads();
+            __syncthreads();  // everyone is done with the previous column chunk / unit slots
             stage_tiles(sm.colG, sm.colF, sm.colBox, cols, cb * kTile, nct, col_tf, sm.ic.tf, kColSentinel);
+            if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
-            build_tile_list(sm, nrt, nct, sm.ic.d2_thres);
-            const int n = sm.list_n;
-            for (int e = warp; e < n; e += kWarps) {
-                const uint32_t ent = sm.list[e];
-                const int rt = (int)(ent >> 16), ct = (int)(ent & 0xffffu);
-                process_entry<KIND>(sm, kp, rt, ct, lane, KIND == PASS_YY ? sm.rowOrig[rt * kTile + lane] : 0, yy_row_min, acc);
+            while (true) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= nunits) break;
+                const int t = u / S, seg = u - t * S;
+                const int c_begin = (int)(((long long)nct * seg) / S), c_end = (int)(((long long)nct * (seg + 1)) / S);
+                process_unit<KIND>(sm, kp, rows, row_tf, t_begin + rb + t, c_begin, c_end, u, cb == 0, yy_row_min);
             }
         }
-    }
-}
-
-// Block reduction + all-gather of the per-CTA partial sums through distributed shared memory;
-// every CTA of the cluster ends with identical totals in sm.sum[dst_off ...].
-template <int NV>
-__device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& cluster, const double* acc, int buf,
-                                                  int dst_off) {
-    constexpr int nv = NV;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
-#pragma unroll
-    for (int i = 0; i < nv; ++i) {
-        const double s = warp_sum(acc[i]);
-        if (lane == 0) sm.red[warp][i] = s;
+        __syncthreads();
+        if (threadIdx.x < NV) {  // fixed-order sum over the unit slots
+            double t = 0.0;
+            for (int u = 0; u < nunits; ++u) t += sm.unitPart[u][threadIdx.x];
+            sm.blockTot[threadIdx.x] += t;
+        }
     }
     __syncthreads();
-    if (threadIdx.x < nv) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += sm.red[w][threadIdx.x];
+}
+
+// All-gather of the per-CTA totals through distributed shared memory; every CTA of the cluster ends with
+// identical cluster totals in sm.sum[dst_off ...] (summed in rank order).
+template <int NV>
+__device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& cluster, const double* src, int buf,
+                                                  int dst_off) {
+    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    if (threadIdx.x < NV) {
+        const double v = src[threadIdx.x];
         for (int r = 0; r < G; ++r) {
             double* dst = cluster.map_shared_rank(&sm.xchg[buf][rank][threadIdx.x], r);
-            *dst = s;
+            *dst = v;
         }
     }
     cluster.sync();
-    if (threadIdx.x < nv) {
-        double s = 0.0;
-        for (int r = 0; r < G; ++r) s += sm.xchg[buf][r][threadIdx.x];
-        sm.sum[dst_off + threadIdx.x] = s;
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int r = 0; r < G; ++r) t += sm.xchg[buf][r][threadIdx.x];
+        sm.sum[dst_off + threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -765,23 +803,22 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         for (int k = 0; k < max_iter; ++k) {
             if (threadIdx.x == 0) prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
             __syncthreads();
-            double acc[kNumAcc];
-#pragma unroll
-            for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
-            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, acc);
+            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0);
+            if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, acc);
-                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, acc);
+                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0);
+                if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
+                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n);
+                if (threadIdx.x < 2) sm.flowTot[ACC_NNZYY + threadIdx.x] = sm.blockTot[threadIdx.x];
             }
-            cluster_allreduce<ACC_FLOW_COUNT>(sm, cluster, acc, 0, kFlowOff);
+            __syncthreads();
+            cluster_allreduce<ACC_FLOW_COUNT>(sm, cluster, sm.flowTot, 0, kFlowOff);
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = 0.0;
             // compute_step_size (src/cvo.cpp:377)
-            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, acc);
-            cluster_allreduce<4>(sm, cluster, acc, 1, 0);
+            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0);
+            cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
             if (threadIdx.x == 0) {
                 // remember the transform used by this iteration: it is what the reference multiplies
                 // into accum_transform when the loop exits here (quirk Q3, src/cvo.cpp:413-414)
@@ -816,11 +853,8 @@ __global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerA
         prepare_iter(sm, args.kp, args.kp.d2c_thres);
     }
     __syncthreads();
-    double acc[kNumAcc];
-#pragma unroll
-    for (int i = 0; i < kNumAcc; ++i) acc[i] = 0.0;
-    run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0, acc);
-    cluster_allreduce<2>(sm, cluster, acc, 0, 0);
+    run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0);
+    cluster_allreduce<2>(sm, cluster, sm.blockTot, 0, 0);
     if (rank == 0 && threadIdx.x == 0) {
         args.out[0] = sm.sum[0];
         args.out[1] = sm.sum[1];

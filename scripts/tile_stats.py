@@ -36,8 +36,9 @@ def stats(x, y, ell, tile=32, rows_per_lane=1):
                 per_lane = pad.reshape(rows_per_lane, tile).sum(0)
                 trips += per_lane.max(); inball += m.sum(); trips_mean += per_lane.mean()
     return dict(tilepairs=nxt*nyt, live=live, live_frac=live/(nxt*nyt), inball=int(inball), trips=int(trips), util=trips_mean/max(trips,1))
-pr = synth.config_pair(2)
-for ell in (0.15, 0.1, 0.06, 0.03):
-    print('ell', ell, stats(pr['x_pos'], pr['y_pos'], ell))
-print('2 rows/lane', stats(pr['x_pos'], pr['y_pos'], 0.1, rows_per_lane=2))
-print('tile16', stats(pr['x_pos'], pr['y_pos'], 0.1, tile=16))
+if __name__ == "__main__":
+  pr = synth.config_pair(2)
+  for ell in (0.15, 0.1, 0.06, 0.03):
+      print('ell', ell, stats(pr['x_pos'], pr['y_pos'], ell))
+  print('2 rows/lane', stats(pr['x_pos'], pr['y_pos'], 0.1, rows_per_lane=2))
+  print('tile16', stats(pr['x_pos'], pr['y_pos'], 0.1, tile=16))
