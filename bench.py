@@ -112,8 +112,13 @@ def cpu_reference_run(n_pairs, seed0, threads=None):
         variant = "ref"
     except Exception:
         O.load("port")
-    if threads:
-        O.set_num_threads(threads, variant)
+    # torchrun exports OMP_NUM_THREADS=1 to its children; the reference arm uses every host core it may run on
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count()
+    O.set_num_threads(threads, variant)
     p = O.default_params("cvo")
     p.ell_policy, p.ell_init, p.fixed_iters = O.ELL_FIXED, FIXED_ELL, FIXED_ITERS
     pairs = [synth.config_pair(2, seed0 + i) for i in range(n_pairs)]
@@ -182,6 +187,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     probe = capi.Context(local_rank, 64, 1)
