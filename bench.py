@@ -8,7 +8,7 @@ Workload (config.workload): BASELINE.json configs[1] -- synthetic 3000 x 3000-po
 ell = 0.10, exactly 100 inner iterations per pair (stop tests off) -- as a batch of `--pairs` independent
 pairs per GPU per step (default 2 x #SMs).  One step = align() of the whole batch.
   value  = pairs / device time of the align kernel (CUDA events on the library's stream), clouds resident in HBM
-  e2e    = pairs / wall time of: upload of every pair from pinned host memory (cvo_b200_set_pair: H2D + on-device
+  e2e    = pairs / wall time of: upload of every pair from pinned host memory (cvo_b200_set_pairs: H2D + on-device
            Morton sort/pack) + cvo_b200_align + the poses coming back to the host (+ NCCL all-gather of the poses
            when N > 1), through the C ABI the reference's frontends would call.
 Multi-GPU: one process per GPU (torchrun), pairs are independent => weak scaling, no data-path collective;
@@ -211,11 +211,11 @@ def main():
     d2h_bytes = int(P * (16 * 4 + 16 * 4 + 4 + 4 + 200))  # poses + state records read back per step
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    counts = np.full(P, N_POINTS, dtype=np.int32)
+
     def upload_all():
-        for s in range(P):
-            rc = ctx.set_pair_raw(s, hx[s], hfx[s], hy[s], hfy[s])
-            if rc != 0:
-                raise RuntimeError("set_pair failed: %d" % rc)
+        # cvo_b200_set_pairs: 4 H2D copies from the pinned arrays + one Morton-sort/pack launch for the batch
+        ctx.set_pairs(slots, hx, hfx, counts, hy, hfy, counts)
 
     def barrier():
         if dist is not None:

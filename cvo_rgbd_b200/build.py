@@ -12,16 +12,18 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
-def build_library(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """out / defines: tuning variants (scripts/build_variants.py); the product is the default build."""
+    out = out or OUT
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc]
     if os.path.exists("/usr/bin/g++"):  # the image exports CXX=/opt/gcc/bin/g++; use the distro host compiler
         cmd += ["-ccbin", "/usr/bin/g++"]
-    cmd += NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd += NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out, SRC]
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 def build_frontend_example():

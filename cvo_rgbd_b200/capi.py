@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvo_b200.so")
+# CVO_B200_LIB selects a tuning variant built by scripts/build_variants.py (still this repo's CUDA library)
+LIB_PATH = os.environ.get("CVO_B200_LIB") or os.path.join(_HERE, "libcvo_b200.so")
 
 MODE_CVO, MODE_ACVO = 0, 1
 ELL_SCHEDULE, ELL_ADAPTIVE, ELL_FIXED = 0, 1, 2
@@ -19,7 +20,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_EMPTY = 0, -1, -2, -3
 # every symbol include/cvo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "cvo_b200_default_params_cvo", "cvo_b200_default_params_acvo", "cvo_b200_create", "cvo_b200_destroy",
-    "cvo_b200_last_error", "cvo_b200_set_pair", "cvo_b200_push_frame", "cvo_b200_eval", "cvo_b200_align",
+    "cvo_b200_last_error", "cvo_b200_set_pair", "cvo_b200_set_pairs", "cvo_b200_push_frame", "cvo_b200_eval", "cvo_b200_align",
     "cvo_b200_align_trace", "cvo_b200_inner_product", "cvo_b200_sync", "cvo_b200_last_kernel_ms",
     "cvo_b200_kernel_launches", "cvo_b200_last_cluster_size", "cvo_b200_last_num_clusters",
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
@@ -81,6 +82,7 @@ def load():
     lib.cvo_b200_last_error.argtypes = [vp]
     lib.cvo_b200_last_error.restype = C.c_char_p
     lib.cvo_b200_set_pair.argtypes = [vp, C.c_int, fp, fp, C.c_int, fp, fp, C.c_int]
+    lib.cvo_b200_set_pairs.argtypes = [vp, ip, C.c_int, fp, fp, ip, fp, fp, ip, C.c_int]
     lib.cvo_b200_push_frame.argtypes = [vp, C.c_int, fp, fp, C.c_int]
     lib.cvo_b200_eval.argtypes = [vp, C.c_int, fp, fp, C.c_float, C.POINTER(Params), C.POINTER(IterRec)]
     lib.cvo_b200_align.argtypes = [vp, ip, C.c_int, C.POINTER(Params), fp, fp, fp, fp, ip, ip]
@@ -166,6 +168,19 @@ class Context:
         """No conversions: arrays must already be C-contiguous float32 (benchmark path)."""
         return self._lib.cvo_b200_set_pair(self._h, slot, _fp(fx), _fp(ff), fx.shape[0], _fp(mx), _fp(mf),
                                            mx.shape[0])
+
+    def set_pairs(self, slots, fx, ff, n_fixed, mx, mf, n_moving):
+        """Batched upload: fx/mx are [P, stride, 3], ff/mf are [P, stride, 5] C-contiguous float32 (no conversion
+        is done: pass pinned arrays for the benchmark path); n_fixed/n_moving are the per-pair point counts."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n_fixed = np.ascontiguousarray(n_fixed, dtype=np.int32)
+        n_moving = np.ascontiguousarray(n_moving, dtype=np.int32)
+        P, stride = slots.shape[0], fx.shape[1]
+        for a, w in ((fx, 3), (ff, 5), (mx, 3), (mf, 5)):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.shape == (P, stride, w)
+        assert n_fixed.shape == (P,) and n_moving.shape == (P,)
+        self._check(self._lib.cvo_b200_set_pairs(self._h, _ipt(slots), P, _fp(fx), _fp(ff), _ipt(n_fixed), _fp(mx),
+                                                 _fp(mf), _ipt(n_moving), stride))
 
     def push_frame(self, slot, xyz, feat):
         x, f = _f32(xyz), _f32(feat)

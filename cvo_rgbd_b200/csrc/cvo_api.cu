@@ -43,6 +43,9 @@ struct cvo_b200_ctx {
     int trace_cap = 0;
     double* d_inner = nullptr;
     PackJob* d_jobs = nullptr;  // descriptors of the pack launch in flight (stream-ordered reuse)
+    PackJob* h_jobs = nullptr;  // pinned, 2 * max_slots (batched upload)
+    float* d_batch_raw = nullptr;  // raw staging of a batched upload (grown on demand)
+    size_t batch_raw_floats = 0;
     double* h_inner = nullptr;  // pinned
 
     float last_ms = 0.f;
@@ -357,7 +360,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     CKC(cudaMalloc(&ctx->d_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMallocHost(&ctx->h_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMalloc(&ctx->d_inner, sizeof(double) * 2));
-    CKC(cudaMalloc(&ctx->d_jobs, sizeof(PackJob) * 2));
+    CKC(cudaMalloc(&ctx->d_jobs, sizeof(PackJob) * 2 * max_slots));
+    CKC(cudaMallocHost(&ctx->h_jobs, sizeof(PackJob) * 2 * max_slots));
     CKC(cudaMallocHost(&ctx->h_inner, sizeof(double) * 2));
     ctx->pack_smem_max = 128 * 1024;
     CKC(cudaFuncSetAttribute(pack_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pack_smem_max));
@@ -391,6 +395,8 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFreeHost(ctx->h_trace);
     cudaFree(ctx->d_inner);
     cudaFree(ctx->d_jobs);
+    cudaFreeHost(ctx->h_jobs);
+    cudaFree(ctx->d_batch_raw);
     cudaFreeHost(ctx->h_inner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -425,6 +431,61 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const
     jobs[0] = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0), slot_idx(ctx, slot, 0), n_fixed, 0};
     jobs[1] = {ctx->d_raw_xyz + mp * 3, ctx->d_raw_feat + mp * 5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1), slot_idx(ctx, slot, 1), n_moving, 0};
     return launch_pack(ctx, jobs, 2, ctx->d_jobs);
+}
+
+int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const float* fixed_xyz,
+                       const float* fixed_feat, const int* n_fixed, const float* moving_xyz, const float* moving_feat,
+                       const int* n_moving, int stride_points) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!slots || !fixed_xyz || !fixed_feat || !moving_xyz || !moving_feat || !n_fixed || !n_moving)
+        return fail_arg(ctx, "null pointer");
+    if (n_pairs <= 0 || n_pairs > ctx->max_slots) return fail_arg(ctx, "bad pair count");
+    if (stride_points <= 0) return fail_arg(ctx, "bad stride");
+    for (int i = 0; i < n_pairs; ++i) {
+        if (slots[i] < 0 || slots[i] >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
+        if (n_fixed[i] <= 0 || n_moving[i] <= 0) {
+            ctx->err = "empty cloud";
+            return CVO_B200_ERR_EMPTY;
+        }
+        if (n_fixed[i] > ctx->max_points || n_moving[i] > ctx->max_points || n_fixed[i] > stride_points ||
+            n_moving[i] > stride_points)
+            return fail_arg(ctx, "cloud larger than max_points / stride");
+    }
+    CK(cudaSetDevice(ctx->device));
+    // one staging area for the whole batch: [fixed xyz | fixed feat | moving xyz | moving feat]
+    const size_t cloud3 = (size_t)stride_points * 3, cloud5 = (size_t)stride_points * 5;
+    const size_t need = (size_t)n_pairs * 2 * (cloud3 + cloud5);
+    if (need > ctx->batch_raw_floats) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_batch_raw);
+        ctx->d_batch_raw = nullptr;
+        ctx->batch_raw_floats = 0;
+        CK(cudaMalloc(&ctx->d_batch_raw, need * sizeof(float)));
+        ctx->batch_raw_floats = need;
+    }
+    float* d_fx = ctx->d_batch_raw;
+    float* d_ff = d_fx + (size_t)n_pairs * cloud3;
+    float* d_mx = d_ff + (size_t)n_pairs * cloud5;
+    float* d_mf = d_mx + (size_t)n_pairs * cloud3;
+    // the pinned job array may still be read by the previous batch's copy: wait for the stream first
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(d_fx, fixed_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ff, fixed_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_mx, moving_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_mf, moving_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < n_pairs; ++i) {
+        const int slot = slots[i];
+        cvo_b200_ctx::Slot& s = ctx->slots[slot];
+        s.fixed_buf = 0;
+        s.n[0] = n_fixed[i];
+        s.n[1] = n_moving[i];
+        s.bound = true;
+        ctx->h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
+                              slot_idx(ctx, slot, 0), n_fixed[i], 0};
+        ctx->h_jobs[2 * i + 1] = {d_mx + i * cloud3, d_mf + i * cloud5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1),
+                                  slot_idx(ctx, slot, 1), n_moving[i], 0};
+    }
+    return launch_pack(ctx, ctx->h_jobs, 2 * n_pairs, ctx->d_jobs);
 }
 
 int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {

@@ -22,7 +22,21 @@ namespace cvo_b200 {
 
 namespace cg = cooperative_groups;
 
-constexpr int kThreads = 512;
+// Build-time tuning knobs (scripts/build_variants.py sweeps them; the defaults are the measured best,
+// profiles/r01_variant_sweep.txt).
+#ifndef CVO_THREADS
+#define CVO_THREADS 512
+#endif
+#ifndef CVO_BODY_ILP
+#define CVO_BODY_ILP 2
+#endif
+#ifndef CVO_UNITS_PER_WARP
+#define CVO_UNITS_PER_WARP 4
+#endif
+#ifndef CVO_GROUP
+#define CVO_GROUP 2
+#endif
+constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 32;
 constexpr int kColChunk = 3072;                 // moving-cloud points resident in shared memory per pass
@@ -31,11 +45,15 @@ constexpr int kMaxCluster = 16;
 constexpr int kNumAcc = 16;
 constexpr int kMaxUnits = 256;                  // work units (row tile x column segment) per scheduling round
 constexpr int kUnitAcc = 9;                     // widest per-unit partial record (flow: omega, v, sum, nnz, dl)
-constexpr int kQueueCap = 32 + kTile * kTile;   // leftovers (< 32) + one full tile pair
+constexpr int kQueueCap = 64 + kTile * kTile;   // leftovers (< 32 * CVO_BODY_ILP) + one full tile pair
 static_assert(kColChunk <= (1 << 12), "queue entries pack row:5 | col:12 bits");
 constexpr int kFlowOff = 4;  // sm.sum[0..3] = B,C,D,E ; sm.sum[kFlowOff + ACC_*] = flow totals
-constexpr float kRowSentinel = 1.0e30f;
-constexpr float kColSentinel = -1.0e30f;
+// padding points: far away from everything, but small enough that their squared norm stays finite
+constexpr float kRowSentinel = 1.0e15f;
+constexpr float kColSentinel = -1.0e15f;
+// Prefilter slack: the mask phase tests the EXPANDED form |c|^2 - 2 c.x + |x|^2 < thr (3 FFMA per candidate) and
+// only has to be a superset of the exact ball; its rounding error is bounded by ~20 * 2^-24 * (|c|^2 + |x|^2).
+constexpr float kPrefilterSlack = 2.0e-6f;
 
 enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INNER = 4 };
 
@@ -103,9 +121,10 @@ struct WarpScratch {
 };
 
 struct Smem {
-    float4 colG[kColChunk];
-    float4 colF[kColChunk];
-    float colBox[kColTiles][8];
+    float4 colG[kColChunk];   // {x, y, z, |c|^2} of the staged (transformed) column points
+    float4 colF[kColChunk];   // {f0, f1, f2, f3}
+    float colF4[kColChunk];   // f4
+    float colBox[kColTiles][8];  // [0..2] lo, [3..5] hi, [6] max |c|^2
     WarpScratch ws[kWarps];
     double unitPart[kMaxUnits][kUnitAcc];  // one fixed slot per work unit => scheduling-independent sums
     double blockTot[kNumAcc];
@@ -444,8 +463,8 @@ __device__ void write_tf44(const float* tf12, float* out) {
 // Stages `ntiles` 32-point tiles starting at point `base` of a packed cloud into shared memory,
 // applying the rigid transform on the way (this is transform_pcd, src/cvo.cpp:310-315: the
 // transformed cloud never exists in HBM) and reducing one bounding box per tile.
-__device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float (*box)[8], const CloudDev& c, int base,
-                                            int ntiles, bool tf, const float* tf12, float sentinel) {
+__device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float* sf4, float (*box)[8], const CloudDev& c,
+                                            int base, int ntiles, bool tf, const float* tf12, float sentinel) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
     for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
@@ -460,13 +479,16 @@ __device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float (*box)
             g = make_float4(sentinel, sentinel, sentinel, 0.f);
             f = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        sg[i] = g;
-        sf[i] = f;
+        const float c2 = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
+        sg[i] = make_float4(g.x, g.y, g.z, c2);
+        sf[i] = make_float4(g.w, f.x, f.y, f.z);
+        sf4[i] = f.w;
         const float lx = warp_min(valid ? g.x : inf), ly = warp_min(valid ? g.y : inf), lz = warp_min(valid ? g.z : inf);
         const float hx = warp_max(valid ? g.x : -inf), hy = warp_max(valid ? g.y : -inf), hz = warp_max(valid ? g.z : -inf);
+        const float c2m = warp_max(valid ? c2 : 0.f);
         if (lane == 0) {
             float* b = box[i >> 5];
-            b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz;
+            b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz; b[6] = c2m;
         }
     }
 }
@@ -475,19 +497,17 @@ __device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float (*box)
 // per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xg,
-                                             const float4& xf, const float4& yg, const float4& yf, float d2,
-                                             float& a) {
-    const float e0 = xg.w - yg.w, e1 = xf.x - yf.x, e2 = xf.y - yf.y, e3 = xf.z - yf.z, e4 = xf.w - yf.w;
+                                             const float4& xf, const float4& yf, float yf4, float d2, float& a) {
+    const float e0 = xg.w - yf.x, e1 = xf.x - yf.y, e2 = xf.y - yf.z, e3 = xf.z - yf.w, e4 = xf.w - yf4;
     float d2c = __fmul_rn(e0, e0);
     d2c = __fadd_rn(d2c, __fmul_rn(e1, e1));
     d2c = __fadd_rn(d2c, __fmul_rn(e2, e2));
     d2c = __fadd_rn(d2c, __fmul_rn(e3, e3));
     d2c = __fadd_rn(d2c, __fmul_rn(e4, e4));
-    if (!(d2c < ic.d2c_thres)) return false;
     const float k = __fmul_rn(kp.s2, expf(-__fmul_rn(d2, ic.inv2l2)));      // src/cvo.cpp:149
     const float ck = __fmul_rn(kp.cs2, expf(-__fmul_rn(d2c, kp.inv2cl2)));  // :150
     a = __fmul_rn(ck, k);                                                   // :151
-    return a > kp.sp_thres;                                                 // :152
+    return (d2c < ic.d2c_thres) && (a > kp.sp_thres);                       // :143, :152
 }
 
 // Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
@@ -497,21 +517,27 @@ struct FlowPartial {
     int cnt;
 };
 
-// Survivor body: one (row, col) pair that passed the ell-ball test.  All 32 lanes of a warp work on 32 different
-// pairs popped from the warp's queue, so the expensive part runs at full lane utilisation.
+// Survivor body: one (row, col) candidate popped from the warp's queue.  All 32 lanes of a warp work on 32
+// different candidates, so the expensive part runs at full lane utilisation.  The body is BRANCH-FREE: the three
+// strict gates of se_kernel (exact ball test on the nanoflann-ordered d2, colour gate, a > sp_thres) fold into
+// one predicate and a rejected candidate contributes a = 0 (adding +0 terms), which lets the compiler interleave
+// several bodies (CVO_BODY_ILP) to hide the LDS / MUFU latencies.
 template <int KIND>
 __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent,
-                                              int yy_row_min, FlowPartial& fp, double* acc) {
+                                              bool live, int yy_row_min, FlowPartial& fp, double* acc) {
     const IterConsts& ic = sm.ic;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
     const float4 yg = sm.colG[col];
     const float4 yf = sm.colF[col];
+    const float yf4 = sm.colF4[col];
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     float a;
-    if (!kernel_value(ic, kp, xg, xf, yg, yf, d2, a)) return;
+    bool ok = kernel_value(ic, kp, xg, xf, yf, yf4, d2, a);
+    ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    a = ok ? a : 0.f;
     if (KIND == PASS_FLOW) {
         const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
         const float cy = xg.z * yg.x - xg.x * yg.z;
@@ -521,15 +547,16 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
         fp.pv0 = fmaf(ad, dx, fp.pv0); fp.pv1 = fmaf(ad, dy, fp.pv1); fp.pv2 = fmaf(ad, dz, fp.pv2);
         fp.psum += a;
         fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:202,228
-        ++fp.cnt;
+        fp.cnt += ok ? 1 : 0;
     } else if (KIND == PASS_XX || KIND == PASS_INNER) {
         fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:210,231
         fp.psum += a;
-        ++fp.cnt;
+        fp.cnt += ok ? 1 : 0;
     } else if (KIND == PASS_YY) {
         // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223); :256,259 otherwise
-        if (ws.rowOrig[row] >= yy_row_min) fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);
-        ++fp.cnt;
+        const float aq = (ws.rowOrig[row] >= yy_row_min) ? a : 0.f;
+        fp.pdl = fmaf(ic.inv_ell3 * aq, dx * dx + dy * dy + dz * dz, fp.pdl);
+        fp.cnt += ok ? 1 : 0;
     } else {  // PASS_STEP: src/cvo.cpp:249-289
         const float rx = -dx, ry = -dy, rz = -dz;  // diff_xy = x - y, :260
         // xi*z+v, xi^2*z+xi*v, ... (src/cvo.cpp:226-234) through z_{k+1} = omega x z_k  (= Omega^k y + Omega^(k-1) v)
@@ -578,46 +605,95 @@ __device__ __forceinline__ void flush_partial(FlowPartial& fp, double* acc) {
     fp.cnt = 0;
 }
 
-// One (row tile, col tile) pair.  Phase 1 (all lanes busy): lane = one row, 32 candidate columns, strict
-// ell-ball test -> 32-bit hit mask.  Phase 2: the hits of all lanes are compacted into the warp's queue
-// (row, col) and popped 32 at a time, so the kernel-value / flow / step arithmetic runs on full warps.
-template <int KIND>
-__device__ __forceinline__ void process_tile_pair(const Smem& sm, WarpScratch& ws, const KParams& kp, const float4& xg,
-                                                  int ct, int lane, int& qn, int yy_row_min, FlowPartial& fp,
-                                                  double* acc) {
-    const float4* cgp = sm.colG + ct * kTile;
-    const float thr = sm.ic.d2_thres;
-    uint32_t mask = 0;
-#pragma unroll
-    for (int jj = 0; jj < kTile; ++jj) {
-        const float4 c = cgp[jj];
-        const float d2 = dist2(c.x - xg.x, c.y - xg.y, c.z - xg.z);
-        mask |= (d2 < thr) ? (1u << jj) : 0u;  // strict <, thirdparty/nanoflann.hpp:249-253
-    }
-    if (__ballot_sync(0xffffffffu, mask != 0) == 0) return;
-    uint32_t* q = ws.queue;
-    const int cnt = __popc(mask);
+// One (row tile, col tile) pair.  Phase 1 (all lanes busy): lane = one row, 32 candidate columns, a conservative
+// ball PREFILTER in expanded form (|c|^2 - 2 c.x < thr + slack - |x|^2: 3 FFMA + compare per candidate) -> 32-bit
+// candidate mask.  Phase 2: the candidates of all lanes are compacted into the warp's queue (row, col) and popped
+// 32 at a time; the survivor body applies the EXACT strict test on the nanoflann-ordered d2 first, then the
+// kernel-value / flow / step arithmetic, on full warps.
+struct RowRegs {
+    float m2x, m2y, m2z;  // -2 x_i
+    float x2;             // |x_i|^2
+};
+// exclusive prefix sum + total of a per-lane count across the warp
+__device__ __forceinline__ void warp_scan_count(int cnt, int lane, int& excl, int& total) {
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int pos = qn + incl - cnt;
-    const uint32_t base = ((uint32_t)lane << 12) | (uint32_t)(ct * kTile);
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    excl = incl - cnt;
+}
+
+// appends one queue entry per set bit of `mask` (this lane's candidate columns of one col tile) at q[pos...]
+__device__ __forceinline__ void push_mask(uint32_t* q, int pos, uint32_t mask, uint32_t base) {
     while (mask) {
         const int jj = __ffs(mask) - 1;
         mask &= mask - 1;
         q[pos++] = base + (uint32_t)jj;
     }
-    qn += total;
-    __syncwarp();
-    while (qn >= 32) {
-        qn -= 32;
-        survivor_body<KIND>(sm, ws, kp, q[qn + lane], yy_row_min, fp, acc);
+}
+
+__device__ __forceinline__ uint32_t prefilter_tile(const Smem& sm, const RowRegs& rr, int ct) {
+    const float4* cgp = sm.colG + ct * kTile;
+    const float t = fmaf(kPrefilterSlack, sm.colBox[ct][6] + rr.x2, sm.ic.d2_thres) - rr.x2;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int jj = 0; jj < kTile; ++jj) {
+        const float4 c = cgp[jj];
+        const float s = fmaf(c.x, rr.m2x, fmaf(c.y, rr.m2y, fmaf(c.z, rr.m2z, c.w)));
+        mask |= (s < t) ? (1u << jj) : 0u;
     }
-    __syncwarp();
+    return mask;
+}
+
+// One row tile against up to two live col tiles (ctB < 0: only ctA).
+template <int KIND>
+__device__ __forceinline__ void process_tile_group(const Smem& sm, WarpScratch& ws, const KParams& kp, const RowRegs& rr,
+                                                   int ctA, int ctB, int lane, int& qn, int yy_row_min, FlowPartial& fp,
+                                                   double* acc) {
+    const uint32_t maskA = prefilter_tile(sm, rr, ctA);
+    const uint32_t maskB = (ctB >= 0) ? prefilter_tile(sm, rr, ctB) : 0u;
+    if (__ballot_sync(0xffffffffu, (maskA | maskB) != 0) == 0) return;
+    uint32_t* q = ws.queue;
+    // the queue holds one full tile pair on top of the leftovers: a (rare) group with more candidates than that
+    // is pushed in two rounds (col tile A, then col tile B)
+    uint32_t mA = maskA, mB = maskB;
+    bool pending = false;
+    while (true) {
+        const int nA = __popc(mA);
+        int excl, total;
+        warp_scan_count(nA + __popc(mB), lane, excl, total);
+        if (total > kTile * kTile) {  // only possible for the combined round
+            mB = 0u;
+            pending = true;
+            continue;
+        }
+        const int pos = qn + excl;
+        push_mask(q, pos, mA, ((uint32_t)lane << 12) | (uint32_t)(ctA * kTile));
+        push_mask(q, pos + nA, mB, ((uint32_t)lane << 12) | (uint32_t)(ctB * kTile));
+        qn += total;
+        __syncwarp();
+#if CVO_BODY_ILP >= 2
+        while (qn >= 64) {  // two independent candidates per lane: the compiler interleaves the two bodies
+            qn -= 64;
+            const uint32_t e0 = q[qn + lane], e1 = q[qn + 32 + lane];
+            survivor_body<KIND>(sm, ws, kp, e0, true, yy_row_min, fp, acc);
+            survivor_body<KIND>(sm, ws, kp, e1, true, yy_row_min, fp, acc);
+        }
+#else
+        while (qn >= 32) {
+            qn -= 32;
+            survivor_body<KIND>(sm, ws, kp, q[qn + lane], true, yy_row_min, fp, acc);
+        }
+#endif
+        __syncwarp();
+        if (!pending) break;
+        pending = false;
+        mA = 0u;
+        mB = maskB;
+    }
 }
 
 template <int KIND> struct PassTraits;
@@ -657,6 +733,9 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     const float hx = warp_max(valid ? xg.x : -inf), hy = warp_max(valid ? xg.y : -inf), hz = warp_max(valid ? xg.z : -inf);
     __syncwarp();
 
+    RowRegs rr;
+    rr.m2x = -2.f * xg.x; rr.m2y = -2.f * xg.y; rr.m2z = -2.f * xg.z;
+    rr.x2 = fmaf(xg.z, xg.z, fmaf(xg.y, xg.y, xg.x * xg.x));
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
@@ -677,15 +756,23 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
         }
         uint32_t lm = __ballot_sync(0xffffffffu, live);
         while (lm) {
-            const int j = __ffs(lm) - 1;
+            const int jA = __ffs(lm) - 1;
             lm &= lm - 1;
-            process_tile_pair<KIND>(sm, ws, kp, xg, c0 + j, lane, qn, yy_row_min, fp, acc);
+            int jB = -1 - c0;
+#if CVO_GROUP >= 2
+            if (lm) {
+                jB = __ffs(lm) - 1;
+                lm &= lm - 1;
+            }
+#endif
+            process_tile_group<KIND>(sm, ws, kp, rr, c0 + jA, c0 + jB, lane, qn, yy_row_min, fp, acc);
         }
     }
-    if (qn > 0) {  // drain the tail of the queue
-        if (lane < qn) survivor_body<KIND>(sm, ws, kp, ws.queue[lane], yy_row_min, fp, acc);
-        __syncwarp();
+    for (int b = 0; b < qn; b += 32) {  // drain the tail of the queue; idle lanes run entry (0, 0) with a = 0
+        const bool live = b + lane < qn;
+        survivor_body<KIND>(sm, ws, kp, live ? ws.queue[b + lane] : 0u, live, yy_row_min, fp, acc);
     }
+    __syncwarp();
     flush_partial<KIND>(fp, acc);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -713,7 +800,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
     // split every row tile's column range into S segments so that there are >= ~4 units per warp
     int S = 1;
     if (my_tiles > 0) {
-        S = (4 * kWarps + my_tiles - 1) / my_tiles;
+        S = (CVO_UNITS_PER_WARP * kWarps + my_tiles - 1) / my_tiles;
         const int s_max = max(1, min(total_ct, kColTiles) / 8);
         S = max(1, min(min(S, s_max), kMaxUnits));
     }
@@ -725,7 +812,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
         for (int cb = 0; cb < total_ct; cb += kColTiles) {
             const int nct = min(kColTiles, total_ct - cb);
             __syncthreads();  // everyone is done with the previous column chunk / unit slots
-            stage_tiles(sm.colG, sm.colF, sm.colBox, cols, cb * kTile, nct, col_tf, sm.ic.tf, kColSentinel);
+            stage_tiles(sm.colG, sm.colF, sm.colF4, sm.colBox, cols, cb * kTile, nct, col_tf, sm.ic.tf, kColSentinel);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
             while (true) {

@@ -102,6 +102,16 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot,
                       const float* fixed_xyz, const float* fixed_feat, int n_fixed,
                       const float* moving_xyz, const float* moving_feat, int n_moving);
 
+/* cvo_b200_set_pair for `n_pairs` independent frame pairs at once (the batch / multi-GPU driver of
+ * BASELINE config 4; the reference binds one pair per object, src/cvo.cpp:343-356): four host->device
+ * copies and ONE pack launch for the whole batch.  Cloud i of every array starts at element
+ * i * stride_points * 3 (xyz) or i * stride_points * 5 (feat) and holds n_fixed[i] / n_moving[i]
+ * (<= stride_points) points.  Same copy / ownership / ordering rules as cvo_b200_set_pair. */
+int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs,
+                       const float* fixed_xyz, const float* fixed_feat, const int* n_fixed,
+                       const float* moving_xyz, const float* moving_feat, const int* n_moving,
+                       int stride_points);
+
 /* Replaces `ptr_fixed_pcd = std::move(ptr_moving_pcd)` (src/cvo.cpp:417) + the next set_pcd():
  * the slot's moving cloud becomes its fixed cloud (pointer swap on the device) and a new moving cloud
  * is uploaded, so a sequence uploads each frame once. */

@@ -171,6 +171,35 @@ def test_batch_of_pairs_equals_one_by_one_and_warm_start_state_round_trips(gpu_c
         assert np.array_equal(cont["transform"][s], full["transform"][s])
 
 
+def test_batched_upload_of_ragged_pairs_equals_single_uploads(gpu_ctx):
+    """cvo_b200_set_pairs (one copy + one pack launch for a batch) binds exactly what cvo_b200_set_pair binds,
+    for ragged cloud sizes (BASELINE config 4: N, M ~ U{2700..3300})."""
+    P = 5
+    prs = [synth.config_pair(4, 100 + i) for i in range(P)]
+    stride = max(max(len(pr["x_pos"]), len(pr["y_pos"])) for pr in prs)
+    fx, mx = np.zeros((P, stride, 3), np.float32), np.zeros((P, stride, 3), np.float32)
+    ff, mf = np.zeros((P, stride, 5), np.float32), np.zeros((P, stride, 5), np.float32)
+    nf, nm = np.zeros(P, np.int32), np.zeros(P, np.int32)
+    for i, pr in enumerate(prs):
+        nf[i], nm[i] = len(pr["x_pos"]), len(pr["y_pos"])
+        fx[i, :nf[i]], ff[i, :nf[i]] = pr["x_pos"], pr["x_feat"]
+        mx[i, :nm[i]], mf[i, :nm[i]] = pr["y_pos"], pr["y_feat"]
+    assert len(set(nf.tolist()) | set(nm.tolist())) > 1  # ragged
+    gp = capi.default_params("cvo")
+    gp.fixed_iters = 5
+    slots = np.arange(10, 10 + P)
+    gpu_ctx.set_pairs(slots, fx, ff, nf, mx, mf, nm)
+    batch = gpu_ctx.align(slots, gp)
+    for i, pr in enumerate(prs):
+        _set(gpu_ctx, 0, pr)
+        one = gpu_ctx.align(np.array([0]), gp)
+        assert np.array_equal(one["transform"][0], batch["transform"][i])
+    with pytest.raises(capi.CvoB200Error):  # an empty cloud anywhere in the batch is refused (ERR_EMPTY)
+        nf0 = nf.copy()
+        nf0[2] = 0
+        gpu_ctx.set_pairs(slots, fx, ff, nf0, mx, mf, nm)
+
+
 def test_permutation_and_rigid_motion_properties_at_full_size(gpu_ctx):
     """Size-independent properties at BASELINE's 10 000-point stress size (config 5)."""
     pr = synth.config_pair(5)
