@@ -24,7 +24,7 @@ struct cvo_b200_ctx {
     // packed clouds: [slot][2][max_points]
     float4* d_pk_g = nullptr;
     float4* d_pk_f = nullptr;
-    int* d_pk_idx = nullptr;
+    float* d_pk_f4 = nullptr;
 
     struct Slot {
         int n[2] = {0, 0};
@@ -84,8 +84,8 @@ float4* slot_g(cvo_b200_ctx* ctx, int slot, int buf) {
 float4* slot_f(cvo_b200_ctx* ctx, int slot, int buf) {
     return ctx->d_pk_f + ((size_t)slot * 2 + buf) * ctx->max_points;
 }
-int* slot_idx(cvo_b200_ctx* ctx, int slot, int buf) {
-    return ctx->d_pk_idx + ((size_t)slot * 2 + buf) * ctx->max_points;
+float* slot_f4(cvo_b200_ctx* ctx, int slot, int buf) {
+    return ctx->d_pk_f4 + ((size_t)slot * 2 + buf) * ctx->max_points;
 }
 
 // Host-side constants in the reference's own arithmetic (src/cvo.cpp:102-103, src/adaptive_cvo.cpp:100-101).
@@ -189,12 +189,12 @@ PairDev make_pair_dev(cvo_b200_ctx* ctx, int slot) {
     const int fb = s.fixed_buf, mb = 1 - s.fixed_buf;
     pd.x.g = slot_g(ctx, slot, fb);
     pd.x.f = slot_f(ctx, slot, fb);
-    pd.x.idx = slot_idx(ctx, slot, fb);
+    pd.x.f4 = slot_f4(ctx, slot, fb);
     pd.x.n = s.n[fb];
     pd.x.pad = 0;
     pd.y.g = slot_g(ctx, slot, mb);
     pd.y.f = slot_f(ctx, slot, mb);
-    pd.y.idx = slot_idx(ctx, slot, mb);
+    pd.y.f4 = slot_f4(ctx, slot, mb);
     pd.y.n = s.n[mb];
     pd.y.pad = 0;
     return pd;
@@ -351,7 +351,11 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     CKC(cudaMalloc(&ctx->d_raw_feat, sizeof(float) * 5 * mp * 2));
     CKC(cudaMalloc(&ctx->d_pk_g, sizeof(float4) * mp * 2 * max_slots));
     CKC(cudaMalloc(&ctx->d_pk_f, sizeof(float4) * mp * 2 * max_slots));
-    CKC(cudaMalloc(&ctx->d_pk_idx, sizeof(int) * mp * 2 * max_slots));
+    CKC(cudaMalloc(&ctx->d_pk_f4, sizeof(float) * mp * 2 * max_slots));
+    // the TMA copies move whole 32-point tiles: the padding behind a cloud's last point must be readable, finite data
+    CKC(cudaMemset(ctx->d_pk_g, 0, sizeof(float4) * mp * 2 * max_slots));
+    CKC(cudaMemset(ctx->d_pk_f, 0, sizeof(float4) * mp * 2 * max_slots));
+    CKC(cudaMemset(ctx->d_pk_f4, 0, sizeof(float) * mp * 2 * max_slots));
     CKC(cudaMalloc(&ctx->d_pairs, sizeof(PairDev) * max_slots));
     CKC(cudaMalloc(&ctx->d_states, sizeof(PairState) * max_slots));
     CKC(cudaMallocHost(&ctx->h_pairs, sizeof(PairDev) * max_slots));
@@ -385,7 +389,7 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFree(ctx->d_raw_feat);
     cudaFree(ctx->d_pk_g);
     cudaFree(ctx->d_pk_f);
-    cudaFree(ctx->d_pk_idx);
+    cudaFree(ctx->d_pk_f4);
     cudaFree(ctx->d_pairs);
     cudaFree(ctx->d_states);
     cudaFreeHost(ctx->h_pairs);
@@ -428,8 +432,8 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const
     s.bound = true;
     PackJob jobs[2];
     const size_t mp = ctx->max_points;
-    jobs[0] = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0), slot_idx(ctx, slot, 0), n_fixed, 0};
-    jobs[1] = {ctx->d_raw_xyz + mp * 3, ctx->d_raw_feat + mp * 5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1), slot_idx(ctx, slot, 1), n_moving, 0};
+    jobs[0] = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0), slot_f4(ctx, slot, 0), n_fixed, 0};
+    jobs[1] = {ctx->d_raw_xyz + mp * 3, ctx->d_raw_feat + mp * 5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1), slot_f4(ctx, slot, 1), n_moving, 0};
     return launch_pack(ctx, jobs, 2, ctx->d_jobs);
 }
 
@@ -481,9 +485,9 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const f
         s.n[1] = n_moving[i];
         s.bound = true;
         ctx->h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
-                              slot_idx(ctx, slot, 0), n_fixed[i], 0};
+                              slot_f4(ctx, slot, 0), n_fixed[i], 0};
         ctx->h_jobs[2 * i + 1] = {d_mx + i * cloud3, d_mf + i * cloud5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1),
-                                  slot_idx(ctx, slot, 1), n_moving[i], 0};
+                                  slot_f4(ctx, slot, 1), n_moving[i], 0};
     }
     return launch_pack(ctx, ctx->h_jobs, 2 * n_pairs, ctx->d_jobs);
 }
@@ -504,7 +508,7 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
     int rc = upload_cloud(ctx, 0, xyz, feat, n);
     if (rc) return rc;
     s.n[mb] = n;
-    PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), slot_idx(ctx, slot, mb), n, 0};
+    PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), slot_f4(ctx, slot, mb), n, 0};
     return launch_pack(ctx, &job, 1, ctx->d_jobs);
 }
 

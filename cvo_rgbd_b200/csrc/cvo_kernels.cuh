@@ -62,10 +62,11 @@ enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZX
        ACC_NNZYY = 11, ACC_SYY = 12, ACC_FLOW_COUNT = 13 };
 static_assert(ACC_FLOW_COUNT <= kNumAcc, "flow accumulators must fit the exchange buffers");
 
+// One packed cloud in HBM: 36 B per point in three planes (see DESIGN.md "Data layout").
 struct CloudDev {
-    const float4* g;  // {x, y, z, f0}
-    const float4* f;  // {f1, f2, f3, f4}
-    const int* idx;   // original (pre-sort) index of every packed point
+    const float4* g;  // {x, y, z, bits of the original (pre-sort) index}
+    const float4* f;  // {f0, f1, f2, f3}   -- moved to shared memory by TMA bulk copies, untouched
+    const float* f4;  // {f4}               -- idem
     int n;
     int pad;
 };
@@ -114,8 +115,8 @@ struct IterConsts {
 
 // Private scratch of one warp: the row tile it currently owns and its survivor queue.
 struct WarpScratch {
-    float4 rowG[kTile];
-    float4 rowF[kTile];
+    float4 rowG[kTile];          // {x, y, z, f4}
+    float4 rowF[kTile];          // {f0, f1, f2, f3}
     int rowOrig[kTile];          // original row indices (PASS_YY only: quirk Q1 is defined on them)
     uint32_t queue[kQueueCap];   // in-ball (row, col) pairs waiting for the survivor body
 };
@@ -137,6 +138,7 @@ struct Smem {
     double sum[kFlowOff + kNumAcc];
     IterConsts ic;
     PairState st;
+    unsigned long long tma_bar;  // mbarrier the TMA bulk copies of a column chunk complete on
 };
 
 static_assert(sizeof(Smem) <= 227 * 1024, "Smem must fit the 227 KB per-CTA shared memory of sm_100");
@@ -163,7 +165,7 @@ struct PackJob {
     const float* feat;  // n x 5
     float4* out_g;
     float4* out_f;
-    int* out_idx;
+    float* out_f4;
     int n;
     int pad;
 };
@@ -460,45 +462,83 @@ __device__ void write_tf44(const float* tf12, float* out) {
 // tile staging
 // --------------------------------------------------------------------------------------------
 
-// Stages `ntiles` 32-point tiles starting at point `base` of a packed cloud into shared memory,
-// applying the rigid transform on the way (this is transform_pcd, src/cvo.cpp:310-315: the
-// transformed cloud never exists in HBM) and reducing one bounding box per tile.
-__device__ __forceinline__ void stage_tiles(float4* sg, float4* sf, float* sf4, float (*box)[8], const CloudDev& c,
-                                            int base, int ntiles, bool tf, const float* tf12, float sentinel) {
+// TMA (cp.async.bulk) + mbarrier plumbing: the feature planes of a column chunk go HBM -> shared memory without
+// passing through registers; completion is signalled on an mbarrier by transaction bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// Stages `ntiles` 32-point tiles starting at point `base` of a packed cloud into shared memory.
+//  * feature planes (20 B / point): two TMA bulk copies issued by one thread, completing on sm.tma_bar;
+//  * geometry plane (16 B / point): float4 loads by all threads, the rigid transform applied on the way (this IS
+//    transform_pcd, src/cvo.cpp:310-315: the transformed cloud never exists in HBM), |c|^2 appended for the
+//    prefilter, and one bounding box per tile reduced with warp shuffles.
+// The caller has synchronised the CTA (nobody still reads the previous chunk) and synchronises again afterwards.
+__device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int base, int ntiles, bool tf,
+                                            float sentinel, uint32_t& tma_phase) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
+    if (threadIdx.x == 0) {
+        const uint32_t bytes_f = (uint32_t)(ntiles * kTile) * 16u, bytes_f4 = (uint32_t)(ntiles * kTile) * 4u;
+        mbar_expect_tx(&sm.tma_bar, bytes_f + bytes_f4);
+        tma_bulk_g2s(sm.colF, c.f + base, bytes_f, &sm.tma_bar);
+        tma_bulk_g2s(sm.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
+    }
+    const float* tf12 = sm.ic.tf;
     for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
         const int p = base + i;
         const bool valid = p < c.n;
-        float4 g, f;
+        float4 g;
         if (valid) {
             g = __ldg(c.g + p);
-            f = __ldg(c.f + p);
             if (tf) apply_tf(tf12, g.x, g.y, g.z);
         } else {
             g = make_float4(sentinel, sentinel, sentinel, 0.f);
-            f = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float c2 = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
-        sg[i] = make_float4(g.x, g.y, g.z, c2);
-        sf[i] = make_float4(g.w, f.x, f.y, f.z);
-        sf4[i] = f.w;
+        sm.colG[i] = make_float4(g.x, g.y, g.z, c2);
         const float lx = warp_min(valid ? g.x : inf), ly = warp_min(valid ? g.y : inf), lz = warp_min(valid ? g.z : inf);
         const float hx = warp_max(valid ? g.x : -inf), hy = warp_max(valid ? g.y : -inf), hz = warp_max(valid ? g.z : -inf);
         const float c2m = warp_max(valid ? c2 : 0.f);
         if (lane == 0) {
-            float* b = box[i >> 5];
+            float* b = sm.colBox[i >> 5];
             b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz; b[6] = c2m;
         }
     }
+    mbar_wait(&sm.tma_bar, tma_phase);
+    tma_phase ^= 1u;
 }
 
 // --------------------------------------------------------------------------------------------
 // per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xg,
-                                             const float4& xf, const float4& yf, float yf4, float d2, float& a) {
-    const float e0 = xg.w - yf.x, e1 = xf.x - yf.y, e2 = xf.y - yf.z, e3 = xf.z - yf.w, e4 = xf.w - yf4;
+__device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xf, float xf4,
+                                             const float4& yf, float yf4, float d2, float& a) {
+    const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
     float d2c = __fmul_rn(e0, e0);
     d2c = __fadd_rn(d2c, __fmul_rn(e1, e1));
     d2c = __fadd_rn(d2c, __fmul_rn(e2, e2));
@@ -535,7 +575,7 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     float a;
-    bool ok = kernel_value(ic, kp, xg, xf, yf, yf4, d2, a);
+    bool ok = kernel_value(ic, kp, xf, xg.w, yf, yf4, d2, a);
     ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
     a = ok ? a : 0.f;
     if (KIND == PASS_FLOW) {
@@ -717,9 +757,12 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     const int p = tile * kTile + lane;
     const bool valid = p < rows.n;
     float4 xg, xf;
+    int orig = -1;
     if (valid) {
         xg = __ldg(rows.g + p);
         xf = __ldg(rows.f + p);
+        orig = __float_as_int(xg.w);
+        xg.w = __ldg(rows.f4 + p);
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
     } else {
         xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
@@ -728,7 +771,7 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     __syncwarp();  // the previous unit's body reads are done
     ws.rowG[lane] = xg;
     ws.rowF[lane] = xf;
-    if (KIND == PASS_YY) ws.rowOrig[lane] = valid ? __ldg(rows.idx + p) : -1;
+    if (KIND == PASS_YY) ws.rowOrig[lane] = orig;
     const float lx = warp_min(valid ? xg.x : inf), ly = warp_min(valid ? xg.y : inf), lz = warp_min(valid ? xg.z : inf);
     const float hx = warp_max(valid ? xg.x : -inf), hy = warp_max(valid ? xg.y : -inf), hz = warp_max(valid ? xg.z : -inf);
     __syncwarp();
@@ -789,7 +832,7 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
 // sm.blockTot[0 .. NV) holds this CTA's totals (valid for threads after the final barrier).
 template <int KIND>
 __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
-                         bool col_tf, int rank, int G, int yy_row_min) {
+                         bool col_tf, int rank, int G, int yy_row_min, uint32_t& tma_phase) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31;
     const int total_rt = (rows.n + kTile - 1) / kTile;
@@ -812,7 +855,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
         for (int cb = 0; cb < total_ct; cb += kColTiles) {
             const int nct = min(kColTiles, total_ct - cb);
             __syncthreads();  // everyone is done with the previous column chunk / unit slots
-            stage_tiles(sm.colG, sm.colF, sm.colF4, sm.colBox, cols, cb * kTile, nct, col_tf, sm.ic.tf, kColSentinel);
+            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
             while (true) {
@@ -868,6 +911,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     const KParams& kp = args.kp;
     const bool acvo = kp.mode == CVO_B200_MODE_ACVO;
     const int max_iter = kp.fixed_iters > 0 ? kp.fixed_iters : kp.max_iter;
+    uint32_t tma_phase = 0;  // parity of sm.tma_bar; every thread tracks it (all threads stage every chunk)
+    if (threadIdx.x == 0) mbar_init(&sm.tma_bar, 1);
+    __syncthreads();
 
     while (true) {
         if (rank == 0 && threadIdx.x == 0) {
@@ -891,12 +937,12 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             if (threadIdx.x == 0) prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
             __syncthreads();
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
-            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0);
+            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0);
+                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n);
+                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZYY + threadIdx.x] = sm.blockTot[threadIdx.x];
             }
             __syncthreads();
@@ -904,7 +950,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
             // compute_step_size (src/cvo.cpp:377)
-            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0);
+            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
             if (threadIdx.x == 0) {
                 // remember the transform used by this iteration: it is what the reference multiplies
@@ -932,7 +978,9 @@ __global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerA
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    uint32_t tma_phase = 0;
     if (threadIdx.x == 0) {
+        mbar_init(&sm.tma_bar, 1);
 #pragma unroll
         for (int i = 0; i < 9; ++i) sm.st.R[i] = (i % 4 == 0) ? 1.f : 0.f;
         sm.st.T[0] = sm.st.T[1] = sm.st.T[2] = 0.f;
@@ -940,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerA
         prepare_iter(sm, args.kp, args.kp.d2c_thres);
     }
     __syncthreads();
-    run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0);
+    run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0, tma_phase);
     cluster_allreduce<2>(sm, cluster, sm.blockTot, 0, 0);
     if (rank == 0 && threadIdx.x == 0) {
         args.out[0] = sm.sum[0];
@@ -1048,9 +1096,9 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_sort_kernel(const PackJo
         const int src = (int)(uint32_t)(keys[i] & 0xffffffffull);
         const float* p = job.xyz + 3 * src;
         const float* f = job.feat + 5 * src;
-        job.out_g[i] = make_float4(p[0], p[1], p[2], f[0]);
-        job.out_f[i] = make_float4(f[1], f[2], f[3], f[4]);
-        job.out_idx[i] = src;
+        job.out_g[i] = make_float4(p[0], p[1], p[2], __int_as_float(src));
+        job.out_f[i] = make_float4(f[0], f[1], f[2], f[3]);
+        job.out_f4[i] = f[4];
     }
 }
 
