@@ -26,18 +26,28 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     return out
 
 
-def build_frontend_example():
-    """Compiles examples/frontend_example.cpp (C++ host classes above the C ABI) against the in-tree library."""
+def _build_example(name, extra_deps=()):
     root = os.path.dirname(_HERE)
-    src = os.path.join(root, "examples", "frontend_example.cpp")
-    out = os.path.join(root, "examples", "frontend_example")
-    deps = [src, os.path.join(root, "include", "cvo_b200_frontend.hpp"), os.path.join(root, "include", "cvo_b200.h"), OUT]
+    src = os.path.join(root, "examples", name + ".cpp")
+    out = os.path.join(root, "examples", name)
+    deps = [src, os.path.join(root, "include", "cvo_b200_frontend.hpp"), os.path.join(root, "include", "cvo_b200.h"),
+            OUT] + [os.path.join(root, "include", d) for d in extra_deps]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + _HERE, "-lcvo_b200",
                     "-Wl,-rpath,$ORIGIN/../cvo_rgbd_b200"], check=True)
     return out
+
+
+def build_frontend_example():
+    """Compiles examples/frontend_example.cpp (C++ host classes above the C ABI) against the in-tree library."""
+    return _build_example("frontend_example")
+
+
+def build_sequence_driver():
+    """Compiles examples/cvo_sequence.cpp: the reference's sequence driver (src/cvo_main.cpp) over PCD files."""
+    return _build_example("cvo_sequence", ("cvo_b200_io.hpp",))
 
 
 if __name__ == "__main__":
