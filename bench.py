@@ -134,8 +134,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_pairs = args.cpu_pairs
-    for _ in range(args.warmup):
+    sample_pairs = args.cpu_pairs or 32
+    for _ in range(min(args.warmup, 1)):
         cpu_reference_run(1, 0)
     times = []
     for s in range(args.steps):
@@ -164,7 +164,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (default 2 x #SMs)")
-    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
+    ap.add_argument("--cpu-pairs", type=int, default=0,
+                    help="pairs in the bounded CPU sample (default: 96 for cpu_baseline ~ 12 s, 32 per step for --impl reference)")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per pair (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -311,7 +312,7 @@ def main():
                            "note": "N*M-equivalent candidate pairs per second vs 148 SM x 128 lanes x f_SM / 7 slots; tile-box culling skips most of them"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(args.cpu_pairs, 10_000)
+            r = cpu_reference_run(args.cpu_pairs or 96, 10_000)
             line["cpu_baseline"] = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
                                     "sample": "%d cfg-2 pairs, sequential, all host threads per pair, %.1f s; %s" % (
                                         r["pairs"], r["seconds"], r["backend"])}
