@@ -24,6 +24,7 @@ EXPORTS = [
     "cvo_b200_align_trace", "cvo_b200_inner_product", "cvo_b200_sync", "cvo_b200_last_kernel_ms",
     "cvo_b200_kernel_launches", "cvo_b200_last_cluster_size", "cvo_b200_last_num_clusters",
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
+    "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds",
 ]
 
 
@@ -101,6 +102,9 @@ def load():
     lib.cvo_b200_last_total_iterations.argtypes = [vp]
     lib.cvo_b200_last_total_iterations.restype = C.c_longlong
     lib.cvo_b200_num_sms.argtypes = [vp]
+    lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
+    lib.cvo_b200_last_list_builds.argtypes = [vp]
+    lib.cvo_b200_last_list_builds.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -238,6 +242,13 @@ class Context:
 
     def set_cluster_size(self, g):
         self._check(self._lib.cvo_b200_set_cluster_size(self._h, g))
+
+    def set_neighbor_lists(self, enable=True, skin=0.08):
+        self._check(self._lib.cvo_b200_set_neighbor_lists(self._h, int(bool(enable)), C.c_float(skin)))
+
+    @property
+    def last_list_builds(self):
+        return int(self._lib.cvo_b200_last_list_builds(self._h))
 
     @property
     def last_kernel_ms(self):

@@ -2,6 +2,7 @@
 // No torch, no CPU fallback: every entry point needs a CUDA device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,6 +48,15 @@ struct cvo_b200_ctx {
     float* d_batch_raw = nullptr;  // raw staging of a batched upload (grown on demand)
     size_t batch_raw_floats = 0;
     double* h_inner = nullptr;  // pinned
+
+    // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
+    uint32_t* d_list_entries = nullptr;
+    uint2* d_list_units = nullptr;
+    unsigned list_cap = 0;
+    bool lists_enabled = true;
+    bool lists_alloc_failed = false;
+    float list_skin = 0.08f;
+    long long last_list_builds = 0;
 
     float last_ms = 0.f;
     long long launches = 0;
@@ -110,6 +120,11 @@ KParams make_kparams(const cvo_b200_params* p, bool for_inner_product) {
     }
     k.d2c_thres = (float)(-2.0 * p->c_ell * p->c_ell * logf(c_gate / p->c_sigma / p->c_sigma));
     k.inv2cl2 = (float)(1.0 / (2.0 * (double)p->c_ell * (double)p->c_ell));
+    k.c2 = (float)(1.4426950408889634 / (2.0 * (double)p->c_ell * (double)p->c_ell));
+    k.s2cs2 = (float)((double)k.s2 * (double)k.cs2);
+    k.c_ell = p->c_ell;
+    k.sp_band = 2.0e-6f * fabsf(p->sp_thres);
+    k.d2c_band = 1.0e-6f * fabsf(k.d2c_thres);
     k.inv_c = 1 / p->c;
     k.inv_d = 1 / p->d;
     k.min_step = p->min_step;
@@ -175,12 +190,34 @@ int launch_cluster_kernel(cvo_b200_ctx* ctx, KernelT kernel, const ArgT& args, i
         return CVO_B200_ERR_CUDA;
     }
     int ncl = want_clusters < max_clusters ? want_clusters : max_clusters;
+    if (ncl * G > ctx->num_sms) ncl = ctx->num_sms / G;  // one CTA per SM: per-CTA scratch is sized by it
     if (ncl < 1) ncl = 1;
     cfg.gridDim = dim3(ncl * G, 1, 1);
     CK(cudaLaunchKernelEx(&cfg, kernel, args));
     ctx->launches += 1;
     if (nclusters_out) *nclusters_out = ncl;
     return CVO_B200_OK;
+}
+
+// The neighbour-list scratch is only ever touched by the CTA it belongs to; it is sized for one CTA per SM.
+// Failing to allocate it is not an error: the passes then run on the fly.
+void ensure_list_scratch(cvo_b200_ctx* ctx) {
+    if (ctx->d_list_entries || ctx->lists_alloc_failed || !ctx->lists_enabled) return;
+    unsigned long long cap = (unsigned long long)ctx->max_points * ctx->max_points / 8;
+    if (cap < (1ull << 18)) cap = 1ull << 18;
+    if (cap > (1ull << 22)) cap = 1ull << 22;
+    const size_t areas = (size_t)ctx->num_sms * LIST_KINDS;
+    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_list_units, areas * kMaxListUnits * sizeof(uint2)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(ctx->d_list_entries);
+        cudaFree(ctx->d_list_units);
+        ctx->d_list_entries = nullptr;
+        ctx->d_list_units = nullptr;
+        ctx->lists_alloc_failed = true;
+        return;
+    }
+    ctx->list_cap = (unsigned)cap;
 }
 
 PairDev make_pair_dev(cvo_b200_ctx* ctx, int slot) {
@@ -233,6 +270,12 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
         args.trace_cap = trace_cap < ctx->trace_cap ? trace_cap : ctx->trace_cap;
     }
     args.kp = make_kparams(p, false);
+    ensure_list_scratch(ctx);
+    const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr;
+    args.list_entries = lists ? ctx->d_list_entries : nullptr;
+    args.list_units = lists ? ctx->d_list_units : nullptr;
+    args.list_cap = ctx->list_cap;
+    args.list_skin = ctx->list_skin;
     CK(cudaMemcpyAsync(ctx->d_pairs, ctx->h_pairs, sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_states, ctx->h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
@@ -254,10 +297,11 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_G = G;
     ctx->last_nclusters = ncl;
-    long long total = 0;
+    long long total = 0, builds = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const PairState& st = ctx->h_states[i];
         total += st.n_run;
+        builds += st.n_builds;
         if (RT_io) {
             memcpy(RT_io + (size_t)i * 12, st.R, sizeof(float) * 9);
             memcpy(RT_io + (size_t)i * 12 + 9, st.T, sizeof(float) * 3);
@@ -269,6 +313,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
         if (status) status[i] = st.status;
     }
     ctx->last_total_iters = total;
+    ctx->last_list_builds = builds;
     if (args.trace) {
         const int n = ctx->h_states[0].n_run < args.trace_cap ? ctx->h_states[0].n_run : args.trace_cap;
         memcpy(trace, ctx->h_trace, sizeof(cvo_b200_iter_rec) * n);
@@ -376,6 +421,10 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     }
     const char* env = getenv("CVO_B200_NO_SORT");
     if (env && env[0] == '1') ctx->sort_points = 0;
+    env = getenv("CVO_B200_NO_LISTS");  // tuning / A-B switch; cvo_b200_set_neighbor_lists is the API
+    if (env && env[0] == '1') ctx->lists_enabled = false;
+    env = getenv("CVO_B200_LIST_SKIN");
+    if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin = (float)atof(env);
 #undef CKC
     *out = ctx;
     return CVO_B200_OK;
@@ -401,6 +450,8 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFree(ctx->d_jobs);
     cudaFreeHost(ctx->h_jobs);
     cudaFree(ctx->d_batch_raw);
+    cudaFree(ctx->d_list_entries);
+    cudaFree(ctx->d_list_units);
     cudaFreeHost(ctx->h_inner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -583,6 +634,14 @@ int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
     return CVO_B200_OK;
 }
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_total_iters : 0; }
+long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_builds : 0; }
+int cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!(skin >= 0.f && skin <= 1.f)) return fail_arg(ctx, "skin must be in [0, 1]");
+    ctx->lists_enabled = enable != 0;
+    ctx->list_skin = skin;
+    return CVO_B200_OK;
+}
 int cvo_b200_num_sms(const cvo_b200_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 
 }  // extern "C"

@@ -44,6 +44,8 @@ constexpr int kColTiles = kColChunk / kTile;
 constexpr int kMaxCluster = 16;
 constexpr int kNumAcc = 16;
 constexpr int kMaxUnits = 256;                  // work units (row tile x column segment) per scheduling round
+static_assert(kMaxUnits == 256, "kMaxListUnits assumes 256 units per round; unit records pack the unit in 8 bits");
+static_assert(kThreads >= 32 + kMaxUnits, "build_list ranks one unit per thread beside the scanning warp");
 constexpr int kUnitAcc = 9;                     // widest per-unit partial record (flow: omega, v, sum, nnz, dl)
 constexpr int kQueueCap = 64 + kTile * kTile;   // leftovers (< 32 * CVO_BODY_ILP) + one full tile pair
 static_assert(kColChunk <= (1 << 12), "queue entries pack row:5 | col:12 bits");
@@ -56,6 +58,15 @@ constexpr float kColSentinel = -1.0e15f;
 constexpr float kPrefilterSlack = 2.0e-6f;
 
 enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INNER = 4 };
+
+// Neighbour candidate lists (the GPU counterpart of the reference's kd-tree, thirdparty/nanoflann.hpp): for one
+// (rows, cols) cloud pair the (row, col) index pairs inside a ball of radius r_build = r * (1 + skin), kept in an
+// L2-resident global scratch area of the CTA and re-used by every all-pairs pass until the pose has moved the
+// column cloud by more than the skin (or ell changed the radius).  Only INDICES are stored: the strict ell-ball
+// test, the colour gate and the kernel value are still evaluated on the fly in every pass, A never exists.
+enum ListKind { LIST_XY = 0, LIST_XX = 1, LIST_YY = 2, LIST_KINDS = 3 };
+constexpr int kMaxListRounds = 12;                       // (row round, column chunk) combinations of one pass
+constexpr int kMaxListUnits = kMaxListRounds * 256;      // unit table entries per list
 
 // accumulator slots of the flow exchange
 enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZXX = 9, ACC_SXX = 10,
@@ -84,7 +95,7 @@ struct PairState {
     int iters;
     int status;
     int n_run;
-    int pad;
+    int n_builds;  // neighbour-list (re)builds of the (x, y) list during this align()
     float tf[16];
     float prev_tf[16];
 };
@@ -100,6 +111,10 @@ struct KParams {
     float log_ratio;   // logf(sp_thres/s2)            (src/cvo.cpp:102; log on a float is f32)
     float d2c_thres;   // colour gate                   (src/cvo.cpp:103 / src/adaptive_cvo.cpp:101)
     float inv2cl2;     // 1/(2 c_ell^2)
+    float c2;          // log2(e)/(2 c_ell^2)
+    float s2cs2;       // sigma^2 c_sigma^2
+    float c_ell;
+    float sp_band, d2c_band;  // half-widths around sp_thres / d2c_thres inside which kernel_value re-decides exactly
     float inv_c, inv_d;
     float min_step, max_step, eps, eps_2;
     double dl_step;
@@ -108,6 +123,8 @@ struct KParams {
 struct IterConsts {
     float tf[12];  // transform: rows of R^T, then -R^T T   (src/cvo.cpp:83-87)
     float d2_thres, d2c_thres, inv2l2, inv_ell3;
+    float c1;  // log2(e)/(2 ell^2)
+    float ell;
     float omega[3], v[3];
     float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
     float temp_coef, m2t, p2t;
@@ -121,6 +138,20 @@ struct WarpScratch {
     uint32_t queue[kQueueCap];   // in-ball (row, col) pairs waiting for the survivor body
 };
 
+struct ListState {
+    float tf[12];     // transform the (x, y) list was built at
+    float r_build;    // radius covered by the list (ball radius at build time * (1 + skin) + margin)
+    float thr_build;  // r_build^2: the threshold of the build prefilter
+    int valid;        // 1: usable, 0: must be built, -1: overflowed its scratch for this pair (on-the-fly passes)
+    int need;         // (re)build before this iteration's passes
+};
+
+struct ListRef {
+    uint32_t* entries;
+    uint2* units;  // (offset, count) of every work unit's entries
+    unsigned cap;
+};
+
 struct Smem {
     float4 colG[kColChunk];   // {x, y, z, |c|^2} of the staged (transformed) column points
     float4 colF[kColChunk];   // {f0, f1, f2, f3}
@@ -130,6 +161,14 @@ struct Smem {
     double unitPart[kMaxUnits][kUnitAcc];  // one fixed slot per work unit => scheduling-independent sums
     double blockTot[kNumAcc];
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
+    int unitCnt[kMaxUnits];   // neighbour-list build: entries per unit, their offsets, and the processing order
+    int unitOff[kMaxUnits];
+    unsigned short unitRank[kMaxUnits];  // rank of unit u when sorted by descending entry count
+    unsigned short unitOrd[kMaxUnits];   // inverse: the unit at rank k
+    float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
+    float ybox[6];            // bounding box of the moving cloud, original coordinates
+    ListState lst[LIST_KINDS];
+    int lst_used, lst_ovf;
     int next_unit;
     int next_pair;
     int done;
@@ -151,6 +190,11 @@ struct AlignArgs {
     cvo_b200_iter_rec* trace;  // records of pair 0 only (align_trace / eval), or nullptr
     int trace_cap;
     KParams kp;
+    // neighbour-list scratch: [gridDim.x][LIST_KINDS] areas of list_cap entries / kMaxListUnits unit records
+    uint32_t* list_entries;  // nullptr: lists disabled, every pass is on the fly
+    uint2* list_units;
+    unsigned list_cap;
+    float list_skin;
 };
 
 struct InnerArgs {
@@ -187,6 +231,12 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // y = R^T p - R^T T with the fma chain documented in DESIGN.md (membership-critical)
@@ -246,6 +296,8 @@ __device__ void prepare_iter(Smem& sm, const KParams& kp, float d2c_thres) {
     ic.d2_thres = (float)(-2.0 * l * l * (double)kp.log_ratio);
     ic.d2c_thres = d2c_thres;
     ic.inv2l2 = (float)(1.0 / (2.0 * l * l));
+    ic.c1 = (float)(1.4426950408889634 / (2.0 * l * l));
+    ic.ell = sm.st.ell;
     const float ell3 = __fmul_rn(__fmul_rn(sm.st.ell, sm.st.ell), sm.st.ell);  // src/adaptive_cvo.cpp:171
     ic.inv_ell3 = 1.0f / ell3;
 }
@@ -536,18 +588,38 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
 // --------------------------------------------------------------------------------------------
 // per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
 // --------------------------------------------------------------------------------------------
+// se_kernel's value and gates in the reference's own arithmetic (src/cvo.cpp:146-152).  Deliberately not inlined:
+// it runs for about one candidate in a million and must not cost the hot loop registers.
+__device__ __noinline__ bool kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
+                                                float e0, float e1, float e2, float e3, float e4, float d2, float& a) {
+    float d2e = __fmul_rn(e0, e0);
+    d2e = __fadd_rn(d2e, __fmul_rn(e1, e1));
+    d2e = __fadd_rn(d2e, __fmul_rn(e2, e2));
+    d2e = __fadd_rn(d2e, __fmul_rn(e3, e3));
+    d2e = __fadd_rn(d2e, __fmul_rn(e4, e4));
+    const double l = (double)ell, cl = (double)c_ell;
+    const float k = (float)((double)s2 * exp(-(double)d2 / (2.0 * l * l)));
+    const float ck = (float)((double)cs2 * exp(-(double)d2e / (2.0 * cl * cl)));
+    a = __fmul_rn(ck, k);
+    return (d2e < d2c_thres) && (a > sp_thres);
+}
+
 __device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xf, float xf4,
                                              const float4& yf, float yf4, float d2, float& a) {
     const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
-    float d2c = __fmul_rn(e0, e0);
-    d2c = __fadd_rn(d2c, __fmul_rn(e1, e1));
-    d2c = __fadd_rn(d2c, __fmul_rn(e2, e2));
-    d2c = __fadd_rn(d2c, __fmul_rn(e3, e3));
-    d2c = __fadd_rn(d2c, __fmul_rn(e4, e4));
-    const float k = __fmul_rn(kp.s2, expf(-__fmul_rn(d2, ic.inv2l2)));      // src/cvo.cpp:149
-    const float ck = __fmul_rn(kp.cs2, expf(-__fmul_rn(d2c, kp.inv2cl2)));  // :150
-    a = __fmul_rn(ck, k);                                                   // :151
-    return (d2c < ic.d2c_thres) && (a > kp.sp_thres);                       // :143, :152
+    const float d2c = fmaf(e4, e4, fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0))));  // src/cvo.cpp:145
+    // k = s2 exp(-d2 / 2l^2), ck = c_sigma^2 exp(-d2c / 2c_ell^2), a = ck k (src/cvo.cpp:149-151) as ONE base-2
+    // exponential of the summed exponents: a = s2 c_sigma^2 2^-(d2 log2e/2l^2 + d2c log2e/2c_ell^2).  Wherever the
+    // result can matter (a > sp_thres => |exponent| < 0.33) MUFU.EX2 is good to 2 ulp and the argument to 1 ulp.
+    const float t = fmaf(d2, ic.c1, __fmul_rn(d2c, kp.c2));
+    a = __fmul_rn(kp.s2cs2, exp2f_approx(-t));
+    bool ok = (d2c < ic.d2c_thres) && (a > kp.sp_thres);  // :148, :152
+    // Within a few ulp of either threshold (about one candidate in a million) the decision -- and the value -- is
+    // re-made in the reference's own arithmetic: colour distance summed left to right, exp() in f64 narrowed to
+    // f32, a = ck * k in f32 (src/cvo.cpp:146-151), so that the gates agree with the CPU path bit for bit.
+    if (fabsf(a - kp.sp_thres) < kp.sp_band || fabsf(d2c - ic.d2c_thres) < kp.d2c_band)
+        ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, e0, e1, e2, e3, e4, d2, a);
+    return ok;
 }
 
 // Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
@@ -675,9 +747,9 @@ __device__ __forceinline__ void push_mask(uint32_t* q, int pos, uint32_t mask, u
     }
 }
 
-__device__ __forceinline__ uint32_t prefilter_tile(const Smem& sm, const RowRegs& rr, int ct) {
+__device__ __forceinline__ uint32_t prefilter_tile(const Smem& sm, const RowRegs& rr, int ct, float thr) {
     const float4* cgp = sm.colG + ct * kTile;
-    const float t = fmaf(kPrefilterSlack, sm.colBox[ct][6] + rr.x2, sm.ic.d2_thres) - rr.x2;
+    const float t = fmaf(kPrefilterSlack, sm.colBox[ct][6] + rr.x2, thr) - rr.x2;
     uint32_t mask = 0;
 #pragma unroll
     for (int jj = 0; jj < kTile; ++jj) {
@@ -693,8 +765,8 @@ template <int KIND>
 __device__ __forceinline__ void process_tile_group(const Smem& sm, WarpScratch& ws, const KParams& kp, const RowRegs& rr,
                                                    int ctA, int ctB, int lane, int& qn, int yy_row_min, FlowPartial& fp,
                                                    double* acc) {
-    const uint32_t maskA = prefilter_tile(sm, rr, ctA);
-    const uint32_t maskB = (ctB >= 0) ? prefilter_tile(sm, rr, ctB) : 0u;
+    const uint32_t maskA = prefilter_tile(sm, rr, ctA, sm.ic.d2_thres);
+    const uint32_t maskB = (ctB >= 0) ? prefilter_tile(sm, rr, ctB, sm.ic.d2_thres) : 0u;
     if (__ballot_sync(0xffffffffu, (maskA | maskB) != 0) == 0) return;
     uint32_t* q = ws.queue;
     // the queue holds one full tile pair on top of the leftovers: a (rare) group with more candidates than that
@@ -827,6 +899,30 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     }
 }
 
+// How one all-pairs pass of rows x cols is cut into work units for the CTA of rank `rank` in a cluster of G:
+// a pure function of the sizes, so that the neighbour-list build and every later pass over the list agree.
+struct PassGeom {
+    int t_begin, my_tiles, total_ct, S, tiles_per_round;
+};
+__device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, int G) {
+    PassGeom pg;
+    const int total_rt = (rows_n + kTile - 1) / kTile;
+    pg.t_begin = (int)(((long long)total_rt * rank) / G);
+    const int t_end = (int)(((long long)total_rt * (rank + 1)) / G);
+    pg.my_tiles = t_end - pg.t_begin;
+    pg.total_ct = (cols_n + kTile - 1) / kTile;
+    // split every row tile's column range into S segments so that there are >= ~4 units per warp
+    int S = 1;
+    if (pg.my_tiles > 0) {
+        S = (CVO_UNITS_PER_WARP * kWarps + pg.my_tiles - 1) / pg.my_tiles;
+        const int s_max = max(1, min(pg.total_ct, kColTiles) / 8);
+        S = max(1, min(min(S, s_max), kMaxUnits));
+    }
+    pg.S = S;
+    pg.tiles_per_round = max(1, kMaxUnits / S);
+    return pg;
+}
+
 // One all-pairs pass of `rows` x `cols` restricted to this CTA's share of the row tiles.  The column cloud is
 // staged (and transformed) once per chunk; warps then pull work units from a shared counter.  On return
 // sm.blockTot[0 .. NV) holds this CTA's totals (valid for threads after the final barrier).
@@ -835,19 +931,9 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
                          bool col_tf, int rank, int G, int yy_row_min, uint32_t& tma_phase) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31;
-    const int total_rt = (rows.n + kTile - 1) / kTile;
-    const int t_begin = (int)(((long long)total_rt * rank) / G);
-    const int t_end = (int)(((long long)total_rt * (rank + 1)) / G);
-    const int my_tiles = t_end - t_begin;
-    const int total_ct = (cols.n + kTile - 1) / kTile;
-    // split every row tile's column range into S segments so that there are >= ~4 units per warp
-    int S = 1;
-    if (my_tiles > 0) {
-        S = (CVO_UNITS_PER_WARP * kWarps + my_tiles - 1) / my_tiles;
-        const int s_max = max(1, min(total_ct, kColTiles) / 8);
-        S = max(1, min(min(S, s_max), kMaxUnits));
-    }
-    const int tiles_per_round = max(1, kMaxUnits / S);
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    const int t_begin = pg.t_begin, my_tiles = pg.my_tiles, total_ct = pg.total_ct, S = pg.S;
+    const int tiles_per_round = pg.tiles_per_round;
     if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
     for (int rb = 0; rb < my_tiles; rb += tiles_per_round) {
         const int ntile = min(tiles_per_round, my_tiles - rb);
@@ -866,6 +952,324 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
                 const int t = u / S, seg = u - t * S;
                 const int c_begin = (int)(((long long)nct * seg) / S), c_end = (int)(((long long)nct * (seg + 1)) / S);
                 process_unit<KIND>(sm, kp, rows, row_tf, t_begin + rb + t, c_begin, c_end, u, cb == 0, yy_row_min);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NV) {  // fixed-order sum over the unit slots
+            double t = 0.0;
+            for (int u = 0; u < nunits; ++u) t += sm.unitPart[u][threadIdx.x];
+            sm.blockTot[threadIdx.x] += t;
+        }
+    }
+    __syncthreads();
+}
+
+// --------------------------------------------------------------------------------------------
+// neighbour candidate lists
+// --------------------------------------------------------------------------------------------
+
+// Decides, for this iteration, which lists must be (re)built (one thread; after prepare_iter).
+// A list built at transform T0 with radius r_build contains every (i, j) with |x_i - T0 y_j| < r_build.  At the
+// current transform T1, |x_i - T1 y_j| < r implies |x_i - T0 y_j| < r + |T1 y_j - T0 y_j| <= r + disp with
+// disp = max_j |(M1 - M0) y_j + (t1 - t0)|, so the list still covers the ell-ball while r + disp <= r_build.
+// The (x, x) list never moves and rigid motion preserves the (y, y) distances: those two only follow ell.
+__device__ void list_policy(Smem& sm, bool acvo, float skin) {
+    const double r_now = sqrt((double)sm.ic.d2_thres);
+    const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
+    const int nk = acvo ? LIST_KINDS : 1;
+    for (int kind = 0; kind < nk; ++kind) {
+        ListState& L = sm.lst[kind];
+        if (L.valid < 0) {  // overflowed earlier for this pair: stay on the fly
+            L.need = 0;
+            continue;
+        }
+        bool need = L.valid == 0;
+        if (!need) {
+            double disp = 0.0;
+            if (kind == LIST_XY) {
+                // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is
+                // attained at one of the 8 corners
+                double dm[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)L.tf[i];
+                for (int c = 0; c < 8; ++c) {
+                    const double px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
+                    const double ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
+                    const double ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
+                    const double ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
+                    disp = fmax(disp, sqrt(ex * ex + ey * ey + ez * ez));
+                }
+                if (!(disp == disp)) disp = 1.0e30;  // NaN state: never trust an old list
+            }
+            // rebuild when the ball is no longer covered, or when ell has shrunk it by > 10 % (a list that is
+            // much too wide costs more in every pass than one rebuild)
+            need = !(r_now + disp + margin <= (double)L.r_build) ||
+                   (r_now * (1.0 + (double)skin) + margin < 0.9 * (double)L.r_build);
+        }
+        L.need = need ? 1 : 0;
+        if (need) {
+            const double rb = r_now * (1.0 + (double)skin) + margin;
+            L.valid = 0;
+            L.r_build = (float)(rb * (1.0 - 1.0e-6));         // rounded DOWN: what the validity test may assume
+            L.thr_build = (float)(rb * rb * (1.0 + 1.0e-6));  // rounded UP: what the build prefilter covers
+#pragma unroll
+            for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i];
+            if (kind == LIST_XY) sm.st.n_builds += 1;
+        }
+    }
+}
+
+__device__ __forceinline__ void push_mask_global(uint32_t* q, int pos, uint32_t mask, uint32_t base) {
+    while (mask) {
+        const int jj = __ffs(mask) - 1;
+        mask &= mask - 1;
+        __stcg(q + pos, base + (uint32_t)jj);
+        ++pos;
+    }
+}
+
+// Build work unit: one 32-row tile against one segment of the staged column tiles.  WRITE = false counts the
+// candidates inside the build radius, WRITE = true stores them at out[0 .. count): (col tile by col tile, lane
+// by lane) -- the same decomposition and the same masks both times, so the two sweeps agree.
+template <bool WRITE>
+__device__ __forceinline__ int list_unit(const Smem& sm, const CloudDev& rows, bool row_tf, int tile, int ct_begin,
+                                         int ct_end, float thr_build, uint32_t* out) {
+    const int lane = threadIdx.x & 31;
+    const float inf = __int_as_float(0x7f800000);
+    const int p = tile * kTile + lane;
+    const bool valid = p < rows.n;
+    float4 xg;
+    if (valid) {
+        xg = __ldg(rows.g + p);
+        if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
+    } else {
+        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
+    }
+    const float lx = warp_min(valid ? xg.x : inf), ly = warp_min(valid ? xg.y : inf), lz = warp_min(valid ? xg.z : inf);
+    const float hx = warp_max(valid ? xg.x : -inf), hy = warp_max(valid ? xg.y : -inf), hz = warp_max(valid ? xg.z : -inf);
+    RowRegs rr;
+    rr.m2x = -2.f * xg.x; rr.m2y = -2.f * xg.y; rr.m2z = -2.f * xg.z;
+    rr.x2 = fmaf(xg.z, xg.z, fmaf(xg.y, xg.y, xg.x * xg.x));
+    const float thr = thr_build * 1.0001f;  // boxes are conservative; keep rounding on the safe side
+    int cnt = 0;  // WRITE: entries stored so far (warp-uniform); else this lane's candidate count
+    for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
+        const int ct = c0 + lane;
+        bool live = false;
+        if (ct < ct_end) {
+            const float* b = sm.colBox[ct];
+            const float gx = fmaxf(0.f, fmaxf(lx - b[3], b[0] - hx));
+            const float gy = fmaxf(0.f, fmaxf(ly - b[4], b[1] - hy));
+            const float gz = fmaxf(0.f, fmaxf(lz - b[5], b[2] - hz));
+            live = (gx * gx + gy * gy + gz * gz) <= thr;
+        }
+        uint32_t lm = __ballot_sync(0xffffffffu, live);
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t mask = prefilter_tile(sm, rr, c0 + j, thr_build);
+            if (!WRITE) {
+                cnt += __popc(mask);
+            } else {
+                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+                int excl, total;
+                warp_scan_count(__popc(mask), lane, excl, total);
+                push_mask_global(out, cnt + excl, mask, ((uint32_t)lane << 12) | (uint32_t)((c0 + j) * kTile));
+                cnt += total;
+            }
+        }
+    }
+    if (!WRITE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    return cnt;
+}
+
+// (Re)builds one neighbour list for this CTA's share of the row tiles: per (row round, column chunk) a counting
+// sweep, an exclusive scan of the unit counts in unit order (=> the layout is a pure function of the inputs, no
+// atomics), and a writing sweep.  On return sm.lst[kind].valid is 1, or -1 if the scratch area was too small.
+__device__ void build_list(Smem& sm, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf, int rank,
+                           int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    const float thr_build = sm.lst[kind].thr_build;
+    if (threadIdx.x == 0) {
+        sm.lst_used = 0;
+        sm.lst_ovf = 0;
+    }
+    int round = 0;
+    bool stop = false;
+    for (int rb = 0; rb < pg.my_tiles && !stop; rb += pg.tiles_per_round) {
+        const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
+        const int nunits = ntile * pg.S;
+        for (int cb = 0; cb < pg.total_ct && !stop; cb += kColTiles, ++round) {
+            const int nct = min(kColTiles, pg.total_ct - cb);
+            __syncthreads();
+            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            if (threadIdx.x == 0) {
+                sm.next_unit = 0;
+                if (round >= kMaxListRounds) sm.lst_ovf = 1;
+            }
+            __syncthreads();
+            if (sm.lst_ovf) {
+                stop = true;
+                break;
+            }
+            while (true) {  // sweep 1: count
+                int u = 0;
+                if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= nunits) break;
+                const int t = u / pg.S, seg = u - t * pg.S;
+                const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
+                const int c = list_unit<false>(sm, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, thr_build, nullptr);
+                if (lane == 0) sm.unitCnt[u] = c;
+            }
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the unit counts (rounded up to 16-byte groups), in unit order
+                int base = sm.lst_used;
+                for (int i0 = 0; i0 < nunits; i0 += 32) {
+                    const int c = (i0 + lane < nunits) ? ((sm.unitCnt[i0 + lane] + 3) & ~3) : 0;
+                    int excl, total;
+                    warp_scan_count(c, lane, excl, total);
+                    if (i0 + lane < nunits) sm.unitOff[i0 + lane] = base + excl;
+                    base += total;
+                }
+                if (lane == 0) {
+                    if ((unsigned)base > lr.cap) sm.lst_ovf = 1;
+                    else sm.lst_used = base;
+                    sm.next_unit = 0;
+                }
+            } else if (threadIdx.x - 32 < nunits) {
+                // longest-processing-time order: rank the units by descending entry count (ties by unit index) so
+                // that the passes hand out the big units first and the small ones fill the tail
+                const int u = threadIdx.x - 32, cu = sm.unitCnt[u];
+                int rank = 0;
+                for (int v = 0; v < nunits; ++v) {
+                    const int cv = sm.unitCnt[v];
+                    rank += (cv > cu || (cv == cu && v < u)) ? 1 : 0;
+                }
+#ifdef CVO_NO_LPT
+                rank = u;
+#endif
+                sm.unitRank[u] = (unsigned short)rank;
+                sm.unitOrd[rank] = (unsigned short)u;
+            }
+            __syncthreads();
+            if (sm.lst_ovf) {
+                stop = true;
+                break;
+            }
+            while (true) {  // sweep 2: write
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k >= nunits) break;
+                const int u = sm.unitOrd[k];
+                const int off = sm.unitOff[u], c = sm.unitCnt[u];
+                if (c > 0) {
+                    const int t = u / pg.S, seg = u - t * pg.S;
+                    const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
+                    list_unit<true>(sm, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, thr_build, lr.entries + off);
+                }
+                if (lane == 0)  // record k of the round: (offset, count | unit << 24)
+                    __stcg(&lr.units[round * kMaxUnits + k], make_uint2((unsigned)off, (unsigned)c | ((unsigned)u << 24)));
+            }
+        }
+    }
+    __syncthreads();  // the list (global memory) is complete and visible to the whole CTA
+    if (threadIdx.x == 0) sm.lst[kind].valid = sm.lst_ovf ? -1 : 1;
+    __syncthreads();
+}
+
+// Pass work unit over a neighbour list: the unit's candidates are read 128 at a time (one 16-byte load per lane,
+// coalesced, L2; the next trip's load is in flight behind this trip's arithmetic) and every lane runs the
+// branch-free survivor body on its four entries; the exact strict ball test is part of the body.
+template <int KIND>
+__device__ __forceinline__ void consume_unit(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, int tile,
+                                             const uint32_t* ent, int cnt, int slot, int yy_row_min) {
+    constexpr int NV = PassTraits<KIND>::NV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* ent4 = reinterpret_cast<const uint4*>(ent);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 cur = (4 * lane < cnt) ? __ldcg(ent4 + lane) : zero4;
+    WarpScratch& ws = sm.ws[warp];
+    const int p = tile * kTile + lane;
+    float4 xg, xf;
+    int orig = -1;
+    if (p < rows.n) {
+        xg = __ldg(rows.g + p);
+        xf = __ldg(rows.f + p);
+        orig = __float_as_int(xg.w);
+        xg.w = __ldg(rows.f4 + p);
+        if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
+    } else {
+        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
+        xf = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();  // the previous unit's body reads are done
+    ws.rowG[lane] = xg;
+    ws.rowF[lane] = xf;
+    if (KIND == PASS_YY) ws.rowOrig[lane] = orig;
+    __syncwarp();
+    FlowPartial fp;
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
+    fp.cnt = 0;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int b = 0; b < cnt; b += 4 * kTile) {
+        const int i0 = b + 4 * lane;
+        const uint4 c = cur;
+        const int nb = i0 + 4 * kTile;
+        cur = (nb < cnt) ? __ldcg(ent4 + (nb >> 2)) : zero4;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {  // two bodies interleaved at a time (register budget: 128 at 512 threads)
+            const int ia = i0 + 2 * h;
+            const bool la = ia < cnt, lb = ia + 1 < cnt;
+            // past the unit's end the 16-byte group holds stale bits: run entry (0, 0) -- real, finite points -- with a = 0
+            const uint32_t ea = la ? (h ? c.z : c.x) : 0u, eb = lb ? (h ? c.w : c.y) : 0u;
+            survivor_body<KIND>(sm, ws, kp, ea, la, yy_row_min, fp, acc);
+            survivor_body<KIND>(sm, ws, kp, eb, lb, yy_row_min, fp, acc);
+        }
+    }
+    __syncwarp();
+    flush_partial<KIND>(fp, acc);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double t = warp_sum(acc[i]);
+        if (lane == 0) sm.unitPart[slot][i] += t;
+    }
+}
+
+// run_pass over a valid neighbour list (same unit decomposition as the build; same fixed-order reductions).
+template <int KIND>
+__device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
+                              bool col_tf, int rank, int G, int yy_row_min, uint32_t& tma_phase, const ListRef& lr) {
+    constexpr int NV = PassTraits<KIND>::NV;
+    const int lane = threadIdx.x & 31;
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
+    int round = 0;
+    for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round) {
+        const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
+        const int nunits = ntile * pg.S;
+        for (int i = threadIdx.x; i < nunits * kUnitAcc; i += kThreads) (&sm.unitPart[0][0])[i] = 0.0;
+        for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
+            const int nct = min(kColTiles, pg.total_ct - cb);
+            __syncthreads();
+            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            if (threadIdx.x == 0) sm.next_unit = 0;
+            __syncthreads();
+            while (true) {  // records are sorted by descending entry count: the first empty one ends the round
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k >= nunits) break;
+                const uint2 rec = __ldcg(&lr.units[round * kMaxUnits + k]);
+                const int cnt = (int)(rec.y & 0xffffffu), u = (int)(rec.y >> 24);
+                if (cnt == 0) break;
+                consume_unit<KIND>(sm, kp, rows, row_tf, pg.t_begin + rb + u / pg.S, lr.entries + rec.x, cnt, u, yy_row_min);
             }
         }
         __syncthreads();
@@ -914,6 +1318,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     uint32_t tma_phase = 0;  // parity of sm.tma_bar; every thread tracks it (all threads stage every chunk)
     if (threadIdx.x == 0) mbar_init(&sm.tma_bar, 1);
     __syncthreads();
+    const bool use_lists = args.list_entries != nullptr;
+    ListRef lref[LIST_KINDS];
+#pragma unroll
+    for (int i = 0; i < LIST_KINDS; ++i) {
+        const size_t area = (size_t)blockIdx.x * LIST_KINDS + i;
+        lref[i].entries = args.list_entries + area * args.list_cap;
+        lref[i].units = args.list_units + area * kMaxListUnits;
+        lref[i].cap = args.list_cap;
+    }
 
     while (true) {
         if (rank == 0 && threadIdx.x == 0) {
@@ -929,20 +1342,60 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             sm.st.iters = max_iter;
             sm.st.status = CVO_B200_STATUS_MAX_ITER;
             sm.st.n_run = 0;
+            sm.st.n_builds = 0;
             sm.done = 0;
+#pragma unroll
+            for (int i = 0; i < LIST_KINDS; ++i) sm.lst[i].valid = sm.lst[i].need = 0;
         }
         __syncthreads();
+        if (use_lists) {  // bounding box of the moving cloud (original coordinates), for list_policy
+            const float inf = __int_as_float(0x7f800000);
+            float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+            for (int i = threadIdx.x; i < pair.y.n; i += kThreads) {
+                const float4 g = __ldg(pair.y.g + i);
+                lo[0] = fminf(lo[0], g.x); lo[1] = fminf(lo[1], g.y); lo[2] = fminf(lo[2], g.z);
+                hi[0] = fmaxf(hi[0], g.x); hi[1] = fmaxf(hi[1], g.y); hi[2] = fmaxf(hi[2], g.z);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float l = warp_min(lo[a]), h = warp_max(hi[a]);
+                if ((threadIdx.x & 31) == 0) {
+                    sm.wred[threadIdx.x >> 5][a] = l;
+                    sm.wred[threadIdx.x >> 5][3 + a] = h;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 6) {
+                float v = sm.wred[0][threadIdx.x];
+                for (int w = 1; w < kWarps; ++w)
+                    v = threadIdx.x < 3 ? fminf(v, sm.wred[w][threadIdx.x]) : fmaxf(v, sm.wred[w][threadIdx.x]);
+                sm.ybox[threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
 
         for (int k = 0; k < max_iter; ++k) {
-            if (threadIdx.x == 0) prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
+            if (threadIdx.x == 0) {
+                prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
+                if (use_lists) list_policy(sm, acvo, args.list_skin);
+            }
             __syncthreads();
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
-            run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
+            if (use_lists && sm.lst[LIST_XY].need) build_list(sm, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
+            const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
+            if (list_xy) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, lref[LIST_XY]);
+            else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
+                if (use_lists && sm.lst[LIST_XX].need) build_list(sm, pair.x, false, pair.x, false, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
+                if (use_lists && sm.lst[LIST_XX].valid > 0)
+                    run_pass_list<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, lref[LIST_XX]);
+                else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
+                if (use_lists && sm.lst[LIST_YY].need) build_list(sm, pair.y, true, pair.y, true, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
+                if (use_lists && sm.lst[LIST_YY].valid > 0)
+                    run_pass_list<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, lref[LIST_YY]);
+                else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZYY + threadIdx.x] = sm.blockTot[threadIdx.x];
             }
             __syncthreads();
@@ -950,7 +1403,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
             // compute_step_size (src/cvo.cpp:377)
-            run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
+            if (list_xy) run_pass_list<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, lref[LIST_XY]);
+            else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
             if (threadIdx.x == 0) {
                 // remember the transform used by this iteration: it is what the reference multiplies

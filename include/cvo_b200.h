@@ -162,6 +162,16 @@ int       cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx);
 int       cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int ctas_per_pair);
 /* Sum over the pairs of the last align call of iterations executed (work accounting for the roofline). */
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
+/* Neighbour candidate lists: the device-side replacement of the kd-tree the reference rebuilds in every
+ * se_kernel call (src/cvo.cpp:106-113, thirdparty/nanoflann.hpp).  Per frame pair the (row, col) index pairs
+ * inside a ball of radius (1 + skin) * r are kept in a per-CTA scratch area and re-used by the passes of the
+ * following iterations until the pose has moved the moving cloud by more than skin * r (or ell changed r);
+ * the strict ell-ball test and the kernel values are still evaluated on the fly, A is never stored.
+ * enable = 0: every pass tests all tile pairs on the fly (also the automatic fallback if a list overflows
+ * its scratch).  Default: enabled, skin = 0.08.  Results agree between the two modes up to f32 summation order. */
+int       cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin);
+/* Sum over the pairs of the last align call of (x, y) list builds. */
+long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx);
 int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
 
 #ifdef __cplusplus

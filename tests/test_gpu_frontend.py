@@ -107,7 +107,8 @@ def test_cpp_sequence_driver_over_pcd_files_equals_python_frontend(tmp_path):
             reg.run_cvo(xyz, cio.cloud_features(rgb, "cvo"))
             if k:
                 got = traj[float(n_)]
-                assert np.abs(got - reg.accum_transform).max() < 1e-6, k
+                # the pose file holds a unit quaternion: the round trip re-normalises the accumulated f32 product
+                assert np.abs(got - reg.accum_transform).max() < 5e-6, k
     finally:
         reg.close()
     # and the recovered trajectory is the camera motion of the synthetic sequence (evaluation harness, 8f row 3)

@@ -163,12 +163,82 @@ def test_batch_of_pairs_equals_one_by_one_and_warm_start_state_round_trips(gpu_c
         one = gpu_ctx.align(np.array([s]), gp, RT=RT[s:s + 1], ell=ell[s:s + 1])
         assert np.array_equal(one["transform"][0], batch["transform"][s])
         assert np.array_equal(one["RT"][0], batch["RT"][s]) and one["ell"][0] == batch["ell"][s]
-    # quirk Q4: R, T (and ell for cvo) carry into the next call; continuing 12+12 equals 24 in one go
-    cont = gpu_ctx.align(np.arange(6), gp, RT=batch["RT"], ell=batch["ell"])
-    gp.fixed_iters = 24
-    full = gpu_ctx.align(np.arange(6), gp, RT=RT, ell=ell)
-    for s in range(6):
-        assert np.array_equal(cont["transform"][s], full["transform"][s])
+    # quirk Q4: R, T (and ell for cvo) carry into the next call; continuing 12+12 equals 24 in one go.
+    # With every pass on the fly the continuation is bit-identical; with neighbour lists the second call starts
+    # from a freshly built list, so the f32 summation order (only that) differs from the uninterrupted run.
+    for lists in (False, True):
+        gpu_ctx.set_neighbor_lists(lists)
+        try:
+            gp.fixed_iters = 12
+            first = gpu_ctx.align(np.arange(6), gp, RT=RT, ell=ell)
+            cont = gpu_ctx.align(np.arange(6), gp, RT=first["RT"], ell=first["ell"])
+            gp.fixed_iters = 24
+            full = gpu_ctx.align(np.arange(6), gp, RT=RT, ell=ell)
+        finally:
+            gpu_ctx.set_neighbor_lists(True)
+        for s in range(6):
+            if lists:
+                rot, tr = pose_diff(cont["transform"][s], full["transform"][s])
+                assert rot < 1e-5 and tr < 1e-5, (s, rot, tr)
+            else:
+                assert np.array_equal(cont["transform"][s], full["transform"][s])
+
+
+@pytest.mark.parametrize("kind,cfg", [("cvo", 2), ("acvo", 3)])
+def test_neighbor_lists_agree_with_on_the_fly_passes(gpu_ctx, kind, cfg):
+    """The neighbour candidate lists only change WHICH index pairs a pass looks at (a superset of the ell-ball);
+    the strict ball test and the kernel values are evaluated per pass either way.  So per iteration the counts are
+    identical and the sums agree to f32 summation order, for every skin, through ell changes and rebuilds."""
+    pr = synth.config_pair(cfg)
+    _set(gpu_ctx, 0, pr)
+    gp = capi.default_params(kind)  # stock run to convergence; cvo crosses the ell schedule steps at k = 3, 10, 20,
+    try:                            # acvo adapts ell every iteration
+        gpu_ctx.set_neighbor_lists(False)
+        ref = gpu_ctx.align_trace(0, gp, trace_cap=40)
+        assert gpu_ctx.last_list_builds == 0
+        for skin in (0.0, 0.08, 0.3):
+            gpu_ctx.set_neighbor_lists(True, skin)
+            got = gpu_ctx.align_trace(0, gp, trace_cap=40)
+            builds = gpu_ctx.last_list_builds
+            assert 1 <= builds <= got["n_iterations_run"]
+            if skin >= 0.08:
+                assert builds < got["n_iterations_run"] // 2  # the list really is re-used across iterations
+            a, b = got["trace"][0], ref["trace"][0]  # identical inputs: exact counts, sums to f32 summation order
+            assert (a["nnz"], a["nnz_xx"], a["nnz_yy"]) == (b["nnz"], b["nnz_xx"], b["nnz_yy"]), skin
+            for key in ("omega", "v", "B", "C", "D", "E", "sum_a"):
+                assert rel_err(a[key], b[key]) < 2e-6, (skin, key)
+            assert abs(a["dl"] - b["dl"]) < 1e-5 * max(abs(b["dl"]), 1e-2)
+            for k in range(1, 8):  # the states have started to drift by rounding: counts within boundary flips
+                a, b = got["trace"][k], ref["trace"][k]
+                assert abs(a["nnz"] - b["nnz"]) <= 3, (skin, k)
+                assert rel_err(a["omega"], b["omega"]) < 1e-4 and rel_err(a["v"], b["v"]) < 1e-4, (skin, k)
+            rot, tr = pose_diff(got["transform"], ref["transform"])  # converged: same fixed point
+            assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (skin, rot, tr)  # line-search noise floor (conftest.py)
+    finally:
+        gpu_ctx.set_neighbor_lists(True)
+
+
+def test_neighbor_list_survives_large_motion_and_cluster_sizes(gpu_ctx, oracle):
+    """Large initial misalignment (many rebuilds while the pose moves by much more than the skin) on every
+    cluster size, checked against the oracle's trajectory."""
+    pr = synth.make_pair(81, 2100, 1900, "cvo", motion_scale=3.0)
+    _set(gpu_ctx, 0, pr)
+    gp, op = capi.default_params("cvo"), oracle.default_params("cvo")
+    for p in (gp, op):
+        p.ell_policy, p.ell_init, p.fixed_iters = capi.ELL_FIXED, 0.12, 10
+    o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], op, trace_cap=16)
+    try:
+        for g in (1, 4, 16):
+            gpu_ctx.set_cluster_size(g)
+            r = gpu_ctx.align_trace(0, gp, trace_cap=16)
+            assert gpu_ctx.last_list_builds >= 2
+            for k in range(5):
+                assert abs(r["trace"][k]["nnz"] - o["trace"][k]["nnz"]) <= 2, (g, k)
+                assert rel_err(r["trace"][k]["omega"], o["trace"][k]["omega"]) < 1e-4, (g, k)
+            rot, tr = pose_diff(r["transform"], o["transform"])
+            assert rot < 1e-4 and tr < 1e-4
+    finally:
+        gpu_ctx.set_cluster_size(0)
 
 
 def test_batched_upload_of_ragged_pairs_equals_single_uploads(gpu_ctx):
