@@ -50,7 +50,7 @@ struct cvo_b200_ctx {
     double* h_inner = nullptr;  // pinned
 
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
-    uint32_t* d_list_entries = nullptr;
+    uint2* d_list_entries = nullptr;
     uint2* d_list_units = nullptr;
     unsigned list_cap = 0;
     bool lists_enabled = true;
@@ -124,7 +124,7 @@ KParams make_kparams(const cvo_b200_params* p, bool for_inner_product) {
     k.s2cs2 = (float)((double)k.s2 * (double)k.cs2);
     k.c_ell = p->c_ell;
     k.sp_band = 2.0e-6f * fabsf(p->sp_thres);
-    k.d2c_band = 1.0e-6f * fabsf(k.d2c_thres);
+    k.t_lim = (float)(log2((double)k.s2cs2 / (double)p->sp_thres) + 1.0e-5);
     k.inv_c = 1 / p->c;
     k.inv_d = 1 / p->d;
     k.min_step = p->min_step;
@@ -205,9 +205,9 @@ void ensure_list_scratch(cvo_b200_ctx* ctx) {
     if (ctx->d_list_entries || ctx->lists_alloc_failed || !ctx->lists_enabled) return;
     unsigned long long cap = (unsigned long long)ctx->max_points * ctx->max_points / 8;
     if (cap < (1ull << 18)) cap = 1ull << 18;
-    if (cap > (1ull << 22)) cap = 1ull << 22;
+    if (cap > (1ull << 21)) cap = 1ull << 21;
     const size_t areas = (size_t)ctx->num_sms * LIST_KINDS;
-    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint32_t)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess ||
         cudaMalloc(&ctx->d_list_units, areas * kMaxListUnits * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(ctx->d_list_entries);

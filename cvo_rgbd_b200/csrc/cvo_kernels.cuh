@@ -114,7 +114,8 @@ struct KParams {
     float c2;          // log2(e)/(2 c_ell^2)
     float s2cs2;       // sigma^2 c_sigma^2
     float c_ell;
-    float sp_band, d2c_band;  // half-widths around sp_thres / d2c_thres inside which kernel_value re-decides exactly
+    float sp_band;     // half-width around sp_thres inside which the kernel value is re-decided exactly
+    float t_lim;       // log2(s2 c_sigma^2 / sp_thres), rounded up: a > sp_thres  <=>  d2 c1 + t_c < t_lim
     float inv_c, inv_d;
     float min_step, max_step, eps, eps_2;
     double dl_step;
@@ -140,15 +141,18 @@ struct WarpScratch {
 
 struct ListState {
     float tf[12];     // transform the (x, y) list was built at
-    float r_build;    // radius covered by the list (ball radius at build time * (1 + skin) + margin)
-    float thr_build;  // r_build^2: the threshold of the build prefilter
+    float r0;         // ell-ball radius at build time
+    float slack;      // how far the cloud may move / the ball may grow before the list misses a neighbour
+    float s_build;    // slack + rounding margin: what the build adds to a pair's own radius
+    float thr_build;  // (r0 + s_build)^2: the build prefilter's ball
+    float inv_c1;     // 2 l^2 / log2(e) at build time: colour exponent -> squared radius
     int valid;        // 1: usable, 0: must be built, -1: overflowed its scratch for this pair (on-the-fly passes)
     int need;         // (re)build before this iteration's passes
 };
 
 struct ListRef {
-    uint32_t* entries;
-    uint2* units;  // (offset, count) of every work unit's entries
+    uint2* entries;  // (row << 12 | col, bits of the colour exponent t_c)
+    uint2* units;    // (offset, count | unit << 24) of every work unit, in processing order
     unsigned cap;
 };
 
@@ -163,8 +167,7 @@ struct Smem {
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
     int unitCnt[kMaxUnits];   // neighbour-list build: entries per unit, their offsets, and the processing order
     int unitOff[kMaxUnits];
-    unsigned short unitRank[kMaxUnits];  // rank of unit u when sorted by descending entry count
-    unsigned short unitOrd[kMaxUnits];   // inverse: the unit at rank k
+    unsigned short unitOrd[kMaxUnits];   // the unit at rank k when sorted by descending entry bound
     float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
     float ybox[6];            // bounding box of the moving cloud, original coordinates
     ListState lst[LIST_KINDS];
@@ -191,7 +194,7 @@ struct AlignArgs {
     int trace_cap;
     KParams kp;
     // neighbour-list scratch: [gridDim.x][LIST_KINDS] areas of list_cap entries / kMaxListUnits unit records
-    uint32_t* list_entries;  // nullptr: lists disabled, every pass is on the fly
+    uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
     uint2* list_units;
     unsigned list_cap;
     float list_skin;
@@ -588,10 +591,12 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
 // --------------------------------------------------------------------------------------------
 // per-pair kernel value: the three strict gates of se_kernel (src/cvo.cpp:143-153)
 // --------------------------------------------------------------------------------------------
-// se_kernel's value and gates in the reference's own arithmetic (src/cvo.cpp:146-152).  Deliberately not inlined:
-// it runs for about one candidate in a million and must not cost the hot loop registers.
+// se_kernel's value and gates in the reference's own arithmetic (src/cvo.cpp:146-152): colour distance summed left
+// to right, exp() in f64 narrowed to f32, a = ck * k in f32.  Deliberately not inlined: it runs for about one
+// candidate in a million (see kernel_a) and must not cost the hot loops registers.
 __device__ __noinline__ bool kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
-                                                float e0, float e1, float e2, float e3, float e4, float d2, float& a) {
+                                                float4 xf, float xf4, float4 yf, float yf4, float d2, float& a) {
+    const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
     float d2e = __fmul_rn(e0, e0);
     d2e = __fadd_rn(d2e, __fmul_rn(e1, e1));
     d2e = __fadd_rn(d2e, __fmul_rn(e2, e2));
@@ -604,22 +609,27 @@ __device__ __noinline__ bool kernel_value_exact(float ell, float d2c_thres, floa
     return (d2e < d2c_thres) && (a > sp_thres);
 }
 
-__device__ __forceinline__ bool kernel_value(const IterConsts& ic, const KParams& kp, const float4& xf, float xf4,
-                                             const float4& yf, float yf4, float d2, float& a) {
+// (feature_x - feature_y).squaredNorm() summed left to right (src/cvo.cpp:145-146); pose-independent.
+__device__ __forceinline__ float colour_d2(const float4& xf, float xf4, const float4& yf, float yf4) {
     const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
-    const float d2c = fmaf(e4, e4, fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0))));  // src/cvo.cpp:145
-    // k = s2 exp(-d2 / 2l^2), ck = c_sigma^2 exp(-d2c / 2c_ell^2), a = ck k (src/cvo.cpp:149-151) as ONE base-2
-    // exponential of the summed exponents: a = s2 c_sigma^2 2^-(d2 log2e/2l^2 + d2c log2e/2c_ell^2).  Wherever the
-    // result can matter (a > sp_thres => |exponent| < 0.33) MUFU.EX2 is good to 2 ulp and the argument to 1 ulp.
-    const float t = fmaf(d2, ic.c1, __fmul_rn(d2c, kp.c2));
-    a = __fmul_rn(kp.s2cs2, exp2f_approx(-t));
-    bool ok = (d2c < ic.d2c_thres) && (a > kp.sp_thres);  // :148, :152
-    // Within a few ulp of either threshold (about one candidate in a million) the decision -- and the value -- is
-    // re-made in the reference's own arithmetic: colour distance summed left to right, exp() in f64 narrowed to
-    // f32, a = ck * k in f32 (src/cvo.cpp:146-151), so that the gates agree with the CPU path bit for bit.
-    if (fabsf(a - kp.sp_thres) < kp.sp_band || fabsf(d2c - ic.d2c_thres) < kp.d2c_band)
-        ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, e0, e1, e2, e3, e4, d2, a);
-    return ok;
+    float d2c = __fmul_rn(e0, e0);
+    d2c = __fadd_rn(d2c, __fmul_rn(e1, e1));
+    d2c = __fadd_rn(d2c, __fmul_rn(e2, e2));
+    d2c = __fadd_rn(d2c, __fmul_rn(e3, e3));
+    d2c = __fadd_rn(d2c, __fmul_rn(e4, e4));
+    return d2c;
+}
+
+// k = s2 exp(-d2 / 2l^2), ck = c_sigma^2 exp(-d2c / 2c_ell^2), a = ck k (src/cvo.cpp:149-151) as ONE base-2
+// exponential of the summed exponents: a = s2 c_sigma^2 2^-(d2 log2e/2l^2 + t_c), t_c = d2c log2e/2c_ell^2 being
+// the pose-independent COLOUR EXPONENT of the pair.  Wherever the result can matter (a > sp_thres => exponent
+// < 0.33) MUFU.EX2 is good to 2 ulp and the argument to 1 ulp; `near` flags the candidates whose a lies within a
+// few ulp of sp_thres (about one in a million): the caller re-decides those with kernel_value_exact so that the
+// gate agrees with the CPU path bit for bit.
+__device__ __forceinline__ float kernel_a(const IterConsts& ic, const KParams& kp, float d2, float t_c, bool& near) {
+    const float a = __fmul_rn(kp.s2cs2, exp2f_approx(-fmaf(d2, ic.c1, t_c)));
+    near = fabsf(a - kp.sp_thres) < kp.sp_band;
+    return a;
 }
 
 // Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
@@ -629,27 +639,12 @@ struct FlowPartial {
     int cnt;
 };
 
-// Survivor body: one (row, col) candidate popped from the warp's queue.  All 32 lanes of a warp work on 32
-// different candidates, so the expensive part runs at full lane utilisation.  The body is BRANCH-FREE: the three
-// strict gates of se_kernel (exact ball test on the nanoflann-ordered d2, colour gate, a > sp_thres) fold into
-// one predicate and a rejected candidate contributes a = 0 (adding +0 terms), which lets the compiler interleave
-// several bodies (CVO_BODY_ILP) to hide the LDS / MUFU latencies.
+// Accumulation tail of a candidate whose kernel value a is known (a = 0 for a rejected one, which then adds +0
+// terms: the bodies are BRANCH-FREE so that the compiler can interleave several of them).
 template <int KIND>
-__device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent,
-                                              bool live, int yy_row_min, FlowPartial& fp, double* acc) {
-    const IterConsts& ic = sm.ic;
-    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
-    const float4 xg = ws.rowG[row];
-    const float4 xf = ws.rowF[row];
-    const float4 yg = sm.colG[col];
-    const float4 yf = sm.colF[col];
-    const float yf4 = sm.colF4[col];
-    const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
-    const float d2 = dist2(dx, dy, dz);
-    float a;
-    bool ok = kernel_value(ic, kp, xf, xg.w, yf, yf4, d2, a);
-    ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
-    a = ok ? a : 0.f;
+__device__ __forceinline__ void accumulate_terms(const IterConsts& ic, const KParams& kp, const float4& xg, const float4& yg,
+                                                 float dx, float dy, float dz, float a, bool ok, bool q1_row,
+                                                 FlowPartial& fp, double* acc) {
     if (KIND == PASS_FLOW) {
         const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
         const float cy = xg.z * yg.x - xg.x * yg.z;
@@ -666,7 +661,7 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
         fp.cnt += ok ? 1 : 0;
     } else if (KIND == PASS_YY) {
         // quirk Q1: rows i < num_fixed never fill sum_diff_yy_2 (src/adaptive_cvo.cpp:213-223); :256,259 otherwise
-        const float aq = (ws.rowOrig[row] >= yy_row_min) ? a : 0.f;
+        const float aq = q1_row ? a : 0.f;
         fp.pdl = fmaf(ic.inv_ell3 * aq, dx * dx + dy * dy + dz * dz, fp.pdl);
         fp.cnt += ok ? 1 : 0;
     } else {  // PASS_STEP: src/cvo.cpp:249-289
@@ -693,6 +688,64 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
         acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
                         (1.0 / 24.0) * (bd * bd) * (bd * bd));                                       // :278-279
     }
+}
+
+// Survivor body of the ON-THE-FLY passes: one (row, col) candidate popped from the warp's queue.  All 32 lanes of
+// a warp work on 32 different candidates, so the expensive part runs at full lane utilisation.  The three strict
+// gates of se_kernel (exact ball test on the nanoflann-ordered d2, colour gate, a > sp_thres) fold into one
+// predicate.
+template <int KIND>
+__device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent,
+                                              bool live, int yy_row_min, FlowPartial& fp, double* acc) {
+    const IterConsts& ic = sm.ic;
+    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
+    const float4 xg = ws.rowG[row];
+    const float4 xf = ws.rowF[row];
+    const float4 yg = sm.colG[col];
+    const float4 yf = sm.colF[col];
+    const float yf4 = sm.colF4[col];
+    const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
+    const float d2 = dist2(dx, dy, dz);
+    const float d2c = colour_d2(xf, xg.w, yf, yf4);
+    bool near;
+    float a = kernel_a(ic, kp, d2, __fmul_rn(d2c, kp.c2), near);
+    bool ok = (d2c < ic.d2c_thres) && (a > kp.sp_thres);  // src/cvo.cpp:148,152
+    if (near) ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, xf, xg.w, yf, yf4, d2, a);
+    ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    a = ok ? a : 0.f;
+    const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
+    accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
+}
+
+// Survivor body of the LIST passes: the candidate comes with its colour exponent t_c (the colour gate was applied
+// when the list was built), so only the geometry is touched; the features are fetched from global memory in the
+// one-in-a-million case that a sits within a few ulp of sp_thres.
+struct ListSrc {
+    const CloudDev* rows;
+    const CloudDev* cols;
+    int row_base, col_base;  // global index of the unit's row 0 / of the staged chunk's column 0
+};
+template <int KIND>
+__device__ __forceinline__ void list_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent, float t_c,
+                                          bool live, int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
+    const IterConsts& ic = sm.ic;
+    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
+    const float4 xg = ws.rowG[row];
+    const float4 yg = sm.colG[col];
+    const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
+    const float d2 = dist2(dx, dy, dz);
+    bool near;
+    float a = kernel_a(ic, kp, d2, t_c, near);
+    bool ok = a > kp.sp_thres;  // src/cvo.cpp:152
+    if (near && live) {
+        const int ri = src.row_base + row, ci = src.col_base + col;
+        ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
+                                __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2, a);
+    }
+    ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    a = ok ? a : 0.f;
+    const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
+    accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
 }
 
 template <int KIND>
@@ -967,12 +1020,17 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // --------------------------------------------------------------------------------------------
 // neighbour candidate lists
 // --------------------------------------------------------------------------------------------
-
-// Decides, for this iteration, which lists must be (re)built (one thread; after prepare_iter).
-// A list built at transform T0 with radius r_build contains every (i, j) with |x_i - T0 y_j| < r_build.  At the
-// current transform T1, |x_i - T1 y_j| < r implies |x_i - T0 y_j| < r + |T1 y_j - T0 y_j| <= r + disp with
-// disp = max_j |(M1 - M0) y_j + (t1 - t0)|, so the list still covers the ell-ball while r + disp <= r_build.
-// The (x, x) list never moves and rigid motion preserves the (y, y) distances: those two only follow ell.
+// A list entry is (row | col, t_c): the index pair and its pose-independent colour exponent
+// t_c = |f_i - g_j|^2 log2(e) / (2 c_ell^2).  With T = log2(s2 c_sigma^2 / sp_thres) the gate a > sp_thres reads
+// d2 log2(e)/(2 l^2) + t_c < T, i.e. every pair has its OWN ball radius r_e = sqrt((T - t_c) 2 l^2 / log2 e) <= r
+// (equal colours: r_e = r, the ell-ball; a colour mismatch shrinks it; t_c >= T or a failed colour gate: never a
+// neighbour).  The build keeps a pair iff |x_i - y_j| < r_e + s at the build pose, s = skin * r being the slack.
+//
+// Validity.  At a later iteration (transform T1, length-scale l1) the pair can only pass if |x_i - T1 y_j| <
+// r_e (l1/l0); it is in the list if |x_i - T0 y_j| < r_e + s, and |x_i - T0 y_j| <= |x_i - T1 y_j| + disp with
+// disp = max_j |(M1 - M0) y_j + (t1 - t0)|.  Since r_e <= r0, the list covers everything that can pass as long as
+// max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
+// the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
 __device__ void list_policy(Smem& sm, bool acvo, float skin) {
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
@@ -1001,17 +1059,20 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin) {
                 }
                 if (!(disp == disp)) disp = 1.0e30;  // NaN state: never trust an old list
             }
-            // rebuild when the ball is no longer covered, or when ell has shrunk it by > 10 % (a list that is
-            // much too wide costs more in every pass than one rebuild)
-            need = !(r_now + disp + margin <= (double)L.r_build) ||
-                   (r_now * (1.0 + (double)skin) + margin < 0.9 * (double)L.r_build);
+            // rebuild when something that can pass may be missing, or when ell has shrunk the ball by > 10 % (a
+            // list that is much too wide costs more in every pass than one rebuild)
+            need = !(fmax(0.0, r_now - (double)L.r0) + disp <= (double)L.slack) || (r_now < 0.9 * (double)L.r0);
         }
         L.need = need ? 1 : 0;
         if (need) {
-            const double rb = r_now * (1.0 + (double)skin) + margin;
+            const double s = (double)skin * r_now;
+            const double rb = r_now + s + margin;
             L.valid = 0;
-            L.r_build = (float)(rb * (1.0 - 1.0e-6));         // rounded DOWN: what the validity test may assume
-            L.thr_build = (float)(rb * rb * (1.0 + 1.0e-6));  // rounded UP: what the build prefilter covers
+            L.r0 = (float)r_now;
+            L.slack = (float)(s * (1.0 - 1.0e-6));            // rounded DOWN: what the validity test may assume
+            L.s_build = (float)((s + margin) * (1.0 + 1.0e-6));  // rounded UP: what the build adds to r_e
+            L.thr_build = (float)(rb * rb * (1.0 + 1.0e-6));  // rounded UP: the build prefilter's ball
+            L.inv_c1 = (float)(2.0 * (double)sm.st.ell * (double)sm.st.ell / 1.4426950408889634 * (1.0 + 1.0e-6));
 #pragma unroll
             for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i];
             if (kind == LIST_XY) sm.st.n_builds += 1;
@@ -1019,80 +1080,141 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin) {
     }
 }
 
-__device__ __forceinline__ void push_mask_global(uint32_t* q, int pos, uint32_t mask, uint32_t base) {
-    while (mask) {
-        const int jj = __ffs(mask) - 1;
-        mask &= mask - 1;
-        __stcg(q + pos, base + (uint32_t)jj);
-        ++pos;
-    }
-}
-
-// Build work unit: one 32-row tile against one segment of the staged column tiles.  WRITE = false counts the
-// candidates inside the build radius, WRITE = true stores them at out[0 .. count): (col tile by col tile, lane
-// by lane) -- the same decomposition and the same masks both times, so the two sweeps agree.
-template <bool WRITE>
-__device__ __forceinline__ int list_unit(const Smem& sm, const CloudDev& rows, bool row_tf, int tile, int ct_begin,
-                                         int ct_end, float thr_build, uint32_t* out) {
+// Row tile of a build / list unit: registers for the prefilter, warp-private shared memory for the per-candidate work.
+struct RowTile {
+    RowRegs rr;
+    float lx, ly, lz, hx, hy, hz;  // bounding box of the valid rows
+};
+template <bool NEED_FEAT, bool NEED_ORIG>
+__device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws, const CloudDev& rows, bool row_tf, int tile) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
     const int p = tile * kTile + lane;
     const bool valid = p < rows.n;
-    float4 xg;
+    float4 xg, xf = make_float4(0.f, 0.f, 0.f, 0.f);
+    int orig = -1;
     if (valid) {
         xg = __ldg(rows.g + p);
+        orig = __float_as_int(xg.w);
+        xg.w = 0.f;
+        if (NEED_FEAT) {
+            xf = __ldg(rows.f + p);
+            xg.w = __ldg(rows.f4 + p);
+        }
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
     } else {
         xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
     }
-    const float lx = warp_min(valid ? xg.x : inf), ly = warp_min(valid ? xg.y : inf), lz = warp_min(valid ? xg.z : inf);
-    const float hx = warp_max(valid ? xg.x : -inf), hy = warp_max(valid ? xg.y : -inf), hz = warp_max(valid ? xg.z : -inf);
-    RowRegs rr;
-    rr.m2x = -2.f * xg.x; rr.m2y = -2.f * xg.y; rr.m2z = -2.f * xg.z;
-    rr.x2 = fmaf(xg.z, xg.z, fmaf(xg.y, xg.y, xg.x * xg.x));
-    const float thr = thr_build * 1.0001f;  // boxes are conservative; keep rounding on the safe side
-    int cnt = 0;  // WRITE: entries stored so far (warp-uniform); else this lane's candidate count
+    __syncwarp();  // the previous unit's reads of the warp scratch are done
+    ws.rowG[lane] = xg;
+    if (NEED_FEAT) ws.rowF[lane] = xf;
+    if (NEED_ORIG) ws.rowOrig[lane] = orig;
+    RowTile rt;
+    rt.lx = warp_min(valid ? xg.x : inf); rt.ly = warp_min(valid ? xg.y : inf); rt.lz = warp_min(valid ? xg.z : inf);
+    rt.hx = warp_max(valid ? xg.x : -inf); rt.hy = warp_max(valid ? xg.y : -inf); rt.hz = warp_max(valid ? xg.z : -inf);
+    __syncwarp();
+    rt.rr.m2x = -2.f * xg.x; rt.rr.m2y = -2.f * xg.y; rt.rr.m2z = -2.f * xg.z;
+    rt.rr.x2 = fmaf(xg.z, xg.z, fmaf(xg.y, xg.y, xg.x * xg.x));
+    return rt;
+}
+
+// ballot of the column tiles [c0, c0 + 32) of the unit whose box is within sqrt(thr) of the row tile's box
+__device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile& rt, int c0, int ct_end, float thr) {
+    const int ct = c0 + (threadIdx.x & 31);
+    bool live = false;
+    if (ct < ct_end) {
+        const float* b = sm.colBox[ct];
+        const float gx = fmaxf(0.f, fmaxf(rt.lx - b[3], b[0] - rt.hx));
+        const float gy = fmaxf(0.f, fmaxf(rt.ly - b[4], b[1] - rt.hy));
+        const float gz = fmaxf(0.f, fmaxf(rt.lz - b[5], b[2] - rt.hz));
+        live = (gx * gx + gy * gy + gz * gz) <= thr;
+    }
+    return __ballot_sync(0xffffffffu, live);
+}
+
+// Build sweep 1: upper bound of the unit's entry count = its candidates inside the build ball (prefilter only).
+__device__ __forceinline__ int build_unit_bound(const Smem& sm, WarpScratch& ws, const CloudDev& rows, bool row_tf, int tile,
+                                                int ct_begin, int ct_end, float thr_build) {
+    const RowTile rt = load_row_tile<false, false>(sm, ws, rows, row_tf, tile);
+    const float thr_box = thr_build * 1.0001f;  // boxes are conservative; keep rounding on the safe side
+    int cnt = 0;
     for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
-        const int ct = c0 + lane;
-        bool live = false;
-        if (ct < ct_end) {
-            const float* b = sm.colBox[ct];
-            const float gx = fmaxf(0.f, fmaxf(lx - b[3], b[0] - hx));
-            const float gy = fmaxf(0.f, fmaxf(ly - b[4], b[1] - hy));
-            const float gz = fmaxf(0.f, fmaxf(lz - b[5], b[2] - hz));
-            live = (gx * gx + gy * gy + gz * gz) <= thr;
-        }
-        uint32_t lm = __ballot_sync(0xffffffffu, live);
+        uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
         while (lm) {
             const int j = __ffs(lm) - 1;
             lm &= lm - 1;
-            const uint32_t mask = prefilter_tile(sm, rr, c0 + j, thr_build);
-            if (!WRITE) {
-                cnt += __popc(mask);
-            } else {
-                if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
-                int excl, total;
-                warp_scan_count(__popc(mask), lane, excl, total);
-                push_mask_global(out, cnt + excl, mask, ((uint32_t)lane << 12) | (uint32_t)((c0 + j) * kTile));
-                cnt += total;
-            }
+            cnt += __popc(prefilter_tile(sm, rt.rr, c0 + j, thr_build));
         }
     }
-    if (!WRITE) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     return cnt;
 }
 
-// (Re)builds one neighbour list for this CTA's share of the row tiles: per (row round, column chunk) a counting
-// sweep, an exclusive scan of the unit counts in unit order (=> the layout is a pure function of the inputs, no
-// atomics), and a writing sweep.  On return sm.lst[kind].valid is 1, or -1 if the scratch area was too small.
-__device__ void build_list(Smem& sm, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf, int rank,
-                           int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
+// Build sweep 2, per candidate: exact distance at the build pose, colour gate and colour exponent (pose-independent,
+// src/cvo.cpp:145-148), and the pair's own radius + slack.  Survivors are appended to the unit's list.
+__device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+                                           uint32_t ent, bool live, uint2* out, int& cursor) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
+    const float4 xg = ws.rowG[row];
+    const float4 xf = ws.rowF[row];
+    const float4 yg = sm.colG[col];
+    const float4 yf = sm.colF[col];
+    const float yf4 = sm.colF4[col];
+    const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
+    const float d2c = colour_d2(xf, xg.w, yf, yf4);
+    const float t_c = __fmul_rn(d2c, kp.c2);
+    const float re2 = (kp.t_lim - t_c) * L.inv_c1;  // the pair's own squared ball radius (rounded up)
+    const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + L.s_build;
+    const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (keep) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent, __float_as_uint(t_c)));
+    cursor += __popc(b);
+}
+
+__device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
+                                                const CloudDev& rows, bool row_tf, int tile, int ct_begin, int ct_end,
+                                                uint2* out) {
+    const int lane = threadIdx.x & 31;
+    const RowTile rt = load_row_tile<true, false>(sm, ws, rows, row_tf, tile);
+    const float thr_box = L.thr_build * 1.0001f;
+    uint32_t* q = ws.queue;
+    int qn = 0, cursor = 0;
+    for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
+        uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
+        while (lm) {
+            const int j = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t mask = prefilter_tile(sm, rt.rr, c0 + j, L.thr_build);
+            if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+            int excl, total;
+            warp_scan_count(__popc(mask), lane, excl, total);
+            push_mask(q, qn + excl, mask, ((uint32_t)lane << 12) | (uint32_t)((c0 + j) * kTile));
+            qn += total;
+            __syncwarp();
+            while (qn >= 32) {
+                qn -= 32;
+                build_eval(sm, ws, kp, L, q[qn + lane], true, out, cursor);
+            }
+            __syncwarp();
+        }
+    }
+    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, out, cursor);
+    __syncwarp();
+    return cursor;
+}
+
+// (Re)builds one neighbour list for this CTA's share of the row tiles.  Per (row round, column chunk): sweep 1
+// bounds every unit's entry count by its prefilter candidates, an exclusive scan of the bounds in unit order lays
+// the units out (a pure function of the inputs, no atomics), sweep 2 evaluates the candidates and writes the
+// entries.  On return sm.lst[kind].valid is 1, or -1 if the scratch area was too small.
+__device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
+                           int rank, int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
-    const float thr_build = sm.lst[kind].thr_build;
+    const ListState& L = sm.lst[kind];
+    WarpScratch& ws = sm.ws[warp];
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
@@ -1115,18 +1237,18 @@ __device__ void build_list(Smem& sm, const CloudDev& rows, bool row_tf, const Cl
                 stop = true;
                 break;
             }
-            while (true) {  // sweep 1: count
+            while (true) {  // sweep 1: bound
                 int u = 0;
                 if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= nunits) break;
                 const int t = u / pg.S, seg = u - t * pg.S;
                 const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
-                const int c = list_unit<false>(sm, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, thr_build, nullptr);
+                const int c = build_unit_bound(sm, ws, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, L.thr_build);
                 if (lane == 0) sm.unitCnt[u] = c;
             }
             __syncthreads();
-            if (warp == 0) {  // exclusive scan of the unit counts (rounded up to 16-byte groups), in unit order
+            if (warp == 0) {  // exclusive scan of the unit bounds (rounded up to 32-byte groups), in unit order
                 int base = sm.lst_used;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
                     const int c = (i0 + lane < nunits) ? ((sm.unitCnt[i0 + lane] + 3) & ~3) : 0;
@@ -1141,36 +1263,33 @@ __device__ void build_list(Smem& sm, const CloudDev& rows, bool row_tf, const Cl
                     sm.next_unit = 0;
                 }
             } else if (threadIdx.x - 32 < nunits) {
-                // longest-processing-time order: rank the units by descending entry count (ties by unit index) so
-                // that the passes hand out the big units first and the small ones fill the tail
+                // longest-processing-time order: rank the units by descending bound (ties by unit index) so that
+                // the passes hand out the big units first and the small ones fill the tail
                 const int u = threadIdx.x - 32, cu = sm.unitCnt[u];
-                int rank = 0;
+                int rk = 0;
                 for (int v = 0; v < nunits; ++v) {
                     const int cv = sm.unitCnt[v];
-                    rank += (cv > cu || (cv == cu && v < u)) ? 1 : 0;
+                    rk += (cv > cu || (cv == cu && v < u)) ? 1 : 0;
                 }
-#ifdef CVO_NO_LPT
-                rank = u;
-#endif
-                sm.unitRank[u] = (unsigned short)rank;
-                sm.unitOrd[rank] = (unsigned short)u;
+                sm.unitOrd[rk] = (unsigned short)u;
             }
             __syncthreads();
             if (sm.lst_ovf) {
                 stop = true;
                 break;
             }
-            while (true) {  // sweep 2: write
+            while (true) {  // sweep 2: evaluate and write
                 int k = 0;
                 if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
                 if (k >= nunits) break;
                 const int u = sm.unitOrd[k];
-                const int off = sm.unitOff[u], c = sm.unitCnt[u];
-                if (c > 0) {
+                const int off = sm.unitOff[u];
+                int c = 0;
+                if (sm.unitCnt[u] > 0) {
                     const int t = u / pg.S, seg = u - t * pg.S;
                     const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
-                    list_unit<true>(sm, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, thr_build, lr.entries + off);
+                    c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, lr.entries + off);
                 }
                 if (lane == 0)  // record k of the round: (offset, count | unit << 24)
                     __stcg(&lr.units[round * kMaxUnits + k], make_uint2((unsigned)off, (unsigned)c | ((unsigned)u << 24)));
@@ -1182,36 +1301,21 @@ __device__ void build_list(Smem& sm, const CloudDev& rows, bool row_tf, const Cl
     __syncthreads();
 }
 
-// Pass work unit over a neighbour list: the unit's candidates are read 128 at a time (one 16-byte load per lane,
-// coalesced, L2; the next trip's load is in flight behind this trip's arithmetic) and every lane runs the
-// branch-free survivor body on its four entries; the exact strict ball test is part of the body.
+// Pass work unit over a neighbour list: the unit's entries are read 128 at a time (two 16-byte loads per lane,
+// coalesced, L2; the next trip's loads are in flight behind this trip's arithmetic) and every lane runs the
+// branch-free list body on its four entries.
 template <int KIND>
 __device__ __forceinline__ void consume_unit(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, int tile,
-                                             const uint32_t* ent, int cnt, int slot, int yy_row_min) {
+                                             const ListSrc& src, const uint2* ent, int cnt, int slot, int yy_row_min) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint4* ent4 = reinterpret_cast<const uint4*>(ent);
+    const uint4* ent4 = reinterpret_cast<const uint4*>(ent);  // two entries per 16 bytes
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    uint4 cur = (4 * lane < cnt) ? __ldcg(ent4 + lane) : zero4;
+    // lane's entries of a trip starting at entry b: b + 2 lane + {0, 1} and b + 64 + 2 lane + {0, 1}
+    uint4 curA = (2 * lane < cnt) ? __ldcg(ent4 + lane) : zero4;
+    uint4 curB = (64 + 2 * lane < cnt) ? __ldcg(ent4 + 32 + lane) : zero4;
     WarpScratch& ws = sm.ws[warp];
-    const int p = tile * kTile + lane;
-    float4 xg, xf;
-    int orig = -1;
-    if (p < rows.n) {
-        xg = __ldg(rows.g + p);
-        xf = __ldg(rows.f + p);
-        orig = __float_as_int(xg.w);
-        xg.w = __ldg(rows.f4 + p);
-        if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
-    } else {
-        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
-        xf = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();  // the previous unit's body reads are done
-    ws.rowG[lane] = xg;
-    ws.rowF[lane] = xf;
-    if (KIND == PASS_YY) ws.rowOrig[lane] = orig;
-    __syncwarp();
+    load_row_tile<false, KIND == PASS_YY>(sm, ws, rows, row_tf, tile);
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
@@ -1219,18 +1323,18 @@ __device__ __forceinline__ void consume_unit(Smem& sm, const KParams& kp, const 
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
     for (int b = 0; b < cnt; b += 4 * kTile) {
-        const int i0 = b + 4 * lane;
-        const uint4 c = cur;
-        const int nb = i0 + 4 * kTile;
-        cur = (nb < cnt) ? __ldcg(ent4 + (nb >> 2)) : zero4;
+        const uint4 cA = curA, cB = curB;
+        const int nb = b + 4 * kTile + 2 * lane;
+        curA = (nb < cnt) ? __ldcg(ent4 + (nb >> 1)) : zero4;
+        curB = (nb + 64 < cnt) ? __ldcg(ent4 + ((nb + 64) >> 1)) : zero4;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {  // two bodies interleaved at a time (register budget: 128 at 512 threads)
-            const int ia = i0 + 2 * h;
+            const uint4 c = h ? cB : cA;
+            const int ia = b + 64 * h + 2 * lane;
             const bool la = ia < cnt, lb = ia + 1 < cnt;
             // past the unit's end the 16-byte group holds stale bits: run entry (0, 0) -- real, finite points -- with a = 0
-            const uint32_t ea = la ? (h ? c.z : c.x) : 0u, eb = lb ? (h ? c.w : c.y) : 0u;
-            survivor_body<KIND>(sm, ws, kp, ea, la, yy_row_min, fp, acc);
-            survivor_body<KIND>(sm, ws, kp, eb, lb, yy_row_min, fp, acc);
+            list_body<KIND>(sm, ws, kp, la ? c.x : 0u, __uint_as_float(c.y), la, yy_row_min, src, fp, acc);
+            list_body<KIND>(sm, ws, kp, lb ? c.z : 0u, __uint_as_float(c.w), lb, yy_row_min, src, fp, acc);
         }
     }
     __syncwarp();
@@ -1250,6 +1354,9 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
     const int lane = threadIdx.x & 31;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
+    ListSrc src;
+    src.rows = &rows;
+    src.cols = &cols;
     int round = 0;
     for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round) {
         const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
@@ -1261,15 +1368,18 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
-            while (true) {  // records are sorted by descending entry count: the first empty one ends the round
+            src.col_base = cb * kTile;
+            while (true) {
                 int k = 0;
                 if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
                 if (k >= nunits) break;
                 const uint2 rec = __ldcg(&lr.units[round * kMaxUnits + k]);
                 const int cnt = (int)(rec.y & 0xffffffu), u = (int)(rec.y >> 24);
-                if (cnt == 0) break;
-                consume_unit<KIND>(sm, kp, rows, row_tf, pg.t_begin + rb + u / pg.S, lr.entries + rec.x, cnt, u, yy_row_min);
+                if (cnt == 0) continue;
+                const int tile = pg.t_begin + rb + u / pg.S;
+                src.row_base = tile * kTile;
+                consume_unit<KIND>(sm, kp, rows, row_tf, tile, src, lr.entries + rec.x, cnt, u, yy_row_min);
             }
         }
         __syncthreads();
@@ -1278,6 +1388,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             for (int u = 0; u < nunits; ++u) t += sm.unitPart[u][threadIdx.x];
             sm.blockTot[threadIdx.x] += t;
         }
+        __syncthreads();  // the slots are zeroed again by the next round
     }
     __syncthreads();
 }
@@ -1381,18 +1492,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             }
             __syncthreads();
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
-            if (use_lists && sm.lst[LIST_XY].need) build_list(sm, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (use_lists && sm.lst[LIST_XY].need) build_list(sm, kp, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
             if (list_xy) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                if (use_lists && sm.lst[LIST_XX].need) build_list(sm, pair.x, false, pair.x, false, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
+                if (use_lists && sm.lst[LIST_XX].need) build_list(sm, kp, pair.x, false, pair.x, false, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
                 if (use_lists && sm.lst[LIST_XX].valid > 0)
                     run_pass_list<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, lref[LIST_XX]);
                 else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                if (use_lists && sm.lst[LIST_YY].need) build_list(sm, pair.y, true, pair.y, true, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
+                if (use_lists && sm.lst[LIST_YY].need) build_list(sm, kp, pair.y, true, pair.y, true, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
                 if (use_lists && sm.lst[LIST_YY].valid > 0)
                     run_pass_list<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, lref[LIST_YY]);
                 else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
