@@ -131,12 +131,23 @@ struct IterConsts {
     float temp_coef, m2t, p2t;
 };
 
-// Private scratch of one warp: the row tile it currently owns and its survivor queue.
+// Private scratch of one warp: the row tile it currently owns.
 struct WarpScratch {
     float4 rowG[kTile];          // {x, y, z, f4}
     float4 rowF[kTile];          // {f0, f1, f2, f3}
     int rowOrig[kTile];          // original row indices (PASS_YY only: quirk Q1 is defined on them)
-    uint32_t queue[kQueueCap];   // in-ball (row, col) pairs waiting for the survivor body
+};
+
+// What sits beside the column geometry depends on the pass: on-the-fly passes and list builds need the column
+// features and the warps' survivor queues; the STEP pass over a list needs the per-column step-size terms instead.
+struct FeatStage {
+    float4 colF[kColChunk];             // {f0, f1, f2, f3}
+    float colF4[kColChunk];             // f4
+    uint32_t queue[kWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
+};
+struct StepStage {
+    float4 colZ1[kColChunk];  // {xi z + v, |xi z + v|^2}                       (src/cvo.cpp:226-228,235)
+    float4 colZ2[kColChunk];  // {xi^2 z + xi v, -(xi z + v).(xi^2 z + xi v)}   (src/cvo.cpp:229-230,236)
 };
 
 struct ListState {
@@ -157,9 +168,12 @@ struct ListRef {
 };
 
 struct Smem {
-    float4 colG[kColChunk];   // {x, y, z, |c|^2} of the staged (transformed) column points
-    float4 colF[kColChunk];   // {f0, f1, f2, f3}
-    float colF4[kColChunk];   // f4
+    float4 colG[kColChunk];   // {x, y, z, w} of the staged (transformed) column points; w = |c|^2 for the prefilter,
+                              // or the step-size term of src/cvo.cpp:237 in the STEP pass over a list
+    union {
+        FeatStage fs;
+        StepStage ss;
+    } u;
     float colBox[kColTiles][8];  // [0..2] lo, [3..5] hi, [6] max |c|^2
     WarpScratch ws[kWarps];
     double unitPart[kMaxUnits][kUnitAcc];  // one fixed slot per work unit => scheduling-independent sums
@@ -225,6 +239,43 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sums NV per-lane values over the warp in a fixed order.  The first 8 go through a transposing butterfly (each
+// xor step halves the number of values a lane still carries: 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 40); value
+// i (i < 8) ends up in lanes with ((lane >> 2) & 7) == i, any further value in every lane.  Lane 0 gets value 0;
+// `out_lane(i)` tells which lane holds value i.
+template <int NV>
+__device__ __forceinline__ void warp_sum_multi(double (&v)[NV], int lane) {
+    if (NV >= 8) {
+        double h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // xor 16: lanes with bit 4 clear keep 0..3, the others 4..7
+            const bool up = (lane & 16) != 0;
+            const double keep = up ? v[4 + i] : v[i], send = up ? v[i] : v[4 + i];
+            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+        double q[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {  // xor 8
+            const bool up = (lane & 8) != 0;
+            const double keep = up ? h[2 + i] : h[i], send = up ? h[i] : h[2 + i];
+            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        const bool up = (lane & 4) != 0;  // xor 4
+        double r = (up ? q[1] : q[0]) + __shfl_xor_sync(0xffffffffu, up ? q[0] : q[1], 4);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        v[0] = r;  // this lane's value index is ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+#pragma unroll
+        for (int i = 8; i < NV; ++i) v[i] = warp_sum(v[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    }
+}
+__device__ __forceinline__ int multi_value_index(int lane) {
+    return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -547,21 +598,47 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phas
         : "memory");
 }
 
+// Step-size terms of one (transformed) moving point z (src/cvo.cpp:226-237) through z_{k+1} = omega x z_k
+// (= Omega^k y + Omega^(k-1) v): z1 = xi z + v, z2 = xi^2 z + xi v, |z1|^2, -z1.z2, |z2|^2 + 2 z1.z3.
+struct StepCol {
+    float z1x, z1y, z1z, nrm;
+    float z2x, z2y, z2z, pdt;
+    float ecn;
+};
+__device__ __forceinline__ StepCol step_col(const IterConsts& ic, float yx, float yy, float yz) {
+    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+    StepCol c;
+    c.z1x = (w1 * yz - w2 * yy) + ic.v[0];
+    c.z1y = (w2 * yx - w0 * yz) + ic.v[1];
+    c.z1z = (w0 * yy - w1 * yx) + ic.v[2];
+    c.z2x = w1 * c.z1z - w2 * c.z1y; c.z2y = w2 * c.z1x - w0 * c.z1z; c.z2z = w0 * c.z1y - w1 * c.z1x;
+    const float z3x = w1 * c.z2z - w2 * c.z2y, z3y = w2 * c.z2x - w0 * c.z2z, z3z = w0 * c.z2y - w1 * c.z2x;
+    c.nrm = (c.z1x * c.z1x + c.z1y * c.z1y) + c.z1z * c.z1z;                                       // normxiz2, :235
+    c.pdt = -((c.z1x * c.z2x + c.z1y * c.z2y) + c.z1z * c.z2z);                                    // xiz_dot_xi2z, :236
+    c.ecn = ((c.z2x * c.z2x + c.z2y * c.z2y) + c.z2z * c.z2z) + 2.f * ((c.z1x * z3x + c.z1y * z3y) + c.z1z * z3z);  // :237
+    return c;
+}
+
 // Stages `ntiles` 32-point tiles starting at point `base` of a packed cloud into shared memory.
-//  * feature planes (20 B / point): two TMA bulk copies issued by one thread, completing on sm.tma_bar;
-//  * geometry plane (16 B / point): float4 loads by all threads, the rigid transform applied on the way (this IS
-//    transform_pcd, src/cvo.cpp:310-315: the transformed cloud never exists in HBM), |c|^2 appended for the
-//    prefilter, and one bounding box per tile reduced with warp shuffles.
+//  STAGE_FULL (on-the-fly passes, list builds):
+//   * feature planes (20 B / point): two TMA bulk copies issued by one thread, completing on sm.tma_bar;
+//   * geometry plane (16 B / point): float4 loads by all threads, the rigid transform applied on the way (this IS
+//     transform_pcd, src/cvo.cpp:310-315: the transformed cloud never exists in HBM), |c|^2 appended for the
+//     prefilter, and one bounding box per tile reduced with warp shuffles.
+//  STAGE_GEOM (FLOW / XX / YY pass over a list): the transformed geometry only.
+//  STAGE_STEP (STEP pass over a list): the transformed geometry plus the per-column step-size terms.
 // The caller has synchronised the CTA (nobody still reads the previous chunk) and synchronises again afterwards.
+enum StageMode { STAGE_FULL = 0, STAGE_GEOM = 1, STAGE_STEP = 2 };
+template <int MODE>
 __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int base, int ntiles, bool tf,
                                             float sentinel, uint32_t& tma_phase) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
-    if (threadIdx.x == 0) {
+    if (MODE == STAGE_FULL && threadIdx.x == 0) {
         const uint32_t bytes_f = (uint32_t)(ntiles * kTile) * 16u, bytes_f4 = (uint32_t)(ntiles * kTile) * 4u;
         mbar_expect_tx(&sm.tma_bar, bytes_f + bytes_f4);
-        tma_bulk_g2s(sm.colF, c.f + base, bytes_f, &sm.tma_bar);
-        tma_bulk_g2s(sm.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
+        tma_bulk_g2s(sm.u.fs.colF, c.f + base, bytes_f, &sm.tma_bar);
+        tma_bulk_g2s(sm.u.fs.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
     }
     const float* tf12 = sm.ic.tf;
     for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
@@ -574,18 +651,29 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
         } else {
             g = make_float4(sentinel, sentinel, sentinel, 0.f);
         }
-        const float c2 = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
-        sm.colG[i] = make_float4(g.x, g.y, g.z, c2);
-        const float lx = warp_min(valid ? g.x : inf), ly = warp_min(valid ? g.y : inf), lz = warp_min(valid ? g.z : inf);
-        const float hx = warp_max(valid ? g.x : -inf), hy = warp_max(valid ? g.y : -inf), hz = warp_max(valid ? g.z : -inf);
-        const float c2m = warp_max(valid ? c2 : 0.f);
-        if (lane == 0) {
-            float* b = sm.colBox[i >> 5];
-            b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz; b[6] = c2m;
+        if (MODE == STAGE_FULL) {
+            const float c2 = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
+            sm.colG[i] = make_float4(g.x, g.y, g.z, c2);
+            const float lx = warp_min(valid ? g.x : inf), ly = warp_min(valid ? g.y : inf), lz = warp_min(valid ? g.z : inf);
+            const float hx = warp_max(valid ? g.x : -inf), hy = warp_max(valid ? g.y : -inf), hz = warp_max(valid ? g.z : -inf);
+            const float c2m = warp_max(valid ? c2 : 0.f);
+            if (lane == 0) {
+                float* b = sm.colBox[i >> 5];
+                b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz; b[6] = c2m;
+            }
+        } else if (MODE == STAGE_GEOM) {
+            sm.colG[i] = make_float4(g.x, g.y, g.z, 0.f);
+        } else {
+            const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
+            sm.colG[i] = make_float4(g.x, g.y, g.z, sc.ecn);
+            sm.u.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
+            sm.u.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
         }
     }
-    mbar_wait(&sm.tma_bar, tma_phase);
-    tma_phase ^= 1u;
+    if (MODE == STAGE_FULL) {
+        mbar_wait(&sm.tma_bar, tma_phase);
+        tma_phase ^= 1u;
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -632,12 +720,35 @@ __device__ __forceinline__ float kernel_a(const IterConsts& ic, const KParams& k
     return a;
 }
 
+__device__ __forceinline__ uint32_t* sm_queue(const Smem& sm) {
+    return const_cast<uint32_t*>(sm.u.fs.queue[threadIdx.x >> 5]);
+}
+
 // Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
 // src/cvo.cpp:197-198); promoted to f64 when the unit is finished (src/cvo.cpp:202-203).
 struct FlowPartial {
     float po0, po1, po2, pv0, pv1, pv2, psum, pdl;
     int cnt;
 };
+
+// One nonzero of A in compute_step_size (src/cvo.cpp:260-279): beta, gamma, delta, epsilon from the column's
+// step-size terms and r = x_i - y_j, and the f64 accumulation of B, C, D, E.
+__device__ __forceinline__ void step_accumulate(const IterConsts& ic, const StepCol& c, float rx, float ry, float rz,
+                                                float a, double* acc) {
+    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+    const float z3x = w1 * c.z2z - w2 * c.z2y, z3y = w2 * c.z2x - w0 * c.z2z, z3z = w0 * c.z2y - w1 * c.z2x;
+    const float z4x = w1 * z3z - w2 * z3y, z4y = w2 * z3x - w0 * z3z, z4z = w0 * z3y - w1 * z3x;
+    const float beta = ic.m2t * ((c.z1x * rx + c.z1y * ry) + c.z1z * rz);                          // :262
+    const float gamma = -ic.temp_coef * (c.nrm + 2.f * ((c.z2x * rx + c.z2y * ry) + c.z2z * rz));  // :264
+    const float delta = ic.p2t * (c.pdt - ((z3x * rx + z3y * ry) + z3z * rz));                     // :267
+    const float epsil = -ic.temp_coef * (c.ecn + 2.f * ((z4x * rx + z4y * ry) + z4z * rz));        // :270
+    const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
+    acc[0] += (double)(a * beta);                                                                  // :275
+    acc[1] += ad * (gd + (double)(beta * beta) * 0.5);                                             // :276
+    acc[2] += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0));  // :277
+    acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
+                    (1.0 / 24.0) * (bd * bd) * (bd * bd));                                         // :278-279
+}
 
 // Accumulation tail of a candidate whose kernel value a is known (a = 0 for a rejected one, which then adds +0
 // terms: the bodies are BRANCH-FREE so that the compiler can interleave several of them).
@@ -665,28 +776,7 @@ __device__ __forceinline__ void accumulate_terms(const IterConsts& ic, const KPa
         fp.pdl = fmaf(ic.inv_ell3 * aq, dx * dx + dy * dy + dz * dz, fp.pdl);
         fp.cnt += ok ? 1 : 0;
     } else {  // PASS_STEP: src/cvo.cpp:249-289
-        const float rx = -dx, ry = -dy, rz = -dz;  // diff_xy = x - y, :260
-        // xi*z+v, xi^2*z+xi*v, ... (src/cvo.cpp:226-234) through z_{k+1} = omega x z_k  (= Omega^k y + Omega^(k-1) v)
-        const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
-        const float z1x = (w1 * yg.z - w2 * yg.y) + ic.v[0];
-        const float z1y = (w2 * yg.x - w0 * yg.z) + ic.v[1];
-        const float z1z = (w0 * yg.y - w1 * yg.x) + ic.v[2];
-        const float z2x = w1 * z1z - w2 * z1y, z2y = w2 * z1x - w0 * z1z, z2z = w0 * z1y - w1 * z1x;
-        const float z3x = w1 * z2z - w2 * z2y, z3y = w2 * z2x - w0 * z2z, z3z = w0 * z2y - w1 * z2x;
-        const float z4x = w1 * z3z - w2 * z3y, z4y = w2 * z3x - w0 * z3z, z4z = w0 * z3y - w1 * z3x;
-        const float nrm = (z1x * z1x + z1y * z1y) + z1z * z1z;                                      // normxiz2, :235
-        const float pdt = -((z1x * z2x + z1y * z2y) + z1z * z2z);                                   // xiz_dot_xi2z, :236
-        const float ecn = ((z2x * z2x + z2y * z2y) + z2z * z2z) + 2.f * ((z1x * z3x + z1y * z3y) + z1z * z3z);  // :237
-        const float beta = ic.m2t * ((z1x * rx + z1y * ry) + z1z * rz);                             // :262
-        const float gamma = -ic.temp_coef * (nrm + 2.f * ((z2x * rx + z2y * ry) + z2z * rz));       // :264
-        const float delta = ic.p2t * (pdt - ((z3x * rx + z3y * ry) + z3z * rz));                    // :267
-        const float epsil = -ic.temp_coef * (ecn + 2.f * ((z4x * rx + z4y * ry) + z4z * rz));       // :270
-        const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
-        acc[0] += (double)(a * beta);                                                                // :275
-        acc[1] += ad * (gd + (double)(beta * beta) * 0.5);                                           // :276
-        acc[2] += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0));  // :277
-        acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
-                        (1.0 / 24.0) * (bd * bd) * (bd * bd));                                       // :278-279
+        step_accumulate(ic, step_col(ic, yg.x, yg.y, yg.z), -dx, -dy, -dz, a, acc);  // diff_xy = x - y, :260
     }
 }
 
@@ -702,8 +792,8 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
     const float4 yg = sm.colG[col];
-    const float4 yf = sm.colF[col];
-    const float yf4 = sm.colF4[col];
+    const float4 yf = sm.u.fs.colF[col];
+    const float yf4 = sm.u.fs.colF4[col];
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     const float d2c = colour_d2(xf, xg.w, yf, yf4);
@@ -727,7 +817,7 @@ struct ListSrc {
 };
 template <int KIND>
 __device__ __forceinline__ void list_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent, float t_c,
-                                          bool live, int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
+                                          int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
     const IterConsts& ic = sm.ic;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
@@ -737,15 +827,24 @@ __device__ __forceinline__ void list_body(const Smem& sm, const WarpScratch& ws,
     bool near;
     float a = kernel_a(ic, kp, d2, t_c, near);
     bool ok = a > kp.sp_thres;  // src/cvo.cpp:152
-    if (near && live) {
+    if (near) {
         const int ri = src.row_base + row, ci = src.col_base + col;
         ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
                                 __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2, a);
     }
-    ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    ok = ok && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
     a = ok ? a : 0.f;
-    const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
-    accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
+    if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
+        const float4 z1 = sm.u.ss.colZ1[col], z2 = sm.u.ss.colZ2[col];
+        StepCol c;
+        c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
+        c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
+        c.ecn = yg.w;
+        step_accumulate(ic, c, -dx, -dy, -dz, a, acc);
+    } else {
+        const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
+        accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
+    }
 }
 
 template <int KIND>
@@ -821,7 +920,7 @@ __device__ __forceinline__ void process_tile_group(const Smem& sm, WarpScratch& 
     const uint32_t maskA = prefilter_tile(sm, rr, ctA, sm.ic.d2_thres);
     const uint32_t maskB = (ctB >= 0) ? prefilter_tile(sm, rr, ctB, sm.ic.d2_thres) : 0u;
     if (__ballot_sync(0xffffffffu, (maskA | maskB) != 0) == 0) return;
-    uint32_t* q = ws.queue;
+    uint32_t* q = sm_queue(sm);
     // the queue holds one full tile pair on top of the leftovers: a (rare) group with more candidates than that
     // is pushed in two rounds (col tile A, then col tile B)
     uint32_t mA = maskA, mB = maskB;
@@ -938,7 +1037,7 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     }
     for (int b = 0; b < qn; b += 32) {  // drain the tail of the queue; idle lanes run entry (0, 0) with a = 0
         const bool live = b + lane < qn;
-        survivor_body<KIND>(sm, ws, kp, live ? ws.queue[b + lane] : 0u, live, yy_row_min, fp, acc);
+        survivor_body<KIND>(sm, ws, kp, live ? sm_queue(sm)[b + lane] : 0u, live, yy_row_min, fp, acc);
     }
     __syncwarp();
     flush_partial<KIND>(fp, acc);
@@ -994,7 +1093,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
         for (int cb = 0; cb < total_ct; cb += kColTiles) {
             const int nct = min(kColTiles, total_ct - cb);
             __syncthreads();  // everyone is done with the previous column chunk / unit slots
-            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
             while (true) {
@@ -1085,7 +1184,7 @@ struct RowTile {
     RowRegs rr;
     float lx, ly, lz, hx, hy, hz;  // bounding box of the valid rows
 };
-template <bool NEED_FEAT, bool NEED_ORIG>
+template <bool NEED_FEAT, bool NEED_ORIG, bool NEED_BOX>
 __device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws, const CloudDev& rows, bool row_tf, int tile) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
@@ -1110,8 +1209,12 @@ __device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws
     if (NEED_FEAT) ws.rowF[lane] = xf;
     if (NEED_ORIG) ws.rowOrig[lane] = orig;
     RowTile rt;
-    rt.lx = warp_min(valid ? xg.x : inf); rt.ly = warp_min(valid ? xg.y : inf); rt.lz = warp_min(valid ? xg.z : inf);
-    rt.hx = warp_max(valid ? xg.x : -inf); rt.hy = warp_max(valid ? xg.y : -inf); rt.hz = warp_max(valid ? xg.z : -inf);
+    if (NEED_BOX) {
+        rt.lx = warp_min(valid ? xg.x : inf); rt.ly = warp_min(valid ? xg.y : inf); rt.lz = warp_min(valid ? xg.z : inf);
+        rt.hx = warp_max(valid ? xg.x : -inf); rt.hy = warp_max(valid ? xg.y : -inf); rt.hz = warp_max(valid ? xg.z : -inf);
+    } else {
+        rt.lx = rt.ly = rt.lz = rt.hx = rt.hy = rt.hz = 0.f;
+    }
     __syncwarp();
     rt.rr.m2x = -2.f * xg.x; rt.rr.m2y = -2.f * xg.y; rt.rr.m2z = -2.f * xg.z;
     rt.rr.x2 = fmaf(xg.z, xg.z, fmaf(xg.y, xg.y, xg.x * xg.x));
@@ -1135,7 +1238,7 @@ __device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile
 // Build sweep 1: upper bound of the unit's entry count = its candidates inside the build ball (prefilter only).
 __device__ __forceinline__ int build_unit_bound(const Smem& sm, WarpScratch& ws, const CloudDev& rows, bool row_tf, int tile,
                                                 int ct_begin, int ct_end, float thr_build) {
-    const RowTile rt = load_row_tile<false, false>(sm, ws, rows, row_tf, tile);
+    const RowTile rt = load_row_tile<false, false, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = thr_build * 1.0001f;  // boxes are conservative; keep rounding on the safe side
     int cnt = 0;
     for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
@@ -1160,8 +1263,8 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
     const float4 yg = sm.colG[col];
-    const float4 yf = sm.colF[col];
-    const float yf4 = sm.colF4[col];
+    const float4 yf = sm.u.fs.colF[col];
+    const float yf4 = sm.u.fs.colF4[col];
     const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
     const float d2c = colour_d2(xf, xg.w, yf, yf4);
     const float t_c = __fmul_rn(d2c, kp.c2);
@@ -1177,9 +1280,9 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
                                                 const CloudDev& rows, bool row_tf, int tile, int ct_begin, int ct_end,
                                                 uint2* out) {
     const int lane = threadIdx.x & 31;
-    const RowTile rt = load_row_tile<true, false>(sm, ws, rows, row_tf, tile);
+    const RowTile rt = load_row_tile<true, false, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = L.thr_build * 1.0001f;
-    uint32_t* q = ws.queue;
+    uint32_t* q = sm_queue(sm);
     int qn = 0, cursor = 0;
     for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
         uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
@@ -1201,6 +1304,10 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
         }
     }
     if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, out, cursor);
+    // pad to a whole 32-entry block with entries that never pass: (row 0, col 0) are real points and
+    // t_c = +inf gives a = 0, so the passes can run without per-entry guards
+    const int pad = (-cursor) & (kTile - 1);
+    if (lane < pad) __stcg(out + cursor + lane, make_uint2(0u, 0x7f800000u));
     __syncwarp();
     return cursor;
 }
@@ -1227,7 +1334,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
         for (int cb = 0; cb < pg.total_ct && !stop; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
             __syncthreads();
-            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) {
                 sm.next_unit = 0;
                 if (round >= kMaxListRounds) sm.lst_ovf = 1;
@@ -1248,10 +1355,10 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 if (lane == 0) sm.unitCnt[u] = c;
             }
             __syncthreads();
-            if (warp == 0) {  // exclusive scan of the unit bounds (rounded up to 32-byte groups), in unit order
+            if (warp == 0) {  // exclusive scan of the unit bounds (rounded up to whole 32-entry blocks), in unit order
                 int base = sm.lst_used;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
-                    const int c = (i0 + lane < nunits) ? ((sm.unitCnt[i0 + lane] + 3) & ~3) : 0;
+                    const int c = (i0 + lane < nunits) ? ((sm.unitCnt[i0 + lane] + kTile - 1) & ~(kTile - 1)) : 0;
                     int excl, total;
                     warp_scan_count(c, lane, excl, total);
                     if (i0 + lane < nunits) sm.unitOff[i0 + lane] = base + excl;
@@ -1301,48 +1408,60 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     __syncthreads();
 }
 
-// Pass work unit over a neighbour list: the unit's entries are read 128 at a time (two 16-byte loads per lane,
-// coalesced, L2; the next trip's loads are in flight behind this trip's arithmetic) and every lane runs the
-// branch-free list body on its four entries.
+// Pass work unit over a neighbour list.  The build padded the unit to whole 32-entry blocks with entries that can
+// never pass (t_c = +inf), so the loop needs no per-entry guards: a trip is up to four blocks (one 8-byte load per
+// lane and block, coalesced, L2), the next trip's loads are in flight behind this trip's arithmetic, and every lane
+// runs the branch-free list body on its entries, two at a time.
 template <int KIND>
 __device__ __forceinline__ void consume_unit(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, int tile,
                                              const ListSrc& src, const uint2* ent, int cnt, int slot, int yy_row_min) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint4* ent4 = reinterpret_cast<const uint4*>(ent);  // two entries per 16 bytes
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    // lane's entries of a trip starting at entry b: b + 2 lane + {0, 1} and b + 64 + 2 lane + {0, 1}
-    uint4 curA = (2 * lane < cnt) ? __ldcg(ent4 + lane) : zero4;
-    uint4 curB = (64 + 2 * lane < cnt) ? __ldcg(ent4 + 32 + lane) : zero4;
+    const int nblk = (cnt + kTile - 1) / kTile;
+    const uint2* e = ent + lane;
+    uint2 n0 = __ldcg(e), n1 = n0, n2 = n0, n3 = n0;
+    if (nblk > 1) n1 = __ldcg(e + kTile);
+    if (nblk > 2) n2 = __ldcg(e + 2 * kTile);
+    if (nblk > 3) n3 = __ldcg(e + 3 * kTile);
     WarpScratch& ws = sm.ws[warp];
-    load_row_tile<false, KIND == PASS_YY>(sm, ws, rows, row_tf, tile);
+    load_row_tile<false, KIND == PASS_YY, false>(sm, ws, rows, row_tf, tile);
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int b = 0; b < cnt; b += 4 * kTile) {
-        const uint4 cA = curA, cB = curB;
-        const int nb = b + 4 * kTile + 2 * lane;
-        curA = (nb < cnt) ? __ldcg(ent4 + (nb >> 1)) : zero4;
-        curB = (nb + 64 < cnt) ? __ldcg(ent4 + ((nb + 64) >> 1)) : zero4;
+    for (int b = 0; b < nblk; b += 4) {
+        const uint2 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        const int left = nblk - b;  // blocks of this trip: min(left, 4); all conditions below are warp-uniform
+        e += 4 * kTile;
+        if (left > 4) n0 = __ldcg(e);
+        if (left > 5) n1 = __ldcg(e + kTile);
+        if (left > 6) n2 = __ldcg(e + 2 * kTile);
+        if (left > 7) n3 = __ldcg(e + 3 * kTile);
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {  // two bodies interleaved at a time (register budget: 128 at 512 threads)
-            const uint4 c = h ? cB : cA;
-            const int ia = b + 64 * h + 2 * lane;
-            const bool la = ia < cnt, lb = ia + 1 < cnt;
-            // past the unit's end the 16-byte group holds stale bits: run entry (0, 0) -- real, finite points -- with a = 0
-            list_body<KIND>(sm, ws, kp, la ? c.x : 0u, __uint_as_float(c.y), la, yy_row_min, src, fp, acc);
-            list_body<KIND>(sm, ws, kp, lb ? c.z : 0u, __uint_as_float(c.w), lb, yy_row_min, src, fp, acc);
+        for (int h = 0; h < 4 && h < left; h += 2) {  // two bodies interleaved at a time (register budget)
+            const uint2 ea = h ? c2 : c0, eb = h ? c3 : c1;
+            if (h + 1 < left) {
+                list_body<KIND>(sm, ws, kp, ea.x, __uint_as_float(ea.y), yy_row_min, src, fp, acc);
+                list_body<KIND>(sm, ws, kp, eb.x, __uint_as_float(eb.y), yy_row_min, src, fp, acc);
+            } else {
+                list_body<KIND>(sm, ws, kp, ea.x, __uint_as_float(ea.y), yy_row_min, src, fp, acc);
+            }
         }
     }
     __syncwarp();
     flush_partial<KIND>(fp, acc);
+    warp_sum_multi<NV>(acc, lane);
+    if (NV >= 8) {
+        if ((lane & 3) == 0) sm.unitPart[slot][multi_value_index(lane)] += acc[0];
+        if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const double t = warp_sum(acc[i]);
-        if (lane == 0) sm.unitPart[slot][i] += t;
+            for (int i = 8; i < NV; ++i) sm.unitPart[slot][i] += acc[i];
+        }
+    } else if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm.unitPart[slot][i] += acc[i];
     }
 }
 
@@ -1365,7 +1484,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
         for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
             __syncthreads();
-            stage_tiles(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            stage_tiles<(KIND == PASS_STEP) ? STAGE_STEP : STAGE_GEOM>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
             src.col_base = cb * kTile;
