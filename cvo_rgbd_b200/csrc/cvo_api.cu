@@ -51,7 +51,6 @@ struct cvo_b200_ctx {
 
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
     uint2* d_list_entries = nullptr;
-    uint2* d_list_units = nullptr;
     unsigned list_cap = 0;
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
@@ -206,14 +205,10 @@ void ensure_list_scratch(cvo_b200_ctx* ctx) {
     unsigned long long cap = (unsigned long long)ctx->max_points * ctx->max_points / 8;
     if (cap < (1ull << 18)) cap = 1ull << 18;
     if (cap > (1ull << 21)) cap = 1ull << 21;
-    const size_t areas = (size_t)ctx->num_sms * LIST_KINDS;
-    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_list_units, areas * kMaxListUnits * sizeof(uint2)) != cudaSuccess) {
+    const size_t areas = (size_t)ctx->num_sms * (LIST_KINDS + 1);  // three lists + the build staging per CTA
+    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();
-        cudaFree(ctx->d_list_entries);
-        cudaFree(ctx->d_list_units);
         ctx->d_list_entries = nullptr;
-        ctx->d_list_units = nullptr;
         ctx->lists_alloc_failed = true;
         return;
     }
@@ -273,7 +268,6 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     ensure_list_scratch(ctx);
     const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr;
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
-    args.list_units = lists ? ctx->d_list_units : nullptr;
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
     CK(cudaMemcpyAsync(ctx->d_pairs, ctx->h_pairs, sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -451,7 +445,6 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFreeHost(ctx->h_jobs);
     cudaFree(ctx->d_batch_raw);
     cudaFree(ctx->d_list_entries);
-    cudaFree(ctx->d_list_units);
     cudaFreeHost(ctx->h_inner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -44,7 +44,6 @@ constexpr int kColTiles = kColChunk / kTile;
 constexpr int kMaxCluster = 16;
 constexpr int kNumAcc = 16;
 constexpr int kMaxUnits = 256;                  // work units (row tile x column segment) per scheduling round
-static_assert(kMaxUnits == 256, "kMaxListUnits assumes 256 units per round; unit records pack the unit in 8 bits");
 static_assert(kThreads >= 32 + kMaxUnits, "build_list ranks one unit per thread beside the scanning warp");
 constexpr int kUnitAcc = 9;                     // widest per-unit partial record (flow: omega, v, sum, nnz, dl)
 constexpr int kQueueCap = 64 + kTile * kTile;   // leftovers (< 32 * CVO_BODY_ILP) + one full tile pair
@@ -65,8 +64,8 @@ enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INN
 // column cloud by more than the skin (or ell changed the radius).  Only INDICES are stored: the strict ell-ball
 // test, the colour gate and the kernel value are still evaluated on the fly in every pass, A never exists.
 enum ListKind { LIST_XY = 0, LIST_XX = 1, LIST_YY = 2, LIST_KINDS = 3 };
-constexpr int kMaxListRounds = 12;                       // (row round, column chunk) combinations of one pass
-constexpr int kMaxListUnits = kMaxListRounds * 256;      // unit table entries per list
+constexpr int kMaxListRounds = 36;  // (row round, column chunk) combinations of one pass: 6 x 6 chunks of 3072 points
+constexpr int kListTrip = 128;      // entries one warp handles per trip of a list pass; rounds are padded to it
 
 // accumulator slots of the flow exchange
 enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZXX = 9, ACC_SXX = 10,
@@ -138,8 +137,9 @@ struct WarpScratch {
     int rowOrig[kTile];          // original row indices (PASS_YY only: quirk Q1 is defined on them)
 };
 
-// What sits beside the column geometry depends on the pass: on-the-fly passes and list builds need the column
-// features and the warps' survivor queues; the STEP pass over a list needs the per-column step-size terms instead.
+// What sits beside the column geometry depends on the pass.  On-the-fly passes and list builds need the column
+// features, the warps' survivor queues and row tiles, and the per-unit partial sums; a pass over a neighbour list
+// needs this CTA's rows (geometry only) and, for the STEP pass, the per-column step-size terms.
 struct FeatStage {
     float4 colF[kColChunk];             // {f0, f1, f2, f3}
     float colF4[kColChunk];             // f4
@@ -148,6 +148,26 @@ struct FeatStage {
 struct StepStage {
     float4 colZ1[kColChunk];  // {xi z + v, |xi z + v|^2}                       (src/cvo.cpp:226-228,235)
     float4 colZ2[kColChunk];  // {xi^2 z + xi v, -(xi z + v).(xi^2 z + xi v)}   (src/cvo.cpp:229-230,236)
+};
+struct BuildUnits {  // neighbour-list build, per unit of the round:
+    int cnt[kMaxUnits];             // entry bound (prefilter candidates)
+    int off[kMaxUnits];             // offset of its staging region
+    int act[kMaxUnits];             // entries it really has
+    int pos[kMaxUnits];             // their position in the round's flat list
+    unsigned short ord[kMaxUnits];  // the unit at rank k when sorted by descending bound
+};
+struct OnTheFlyStage {
+    FeatStage fs;
+    WarpScratch ws[kWarps];
+    union {
+        double unitPart[kMaxUnits][kUnitAcc];  // on-the-fly pass: one fixed slot per work unit => scheduling-independent sums
+        BuildUnits bu;                         // list build
+    };
+};
+struct ListStage {
+    float4 rowG[kColChunk];  // {x, y, z, bits of the original index} of the round's (transformed) rows
+    StepStage ss;
+    double warpTot[kWarps][kNumAcc];  // one total per warp, summed in warp order
 };
 
 struct ListState {
@@ -162,8 +182,8 @@ struct ListState {
 };
 
 struct ListRef {
-    uint2* entries;  // (row << 12 | col, bits of the colour exponent t_c)
-    uint2* units;    // (offset, count | unit << 24) of every work unit, in processing order
+    uint2* entries;  // the flat list: (row << 12 | col within the round's chunks, bits of the colour exponent t_c)
+    uint2* staging;  // build scratch of the CTA (shared by its three lists): per-unit regions before compaction
     unsigned cap;
 };
 
@@ -171,17 +191,14 @@ struct Smem {
     float4 colG[kColChunk];   // {x, y, z, w} of the staged (transformed) column points; w = |c|^2 for the prefilter,
                               // or the step-size term of src/cvo.cpp:237 in the STEP pass over a list
     union {
-        FeatStage fs;
-        StepStage ss;
+        OnTheFlyStage of;
+        ListStage ls;
     } u;
     float colBox[kColTiles][8];  // [0..2] lo, [3..5] hi, [6] max |c|^2
-    WarpScratch ws[kWarps];
-    double unitPart[kMaxUnits][kUnitAcc];  // one fixed slot per work unit => scheduling-independent sums
     double blockTot[kNumAcc];
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
-    int unitCnt[kMaxUnits];   // neighbour-list build: entries per unit, their offsets, and the processing order
-    int unitOff[kMaxUnits];
-    unsigned short unitOrd[kMaxUnits];   // the unit at rank k when sorted by descending entry bound
+    uint2 lround[LIST_KINDS][kMaxListRounds];  // (offset, entries) of every round of a list; entries % kListTrip == 0
+    int lst_base;
     float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
     float ybox[6];            // bounding box of the moving cloud, original coordinates
     ListState lst[LIST_KINDS];
@@ -197,6 +214,10 @@ struct Smem {
     unsigned long long tma_bar;  // mbarrier the TMA bulk copies of a column chunk complete on
 };
 
+#ifdef CVO_PRINT_SMEM
+template <size_t N> struct SmemSizeIs;
+SmemSizeIs<sizeof(Smem)> smem_size_probe;
+#endif
 static_assert(sizeof(Smem) <= 227 * 1024, "Smem must fit the 227 KB per-CTA shared memory of sm_100");
 
 struct AlignArgs {
@@ -207,9 +228,8 @@ struct AlignArgs {
     cvo_b200_iter_rec* trace;  // records of pair 0 only (align_trace / eval), or nullptr
     int trace_cap;
     KParams kp;
-    // neighbour-list scratch: [gridDim.x][LIST_KINDS] areas of list_cap entries / kMaxListUnits unit records
+    // neighbour-list scratch: [gridDim.x][LIST_KINDS + 1] areas of list_cap entries (three lists + build staging)
     uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
-    uint2* list_units;
     unsigned list_cap;
     float list_skin;
 };
@@ -634,11 +654,17 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
                                             float sentinel, uint32_t& tma_phase) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
+    if (MODE == STAGE_FULL) {
+        // the feature stage shares its shared memory with the list passes' row / step stages, which are written
+        // with ordinary stores: order those before the bulk copies of the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
     if (MODE == STAGE_FULL && threadIdx.x == 0) {
         const uint32_t bytes_f = (uint32_t)(ntiles * kTile) * 16u, bytes_f4 = (uint32_t)(ntiles * kTile) * 4u;
         mbar_expect_tx(&sm.tma_bar, bytes_f + bytes_f4);
-        tma_bulk_g2s(sm.u.fs.colF, c.f + base, bytes_f, &sm.tma_bar);
-        tma_bulk_g2s(sm.u.fs.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
+        tma_bulk_g2s(sm.u.of.fs.colF, c.f + base, bytes_f, &sm.tma_bar);
+        tma_bulk_g2s(sm.u.of.fs.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
     }
     const float* tf12 = sm.ic.tf;
     for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
@@ -666,8 +692,8 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
         } else {
             const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
             sm.colG[i] = make_float4(g.x, g.y, g.z, sc.ecn);
-            sm.u.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
-            sm.u.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
+            sm.u.ls.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
+            sm.u.ls.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
         }
     }
     if (MODE == STAGE_FULL) {
@@ -721,7 +747,7 @@ __device__ __forceinline__ float kernel_a(const IterConsts& ic, const KParams& k
 }
 
 __device__ __forceinline__ uint32_t* sm_queue(const Smem& sm) {
-    return const_cast<uint32_t*>(sm.u.fs.queue[threadIdx.x >> 5]);
+    return const_cast<uint32_t*>(sm.u.of.fs.queue[threadIdx.x >> 5]);
 }
 
 // Per-lane f32 partial sums of one work unit (a few dozen terms each, like the reference's per-row f32 sums,
@@ -792,8 +818,8 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
     const float4 yg = sm.colG[col];
-    const float4 yf = sm.u.fs.colF[col];
-    const float yf4 = sm.u.fs.colF4[col];
+    const float4 yf = sm.u.of.fs.colF[col];
+    const float yf4 = sm.u.of.fs.colF4[col];
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     const float d2c = colour_d2(xf, xg.w, yf, yf4);
@@ -816,11 +842,11 @@ struct ListSrc {
     int row_base, col_base;  // global index of the unit's row 0 / of the staged chunk's column 0
 };
 template <int KIND>
-__device__ __forceinline__ void list_body(const Smem& sm, const WarpScratch& ws, const KParams& kp, uint32_t ent, float t_c,
-                                          int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
+__device__ __forceinline__ void list_body(const Smem& sm, const KParams& kp, uint32_t ent, float t_c, int yy_row_min,
+                                          const ListSrc& src, FlowPartial& fp, double* acc) {
     const IterConsts& ic = sm.ic;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
-    const float4 xg = ws.rowG[row];
+    const float4 xg = sm.u.ls.rowG[row];
     const float4 yg = sm.colG[col];
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
@@ -835,14 +861,15 @@ __device__ __forceinline__ void list_body(const Smem& sm, const WarpScratch& ws,
     ok = ok && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
     a = ok ? a : 0.f;
     if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
-        const float4 z1 = sm.u.ss.colZ1[col], z2 = sm.u.ss.colZ2[col];
+        const float4 z1 = sm.u.ls.ss.colZ1[col], z2 = sm.u.ls.ss.colZ2[col];
         StepCol c;
         c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
         c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
         c.ecn = yg.w;
         step_accumulate(ic, c, -dx, -dy, -dz, a, acc);
     } else {
-        const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
+        // quirk Q1 is defined on the ORIGINAL row index, carried in the w lane of the staged row
+        const bool q1 = (KIND == PASS_YY) ? (__float_as_int(xg.w) >= yy_row_min) : true;
         accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
     }
 }
@@ -975,7 +1002,7 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
                                              int ct_begin, int ct_end, int slot, bool first_chunk, int yy_row_min) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = sm.ws[warp];
+    WarpScratch& ws = sm.u.of.ws[warp];
     const float inf = __int_as_float(0x7f800000);
     // stage the row tile: registers for the mask phase, warp-private shared memory for the survivor body
     const int p = tile * kTile + lane;
@@ -1045,8 +1072,8 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     for (int i = 0; i < NV; ++i) {
         const double t = warp_sum(acc[i]);
         if (lane == 0) {
-            if (first_chunk) sm.unitPart[slot][i] = t;
-            else sm.unitPart[slot][i] += t;
+            if (first_chunk) sm.u.of.unitPart[slot][i] = t;
+            else sm.u.of.unitPart[slot][i] += t;
         }
     }
 }
@@ -1071,7 +1098,7 @@ __device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, 
         S = max(1, min(min(S, s_max), kMaxUnits));
     }
     pg.S = S;
-    pg.tiles_per_round = max(1, kMaxUnits / S);
+    pg.tiles_per_round = max(1, min(kMaxUnits / S, kColTiles));  // a round's rows fit the list passes' row stage
     return pg;
 }
 
@@ -1109,7 +1136,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
         __syncthreads();
         if (threadIdx.x < NV) {  // fixed-order sum over the unit slots
             double t = 0.0;
-            for (int u = 0; u < nunits; ++u) t += sm.unitPart[u][threadIdx.x];
+            for (int u = 0; u < nunits; ++u) t += sm.u.of.unitPart[u][threadIdx.x];
             sm.blockTot[threadIdx.x] += t;
         }
     }
@@ -1255,16 +1282,17 @@ __device__ __forceinline__ int build_unit_bound(const Smem& sm, WarpScratch& ws,
 }
 
 // Build sweep 2, per candidate: exact distance at the build pose, colour gate and colour exponent (pose-independent,
-// src/cvo.cpp:145-148), and the pair's own radius + slack.  Survivors are appended to the unit's list.
+// src/cvo.cpp:145-148), and the pair's own radius + slack.  Survivors are appended to the unit's staging region with
+// their row index made relative to the round (`row_off` = 32 * the unit's row tile within the round).
 __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
-                                           uint32_t ent, bool live, uint2* out, int& cursor) {
+                                           uint32_t ent, bool live, uint32_t row_off, uint2* out, int& cursor) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
     const float4 yg = sm.colG[col];
-    const float4 yf = sm.u.fs.colF[col];
-    const float yf4 = sm.u.fs.colF4[col];
+    const float4 yf = sm.u.of.fs.colF[col];
+    const float yf4 = sm.u.of.fs.colF4[col];
     const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
     const float d2c = colour_d2(xf, xg.w, yf, yf4);
     const float t_c = __fmul_rn(d2c, kp.c2);
@@ -1272,13 +1300,13 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + L.s_build;
     const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    if (keep) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent, __float_as_uint(t_c)));
+    if (keep) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent + (row_off << 12), __float_as_uint(t_c)));
     cursor += __popc(b);
 }
 
 __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
-                                                const CloudDev& rows, bool row_tf, int tile, int ct_begin, int ct_end,
-                                                uint2* out) {
+                                                const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int ct_begin,
+                                                int ct_end, uint2* out) {
     const int lane = threadIdx.x & 31;
     const RowTile rt = load_row_tile<true, false, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = L.thr_build * 1.0001f;
@@ -1298,30 +1326,38 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
             __syncwarp();
             while (qn >= 32) {
                 qn -= 32;
-                build_eval(sm, ws, kp, L, q[qn + lane], true, out, cursor);
+                build_eval(sm, ws, kp, L, q[qn + lane], true, row_off, out, cursor);
             }
             __syncwarp();
         }
     }
-    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, out, cursor);
-    // pad to a whole 32-entry block with entries that never pass: (row 0, col 0) are real points and
-    // t_c = +inf gives a = 0, so the passes can run without per-entry guards
-    const int pad = (-cursor) & (kTile - 1);
-    if (lane < pad) __stcg(out + cursor + lane, make_uint2(0u, 0x7f800000u));
+    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, out, cursor);
     __syncwarp();
     return cursor;
 }
 
-// (Re)builds one neighbour list for this CTA's share of the row tiles.  Per (row round, column chunk): sweep 1
-// bounds every unit's entry count by its prefilter candidates, an exclusive scan of the bounds in unit order lays
-// the units out (a pure function of the inputs, no atomics), sweep 2 evaluates the candidates and writes the
-// entries.  On return sm.lst[kind].valid is 1, or -1 if the scratch area was too small.
+// pulls the next work unit of a sweep from the CTA's shared counter (warp-uniform result)
+__device__ __forceinline__ int next_unit(Smem& sm) {
+    int u = 0;
+    if ((threadIdx.x & 31) == 0) u = atomicAdd(&sm.next_unit, 1);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+
+// (Re)builds one neighbour list for this CTA's share of the row tiles.  Per round (row chunk x column chunk):
+//   sweep 1  bounds every unit's entry count by its prefilter candidates; an exclusive scan lays out the units'
+//            staging regions;
+//   sweep 2  evaluates the candidates and writes each unit's entries to its staging region;
+//   compact  an exclusive scan of the actual counts in unit order gives every unit its place in the round's FLAT
+//            list, the entries are copied there and the round is padded to a whole trip with entries that can never
+//            pass ((row 0, col 0) are real points, t_c = +inf gives a = 0).
+// The layout is a pure function of the inputs (no atomics decide where anything goes).  On return
+// sm.lst[kind].valid is 1, or -1 if a scratch area was too small.
 __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
                            int rank, int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     const ListState& L = sm.lst[kind];
-    WarpScratch& ws = sm.ws[warp];
+    WarpScratch& ws = sm.u.of.ws[warp];
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
@@ -1345,61 +1381,94 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 break;
             }
             while (true) {  // sweep 1: bound
-                int u = 0;
-                if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
-                u = __shfl_sync(0xffffffffu, u, 0);
+                const int u = next_unit(sm);
                 if (u >= nunits) break;
                 const int t = u / pg.S, seg = u - t * pg.S;
                 const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
                 const int c = build_unit_bound(sm, ws, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, L.thr_build);
-                if (lane == 0) sm.unitCnt[u] = c;
+                if (lane == 0) sm.u.of.bu.cnt[u] = c;
             }
             __syncthreads();
-            if (warp == 0) {  // exclusive scan of the unit bounds (rounded up to whole 32-entry blocks), in unit order
-                int base = sm.lst_used;
+            if (warp == 0) {  // staging regions: exclusive scan of the bounds in unit order
+                int base = 0;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
-                    const int c = (i0 + lane < nunits) ? ((sm.unitCnt[i0 + lane] + kTile - 1) & ~(kTile - 1)) : 0;
+                    const int c = (i0 + lane < nunits) ? sm.u.of.bu.cnt[i0 + lane] : 0;
                     int excl, total;
                     warp_scan_count(c, lane, excl, total);
-                    if (i0 + lane < nunits) sm.unitOff[i0 + lane] = base + excl;
+                    if (i0 + lane < nunits) sm.u.of.bu.off[i0 + lane] = base + excl;
                     base += total;
                 }
                 if (lane == 0) {
                     if ((unsigned)base > lr.cap) sm.lst_ovf = 1;
-                    else sm.lst_used = base;
                     sm.next_unit = 0;
                 }
             } else if (threadIdx.x - 32 < nunits) {
                 // longest-processing-time order: rank the units by descending bound (ties by unit index) so that
-                // the passes hand out the big units first and the small ones fill the tail
-                const int u = threadIdx.x - 32, cu = sm.unitCnt[u];
+                // sweep 2 hands out the big units first and the small ones fill the tail
+                const int u = threadIdx.x - 32, cu = sm.u.of.bu.cnt[u];
                 int rk = 0;
                 for (int v = 0; v < nunits; ++v) {
-                    const int cv = sm.unitCnt[v];
+                    const int cv = sm.u.of.bu.cnt[v];
                     rk += (cv > cu || (cv == cu && v < u)) ? 1 : 0;
                 }
-                sm.unitOrd[rk] = (unsigned short)u;
+                sm.u.of.bu.ord[rk] = (unsigned short)u;
             }
             __syncthreads();
             if (sm.lst_ovf) {
                 stop = true;
                 break;
             }
-            while (true) {  // sweep 2: evaluate and write
-                int k = 0;
-                if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
-                k = __shfl_sync(0xffffffffu, k, 0);
+            while (true) {  // sweep 2: evaluate and write to the staging regions
+                const int k = next_unit(sm);
                 if (k >= nunits) break;
-                const int u = sm.unitOrd[k];
-                const int off = sm.unitOff[u];
+                const int u = sm.u.of.bu.ord[k];
                 int c = 0;
-                if (sm.unitCnt[u] > 0) {
+                if (sm.u.of.bu.cnt[u] > 0) {
                     const int t = u / pg.S, seg = u - t * pg.S;
                     const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
-                    c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, lr.entries + off);
+                    c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile), c_begin, c_end,
+                                         lr.staging + sm.u.of.bu.off[u]);
                 }
-                if (lane == 0)  // record k of the round: (offset, count | unit << 24)
-                    __stcg(&lr.units[round * kMaxUnits + k], make_uint2((unsigned)off, (unsigned)c | ((unsigned)u << 24)));
+                if (lane == 0) sm.u.of.bu.act[u] = c;
+            }
+            __syncthreads();
+            if (warp == 0) {  // places in the flat list: exclusive scan of the actual counts in unit order
+                int base = 0;
+                for (int i0 = 0; i0 < nunits; i0 += 32) {
+                    const int c = (i0 + lane < nunits) ? sm.u.of.bu.act[i0 + lane] : 0;
+                    int excl, total;
+                    warp_scan_count(c, lane, excl, total);
+                    if (i0 + lane < nunits) sm.u.of.bu.pos[i0 + lane] = base + excl;
+                    base += total;
+                }
+                const int padded = (base + kListTrip - 1) / kListTrip * kListTrip;
+                const int at = sm.lst_used;
+                const bool fits = (unsigned)(at + padded) <= lr.cap;
+                if (fits)
+                    for (int i = base + lane; i < padded; i += 32) __stcg(lr.entries + at + i, make_uint2(0u, 0x7f800000u));
+                if (lane == 0) {
+                    if (fits) {
+                        sm.lround[kind][round] = make_uint2((unsigned)at, (unsigned)padded);
+                        sm.lst_base = at;
+                        sm.lst_used = at + padded;
+                    } else {
+                        sm.lst_ovf = 1;
+                    }
+                    sm.next_unit = 0;
+                }
+            }
+            __syncthreads();
+            if (sm.lst_ovf) {
+                stop = true;
+                break;
+            }
+            while (true) {  // compaction: staging regions -> flat list
+                const int u = next_unit(sm);
+                if (u >= nunits) break;
+                const uint2* src = lr.staging + sm.u.of.bu.off[u];
+                uint2* dst = lr.entries + sm.lst_base + sm.u.of.bu.pos[u];
+                const int c = sm.u.of.bu.act[u];
+                for (int i = lane; i < c; i += 32) __stcg(dst + i, __ldcg(src + i));
             }
         }
     }
@@ -1408,106 +1477,98 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     __syncthreads();
 }
 
-// Pass work unit over a neighbour list.  The build padded the unit to whole 32-entry blocks with entries that can
-// never pass (t_c = +inf), so the loop needs no per-entry guards: a trip is up to four blocks (one 8-byte load per
-// lane and block, coalesced, L2), the next trip's loads are in flight behind this trip's arithmetic, and every lane
-// runs the branch-free list body on its entries, two at a time.
+// Stages this CTA's rows [first, first + n) of a packed cloud for a pass over a list: geometry only (transformed
+// if the rows are the moving cloud), the original index in the w lane; rows past the cloud's end are far away.
+__device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int first, int n, bool tf) {
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const int p = first + i;
+        float4 g;
+        if (p < c.n) {
+            g = __ldg(c.g + p);
+            if (tf) apply_tf(sm.ic.tf, g.x, g.y, g.z);
+        } else {
+            g = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, __int_as_float(-1));
+        }
+        sm.u.ls.rowG[i] = g;
+    }
+}
+
+// One all-pairs pass over a valid neighbour list.  Rows and columns of the round are staged once; the round's flat
+// list is then dealt to the warps a trip (kListTrip entries: four coalesced 8-byte loads per lane, the next trip's
+// loads in flight behind this trip's arithmetic) at a time, round-robin, so every warp does the same amount of
+// branch-free work and there is no per-unit overhead.  Per-lane f32 partials are promoted to f64 every few trips
+// (src/cvo.cpp:197-203); the warp totals are summed in warp order: bit-deterministic.
 template <int KIND>
-__device__ __forceinline__ void consume_unit(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, int tile,
-                                             const ListSrc& src, const uint2* ent, int cnt, int slot, int yy_row_min) {
+__device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
+                              bool col_tf, int rank, int G, int yy_row_min, uint32_t& tma_phase, int kind, const ListRef& lr) {
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nblk = (cnt + kTile - 1) / kTile;
-    const uint2* e = ent + lane;
-    uint2 n0 = __ldcg(e), n1 = n0, n2 = n0, n3 = n0;
-    if (nblk > 1) n1 = __ldcg(e + kTile);
-    if (nblk > 2) n2 = __ldcg(e + 2 * kTile);
-    if (nblk > 3) n3 = __ldcg(e + 3 * kTile);
-    WarpScratch& ws = sm.ws[warp];
-    load_row_tile<false, KIND == PASS_YY, false>(sm, ws, rows, row_tf, tile);
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    ListSrc src;
+    src.rows = &rows;
+    src.cols = &cols;
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int b = 0; b < nblk; b += 4) {
-        const uint2 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-        const int left = nblk - b;  // blocks of this trip: min(left, 4); all conditions below are warp-uniform
-        e += 4 * kTile;
-        if (left > 4) n0 = __ldcg(e);
-        if (left > 5) n1 = __ldcg(e + kTile);
-        if (left > 6) n2 = __ldcg(e + 2 * kTile);
-        if (left > 7) n3 = __ldcg(e + 3 * kTile);
-#pragma unroll 1
-        for (int h = 0; h < 4 && h < left; h += 2) {  // two bodies interleaved at a time (register budget)
-            const uint2 ea = h ? c2 : c0, eb = h ? c3 : c1;
-            if (h + 1 < left) {
-                list_body<KIND>(sm, ws, kp, ea.x, __uint_as_float(ea.y), yy_row_min, src, fp, acc);
-                list_body<KIND>(sm, ws, kp, eb.x, __uint_as_float(eb.y), yy_row_min, src, fp, acc);
-            } else {
-                list_body<KIND>(sm, ws, kp, ea.x, __uint_as_float(ea.y), yy_row_min, src, fp, acc);
-            }
-        }
-    }
-    __syncwarp();
-    flush_partial<KIND>(fp, acc);
-    warp_sum_multi<NV>(acc, lane);
-    if (NV >= 8) {
-        if ((lane & 3) == 0) sm.unitPart[slot][multi_value_index(lane)] += acc[0];
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 8; i < NV; ++i) sm.unitPart[slot][i] += acc[i];
-        }
-    } else if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) sm.unitPart[slot][i] += acc[i];
-    }
-}
-
-// run_pass over a valid neighbour list (same unit decomposition as the build; same fixed-order reductions).
-template <int KIND>
-__device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols,
-                              bool col_tf, int rank, int G, int yy_row_min, uint32_t& tma_phase, const ListRef& lr) {
-    constexpr int NV = PassTraits<KIND>::NV;
-    const int lane = threadIdx.x & 31;
-    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
-    if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
-    ListSrc src;
-    src.rows = &rows;
-    src.cols = &cols;
     int round = 0;
     for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round) {
         const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
-        const int nunits = ntile * pg.S;
-        for (int i = threadIdx.x; i < nunits * kUnitAcc; i += kThreads) (&sm.unitPart[0][0])[i] = 0.0;
         for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
-            __syncthreads();
+            __syncthreads();  // everyone is done with the previous round's stage
             stage_tiles<(KIND == PASS_STEP) ? STAGE_STEP : STAGE_GEOM>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
-            if (threadIdx.x == 0) sm.next_unit = 0;
+            if (cb == 0) stage_rows(sm, rows, (pg.t_begin + rb) * kTile, ntile * kTile, row_tf);
             __syncthreads();
+            src.row_base = (pg.t_begin + rb) * kTile;
             src.col_base = cb * kTile;
-            while (true) {
-                int k = 0;
-                if (lane == 0) k = atomicAdd(&sm.next_unit, 1);
-                k = __shfl_sync(0xffffffffu, k, 0);
-                if (k >= nunits) break;
-                const uint2 rec = __ldcg(&lr.units[round * kMaxUnits + k]);
-                const int cnt = (int)(rec.y & 0xffffffu), u = (int)(rec.y >> 24);
-                if (cnt == 0) continue;
-                const int tile = pg.t_begin + rb + u / pg.S;
-                src.row_base = tile * kTile;
-                consume_unit<KIND>(sm, kp, rows, row_tf, tile, src, lr.entries + rec.x, cnt, u, yy_row_min);
+            const uint2 rd = sm.lround[kind][round];
+            const int ntrip = (int)rd.y / kListTrip;
+            const uint2* e = lr.entries + rd.x + lane;
+            int t = warp;
+            uint2 n0 = make_uint2(0u, 0x7f800000u), n1 = n0, n2 = n0, n3 = n0;
+            if (t < ntrip) {
+                const uint2* q = e + (size_t)t * kListTrip;
+                n0 = __ldcg(q); n1 = __ldcg(q + kTile); n2 = __ldcg(q + 2 * kTile); n3 = __ldcg(q + 3 * kTile);
             }
+            int since_flush = 0;
+            for (; t < ntrip; t += kWarps) {
+                const uint2 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+                {   // the warp's next trip (clamped to its last one: always readable, never a branch)
+                    const uint2* q = e + (size_t)min(t + kWarps, ntrip - 1) * kListTrip;
+                    n0 = __ldcg(q); n1 = __ldcg(q + kTile); n2 = __ldcg(q + 2 * kTile); n3 = __ldcg(q + 3 * kTile);
+                }
+                list_body<KIND>(sm, kp, c0.x, __uint_as_float(c0.y), yy_row_min, src, fp, acc);
+                list_body<KIND>(sm, kp, c1.x, __uint_as_float(c1.y), yy_row_min, src, fp, acc);
+                list_body<KIND>(sm, kp, c2.x, __uint_as_float(c2.y), yy_row_min, src, fp, acc);
+                list_body<KIND>(sm, kp, c3.x, __uint_as_float(c3.y), yy_row_min, src, fp, acc);
+                if (++since_flush == 4) {  // <= 16 terms per f32 partial, like a short row of A
+                    flush_partial<KIND>(fp, acc);
+                    since_flush = 0;
+                }
+            }
+            flush_partial<KIND>(fp, acc);
         }
-        __syncthreads();
-        if (threadIdx.x < NV) {  // fixed-order sum over the unit slots
-            double t = 0.0;
-            for (int u = 0; u < nunits; ++u) t += sm.unitPart[u][threadIdx.x];
-            sm.blockTot[threadIdx.x] += t;
+    }
+    warp_sum_multi<NV>(acc, lane);
+    if (NV >= 8) {
+        if ((lane & 3) == 0) sm.u.ls.warpTot[warp][multi_value_index(lane)] = acc[0];
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 8; i < NV; ++i) sm.u.ls.warpTot[warp][i] = acc[i];
         }
-        __syncthreads();  // the slots are zeroed again by the next round
+    } else if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm.u.ls.warpTot[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumAcc) {  // fixed-order sum over the warps
+        double t = 0.0;
+        if (threadIdx.x < NV)
+            for (int w = 0; w < kWarps; ++w) t += sm.u.ls.warpTot[w][threadIdx.x];
+        sm.blockTot[threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -1552,9 +1613,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     ListRef lref[LIST_KINDS];
 #pragma unroll
     for (int i = 0; i < LIST_KINDS; ++i) {
-        const size_t area = (size_t)blockIdx.x * LIST_KINDS + i;
-        lref[i].entries = args.list_entries + area * args.list_cap;
-        lref[i].units = args.list_units + area * kMaxListUnits;
+        const size_t area = (size_t)blockIdx.x * (LIST_KINDS + 1);
+        lref[i].entries = args.list_entries + (area + i) * args.list_cap;
+        lref[i].staging = args.list_entries + (area + LIST_KINDS) * args.list_cap;
         lref[i].cap = args.list_cap;
     }
 
@@ -1613,18 +1674,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             if (use_lists && sm.lst[LIST_XY].need) build_list(sm, kp, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
-            if (list_xy) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, lref[LIST_XY]);
+            if (list_xy) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
                 if (use_lists && sm.lst[LIST_XX].need) build_list(sm, kp, pair.x, false, pair.x, false, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
                 if (use_lists && sm.lst[LIST_XX].valid > 0)
-                    run_pass_list<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, lref[LIST_XX]);
+                    run_pass_list<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
                 else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
                 if (use_lists && sm.lst[LIST_YY].need) build_list(sm, kp, pair.y, true, pair.y, true, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
                 if (use_lists && sm.lst[LIST_YY].valid > 0)
-                    run_pass_list<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, lref[LIST_YY]);
+                    run_pass_list<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
                 else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZYY + threadIdx.x] = sm.blockTot[threadIdx.x];
             }
@@ -1633,7 +1694,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
             // compute_step_size (src/cvo.cpp:377)
-            if (list_xy) run_pass_list<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, lref[LIST_XY]);
+            if (list_xy) run_pass_list<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
             if (threadIdx.x == 0) {

@@ -178,8 +178,8 @@ def test_batch_of_pairs_equals_one_by_one_and_warm_start_state_round_trips(gpu_c
             gpu_ctx.set_neighbor_lists(True)
         for s in range(6):
             if lists:
-                rot, tr = pose_diff(cont["transform"][s], full["transform"][s])
-                assert rot < 1e-5 and tr < 1e-5, (s, rot, tr)
+                rot, tr = pose_diff(cont["transform"][s], full["transform"][s])  # 12 unconverged iterations amplify
+                assert rot < POSE_ROT_TOL and tr < POSE_TRANS_TOL, (s, rot, tr)   # the rounding differences
             else:
                 assert np.array_equal(cont["transform"][s], full["transform"][s])
 
