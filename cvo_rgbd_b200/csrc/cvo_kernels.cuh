@@ -625,7 +625,8 @@ struct StepCol {
     float z2x, z2y, z2z, pdt;
     float ecn;
 };
-__device__ __forceinline__ StepCol step_col(const IterConsts& ic, float yx, float yy, float yz) {
+template <class IC>
+__device__ __forceinline__ StepCol step_col(const IC& ic, float yx, float yy, float yz) {
     const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
     StepCol c;
     c.z1x = (w1 * yz - w2 * yy) + ic.v[0];
@@ -708,8 +709,8 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
 // se_kernel's value and gates in the reference's own arithmetic (src/cvo.cpp:146-152): colour distance summed left
 // to right, exp() in f64 narrowed to f32, a = ck * k in f32.  Deliberately not inlined: it runs for about one
 // candidate in a million (see kernel_a) and must not cost the hot loops registers.
-__device__ __noinline__ bool kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
-                                                float4 xf, float xf4, float4 yf, float yf4, float d2, float& a) {
+__device__ __noinline__ float kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
+                                                 float4 xf, float xf4, float4 yf, float yf4, float d2) {
     const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
     float d2e = __fmul_rn(e0, e0);
     d2e = __fadd_rn(d2e, __fmul_rn(e1, e1));
@@ -719,8 +720,8 @@ __device__ __noinline__ bool kernel_value_exact(float ell, float d2c_thres, floa
     const double l = (double)ell, cl = (double)c_ell;
     const float k = (float)((double)s2 * exp(-(double)d2 / (2.0 * l * l)));
     const float ck = (float)((double)cs2 * exp(-(double)d2e / (2.0 * cl * cl)));
-    a = __fmul_rn(ck, k);
-    return (d2e < d2c_thres) && (a > sp_thres);
+    const float a = __fmul_rn(ck, k);
+    return ((d2e < d2c_thres) && (a > sp_thres)) ? a : 0.f;  // a > sp_thres > 0 when accepted
 }
 
 // (feature_x - feature_y).squaredNorm() summed left to right (src/cvo.cpp:145-146); pose-independent.
@@ -740,7 +741,8 @@ __device__ __forceinline__ float colour_d2(const float4& xf, float xf4, const fl
 // < 0.33) MUFU.EX2 is good to 2 ulp and the argument to 1 ulp; `near` flags the candidates whose a lies within a
 // few ulp of sp_thres (about one in a million): the caller re-decides those with kernel_value_exact so that the
 // gate agrees with the CPU path bit for bit.
-__device__ __forceinline__ float kernel_a(const IterConsts& ic, const KParams& kp, float d2, float t_c, bool& near) {
+template <class IC>
+__device__ __forceinline__ float kernel_a(const IC& ic, const KParams& kp, float d2, float t_c, bool& near) {
     const float a = __fmul_rn(kp.s2cs2, exp2f_approx(-fmaf(d2, ic.c1, t_c)));
     near = fabsf(a - kp.sp_thres) < kp.sp_band;
     return a;
@@ -759,8 +761,9 @@ struct FlowPartial {
 
 // One nonzero of A in compute_step_size (src/cvo.cpp:260-279): beta, gamma, delta, epsilon from the column's
 // step-size terms and r = x_i - y_j, and the f64 accumulation of B, C, D, E.
-__device__ __forceinline__ void step_accumulate(const IterConsts& ic, const StepCol& c, float rx, float ry, float rz,
-                                                float a, double* acc) {
+template <class IC>
+__device__ __forceinline__ void step_accumulate(const IC& ic, const StepCol& c, float rx, float ry, float rz, float a,
+                                                double* acc) {
     const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
     const float z3x = w1 * c.z2z - w2 * c.z2y, z3y = w2 * c.z2x - w0 * c.z2z, z3z = w0 * c.z2y - w1 * c.z2x;
     const float z4x = w1 * z3z - w2 * z3y, z4y = w2 * z3x - w0 * z3z, z4z = w0 * z3y - w1 * z3x;
@@ -778,8 +781,8 @@ __device__ __forceinline__ void step_accumulate(const IterConsts& ic, const Step
 
 // Accumulation tail of a candidate whose kernel value a is known (a = 0 for a rejected one, which then adds +0
 // terms: the bodies are BRANCH-FREE so that the compiler can interleave several of them).
-template <int KIND>
-__device__ __forceinline__ void accumulate_terms(const IterConsts& ic, const KParams& kp, const float4& xg, const float4& yg,
+template <int KIND, class IC>
+__device__ __forceinline__ void accumulate_terms(const IC& ic, const KParams& kp, const float4& xg, const float4& yg,
                                                  float dx, float dy, float dz, float a, bool ok, bool q1_row,
                                                  FlowPartial& fp, double* acc) {
     if (KIND == PASS_FLOW) {
@@ -826,7 +829,10 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
     bool near;
     float a = kernel_a(ic, kp, d2, __fmul_rn(d2c, kp.c2), near);
     bool ok = (d2c < ic.d2c_thres) && (a > kp.sp_thres);  // src/cvo.cpp:148,152
-    if (near) ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, xf, xg.w, yf, yf4, d2, a);
+    if (near) {
+        a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, xf, xg.w, yf, yf4, d2);
+        ok = a > 0.f;
+    }
     ok = ok && live && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
     a = ok ? a : 0.f;
     const bool q1 = (KIND == PASS_YY) ? (ws.rowOrig[row] >= yy_row_min) : true;
@@ -841,24 +847,38 @@ struct ListSrc {
     const CloudDev* cols;
     int row_base, col_base;  // global index of the unit's row 0 / of the staged chunk's column 0
 };
+// The per-iteration constants a list body reads, held in registers for the whole pass (IterConsts lives in shared memory).
+struct HotConsts {
+    float c1, d2_thres, inv_ell3, m2t, temp_coef, p2t;
+    float omega[3], v[3];
+};
+__device__ __forceinline__ HotConsts hot_consts(const IterConsts& ic) {
+    HotConsts h;
+    h.c1 = ic.c1; h.d2_thres = ic.d2_thres; h.inv_ell3 = ic.inv_ell3;
+    h.m2t = ic.m2t; h.temp_coef = ic.temp_coef; h.p2t = ic.p2t;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { h.omega[i] = ic.omega[i]; h.v[i] = ic.v[i]; }
+    return h;
+}
+
 template <int KIND>
-__device__ __forceinline__ void list_body(const Smem& sm, const KParams& kp, uint32_t ent, float t_c, int yy_row_min,
-                                          const ListSrc& src, FlowPartial& fp, double* acc) {
-    const IterConsts& ic = sm.ic;
+__device__ __forceinline__ void list_body(const Smem& sm, const HotConsts& hc, const KParams& kp, uint32_t ent, float t_c,
+                                          int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = sm.u.ls.rowG[row];
     const float4 yg = sm.colG[col];
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     bool near;
-    float a = kernel_a(ic, kp, d2, t_c, near);
-    bool ok = a > kp.sp_thres;  // src/cvo.cpp:152
+    float a = kernel_a(hc, kp, d2, t_c, near);
     if (near) {
+        const IterConsts& ic = sm.ic;
         const int ri = src.row_base + row, ci = src.col_base + col;
-        ok = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
-                                __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2, a);
+        a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
+                               __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     }
-    ok = ok && (d2 < ic.d2_thres);  // the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    // src/cvo.cpp:152 and the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
+    const bool ok = (a > kp.sp_thres) && (d2 < hc.d2_thres);
     a = ok ? a : 0.f;
     if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
         const float4 z1 = sm.u.ls.ss.colZ1[col], z2 = sm.u.ls.ss.colZ2[col];
@@ -866,11 +886,11 @@ __device__ __forceinline__ void list_body(const Smem& sm, const KParams& kp, uin
         c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
         c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
         c.ecn = yg.w;
-        step_accumulate(ic, c, -dx, -dy, -dz, a, acc);
+        step_accumulate(hc, c, -dx, -dy, -dz, a, acc);
     } else {
         // quirk Q1 is defined on the ORIGINAL row index, carried in the w lane of the staged row
         const bool q1 = (KIND == PASS_YY) ? (__float_as_int(xg.w) >= yy_row_min) : true;
-        accumulate_terms<KIND>(ic, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
+        accumulate_terms<KIND>(hc, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
     }
 }
 
@@ -1507,6 +1527,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
     ListSrc src;
     src.rows = &rows;
     src.cols = &cols;
+    const HotConsts hc = hot_consts(sm.ic);
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
@@ -1527,28 +1548,40 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             const uint2 rd = sm.lround[kind][round];
             const int ntrip = (int)rd.y / kListTrip;
             const uint2* e = lr.entries + rd.x + lane;
+            // Two register sets (A, B) alternate between "being processed" and "being loaded" without ever being
+            // copied: a copy would have to wait for the load it copies.  Loads past the warp's last trip are clamped
+            // to it (always readable, never a branch).
+            uint2 a0, a1, a2, a3, b0, b1, b2, b3;
+#define CVO_LOAD_TRIP(x0, x1, x2, x3, tt)                                                        \
+    {                                                                                            \
+        const uint2* q = e + (size_t)min((tt), ntrip - 1) * kListTrip;                           \
+        x0 = __ldcg(q); x1 = __ldcg(q + kTile); x2 = __ldcg(q + 2 * kTile); x3 = __ldcg(q + 3 * kTile); \
+    }
+#define CVO_RUN_TRIP(x0, x1, x2, x3)                                                             \
+    {                                                                                            \
+        list_body<KIND>(sm, hc, kp, x0.x, __uint_as_float(x0.y), yy_row_min, src, fp, acc);      \
+        list_body<KIND>(sm, hc, kp, x1.x, __uint_as_float(x1.y), yy_row_min, src, fp, acc);      \
+        list_body<KIND>(sm, hc, kp, x2.x, __uint_as_float(x2.y), yy_row_min, src, fp, acc);      \
+        list_body<KIND>(sm, hc, kp, x3.x, __uint_as_float(x3.y), yy_row_min, src, fp, acc);      \
+    }
             int t = warp;
-            uint2 n0 = make_uint2(0u, 0x7f800000u), n1 = n0, n2 = n0, n3 = n0;
             if (t < ntrip) {
-                const uint2* q = e + (size_t)t * kListTrip;
-                n0 = __ldcg(q); n1 = __ldcg(q + kTile); n2 = __ldcg(q + 2 * kTile); n3 = __ldcg(q + 3 * kTile);
-            }
-            int since_flush = 0;
-            for (; t < ntrip; t += kWarps) {
-                const uint2 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-                {   // the warp's next trip (clamped to its last one: always readable, never a branch)
-                    const uint2* q = e + (size_t)min(t + kWarps, ntrip - 1) * kListTrip;
-                    n0 = __ldcg(q); n1 = __ldcg(q + kTile); n2 = __ldcg(q + 2 * kTile); n3 = __ldcg(q + 3 * kTile);
-                }
-                list_body<KIND>(sm, kp, c0.x, __uint_as_float(c0.y), yy_row_min, src, fp, acc);
-                list_body<KIND>(sm, kp, c1.x, __uint_as_float(c1.y), yy_row_min, src, fp, acc);
-                list_body<KIND>(sm, kp, c2.x, __uint_as_float(c2.y), yy_row_min, src, fp, acc);
-                list_body<KIND>(sm, kp, c3.x, __uint_as_float(c3.y), yy_row_min, src, fp, acc);
-                if (++since_flush == 4) {  // <= 16 terms per f32 partial, like a short row of A
-                    flush_partial<KIND>(fp, acc);
-                    since_flush = 0;
+                CVO_LOAD_TRIP(a0, a1, a2, a3, t)
+#pragma unroll 1
+                while (true) {
+                    CVO_LOAD_TRIP(b0, b1, b2, b3, t + kWarps)
+                    CVO_RUN_TRIP(a0, a1, a2, a3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(a0, a1, a2, a3, t + kWarps)
+                    CVO_RUN_TRIP(b0, b1, b2, b3)
+                    flush_partial<KIND>(fp, acc);  // <= 8 terms per f32 partial, like a short row of A
+                    t += kWarps;
+                    if (t >= ntrip) break;
                 }
             }
+#undef CVO_LOAD_TRIP
+#undef CVO_RUN_TRIP
             flush_partial<KIND>(fp, acc);
         }
     }
