@@ -181,6 +181,16 @@ struct ListState {
     int need;         // (re)build before this iteration's passes
 };
 
+// Identity of the points a shared-memory stage holds: (cloud, first point, count, pose).  `serial` is the iteration
+// whose transform was applied, -1 for untransformed points, -2 for "nothing usable".
+struct StageTag {
+    const float4* g;
+    int first, n, serial;
+};
+__device__ __forceinline__ bool tag_is(const StageTag& t, const float4* g, int first, int n, int serial) {
+    return t.g == g && t.first == first && t.n == n && t.serial == serial;
+}
+
 struct ListRef {
     uint2* entries;  // the flat list: (row << 12 | col within the round's chunks, bits of the colour exponent t_c)
     uint2* staging;  // build scratch of the CTA (shared by its three lists): per-unit regions before compaction
@@ -199,6 +209,8 @@ struct Smem {
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
     uint2 lround[LIST_KINDS][kMaxListRounds];  // (offset, entries) of every round of a list; entries % kListTrip == 0
     int lst_base;
+    StageTag colTag, rowTag;  // what the column / row stages of the list passes currently hold
+    int serial;               // running iteration number of this CTA: identifies "transformed with this iteration's pose"
     float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
     float ybox[6];            // bounding box of the moving cloud, original coordinates
     ListState lst[LIST_KINDS];
@@ -1134,6 +1146,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
     const int t_begin = pg.t_begin, my_tiles = pg.my_tiles, total_ct = pg.total_ct, S = pg.S;
     const int tiles_per_round = pg.tiles_per_round;
     if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) sm.colTag.serial = sm.rowTag.serial = -2;  // this pass overwrites the list passes' stages
     for (int rb = 0; rb < my_tiles; rb += tiles_per_round) {
         const int ntile = min(tiles_per_round, my_tiles - rb);
         const int nunits = ntile * S;
@@ -1381,6 +1394,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
+        sm.colTag.serial = sm.rowTag.serial = -2;  // the build's stage overwrites the list passes' stages
     }
     int round = 0;
     bool stop = false;
@@ -1497,6 +1511,17 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     __syncthreads();
 }
 
+// STEP pass over a list right after a pass that staged the same transformed columns: only the step-size terms are new.
+__device__ __forceinline__ void stage_step_terms(Smem& sm, int n) {
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float4 g = sm.colG[i];
+        const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
+        sm.colG[i].w = sc.ecn;
+        sm.u.ls.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
+        sm.u.ls.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
+    }
+}
+
 // Stages this CTA's rows [first, first + n) of a packed cloud for a pass over a list: geometry only (transformed
 // if the rows are the moving cloud), the original index in the w lane; rows past the cloud's end are far away.
 __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int first, int n, bool tf) {
@@ -1539,12 +1564,27 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
         const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
         for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
-            __syncthreads();  // everyone is done with the previous round's stage
-            stage_tiles<(KIND == PASS_STEP) ? STAGE_STEP : STAGE_GEOM>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
-            if (cb == 0) stage_rows(sm, rows, (pg.t_begin + rb) * kTile, ntile * kTile, row_tf);
+            __syncthreads();  // everyone is done with the previous round's stage (and its tags are written)
+            // Stage only what is not there already: the fixed cloud's rows survive from pass to pass and from
+            // iteration to iteration, and the STEP pass finds the columns the FLOW pass transformed.
+            const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
+            const int row_serial = row_tf ? sm.serial : -1, col_serial = col_tf ? sm.serial : -1;
+            const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, col_serial);
+            const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, row_serial);
+            if (KIND == PASS_STEP) {
+                if (have_cols) stage_step_terms(sm, nct * kTile);
+                else stage_tiles<STAGE_STEP>(sm, cols, col_first, nct, col_tf, kColSentinel, tma_phase);
+            } else if (!have_cols) {
+                stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, col_tf, kColSentinel, tma_phase);
+            }
+            if (!have_rows) stage_rows(sm, rows, row_first, ntile * kTile, row_tf);
             __syncthreads();
-            src.row_base = (pg.t_begin + rb) * kTile;
-            src.col_base = cb * kTile;
+            if (threadIdx.x == 0) {  // read again only after the next barrier
+                sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = col_serial;
+                sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = row_serial;
+            }
+            src.row_base = row_first;
+            src.col_base = col_first;
             const uint2 rd = sm.lround[kind][round];
             const int ntrip = (int)rd.y / kListTrip;
             const uint2* e = lr.entries + rd.x + lane;
@@ -1640,7 +1680,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     const bool acvo = kp.mode == CVO_B200_MODE_ACVO;
     const int max_iter = kp.fixed_iters > 0 ? kp.fixed_iters : kp.max_iter;
     uint32_t tma_phase = 0;  // parity of sm.tma_bar; every thread tracks it (all threads stage every chunk)
-    if (threadIdx.x == 0) mbar_init(&sm.tma_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.tma_bar, 1);
+        sm.serial = 0;
+    }
     __syncthreads();
     const bool use_lists = args.list_entries != nullptr;
     ListRef lref[LIST_KINDS];
@@ -1668,6 +1711,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             sm.st.n_run = 0;
             sm.st.n_builds = 0;
             sm.done = 0;
+            sm.colTag.serial = sm.rowTag.serial = -2;
 #pragma unroll
             for (int i = 0; i < LIST_KINDS; ++i) sm.lst[i].valid = sm.lst[i].need = 0;
         }
@@ -1700,6 +1744,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
 
         for (int k = 0; k < max_iter; ++k) {
             if (threadIdx.x == 0) {
+                sm.serial += 1;
                 prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
                 if (use_lists) list_policy(sm, acvo, args.list_skin);
             }
