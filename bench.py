@@ -10,7 +10,9 @@ pairs per GPU per step (default 2 x #SMs).  One step = align() of the whole batc
   value  = pairs / device time of the align kernel (CUDA events on the library's stream), clouds resident in HBM
   e2e    = pairs / wall time of: upload of every pair from pinned host memory (cvo_b200_set_pairs: H2D + on-device
            Morton sort/pack) + cvo_b200_align + the poses coming back to the host (+ NCCL all-gather of the poses
-           when N > 1), through the C ABI the reference's frontends would call.
+           when N > 1), through the C ABI the reference's frontends would call.  Every step uploads its own batch;
+           the batches alternate between two sets of slots so that the upload of step k+1 overlaps the align
+           kernel of step k (the pipelining cvo_b200_set_pairs documents).
 Multi-GPU: one process per GPU (torchrun), pairs are independent => weak scaling, no data-path collective;
 the only exchange is one all-gather of the 4x4 poses per step.
 """
@@ -196,7 +198,7 @@ def main():
     num_sms = probe.num_sms
     probe.close()
     P = args.pairs if args.pairs > 0 else 2 * num_sms
-    ctx = capi.Context(local_rank, max_points=N_POINTS + 72, max_slots=P)
+    ctx = capi.Context(local_rank, max_points=N_POINTS + 72, max_slots=2 * P)
     if args.cluster:
         ctx.set_cluster_size(args.cluster)
     params = make_params(capi)
@@ -214,9 +216,11 @@ def main():
 
     counts = np.full(P, N_POINTS, dtype=np.int32)
 
-    def upload_all():
+    slots_b = slots + P  # second slot set of the end-to-end pipeline
+
+    def upload_all(to=slots):
         # cvo_b200_set_pairs: 4 H2D copies from the pinned arrays + one Morton-sort/pack launch for the batch
-        ctx.set_pairs(slots, hx, hfx, counts, hy, hfy, counts)
+        ctx.set_pairs(to, hx, hfx, counts, hy, hfy, counts)
 
     def barrier():
         if dist is not None:
@@ -241,7 +245,7 @@ def main():
     barrier()
     sampler.start()
     launches0 = ctx.kernel_launches
-    kernel_ms, total_iters = [], 0
+    kernel_ms, total_iters, list_builds = [], 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations
@@ -249,6 +253,7 @@ def main():
         res = ctx.align(slots, params)
         kernel_ms.append(ctx.last_kernel_ms)
         total_iters += ctx.last_total_iterations
+        list_builds += ctx.last_list_builds
     barrier()
     wall_resident = time.perf_counter() - t0
     launches = ctx.kernel_launches - launches0
@@ -256,18 +261,23 @@ def main():
     dev_s = float(np.sum(kernel_ms)) / 1e3
 
     # ---------------- end-to-end arm: host buffers -> poses on the host ----------------
-    for _ in range(min(args.warmup, 2)):
-        upload_all()
-        gather_poses(ctx.align(slots, params))
+    def e2e_steps(n):
+        # step k: (upload of step k+1 enqueued) -> align of step k -> poses on the host (-> all-gather)
+        sets = (slots, slots_b)
+        upload_all(sets[0])
+        for k in range(n):
+            if k + 1 < n:
+                upload_all(sets[(k + 1) % 2])
+            gather_poses(ctx.align(sets[k % 2], params))
+
+    e2e_steps(min(args.warmup, 2))
     barrier()
+    launches1 = ctx.kernel_launches
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        upload_all()
-        res = ctx.align(slots, params)
-        gather_poses(res)
+    e2e_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_launches = ctx.kernel_launches - launches0 - launches
+    e2e_launches = ctx.kernel_launches - launches1
 
     if dist is not None:
         t = torch.tensor([dev_s, e2e_s, wall_resident], dtype=torch.float64, device="cuda")
@@ -297,6 +307,7 @@ def main():
             "config": {"workload": "cfg2: 3000x3000 synthetic RGB-D pairs, fixed ell=0.10, 100 inner iterations per pair",
                        "pairs_per_gpu_per_step": P, "points": [N_POINTS, N_POINTS], "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "ctas_per_pair": ctx.last_cluster_size, "clusters": ctx.last_num_clusters,
+                       "neighbour_list_builds_per_pair": list_builds / (args.steps * P),
                        "l2": "256 MiB device memset between timed steps (flush)", "timing": "CUDA events on the library stream around the align kernel"},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "launches_per_step": e2e_launches / args.steps},
@@ -305,11 +316,11 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "note": "BASELINE.json asks for HBM GB/s, but with A never materialised the kernel is FP32-issue-bound (SURVEY.md 8d): see issue_roof",
+                         "note": "achieved = SURVEY.md 8d algorithmic bytes (64(N+M)+96 per iteration) / kernel time; traffic = DRAM bytes of one launch from the committed ncu capture (mostly the neighbour candidate lists streaming through L2); the kernel is issue-bound, not HBM-bound: see issue_roof",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel": "cvo_b200::align_kernel", "kernel_ms": 1e3 * launch_s},
             "issue_roof": {"pair_evals_per_s": pass_evals / launch_s, "roof_pair_evals_per_s": issue_roof,
                            "frac_nm_equivalent": pass_evals / launch_s / issue_roof,
-                           "note": "N*M-equivalent candidate pairs per second vs 148 SM x 128 lanes x f_SM / 7 slots; tile-box culling skips most of them"},
+                           "note": "N*M-equivalent candidate pairs per second vs 148 SM x 128 lanes x f_SM / 7 slots; neighbour lists and tile-box culling skip most of them"},
         }
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(args.cpu_pairs or 96, 10_000)

@@ -31,6 +31,7 @@ struct cvo_b200_ctx {
         int n[2] = {0, 0};
         int fixed_buf = 0;  // which of the two buffers currently holds the fixed cloud
         bool bound = false;
+        int pending_batch = -1;  // batched upload whose pack launch has not been enqueued yet
     };
     std::vector<Slot> slots;
 
@@ -44,9 +45,25 @@ struct cvo_b200_ctx {
     int trace_cap = 0;
     double* d_inner = nullptr;
     PackJob* d_jobs = nullptr;  // descriptors of the pack launch in flight (stream-ordered reuse)
-    PackJob* h_jobs = nullptr;  // pinned, 2 * max_slots (batched upload)
-    float* d_batch_raw = nullptr;  // raw staging of a batched upload (grown on demand)
-    size_t batch_raw_floats = 0;
+
+    // Batched upload (cvo_b200_set_pairs): two staging areas so that the host->device copies of one batch run on
+    // `copy_stream` while the align kernel of the previous batch runs on `stream`.  The pack launch of a batch is
+    // deferred until something needs its slots (it could not overlap the persistent align kernel anyway and must
+    // not be queued in front of it).
+    struct Batch {
+        float* d_raw = nullptr;       // [fixed xyz | fixed feat | moving xyz | moving feat]
+        size_t raw_floats = 0;
+        PackJob* d_jobs = nullptr;    // 2 * max_slots
+        PackJob* h_jobs = nullptr;    // pinned
+        cudaEvent_t copied = nullptr; // recorded on copy_stream after the batch's copies
+        cudaEvent_t packed = nullptr; // recorded on stream after the pack that read d_raw
+        bool pending = false;         // copies enqueued, pack not yet
+        bool used = false;
+        int njobs = 0;
+        std::vector<int> slots;
+    } batch[2];
+    int next_batch = 0;
+    cudaStream_t copy_stream = nullptr;
     double* h_inner = nullptr;  // pinned
 
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
@@ -156,6 +173,33 @@ int launch_pack(cvo_b200_ctx* ctx, const PackJob* jobs_host, int njobs, PackJob*
     return CVO_B200_OK;
 }
 
+// Enqueues the deferred pack launch of a batched upload on the main stream (after its copies).
+int flush_batch(cvo_b200_ctx* ctx, int b) {
+    cvo_b200_ctx::Batch& B = ctx->batch[b];
+    if (!B.pending) return CVO_B200_OK;
+    B.pending = false;
+    for (int s : B.slots)
+        if (ctx->slots[s].pending_batch == b) ctx->slots[s].pending_batch = -1;
+    int nmax = 0;
+    for (int i = 0; i < B.njobs; ++i) nmax = B.h_jobs[i].n > nmax ? B.h_jobs[i].n : nmax;
+    int npad = 1;
+    while (npad < nmax) npad <<= 1;
+    const size_t smem = (size_t)npad * sizeof(unsigned long long);
+    CK(cudaStreamWaitEvent(ctx->stream, B.copied, 0));
+    pack_sort_kernel<<<B.njobs, kPackThreads, smem, ctx->stream>>>(B.d_jobs, ctx->sort_points);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(B.packed, ctx->stream));
+    ctx->launches += 1;
+    return CVO_B200_OK;
+}
+int flush_all_batches(cvo_b200_ctx* ctx) {
+    for (int b = 0; b < 2; ++b) {
+        const int rc = flush_batch(ctx, b);
+        if (rc) return rc;
+    }
+    return CVO_B200_OK;
+}
+
 int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
     if (ctx->force_G > 0) return ctx->force_G;
     int G = 1;
@@ -241,6 +285,10 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     for (int i = 0; i < n_pairs; ++i) {
         const int s = slots[i];
         if (s < 0 || s >= ctx->max_slots || !ctx->slots[s].bound) return fail_arg(ctx, "slot not bound");
+        if (ctx->slots[s].pending_batch >= 0) {
+            const int rc = flush_batch(ctx, ctx->slots[s].pending_batch);
+            if (rc) return rc;
+        }
         ctx->h_pairs[i] = make_pair_dev(ctx, s);
         PairState& st = ctx->h_states[i];
         memset(&st, 0, sizeof(st));
@@ -403,8 +451,14 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     CKC(cudaMalloc(&ctx->d_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMallocHost(&ctx->h_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMalloc(&ctx->d_inner, sizeof(double) * 2));
-    CKC(cudaMalloc(&ctx->d_jobs, sizeof(PackJob) * 2 * max_slots));
-    CKC(cudaMallocHost(&ctx->h_jobs, sizeof(PackJob) * 2 * max_slots));
+    CKC(cudaMalloc(&ctx->d_jobs, sizeof(PackJob) * 2));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CKC(cudaMalloc(&ctx->batch[b].d_jobs, sizeof(PackJob) * 2 * max_slots));
+        CKC(cudaMallocHost(&ctx->batch[b].h_jobs, sizeof(PackJob) * 2 * max_slots));
+        CKC(cudaEventCreateWithFlags(&ctx->batch[b].copied, cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->batch[b].packed, cudaEventDisableTiming));
+    }
     CKC(cudaMallocHost(&ctx->h_inner, sizeof(double) * 2));
     ctx->pack_smem_max = 128 * 1024;
     CKC(cudaFuncSetAttribute(pack_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pack_smem_max));
@@ -442,8 +496,15 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFreeHost(ctx->h_trace);
     cudaFree(ctx->d_inner);
     cudaFree(ctx->d_jobs);
-    cudaFreeHost(ctx->h_jobs);
-    cudaFree(ctx->d_batch_raw);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->batch[b].d_raw);
+        cudaFree(ctx->batch[b].d_jobs);
+        cudaFreeHost(ctx->batch[b].h_jobs);
+        if (ctx->batch[b].copied) cudaEventDestroy(ctx->batch[b].copied);
+        if (ctx->batch[b].packed) cudaEventDestroy(ctx->batch[b].packed);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_list_entries);
     cudaFreeHost(ctx->h_inner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -465,7 +526,9 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const
     }
     if (n_fixed > ctx->max_points || n_moving > ctx->max_points) return fail_arg(ctx, "cloud larger than max_points");
     CK(cudaSetDevice(ctx->device));
-    int rc = upload_cloud(ctx, 0, fixed_xyz, fixed_feat, n_fixed);
+    int rc = flush_all_batches(ctx);
+    if (rc) return rc;
+    rc = upload_cloud(ctx, 0, fixed_xyz, fixed_feat, n_fixed);
     if (rc) return rc;
     rc = upload_cloud(ctx, 1, moving_xyz, moving_feat, n_moving);
     if (rc) return rc;
@@ -500,40 +563,65 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const f
             return fail_arg(ctx, "cloud larger than max_points / stride");
     }
     CK(cudaSetDevice(ctx->device));
+    const int b = ctx->next_batch;
+    ctx->next_batch ^= 1;
+    cvo_b200_ctx::Batch& B = ctx->batch[b];
+    if (B.pending) {  // a batch nobody consumed: its pack still has to run before its staging area is reused
+        const int rc = flush_batch(ctx, b);
+        if (rc) return rc;
+    }
+    if (B.used) {
+        CK(cudaEventSynchronize(B.copied));                    // the pinned job array may be rewritten
+        CK(cudaStreamWaitEvent(ctx->copy_stream, B.packed, 0));  // the staging area may be overwritten
+    }
     // one staging area for the whole batch: [fixed xyz | fixed feat | moving xyz | moving feat]
     const size_t cloud3 = (size_t)stride_points * 3, cloud5 = (size_t)stride_points * 5;
     const size_t need = (size_t)n_pairs * 2 * (cloud3 + cloud5);
-    if (need > ctx->batch_raw_floats) {
+    if (need > B.raw_floats) {
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_batch_raw);
-        ctx->d_batch_raw = nullptr;
-        ctx->batch_raw_floats = 0;
-        CK(cudaMalloc(&ctx->d_batch_raw, need * sizeof(float)));
-        ctx->batch_raw_floats = need;
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        cudaFree(B.d_raw);
+        B.d_raw = nullptr;
+        B.raw_floats = 0;
+        CK(cudaMalloc(&B.d_raw, need * sizeof(float)));
+        B.raw_floats = need;
     }
-    float* d_fx = ctx->d_batch_raw;
+    float* d_fx = B.d_raw;
     float* d_ff = d_fx + (size_t)n_pairs * cloud3;
     float* d_mx = d_ff + (size_t)n_pairs * cloud5;
     float* d_mf = d_mx + (size_t)n_pairs * cloud3;
-    // the pinned job array may still be read by the previous batch's copy: wait for the stream first
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpyAsync(d_fx, fixed_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_ff, fixed_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_mx, moving_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_mf, moving_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, ctx->stream));
+    B.slots.assign(slots, slots + n_pairs);
     for (int i = 0; i < n_pairs; ++i) {
         const int slot = slots[i];
         cvo_b200_ctx::Slot& s = ctx->slots[slot];
+        if (s.pending_batch >= 0 && s.pending_batch != b) {  // an older, unconsumed upload of this slot goes first
+            const int rc = flush_batch(ctx, s.pending_batch);
+            if (rc) return rc;
+        }
         s.fixed_buf = 0;
         s.n[0] = n_fixed[i];
         s.n[1] = n_moving[i];
         s.bound = true;
-        ctx->h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
-                              slot_f4(ctx, slot, 0), n_fixed[i], 0};
-        ctx->h_jobs[2 * i + 1] = {d_mx + i * cloud3, d_mf + i * cloud5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1),
-                                  slot_f4(ctx, slot, 1), n_moving[i], 0};
+        s.pending_batch = b;
+        B.h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
+                           slot_f4(ctx, slot, 0), n_fixed[i], 0};
+        B.h_jobs[2 * i + 1] = {d_mx + i * cloud3, d_mf + i * cloud5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1),
+                               slot_f4(ctx, slot, 1), n_moving[i], 0};
+        if ((size_t)n_fixed[i] * sizeof(unsigned long long) > ctx->pack_smem_max ||
+            (size_t)n_moving[i] * sizeof(unsigned long long) > ctx->pack_smem_max)
+            return fail_arg(ctx, "cloud too large for the single-CTA sort");
     }
-    return launch_pack(ctx, ctx->h_jobs, 2 * n_pairs, ctx->d_jobs);
+    B.njobs = 2 * n_pairs;
+    cudaStream_t cs = ctx->copy_stream;
+    CK(cudaMemcpyAsync(d_fx, fixed_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_ff, fixed_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_mx, moving_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_mf, moving_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(B.d_jobs, B.h_jobs, sizeof(PackJob) * B.njobs, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(B.copied, cs));
+    B.pending = true;
+    B.used = true;
+    return CVO_B200_OK;
 }
 
 int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {
@@ -546,10 +634,12 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
     }
     if (n > ctx->max_points) return fail_arg(ctx, "cloud larger than max_points");
     CK(cudaSetDevice(ctx->device));
+    int rc = flush_all_batches(ctx);
+    if (rc) return rc;
     cvo_b200_ctx::Slot& s = ctx->slots[slot];
     s.fixed_buf = 1 - s.fixed_buf;  // moving becomes fixed (src/cvo.cpp:417)
     const int mb = 1 - s.fixed_buf;
-    int rc = upload_cloud(ctx, 0, xyz, feat, n);
+    rc = upload_cloud(ctx, 0, xyz, feat, n);
     if (rc) return rc;
     s.n[mb] = n;
     PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), slot_f4(ctx, slot, mb), n, 0};
@@ -589,6 +679,10 @@ int cvo_b200_inner_product(cvo_b200_ctx* ctx, int slot, float ell, const cvo_b20
     if (slot < 0 || slot >= ctx->max_slots || !ctx->slots[slot].bound) return fail_arg(ctx, "slot not bound");
     if (!p) return fail_arg(ctx, "null params");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rc = flush_all_batches(ctx);
+        if (rc) return rc;
+    }
     InnerArgs args;
     args.pair = make_pair_dev(ctx, slot);
     args.kp = make_kparams(p, true);
@@ -612,6 +706,11 @@ int cvo_b200_inner_product(cvo_b200_ctx* ctx, int slot, float ell, const cvo_b20
 int cvo_b200_sync(cvo_b200_ctx* ctx) {
     if (!ctx) return CVO_B200_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rc = flush_all_batches(ctx);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return CVO_B200_OK;
 }
