@@ -66,6 +66,10 @@ enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INN
 enum ListKind { LIST_XY = 0, LIST_XX = 1, LIST_YY = 2, LIST_KINDS = 3 };
 constexpr int kMaxListRounds = 36;  // (row round, column chunk) combinations of one pass: 6 x 6 chunks of 3072 points
 constexpr int kListTrip = 128;      // entries one warp handles per trip of a list pass; rounds are padded to it
+#ifndef CVO_PREFETCH_TRIPS
+#define CVO_PREFETCH_TRIPS 4
+#endif
+constexpr int kPrefetchTrips = CVO_PREFETCH_TRIPS;  // how many of its own trips ahead a warp prefetches the list into L2
 
 // accumulator slots of the flow exchange
 enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZXX = 9, ACC_SXX = 10,
@@ -150,11 +154,9 @@ struct StepStage {
     float4 colZ2[kColChunk];  // {xi^2 z + xi v, -(xi z + v).(xi^2 z + xi v)}   (src/cvo.cpp:229-230,236)
 };
 struct BuildUnits {  // neighbour-list build, per unit of the round:
-    int cnt[kMaxUnits];             // entry bound (prefilter candidates)
-    int off[kMaxUnits];             // offset of its staging region
-    int act[kMaxUnits];             // entries it really has
-    int pos[kMaxUnits];             // their position in the round's flat list
-    unsigned short ord[kMaxUnits];  // the unit at rank k when sorted by descending bound
+    int off[kMaxUnits];  // where its entries sit in the staging area
+    int act[kMaxUnits];  // how many it has
+    int pos[kMaxUnits];  // their position in the round's flat list
 };
 struct OnTheFlyStage {
     FeatStage fs;
@@ -1295,30 +1297,11 @@ __device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile
     return __ballot_sync(0xffffffffu, live);
 }
 
-// Build sweep 1: upper bound of the unit's entry count = its candidates inside the build ball (prefilter only).
-__device__ __forceinline__ int build_unit_bound(const Smem& sm, WarpScratch& ws, const CloudDev& rows, bool row_tf, int tile,
-                                                int ct_begin, int ct_end, float thr_build) {
-    const RowTile rt = load_row_tile<false, false, true>(sm, ws, rows, row_tf, tile);
-    const float thr_box = thr_build * 1.0001f;  // boxes are conservative; keep rounding on the safe side
-    int cnt = 0;
-    for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
-        uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
-        while (lm) {
-            const int j = __ffs(lm) - 1;
-            lm &= lm - 1;
-            cnt += __popc(prefilter_tile(sm, rt.rr, c0 + j, thr_build));
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    return cnt;
-}
-
-// Build sweep 2, per candidate: exact distance at the build pose, colour gate and colour exponent (pose-independent,
+// Build, per candidate: exact distance at the build pose, colour gate and colour exponent (pose-independent,
 // src/cvo.cpp:145-148), and the pair's own radius + slack.  Survivors are appended to the unit's staging region with
 // their row index made relative to the round (`row_off` = 32 * the unit's row tile within the round).
 __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
-                                           uint32_t ent, bool live, uint32_t row_off, uint2* out, int& cursor) {
+                                           uint32_t ent, bool live, uint32_t row_off, uint2* out, int limit, int& cursor) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
@@ -1333,13 +1316,15 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + L.s_build;
     const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    if (keep) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent + (row_off << 12), __float_as_uint(t_c)));
+    // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
+    if (keep && cursor + kTile <= limit)
+        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent + (row_off << 12), __float_as_uint(t_c)));
     cursor += __popc(b);
 }
 
 __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
                                                 const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int ct_begin,
-                                                int ct_end, uint2* out) {
+                                                int ct_end, uint2* out, int limit) {
     const int lane = threadIdx.x & 31;
     const RowTile rt = load_row_tile<true, false, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = L.thr_build * 1.0001f;
@@ -1359,12 +1344,12 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
             __syncwarp();
             while (qn >= 32) {
                 qn -= 32;
-                build_eval(sm, ws, kp, L, q[qn + lane], true, row_off, out, cursor);
+                build_eval(sm, ws, kp, L, q[qn + lane], true, row_off, out, limit, cursor);
             }
             __syncwarp();
         }
     }
-    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, out, cursor);
+    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, out, limit, cursor);
     __syncwarp();
     return cursor;
 }
@@ -1377,13 +1362,12 @@ __device__ __forceinline__ int next_unit(Smem& sm) {
 }
 
 // (Re)builds one neighbour list for this CTA's share of the row tiles.  Per round (row chunk x column chunk):
-//   sweep 1  bounds every unit's entry count by its prefilter candidates; an exclusive scan lays out the units'
-//            staging regions;
-//   sweep 2  evaluates the candidates and writes each unit's entries to its staging region;
-//   compact  an exclusive scan of the actual counts in unit order gives every unit its place in the round's FLAT
-//            list, the entries are copied there and the round is padded to a whole trip with entries that can never
-//            pass ((row 0, col 0) are real points, t_c = +inf gives a = 0).
-// The layout is a pure function of the inputs (no atomics decide where anything goes).  On return
+//   evaluate  every warp pulls work units (row tile x column segment), runs prefilter -> queue -> per-candidate
+//             evaluation and appends the unit's entries to ITS OWN segment of the staging area;
+//   compact   an exclusive scan of the unit counts in unit order gives every unit its place in the round's FLAT
+//             list, the entries are copied there and the round is padded to a whole trip with entries that can never
+//             pass ((row 0, col 0) are real points, t_c = +inf gives a = 0).
+// Which warp evaluated which unit does not matter: the flat list is a pure function of the inputs.  On return
 // sm.lst[kind].valid is 1, or -1 if a scratch area was too small.
 __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
                            int rank, int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
@@ -1391,6 +1375,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     const ListState& L = sm.lst[kind];
     WarpScratch& ws = sm.u.of.ws[warp];
+    const int seg = (int)(lr.cap / kWarps) & ~3;  // this warp's staging segment
+    uint2* const stage = lr.staging + (size_t)warp * seg;
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
@@ -1414,59 +1400,23 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 stop = true;
                 break;
             }
-            while (true) {  // sweep 1: bound
+            int wcur = 0;  // entries this warp has staged in this round
+            while (true) {  // evaluate
                 const int u = next_unit(sm);
                 if (u >= nunits) break;
-                const int t = u / pg.S, seg = u - t * pg.S;
-                const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
-                const int c = build_unit_bound(sm, ws, rows, row_tf, pg.t_begin + rb + t, c_begin, c_end, L.thr_build);
-                if (lane == 0) sm.u.of.bu.cnt[u] = c;
-            }
-            __syncthreads();
-            if (warp == 0) {  // staging regions: exclusive scan of the bounds in unit order
-                int base = 0;
-                for (int i0 = 0; i0 < nunits; i0 += 32) {
-                    const int c = (i0 + lane < nunits) ? sm.u.of.bu.cnt[i0 + lane] : 0;
-                    int excl, total;
-                    warp_scan_count(c, lane, excl, total);
-                    if (i0 + lane < nunits) sm.u.of.bu.off[i0 + lane] = base + excl;
-                    base += total;
-                }
+                const int t = u / pg.S, sg = u - t * pg.S;
+                const int c_begin = (int)(((long long)nct * sg) / pg.S), c_end = (int)(((long long)nct * (sg + 1)) / pg.S);
+                const int c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile), c_begin,
+                                               c_end, stage + wcur, seg - wcur);
                 if (lane == 0) {
-                    if ((unsigned)base > lr.cap) sm.lst_ovf = 1;
-                    sm.next_unit = 0;
+                    sm.u.of.bu.off[u] = warp * seg + wcur;
+                    sm.u.of.bu.act[u] = c;
+                    if (wcur + c > seg) sm.lst_ovf = 1;
                 }
-            } else if (threadIdx.x - 32 < nunits) {
-                // longest-processing-time order: rank the units by descending bound (ties by unit index) so that
-                // sweep 2 hands out the big units first and the small ones fill the tail
-                const int u = threadIdx.x - 32, cu = sm.u.of.bu.cnt[u];
-                int rk = 0;
-                for (int v = 0; v < nunits; ++v) {
-                    const int cv = sm.u.of.bu.cnt[v];
-                    rk += (cv > cu || (cv == cu && v < u)) ? 1 : 0;
-                }
-                sm.u.of.bu.ord[rk] = (unsigned short)u;
+                wcur = min(wcur + c, seg);
             }
             __syncthreads();
-            if (sm.lst_ovf) {
-                stop = true;
-                break;
-            }
-            while (true) {  // sweep 2: evaluate and write to the staging regions
-                const int k = next_unit(sm);
-                if (k >= nunits) break;
-                const int u = sm.u.of.bu.ord[k];
-                int c = 0;
-                if (sm.u.of.bu.cnt[u] > 0) {
-                    const int t = u / pg.S, seg = u - t * pg.S;
-                    const int c_begin = (int)(((long long)nct * seg) / pg.S), c_end = (int)(((long long)nct * (seg + 1)) / pg.S);
-                    c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile), c_begin, c_end,
-                                         lr.staging + sm.u.of.bu.off[u]);
-                }
-                if (lane == 0) sm.u.of.bu.act[u] = c;
-            }
-            __syncthreads();
-            if (warp == 0) {  // places in the flat list: exclusive scan of the actual counts in unit order
+            if (warp == 0) {  // places in the flat list: exclusive scan of the unit counts in unit order
                 int base = 0;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
                     const int c = (i0 + lane < nunits) ? sm.u.of.bu.act[i0 + lane] : 0;
@@ -1477,9 +1427,10 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 }
                 const int padded = (base + kListTrip - 1) / kListTrip * kListTrip;
                 const int at = sm.lst_used;
-                const bool fits = (unsigned)(at + padded) <= lr.cap;
+                const bool fits = !sm.lst_ovf && (unsigned)(at + padded) <= lr.cap;
                 if (fits)
                     for (int i = base + lane; i < padded; i += 32) __stcg(lr.entries + at + i, make_uint2(0u, 0x7f800000u));
+                __syncwarp();
                 if (lane == 0) {
                     if (fits) {
                         sm.lround[kind][round] = make_uint2((unsigned)at, (unsigned)padded);
@@ -1496,7 +1447,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 stop = true;
                 break;
             }
-            while (true) {  // compaction: staging regions -> flat list
+            while (true) {  // compaction: staging segments -> flat list
                 const int u = next_unit(sm);
                 if (u >= nunits) break;
                 const uint2* src = lr.staging + sm.u.of.bu.off[u];
@@ -1587,15 +1538,22 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             src.col_base = col_first;
             const uint2 rd = sm.lround[kind][round];
             const int ntrip = (int)rd.y / kListTrip;
-            const uint2* e = lr.entries + rd.x + lane;
+            const uint2* e0 = lr.entries + rd.x;
+            const uint2* e = e0 + lane;
             // Two register sets (A, B) alternate between "being processed" and "being loaded" without ever being
             // copied: a copy would have to wait for the load it copies.  Loads past the warp's last trip are clamped
             // to it (always readable, never a branch).
             uint2 a0, a1, a2, a3, b0, b1, b2, b3;
+            // The lists stream from HBM (they are larger than this SM's share of L2): an L2 prefetch a few trips
+            // ahead (8 lines of 128 B per trip, one per lane 0..7) leaves the register loads only L2 latency to cover.
 #define CVO_LOAD_TRIP(x0, x1, x2, x3, tt)                                                        \
     {                                                                                            \
         const uint2* q = e + (size_t)min((tt), ntrip - 1) * kListTrip;                           \
         x0 = __ldcg(q); x1 = __ldcg(q + kTile); x2 = __ldcg(q + 2 * kTile); x3 = __ldcg(q + 3 * kTile); \
+        if (lane < 8) {                                                                          \
+            const uint2* f = e0 + (size_t)min((tt) + kPrefetchTrips * kWarps, ntrip - 1) * kListTrip + lane * 16; \
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(f));                                   \
+        }                                                                                        \
     }
 #define CVO_RUN_TRIP(x0, x1, x2, x3)                                                             \
     {                                                                                            \
