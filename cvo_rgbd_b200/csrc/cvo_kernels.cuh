@@ -56,7 +56,8 @@ constexpr float kColSentinel = -1.0e15f;
 // only has to be a superset of the exact ball; its rounding error is bounded by ~20 * 2^-24 * (|c|^2 + |x|^2).
 constexpr float kPrefilterSlack = 2.0e-6f;
 
-enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INNER = 4 };
+enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INNER = 4,
+                PASS_FLOW_CVO = 5 };  // FLOW without the length-scale gradient term (only acvo uses it)
 
 // Neighbour candidate lists (the GPU counterpart of the reference's kd-tree, thirdparty/nanoflann.hpp): for one
 // (rows, cols) cloud pair the (row, col) index pairs inside a ball of radius r_build = r * (1 + skin), kept in an
@@ -799,7 +800,7 @@ template <int KIND, class IC>
 __device__ __forceinline__ void accumulate_terms(const IC& ic, const KParams& kp, const float4& xg, const float4& yg,
                                                  float dx, float dy, float dz, float a, bool ok, bool q1_row,
                                                  FlowPartial& fp, double* acc) {
-    if (KIND == PASS_FLOW) {
+    if (KIND == PASS_FLOW || KIND == PASS_FLOW_CVO) {
         const float cx = xg.y * yg.z - xg.z * yg.y;  // x_i x y_j, src/cvo.cpp:191
         const float cy = xg.z * yg.x - xg.x * yg.z;
         const float cz = xg.x * yg.y - xg.y * yg.x;
@@ -807,7 +808,7 @@ __device__ __forceinline__ void accumulate_terms(const IC& ic, const KParams& kp
         fp.po0 = fmaf(ac, cx, fp.po0); fp.po1 = fmaf(ac, cy, fp.po1); fp.po2 = fmaf(ac, cz, fp.po2);
         fp.pv0 = fmaf(ad, dx, fp.pv0); fp.pv1 = fmaf(ad, dy, fp.pv1); fp.pv2 = fmaf(ad, dz, fp.pv2);
         fp.psum += a;
-        fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:202,228
+        if (KIND == PASS_FLOW) fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:202,228
         fp.cnt += ok ? 1 : 0;
     } else if (KIND == PASS_XX || KIND == PASS_INNER) {
         fp.pdl = fmaf(ic.inv_ell3 * a, dx * dx + dy * dy + dz * dz, fp.pdl);  // src/adaptive_cvo.cpp:210,231
@@ -912,7 +913,7 @@ template <int KIND>
 __device__ __forceinline__ void flush_partial(FlowPartial& fp, double* acc) {
     if (KIND == PASS_STEP) return;
     if (fp.cnt) {
-        if (KIND == PASS_FLOW) {
+        if (KIND == PASS_FLOW || KIND == PASS_FLOW_CVO) {
             acc[ACC_W0] += (double)fp.po0; acc[ACC_W0 + 1] += (double)fp.po1; acc[ACC_W0 + 2] += (double)fp.po2;
             acc[ACC_V0] += (double)fp.pv0; acc[ACC_V0 + 1] += (double)fp.pv1; acc[ACC_V0 + 2] += (double)fp.pv2;
             acc[ACC_SUMA] += (double)fp.psum;
@@ -1027,6 +1028,7 @@ template <> struct PassTraits<PASS_XX>    { static constexpr int NV = 2; };
 template <> struct PassTraits<PASS_YY>    { static constexpr int NV = 2; };
 template <> struct PassTraits<PASS_STEP>  { static constexpr int NV = 4; };
 template <> struct PassTraits<PASS_INNER> { static constexpr int NV = 2; };
+template <> struct PassTraits<PASS_FLOW_CVO> { static constexpr int NV = 9; };
 
 // One work unit = one 32-row tile against one segment of the staged column tiles, done by ONE warp with no
 // block-level synchronisation.  The unit's totals go to its own slot, so the block sum does not depend on
@@ -1710,7 +1712,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             if (use_lists && sm.lst[LIST_XY].need) build_list(sm, kp, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
-            if (list_xy) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            else if (list_xy) run_pass_list<PASS_FLOW_CVO>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
