@@ -249,6 +249,10 @@ void ensure_list_scratch(cvo_b200_ctx* ctx) {
     unsigned long long cap = (unsigned long long)ctx->max_points * ctx->max_points / 8;
     if (cap < (1ull << 18)) cap = 1ull << 18;
     if (cap > (1ull << 21)) cap = 1ull << 21;
+    if (const char* env = getenv("CVO_B200_LIST_CAP")) {  // test hook: a small area forces the overflow fallback
+        const long long v = atoll(env);
+        if (v >= 1024) cap = (unsigned long long)v & ~1023ull;
+    }
     const size_t areas = (size_t)ctx->num_sms * (LIST_KINDS + 1);  // three lists + the build staging per CTA
     if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();

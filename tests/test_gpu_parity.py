@@ -341,3 +341,64 @@ def test_error_paths(gpu_ctx):
     assert b"max_points" in lib.cvo_b200_last_error(h)
     with pytest.raises(capi.CvoB200Error):
         gpu_ctx.align(np.array([63]), capi.default_params("cvo"))  # slot never bound
+
+
+def test_multi_round_lists_on_one_cta_match_the_cluster_result(gpu_ctx, oracle):
+    """10 000 x 10 000 points on ONE CTA: 4 row chunks x 4 column chunks = 16 list rounds, against the 16-CTA cluster
+    (625 rows per CTA, 4 rounds each) and the oracle."""
+    pr = synth.config_pair(5)
+    _set(gpu_ctx, 0, pr)
+    gp = capi.default_params("acvo")  # acvo parameters on cvo-flavoured features: exercises all three lists
+    gp.c_ell = 200.0
+    op = oracle.default_params("acvo")
+    op.c_ell = 200.0
+    o = oracle.evaluate(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], R0, T0, 0.07, op)
+    try:
+        res = {}
+        for g in (1, 16):
+            gpu_ctx.set_cluster_size(g)
+            res[g] = gpu_ctx.eval(0, R0, T0, 0.07, gp)
+            _check_eval(res[g], o, True)
+        assert (res[1]["nnz"], res[1]["nnz_xx"], res[1]["nnz_yy"]) == (res[16]["nnz"], res[16]["nnz_xx"], res[16]["nnz_yy"])
+        for k in ("omega", "v", "B", "C", "D", "E"):
+            assert rel_err(res[1][k], res[16][k]) < 1e-6, k
+    finally:
+        gpu_ctx.set_cluster_size(0)
+
+
+def test_list_scratch_overflow_falls_back_to_on_the_fly_passes(oracle, monkeypatch):
+    """A neighbour list that outgrows its scratch area is abandoned for that pair: the passes run on the fly and the
+    results are the on-the-fly results (CVO_B200_LIST_CAP is a test hook that shrinks the area)."""
+    pr = synth.config_pair(2)
+    gp = capi.default_params("cvo")
+    gp.fixed_iters = 6
+    monkeypatch.setenv("CVO_B200_LIST_CAP", "4096")
+    with capi.Context(0, max_points=3072, max_slots=1) as small:
+        _set(small, 0, pr)
+        a = small.align_trace(0, gp, trace_cap=8)
+        assert small.last_list_builds >= 1  # it tried
+        small.set_neighbor_lists(False)
+        b = small.align_trace(0, gp, trace_cap=8)
+    for k in range(6):
+        for key in ("nnz", "B", "E", "sum_a"):
+            assert a["trace"][k][key] == b["trace"][k][key], (k, key)  # bit-identical: the same on-the-fly passes
+    assert np.array_equal(a["transform"], b["transform"])
+    o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], _fixed(oracle.default_params("cvo"), 6), trace_cap=8)
+    assert abs(a["trace"][0]["nnz"] - o["trace"][0]["nnz"]) <= 2
+
+
+def _fixed(p, n):
+    p.fixed_iters = n
+    return p
+
+
+def test_maximum_cloud_size(oracle):
+    """16 384 points per cloud (the single-CTA sort's capacity, cvo_b200_create's limit): one evaluation against the oracle."""
+    pr = synth.make_pair(91, 16384, 16000, "cvo")
+    with capi.Context(0, max_points=16384, max_slots=1) as big:
+        _set(big, 0, pr)
+        g = big.eval(0, R0, T0, 0.05, capi.default_params("cvo"))
+    o = oracle.evaluate(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], R0, T0, 0.05, oracle.default_params("cvo"))
+    _check_eval(g, o, False)
+    with pytest.raises(capi.CvoB200Error):
+        capi.Context(0, max_points=16385, max_slots=1)
