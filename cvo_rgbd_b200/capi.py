@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("CVO_B200_LIB") or os.path.join(_HERE, "libcvo_b200.so
 MODE_CVO, MODE_ACVO = 0, 1
 ELL_SCHEDULE, ELL_ADAPTIVE, ELL_FIXED = 0, 1, 2
 STATUS_MAX_ITER, STATUS_CONVERGED_TWIST, STATUS_CONVERGED_UPDATE, STATUS_NAN = 0, 1, 2, 3
-OK, ERR_ARG, ERR_CUDA, ERR_EMPTY = 0, -1, -2, -3
+OK, ERR_ARG, ERR_CUDA, ERR_EMPTY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
 # every symbol include/cvo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -25,6 +25,7 @@ EXPORTS = [
     "cvo_b200_kernel_launches", "cvo_b200_last_cluster_size", "cvo_b200_last_num_clusters",
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds",
+    "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
 ]
 
 
@@ -59,7 +60,9 @@ class IterRec(C.Structure):
 
 
 class CvoB200Error(RuntimeError):
-    pass
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 _lib = None
@@ -102,11 +105,25 @@ def load():
     lib.cvo_b200_last_total_iterations.argtypes = [vp]
     lib.cvo_b200_last_total_iterations.restype = C.c_longlong
     lib.cvo_b200_num_sms.argtypes = [vp]
+    lib.cvo_b200_push_frame_images.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ushort), C.c_int, C.c_int,
+                                               C.c_int, C.c_int, ip]
+    lib.cvo_b200_last_generated_cloud.argtypes = [vp, fp, fp, C.c_int, ip]
+    lib.cvo_b200_reset_slot.argtypes = [vp, C.c_int]
+    lib.cvo_b200_selftest_rand_bytes.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_ubyte)]
     lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
     lib.cvo_b200_last_list_builds.argtypes = [vp]
     lib.cvo_b200_last_list_builds.restype = C.c_longlong
     _lib = lib
     return lib
+
+
+def selftest_rand_bytes(seed, n):
+    """`rand() & 0xFF` of glibc after srand(seed), from the library's own restatement (host code, no GPU needed)."""
+    out = np.zeros(n, np.uint8)
+    rc = load().cvo_b200_selftest_rand_bytes(seed, n, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    if rc != OK:
+        raise CvoB200Error("selftest_rand_bytes failed", rc)
+    return out
 
 
 def default_params(kind="cvo"):
@@ -159,7 +176,7 @@ class Context:
 
     def _check(self, rc):
         if rc != OK:
-            raise CvoB200Error("libcvo_b200 error %d: %s" % (rc, self._lib.cvo_b200_last_error(self._h).decode()))
+            raise CvoB200Error("libcvo_b200 error %d: %s" % (rc, self._lib.cvo_b200_last_error(self._h).decode()), rc)
 
     def set_pair(self, slot, fixed_xyz, fixed_feat, moving_xyz, moving_feat):
         fx, ff, mx, mf = _f32(fixed_xyz), _f32(fixed_feat), _f32(moving_xyz), _f32(moving_feat)
@@ -189,6 +206,29 @@ class Context:
     def push_frame(self, slot, xyz, feat):
         x, f = _f32(xyz), _f32(feat)
         self._check(self._lib.cvo_b200_push_frame(self._h, slot, _fp(x), _fp(f), x.shape[0]))
+
+    def push_frame_images(self, slot, img3, depth, dataset_seq=1, feature_type=1):
+        """Image front door: h x w x 3 uint8 (as cv::imread returns it) + h x w uint16 depth -> the slot's next cloud,
+        generated on the device.  Returns the number of points."""
+        img3 = np.ascontiguousarray(img3, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        assert img3.ndim == 3 and img3.shape[2] == 3 and depth.shape == img3.shape[:2]
+        n = C.c_int(0)
+        self._check(self._lib.cvo_b200_push_frame_images(
+            self._h, slot, img3.ctypes.data_as(C.POINTER(C.c_ubyte)), depth.ctypes.data_as(C.POINTER(C.c_ushort)),
+            img3.shape[1], img3.shape[0], dataset_seq, feature_type, C.byref(n)))
+        return n.value
+
+    def last_generated_cloud(self):
+        """(xyz[n,3], feat[n,5]) of the last push_frame_images, in the reference's raster order."""
+        n = C.c_int(0)
+        self._check(self._lib.cvo_b200_last_generated_cloud(self._h, None, None, 0, C.byref(n)))
+        xyz, feat = np.zeros((n.value, 3), np.float32), np.zeros((n.value, 5), np.float32)
+        self._check(self._lib.cvo_b200_last_generated_cloud(self._h, _fp(xyz), _fp(feat), n.value, C.byref(n)))
+        return xyz, feat
+
+    def reset_slot(self, slot):
+        self._check(self._lib.cvo_b200_reset_slot(self._h, slot))
 
     def eval(self, slot, R, T, ell, params):
         R, T = _f32(R).reshape(3, 3), _f32(T).reshape(3)

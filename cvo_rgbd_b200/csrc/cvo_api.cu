@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "cvo_kernels.cuh"
+#include "pcd_kernels.cuh"
 
 using namespace cvo_b200;
 
@@ -31,6 +32,7 @@ struct cvo_b200_ctx {
         int n[2] = {0, 0};
         int fixed_buf = 0;  // which of the two buffers currently holds the fixed cloud
         bool bound = false;
+        bool have_fixed = false;  // a fixed cloud is in place (image front door: the first frame of a sequence)
         int pending_batch = -1;  // batched upload whose pack launch has not been enqueued yet
     };
     std::vector<Slot> slots;
@@ -64,6 +66,21 @@ struct cvo_b200_ctx {
     } batch[2];
     int next_batch = 0;
     cudaStream_t copy_stream = nullptr;
+
+    // image front end (cvo_b200_push_frame_images), allocated on first use for one image size
+    struct ImagePipe {
+        int w = 0, h = 0;
+        uint8_t* d_img3 = nullptr;
+        uint16_t* d_depth = nullptr;
+        float* d_pyr = nullptr;      // I, dx, dy, g2 of the three levels, one allocation
+        float* d_ths = nullptr;      // ths | thsSmoothed
+        uint8_t* d_map = nullptr;
+        uint8_t* d_rnd = nullptr;    // the selector's randomPattern
+        SelCtl* d_ctl = nullptr;
+        SelCtl* h_ctl = nullptr;     // pinned
+        bool tables = false;
+    } pipe;
+    int last_gen_n = 0;
     double* h_inner = nullptr;  // pinned
 
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
@@ -261,6 +278,83 @@ void ensure_list_scratch(cvo_b200_ctx* ctx) {
         return;
     }
     ctx->list_cap = (unsigned)cap;
+}
+
+
+// glibc's rand() after srand(seed) (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31]), restated so that
+// the selector's randomPattern (thirdparty/PixelSelector2.cpp:36-38: srand(3141592); rand() & 0xFF) can be produced
+// without touching the process-wide C random state.  tests/test_pcd_frontend.py checks it against libc.
+void glibc_rand_bytes(unsigned seed, size_t n, uint8_t* out) {
+    std::vector<int32_t> r(344 + n);
+    r[0] = (int32_t)(seed == 0 ? 1u : seed);  // srandom: "we must make sure the seed is not 0"
+    for (int i = 1; i < 31; ++i) {
+        const int64_t hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        int64_t word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        r[i] = (int32_t)word;
+    }
+    for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+    for (size_t i = 34; i < 344 + n; ++i) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+    for (size_t k = 0; k < n; ++k) out[k] = (uint8_t)(((uint32_t)r[k + 344] >> 1) & 0xFF);
+}
+
+CamInfo camera_info(int dataset_seq) {  // src/pcd_generator.cpp:241-302
+    switch (dataset_seq) {
+        case 1: return {5000.0f, 517.3f, 516.5f, 318.6f, 255.3f};
+        case 2: return {5000.0f, 520.9f, 521.0f, 325.1f, 249.7f};
+        case 3: return {5000.0f, 535.4f, 539.2f, 320.1f, 247.6f};
+        case 4: return {2000.0f, 718.856f, 718.856f, 607.1928f, 185.2157f};
+        case 5: return {2000.0f, 707.0912f, 707.0912f, 601.8873f, 183.1104f};
+        default: return {1000.0f, 616.368f, 616.745f, 319.935f, 243.639f};
+    }
+}
+
+void free_image_pipe(cvo_b200_ctx* ctx) {
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
+    cudaFree(P.d_img3); cudaFree(P.d_depth); cudaFree(P.d_pyr); cudaFree(P.d_ths); cudaFree(P.d_map); cudaFree(P.d_rnd);
+    cudaFree(P.d_ctl);
+    if (P.h_ctl) cudaFreeHost(P.h_ctl);
+    P = cvo_b200_ctx::ImagePipe();
+}
+
+size_t pyr_floats(int w, int h) {
+    size_t n = 0;
+    for (int l = 0; l < 3; ++l) {
+        n += (size_t)w * h;
+        w /= 2;
+        h /= 2;
+    }
+    return n;
+}
+
+int ensure_image_pipe(cvo_b200_ctx* ctx, int w, int h) {
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
+    if (P.w == w && P.h == h) return CVO_B200_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_image_pipe(ctx);
+    const size_t wh = (size_t)w * h;
+    CK(cudaMalloc(&P.d_img3, wh * 3));
+    CK(cudaMalloc(&P.d_depth, wh * sizeof(uint16_t)));
+    CK(cudaMalloc(&P.d_pyr, pyr_floats(w, h) * 4 * sizeof(float)));
+    CK(cudaMalloc(&P.d_ths, (size_t)(w / 32) * (h / 32) * 2 * sizeof(float)));
+    CK(cudaMalloc(&P.d_map, wh));
+    CK(cudaMalloc(&P.d_rnd, wh));
+    CK(cudaMalloc(&P.d_ctl, sizeof(SelCtl)));
+    CK(cudaMallocHost(&P.h_ctl, sizeof(SelCtl)));
+    std::vector<uint8_t> rnd(wh);
+    glibc_rand_bytes(3141592u, wh, rnd.data());
+    CK(cudaMemcpy(P.d_rnd, rnd.data(), wh, cudaMemcpyHostToDevice));
+    int sdiv[256], hdiv[256];  // OpenCV's 8-bit HSV tables (hsv_shift = 12), round half to even like cv::saturate_cast
+    sdiv[0] = hdiv[0] = 0;
+    for (int i = 1; i < 256; ++i) {
+        sdiv[i] = (int)lrint((255 << 12) / (1. * i));
+        hdiv[i] = (int)lrint((180 << 12) / (6. * i));
+    }
+    CK(cudaMemcpyToSymbol(c_sdiv, sdiv, sizeof(sdiv)));
+    CK(cudaMemcpyToSymbol(c_hdiv, hdiv, sizeof(hdiv)));
+    P.w = w;
+    P.h = h;
+    return CVO_B200_OK;
 }
 
 PairDev make_pair_dev(cvo_b200_ctx* ctx, int slot) {
@@ -509,6 +603,7 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
         if (ctx->batch[b].packed) cudaEventDestroy(ctx->batch[b].packed);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    free_image_pipe(ctx);
     cudaFree(ctx->d_list_entries);
     cudaFreeHost(ctx->h_inner);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -541,6 +636,7 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const
     s.n[0] = n_fixed;
     s.n[1] = n_moving;
     s.bound = true;
+    s.have_fixed = true;
     PackJob jobs[2];
     const size_t mp = ctx->max_points;
     jobs[0] = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0), slot_f4(ctx, slot, 0), n_fixed, 0};
@@ -606,6 +702,7 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const f
         s.n[0] = n_fixed[i];
         s.n[1] = n_moving[i];
         s.bound = true;
+        s.have_fixed = true;
         s.pending_batch = b;
         B.h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
                            slot_f4(ctx, slot, 0), n_fixed[i], 0};
@@ -648,6 +745,126 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
     s.n[mb] = n;
     PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), slot_f4(ctx, slot, mb), n, 0};
     return launch_pack(ctx, &job, 1, ctx->d_jobs);
+}
+
+int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth, int width,
+                               int height, int dataset_seq, int feature_type, int* num_points) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
+    if (!img3 || !depth) return fail_arg(ctx, "null image pointer");
+    if (width < 64 || height < 64 || width % 32 || height % 32 || (long long)width * height > (1 << 24))
+        return fail_arg(ctx, "image size must be a multiple of 32 in both directions (the selector's block thresholds, "
+                             "thirdparty/PixelSelector2.cpp:367, are only defined then)");
+    if (feature_type != 0 && feature_type != 1) return fail_arg(ctx, "feature_type must be 0 (acvo) or 1 (cvo)");
+    CK(cudaSetDevice(ctx->device));
+    int rc = flush_all_batches(ctx);
+    if (rc) return rc;
+    rc = ensure_image_pipe(ctx, width, height);
+    if (rc) return rc;
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
+    cvo_b200_ctx::Slot& s = ctx->slots[slot];
+    // where the new cloud goes: the first frame of a sequence is the fixed cloud (src/cvo.cpp:326-334), every later
+    // one the moving cloud, the previous moving cloud having become the fixed one (:417)
+    int fixed_buf = s.fixed_buf, target;
+    if (!s.have_fixed) { fixed_buf = 0; target = 0; }
+    else if (!s.bound) target = 1 - fixed_buf;
+    else { fixed_buf = 1 - fixed_buf; target = 1 - fixed_buf; }
+    const int w = width, h = height, wh = w * h;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(P.d_img3, img3, (size_t)wh * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(P.d_depth, depth, (size_t)wh * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    PcdBuffers B;
+    B.w = w; B.h = h; B.img3 = P.d_img3; B.depth = P.d_depth;
+    {
+        float* p = P.d_pyr;
+        int wl = w, hl = h;
+        for (int l = 0; l < 3; ++l) {
+            const size_t n = (size_t)wl * hl;
+            B.I[l] = p; B.dx[l] = p + n; B.dy[l] = p + 2 * n; B.g2[l] = p + 3 * n;
+            p += 4 * n;
+            wl /= 2; hl /= 2;
+        }
+    }
+    B.ths = P.d_ths;
+    B.thsSmoothed = P.d_ths + (size_t)(w / 32) * (h / 32);
+    B.map = P.d_map;
+    B.randomPattern = P.d_rnd;
+    B.ctl = P.d_ctl;
+    const int T = 256;
+    pcd_gray_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, 3000);  // num_want (src/pcd_generator.cpp:22)
+    {
+        int wl = w, hl = h;
+        for (int l = 0; l < 3; ++l) {
+            if (l > 0) pcd_down_kernel<<<(wl * hl + T - 1) / T, T, 0, st>>>(B.I[l - 1], B.I[l], wl, hl);
+            pcd_grad_kernel<<<(wl * hl + T - 1) / T, T, 0, st>>>(B.I[l], B.dx[l], B.dy[l], B.g2[l], wl, hl);
+            wl /= 2; hl /= 2;
+        }
+    }
+    const int nb32 = (w / 32) * (h / 32);
+    pcd_hist_kernel<<<nb32, 1024, 0, st>>>(B);
+    pcd_smooth_kernel<<<(nb32 + T - 1) / T, T, 0, st>>>(B);
+    const int max_blocks = ((w + 3) / 4) * ((h + 3) / 4);  // potential 1: 4 x 4 blocks
+    for (int stage = 0; stage < 2; ++stage) {
+        pcd_clear_map_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, stage);
+        pcd_select_kernel<<<(max_blocks + T - 1) / T, T, 0, st>>>(B, stage);
+        pcd_decide_kernel<<<1, 1, 0, st>>>(B, stage);
+    }
+    pcd_subsample_kernel<<<1, 1024, 0, st>>>(B);
+    PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, target), slot_f(ctx, slot, target),
+                   slot_f4(ctx, slot, target), 0, 0};
+    CK(cudaMemcpyAsync(ctx->d_jobs, &job, sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    pcd_points_kernel<<<1, 1024, 0, st>>>(B, camera_info(dataset_seq), feature_type, ctx->d_raw_xyz, ctx->d_raw_feat,
+                                         ctx->max_points, &ctx->d_jobs->n);
+    pack_sort_kernel<<<1, kPackThreads, ctx->pack_smem_max, st>>>(ctx->d_jobs, ctx->sort_points);
+    CK(cudaGetLastError());
+    ctx->launches += 14;
+    CK(cudaMemcpyAsync(P.h_ctl, P.d_ctl, sizeof(SelCtl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const SelCtl& c = *P.h_ctl;
+    ctx->last_gen_n = c.num_points < ctx->max_points ? c.num_points : ctx->max_points;
+    if (num_points) *num_points = c.num_points;
+    if (c.status == PCD_STATUS_NEEDS_CANNY) {
+        ctx->err = "low-texture frame: the selector kept fewer than num_want/3 pixels and the reference would add Canny "
+                   "edges (src/pcd_generator.cpp:135-163); that top-up is not built";
+        return CVO_B200_ERR_UNSUPPORTED;
+    }
+    if (c.status == PCD_STATUS_TOO_MANY_POINTS) return fail_arg(ctx, "the frame yields more points than max_points");
+    if (c.num_points <= 0) {
+        ctx->err = "empty cloud";
+        return CVO_B200_ERR_EMPTY;
+    }
+    s.fixed_buf = fixed_buf;
+    s.n[target] = c.num_points;
+    if (!s.have_fixed) s.have_fixed = true;
+    else s.bound = true;
+    return CVO_B200_OK;
+}
+
+int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!n) return fail_arg(ctx, "null pointer");
+    CK(cudaSetDevice(ctx->device));
+    *n = ctx->last_gen_n;
+    const int m = ctx->last_gen_n < capacity ? ctx->last_gen_n : capacity;
+    if (m > 0 && xyz) CK(cudaMemcpyAsync(xyz, ctx->d_raw_xyz, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m > 0 && feat) CK(cudaMemcpyAsync(feat, ctx->d_raw_feat, sizeof(float) * 5 * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CVO_B200_OK;
+}
+
+int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
+    const int rc = flush_all_batches(ctx);
+    if (rc) return rc;
+    ctx->slots[slot] = cvo_b200_ctx::Slot();
+    return CVO_B200_OK;
+}
+
+int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out) {
+    if (n < 0 || !out) return CVO_B200_ERR_ARG;
+    glibc_rand_bytes(seed, (size_t)n, out);
+    return CVO_B200_OK;
 }
 
 int cvo_b200_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, float* RT_io,

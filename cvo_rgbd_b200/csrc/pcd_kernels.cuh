@@ -1,0 +1,387 @@
+// pcd_kernels.cuh -- sm_100a kernels for the image front end that feeds the registration loop
+// (SURVEY.md 8f row 2): 8-bit colour image + 16-bit depth image -> selected pixels -> packed point cloud, all on
+// the device, stream-ordered, without a host round trip before the final point count.
+//
+// Replaces, in the reference (paths relative to cpp/rkhs_registration/):
+//   pcd_generator::load_image              src/pcd_generator.cpp:384-396   (cv::cvtColor RGB2GRAY / RGB2HSV, 8-bit)
+//   pcd_generator::make_pyramid            src/pcd_generator.cpp:33-120
+//   dso::PixelSelector::makeHists          thirdparty/PixelSelector2.cpp:71-136
+//   dso::PixelSelector::select / makeMaps  thirdparty/PixelSelector2.cpp:137-282, 286-435
+//   pcd_generator::get_points_from_pixels  src/pcd_generator.cpp:233-327
+//   pcd_generator::get_features            src/pcd_generator.cpp:329-382
+// Every integer / byte step is bit-exact; the float steps use explicitly rounded operations (no FMA contraction) in
+// the reference's order, so the generated cloud equals the CPU restatement used by the tests bit for bit.
+//
+// What makes it parallel: with setting_selectDirectionDistribution == false (thirdparty/PixelSelector2.h:31) the
+// selector's "random direction" never enters a comparison, so a 4pot x 4pot block's picks depend on that block
+// only -- one thread walks one block with the reference's own loop nest; the two raster-order passes of the
+// reference (the random sub-sampling, PixelSelector2.cpp:226-243, indexed by the RANK of a selected pixel, and the
+// point / feature emission) are exclusive scans over the pixel flags.
+//
+// Not built: the Canny top-up for low-texture frames (src/pcd_generator.cpp:135-163, cv::blur + cv::Canny); such a
+// frame is reported (PCD_STATUS_NEEDS_CANNY) instead of being processed differently from the reference.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvo_b200 {
+
+enum { PCD_STATUS_OK = 0, PCD_STATUS_NEEDS_CANNY = 1, PCD_STATUS_TOO_MANY_POINTS = 2 };
+
+struct CamInfo {
+    float scaling_factor, fx, fy, cx, cy;
+};
+
+// device-resident control block of one image push (decisions of makeMaps are taken on the device)
+struct SelCtl {
+    int pot[2];       // potential of the first / second select()
+    int run[2];       // whether that select() runs
+    int n[2][3];      // picks per level of each select()
+    float quotia;     // numWant / numHave of the select() that counts
+    int num_have;     // picks of that select()
+    int num_selected; // after the random sub-sampling (makeMaps' return value)
+    int num_points;   // selected pixels with a depth reading: the cloud size
+    int status;
+    int num_want;
+};
+
+struct PcdBuffers {
+    int w, h;
+    const uint8_t* img3;     // h x w x 3
+    const uint16_t* depth;   // h x w
+    float* I[3];             // dI[.][0] per pyramid level
+    float* dx[3];
+    float* dy[3];
+    float* g2[3];            // abs_squared_grad
+    float* ths;              // (w/32) * (h/32)
+    float* thsSmoothed;
+    uint8_t* map;            // 0 / 1 / 2 / 4 per pixel
+    const uint8_t* randomPattern;
+    SelCtl* ctl;
+};
+
+__constant__ int c_sdiv[256];
+__constant__ int c_hdiv[256];
+
+// cv::cvtColor(..., COLOR_RGB2GRAY), 8-bit: 15-bit fixed-point luma, channel 0 weighted as "R"
+__device__ __forceinline__ int rgb2gray_u8(int c0, int c1, int c2) { return (c0 * 9798 + c1 * 19235 + c2 * 3735 + (1 << 14)) >> 15; }
+
+// cv::cvtColor(..., COLOR_RGB2HSV), 8-bit, H in [0, 180)
+__device__ __forceinline__ void rgb2hsv_u8(int r, int g, int b, int& hh, int& s, int& v) {
+    v = max(b, max(g, r));
+    const int vmin = min(b, min(g, r));
+    const int diff = v - vmin;
+    const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
+    s = (diff * c_sdiv[v] + (1 << 11)) >> 12;
+    hh = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
+    hh = (hh * c_hdiv[diff] + (1 << 11)) >> 12;
+    hh += hh < 0 ? 180 : 0;
+}
+
+// level 0 intensity (src/pcd_generator.cpp:52-60) + reset of the control block
+__global__ void pcd_gray_kernel(PcdBuffers b, int num_want) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        SelCtl& c = *b.ctl;
+        c.pot[0] = 3; c.pot[1] = 0;   // currentPotential = 3 of a fresh PixelSelector (PixelSelector2.cpp:40)
+        c.run[0] = 1; c.run[1] = 0;
+        for (int s = 0; s < 2; ++s) c.n[s][0] = c.n[s][1] = c.n[s][2] = 0;
+        c.quotia = 0.f; c.num_have = 0; c.num_selected = 0; c.num_points = 0; c.status = PCD_STATUS_OK;
+        c.num_want = num_want;
+    }
+    if (i >= b.w * b.h) return;
+    b.I[0][i] = (float)rgb2gray_u8(b.img3[3 * i], b.img3[3 * i + 1], b.img3[3 * i + 2]);
+}
+
+// 2x2 box downsampling (src/pcd_generator.cpp:78-92), summed left to right
+__global__ void pcd_down_kernel(const float* prev, float* cur, int wl, int hl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wl * hl) return;
+    const int x = i % wl, y = i / wl, pw = wl * 2;
+    const float* q = prev + 2 * x + 2 * y * pw;
+    cur[i] = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), q[pw]), q[pw + 1]));
+}
+
+// central differences and squared gradient magnitude (src/pcd_generator.cpp:94-112); the first and last rows, which
+// the reference leaves uninitialised, are defined as 0
+__global__ void pcd_grad_kernel(const float* I, float* dx, float* dy, float* g2, int wl, int hl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wl * hl) return;
+    float gx = 0.f, gy = 0.f, g = 0.f;
+    if (i >= wl && i < wl * (hl - 1)) {
+        gx = __fmul_rn(0.5f, __fsub_rn(I[i + 1], I[i - 1]));
+        gy = __fmul_rn(0.5f, __fsub_rn(I[i + wl], I[i - wl]));
+        if (!isfinite(gx)) gx = 0.f;
+        if (!isfinite(gy)) gy = 0.f;
+        g = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
+    }
+    dx[i] = gx;
+    dy[i] = gy;
+    g2[i] = g;
+}
+
+// one CTA per 32 x 32 block: gradient-magnitude histogram -> median-based threshold (PixelSelector2.cpp:84-108)
+__global__ void __launch_bounds__(1024) pcd_hist_kernel(PcdBuffers b) {
+    __shared__ int hist[52];
+    const int w = b.w, h = b.h, w32 = w / 32;
+    const int bx = blockIdx.x % w32, by = blockIdx.x / w32;
+    if (threadIdx.x < 52) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int it = i + 32 * bx, jt = j + 32 * by;
+    if (!(it > w - 2 || jt > h - 2 || it < 1 || jt < 1)) {
+        int g = (int)sqrtf(b.g2[0][it + jt * w]);
+        if (g > 48) g = 48;
+        atomicAdd(&hist[g + 1], 1);
+        atomicAdd(&hist[0], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // computeHistQuantil(hist, 0.5) + setting_minGradHistAdd (:58-67,105)
+        int th = (int)(hist[0] * 0.5f + 0.5f);
+        int q = 90;
+        for (int k = 0; k < 90; ++k) {
+            th -= (k + 1 < 52) ? hist[k + 1] : 0;
+            if (th < 0) { q = k; break; }
+        }
+        b.ths[bx + by * w32] = (float)(q + 7);
+    }
+}
+
+// 3 x 3 smoothing of the block thresholds, squared (PixelSelector2.cpp:110-133)
+__global__ void pcd_smooth_kernel(PcdBuffers b) {
+    const int w32 = b.w / 32, h32 = b.h / 32;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w32 * h32) return;
+    const int x = t % w32, y = t / w32;
+    const float* ths = b.ths;
+    float sum = 0.f, num = 0.f;
+    if (x > 0) {
+        if (y > 0) { num += 1.f; sum = __fadd_rn(sum, ths[x - 1 + (y - 1) * w32]); }
+        if (y < h32 - 1) { num += 1.f; sum = __fadd_rn(sum, ths[x - 1 + (y + 1) * w32]); }
+        num += 1.f; sum = __fadd_rn(sum, ths[x - 1 + y * w32]);
+    }
+    if (x < w32 - 1) {
+        if (y > 0) { num += 1.f; sum = __fadd_rn(sum, ths[x + 1 + (y - 1) * w32]); }
+        if (y < h32 - 1) { num += 1.f; sum = __fadd_rn(sum, ths[x + 1 + (y + 1) * w32]); }
+        num += 1.f; sum = __fadd_rn(sum, ths[x + 1 + y * w32]);
+    }
+    if (y > 0) { num += 1.f; sum = __fadd_rn(sum, ths[x + (y - 1) * w32]); }
+    if (y < h32 - 1) { num += 1.f; sum = __fadd_rn(sum, ths[x + (y + 1) * w32]); }
+    num += 1.f; sum = __fadd_rn(sum, ths[x + y * w32]);
+    const float m = __fdiv_rn(sum, num);
+    b.thsSmoothed[t] = __fmul_rn(m, m);
+}
+
+// clears the selection map if stage `s` runs
+__global__ void pcd_clear_map_kernel(PcdBuffers b, int s) {
+    if (!b.ctl->run[s]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.w * b.h) b.map[i] = 0;
+}
+
+// select() (PixelSelector2.cpp:286-435): one thread = one 4pot x 4pot block, the reference's loop nest.
+__global__ void pcd_select_kernel(PcdBuffers b, int s) {
+    SelCtl& c = *b.ctl;
+    if (!c.run[s]) return;
+    const int pot = c.pot[s];
+    const int w = b.w, h = b.h, w1 = w / 2, w2 = w / 4, w32 = w / 32;
+    const int nbx = (w + 4 * pot - 1) / (4 * pot), nby = (h + 4 * pot - 1) / (4 * pot);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbx * nby) return;
+    const int x4 = (t % nbx) * 4 * pot, y4 = (t / nbx) * 4 * pot;
+    const float* mapmax0 = b.g2[0];
+    const float* mapmax1 = b.g2[1];
+    const float* mapmax2 = b.g2[2];
+    const float dw1 = 0.75f, dw2 = __fmul_rn(dw1, dw1);  // setting_gradDownweightPerLevel
+    const float thFactor = 1.f;
+    int n2 = 0, n3 = 0, n4 = 0;
+    const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
+    int bestIdx4 = -1;
+    float bestVal4 = 0.f;
+    for (int y3 = 0; y3 < my3; y3 += 2 * pot)
+        for (int x3 = 0; x3 < mx3; x3 += 2 * pot) {
+            const int x34 = x3 + x4, y34 = y3 + y4;
+            const int my2 = min(2 * pot, h - y34), mx2 = min(2 * pot, w - x34);
+            int bestIdx3 = -1;
+            float bestVal3 = 0.f;
+            for (int y2 = 0; y2 < my2; y2 += pot)
+                for (int x2 = 0; x2 < mx2; x2 += pot) {
+                    const int x234 = x2 + x34, y234 = y2 + y34;
+                    const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
+                    int bestIdx2 = -1;
+                    float bestVal2 = 0.f;
+                    for (int y1 = 0; y1 < my1; ++y1)
+                        for (int x1 = 0; x1 < mx1; ++x1) {
+                            const int xf = x1 + x234, yf = y1 + y234;
+                            const int idx = xf + w * yf;
+                            if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
+                            const float pixelTH0 = b.thsSmoothed[(xf >> 5) + (yf >> 5) * w32];
+                            const float pixelTH1 = __fmul_rn(pixelTH0, dw1);
+                            const float pixelTH2 = __fmul_rn(pixelTH1, dw2);
+                            const float ag0 = mapmax0[idx];
+                            if (ag0 > __fmul_rn(pixelTH0, thFactor)) {
+                                if (ag0 > bestVal2) { bestVal2 = ag0; bestIdx2 = idx; bestIdx3 = -2; bestIdx4 = -2; }
+                            }
+                            if (bestIdx3 == -2) continue;
+                            const float ag1 = mapmax1[(int)__fadd_rn(__fmul_rn((float)xf, 0.5f), 0.25f) +
+                                                      (int)__fadd_rn(__fmul_rn((float)yf, 0.5f), 0.25f) * w1];
+                            if (ag1 > __fmul_rn(pixelTH1, thFactor)) {
+                                if (ag1 > bestVal3) { bestVal3 = ag1; bestIdx3 = idx; bestIdx4 = -2; }
+                            }
+                            if (bestIdx4 == -2) continue;
+                            // (int)(xf*0.25f+0.125): the literal 0.125 is a double there; exact either way
+                            const float ag2 = mapmax2[(int)((double)__fmul_rn((float)xf, 0.25f) + 0.125) +
+                                                      (int)((double)__fmul_rn((float)yf, 0.25f) + 0.125) * w2];
+                            if (ag2 > __fmul_rn(pixelTH2, thFactor)) {
+                                if (ag2 > bestVal4) { bestVal4 = ag2; bestIdx4 = idx; }
+                            }
+                        }
+                    if (bestIdx2 > 0) { b.map[bestIdx2] = 1; bestVal3 = 1e10f; n2++; }
+                }
+            if (bestIdx3 > 0) { b.map[bestIdx3] = 2; bestVal4 = 1e10f; n3++; }
+        }
+    if (bestIdx4 > 0) { b.map[bestIdx4] = 4; n4++; }
+    if (n2) atomicAdd(&c.n[s][0], n2);
+    if (n3) atomicAdd(&c.n[s][1], n3);
+    if (n4) atomicAdd(&c.n[s][2], n4);
+}
+
+// makeMaps' decisions after a select() (PixelSelector2.cpp:181-224), one thread.  Stage 0 may schedule ONE
+// re-selection (recursionsLeft = 1); stage 1 only records its result.
+__global__ void pcd_decide_kernel(PcdBuffers b, int s) {
+    SelCtl& c = *b.ctl;
+    if (!c.run[s]) return;
+    const int cur = c.pot[s];
+    const float numHave = (float)(c.n[s][0] + c.n[s][1] + c.n[s][2]);
+    const float numWant = (float)c.num_want;
+    const float quotia = __fdiv_rn(numWant, numHave);
+    const float K = __fmul_rn(__fmul_rn(numHave, (float)(cur + 1)), (float)(cur + 1));
+    int ideal = (int)__fsub_rn(sqrtf(__fdiv_rn(K, numWant)), 1.f);
+    if (ideal < 1) ideal = 1;
+    c.quotia = quotia;
+    c.num_have = (int)numHave;
+    if (s == 0) {
+        if ((double)quotia > 1.25 && cur > 1) {
+            if (ideal >= cur) ideal = cur - 1;
+            c.pot[1] = ideal;
+            c.run[1] = 1;
+        } else if ((double)quotia < 0.25) {
+            if (ideal <= cur) ideal = cur + 1;
+            c.pot[1] = ideal;
+            c.run[1] = 1;
+        }
+    }
+}
+
+// exclusive scan over one flag per pixel in raster order, single CTA: thread t owns the contiguous pixel range
+// [t * per, (t + 1) * per).  Returns this thread's exclusive prefix; *total = number of flagged pixels.
+template <class F>
+__device__ __forceinline__ int raster_rank(int npix, int per, F flag, int* total) {
+    __shared__ int wsum[32];
+    __shared__ int stotal;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lo = min(t * per, npix), hi = min(lo + per, npix);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += flag(i) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        wsum[lane] = iv - v;
+        if (lane == 31) stotal = iv;
+    }
+    __syncthreads();
+    *total = stotal;
+    return wsum[warp] + incl - cnt;
+}
+
+// the random sub-sampling of makeMaps (PixelSelector2.cpp:226-243): the rn-th selected pixel in raster order is
+// dropped if randomPattern[rn] > 255 * quotia.  Also raises the Canny condition of select_point (:135).
+__global__ void __launch_bounds__(1024) pcd_subsample_kernel(PcdBuffers b) {
+    SelCtl& c = *b.ctl;
+    const int npix = b.w * b.h, per = (npix + 1023) / 1024;
+    const float quotia = c.quotia;
+    int num = c.num_have;
+    if ((double)quotia < 0.95) {  // float against the double literal, as there
+        int total;
+        uint8_t* map = b.map;
+        int rn = raster_rank(npix, per, [map](int i) { return map[i] != 0; }, &total);
+        const unsigned char charTH = (unsigned char)__fmul_rn(255.f, quotia);
+        const int lo = min((int)threadIdx.x * per, npix), hi = min(lo + per, npix);
+        int dropped = 0;
+        for (int i = lo; i < hi; ++i)
+            if (map[i] != 0) {
+                if (b.randomPattern[rn] > charTH) { map[i] = 0; ++dropped; }
+                ++rn;
+            }
+        __shared__ int sdrop;
+        if (threadIdx.x == 0) sdrop = 0;
+        __syncthreads();
+        if (dropped) atomicAdd(&sdrop, dropped);
+        __syncthreads();
+        num -= sdrop;
+    }
+    if (threadIdx.x == 0) {
+        c.num_selected = num;
+        if (num < c.num_want / 3) c.status = PCD_STATUS_NEEDS_CANNY;
+    }
+}
+
+// get_points_from_pixels + get_features (src/pcd_generator.cpp:304-381): the selected pixels with a depth reading,
+// in raster order, as n x 3 positions and n x 5 features (row-major), plus the point count for the pack job.
+__global__ void __launch_bounds__(1024) pcd_points_kernel(PcdBuffers b, CamInfo cam, int feature_type, float* xyz, float* feat,
+                                                          int max_points, int* job_n) {
+    SelCtl& c = *b.ctl;
+    const int npix = b.w * b.h, per = (npix + 1023) / 1024, w = b.w;
+    const uint8_t* map = b.map;
+    const uint16_t* depth = b.depth;
+    int total;
+    int idx = raster_rank(npix, per, [map, depth](int i) { return map[i] != 0 && depth[i] != 0; }, &total);
+    const int lo = min((int)threadIdx.x * per, npix), hi = min(lo + per, npix);
+    for (int i = lo; i < hi; ++i) {
+        if (!(map[i] != 0 && depth[i] != 0)) continue;
+        if (idx < max_points) {
+            const int x = i % w, y = i / w;
+            const float z = __fdiv_rn((float)depth[i], cam.scaling_factor);
+            xyz[3 * idx + 2] = z;
+            xyz[3 * idx + 0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, cam.cx), z), cam.fx);
+            xyz[3 * idx + 1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)y, cam.cy), z), cam.fy);
+            const int c0 = b.img3[3 * i], c1 = b.img3[3 * i + 1], c2 = b.img3[3 * i + 2];
+            if (feature_type == 0) {  // HSV / [180, 255, 255] and gradient * 2 / 255, evaluated in double (:336-358)
+                int hh, s, v;
+                rgb2hsv_u8(c0, c1, c2, hh, s, v);
+                feat[5 * idx + 0] = (float)((double)hh / 180.0);
+                feat[5 * idx + 1] = (float)((double)s / 255.0);
+                feat[5 * idx + 2] = (float)((double)v / 255.0);
+                feat[5 * idx + 3] = (float)((double)b.dx[0][i] / 255.0 * 2.0);
+                feat[5 * idx + 4] = (float)((double)b.dy[0][i] / 255.0 * 2.0);
+            } else {  // raw channels and raw gradient (:359-381)
+                feat[5 * idx + 0] = (float)c0;
+                feat[5 * idx + 1] = (float)c1;
+                feat[5 * idx + 2] = (float)c2;
+                feat[5 * idx + 3] = b.dx[0][i];
+                feat[5 * idx + 4] = b.dy[0][i];
+            }
+        }
+        ++idx;
+    }
+    if (threadIdx.x == 0) {
+        c.num_points = total;
+        if (total > max_points) c.status = PCD_STATUS_TOO_MANY_POINTS;
+        *job_n = total > max_points ? max_points : total;
+    }
+}
+
+}  // namespace cvo_b200

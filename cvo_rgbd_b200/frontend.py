@@ -2,8 +2,8 @@
 include/cvo_b200_frontend.hpp; reference: cpp/rkhs_registration/include/cvo.hpp:101-107,171-192 and
 include/adaptive_cvo.hpp:108-114,169-195).  Used by the tests and the benchmark driver; PyTorch-free.
 
-Inputs are the OUTPUT contract of the reference's image front-end (pcd_generator, out of scope):
-xyz N x 3 and features N x 5 (row-major)."""
+Inputs are either the OUTPUT contract of the reference's image front end (pcd_generator):
+xyz N x 3 and features N x 5 (row-major), or the images themselves (set_pcd_images: the front end runs on the device)."""
 import numpy as np
 
 from . import capi
@@ -27,6 +27,7 @@ class _Registration:
         self._RT = np.concatenate([np.eye(3).reshape(9), np.zeros(3)]).astype(np.float32)
         self._ell = float(self.params.ell_init)
         self._first = None
+        self._images = False
         self._bound = False
         self._have_moving = False
         self.status = 0
@@ -55,6 +56,30 @@ class _Registration:
         if self._KIND == "acvo":  # src/adaptive_cvo.cpp:476-478
             self._ell = float(self.params.ell_init)
         self._have_moving = True
+
+    def set_pcd_images(self, dataset_seq, img3, depth):
+        """set_pcd(dataset_seq, RGB, depth, ...) (src/cvo.cpp:319-357) with the image front end on the device:
+        pcd_generator::load_image + create_pointcloud(feature_type 1 for cvo, 0 for acvo; src/cvo.cpp:329,
+        src/adaptive_cvo.cpp:451)."""
+        if self._first is not None or (self.init and not self._images):
+            raise RuntimeError("one frontend object takes either arrays or images, not both")
+        self._images = True
+        n = self._ctx.push_frame_images(self._slot, img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1)
+        if not self.init:
+            self.init = True
+            return n
+        self._bound = True
+        if self._KIND == "acvo":  # src/adaptive_cvo.cpp:476-478
+            self._ell = float(self.params.ell_init)
+        self._have_moving = True
+        return n
+
+    def run_cvo_images(self, dataset_seq, img3, depth):
+        """run_cvo(dataset_seq, RGB, depth, ...) (src/cvo.cpp:422-435)."""
+        first = not self.init
+        self.set_pcd_images(dataset_seq, img3, depth)
+        if not first:
+            self.align()
 
     def align(self):
         """align (src/cvo.cpp:361-420)."""

@@ -149,3 +149,40 @@ def config_pair(cfg, pair_index=0):
     if cfg == 5:
         return make_pair(seed, 10000, 10000, "cvo")
     raise ValueError("cfg must be 1..5")
+
+
+def make_frame(seed, w=640, h=480, texture=1.0):
+    """A seeded synthetic RGB-D frame shaped like the reference's image inputs (src/cvo_main.cpp:104-107): an 8-bit
+    3-channel image of random overlapping rectangles, discs and line segments (edges and texture for the DSO pixel
+    selector, src/pcd_generator.cpp:122-164) with sensor noise, and a 16-bit depth image (TUM scaling 5000/m) of a
+    tilted plane with boxes and a few zero-depth holes.  `texture` < 1 thins the structure out (low-texture frames
+    exercise the selector's re-selection and the Canny top-up).  Returns (img3 uint8[h,w,3], depth uint16[h,w])."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.empty((h, w, 3), np.float32)
+    base = rng.uniform(60, 190, 3)
+    img[:] = base + 25.0 * np.stack([np.sin(xx / 97.0 + i) * np.cos(yy / 71.0 - i) for i in range(3)], axis=-1)
+    depth_m = 1.0 + 0.6 * (yy / h) + 0.2 * (xx / w)
+    n_shapes = max(1, int(40 * texture))
+    for _ in range(n_shapes):
+        col = rng.uniform(10, 245, 3)
+        if rng.uniform() < 0.6:
+            x0, y0 = rng.integers(0, w - 20), rng.integers(0, h - 20)
+            x1, y1 = x0 + rng.integers(15, 220), y0 + rng.integers(15, 160)
+            m = (xx >= x0) & (xx < x1) & (yy >= y0) & (yy < y1)
+            depth_m[m] = rng.uniform(0.7, 1.9)
+        else:
+            cx, cy, r = rng.integers(0, w), rng.integers(0, h), rng.integers(8, 70)
+            m = (xx - cx) ** 2 + (yy - cy) ** 2 < r * r
+        img[m] = col + 12.0 * np.sin((xx[m] + 2 * yy[m]) / rng.uniform(3, 15))[:, None]
+    for _ in range(int(25 * texture)):
+        x0, y0, x1, y1 = rng.uniform(0, w), rng.uniform(0, h), rng.uniform(0, w), rng.uniform(0, h)
+        d = np.abs((y1 - y0) * xx - (x1 - x0) * yy + x1 * y0 - y1 * x0) / max(np.hypot(y1 - y0, x1 - x0), 1.0)
+        img[d < rng.uniform(0.7, 2.0)] = rng.uniform(0, 255, 3)
+    img += rng.normal(0, 2.0 * texture + 0.3, img.shape)
+    img3 = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    depth = np.clip(np.rint(depth_m * 5000.0), 0, 65535).astype(np.uint16)
+    for _ in range(6):  # holes: the sensor returns 0 where it has no reading
+        x0, y0 = rng.integers(0, w - 40), rng.integers(0, h - 30)
+        depth[y0:y0 + rng.integers(5, 30), x0:x0 + rng.integers(5, 40)] = 0
+    return img3, depth

@@ -27,8 +27,9 @@ typedef struct cvo_b200_ctx cvo_b200_ctx;
 enum { CVO_B200_OK = 0,
        CVO_B200_ERR_ARG = -1,     /* bad slot / size / NULL pointer                     */
        CVO_B200_ERR_CUDA = -2,    /* CUDA runtime error; see cvo_b200_last_error()      */
-       CVO_B200_ERR_EMPTY = -3 }; /* empty cloud (the reference asserts in nanoflann,
+       CVO_B200_ERR_EMPTY = -3,   /* empty cloud (the reference asserts in nanoflann,
                                      thirdparty/KDTreeVectorOfVectorsAdaptor.h:61)      */
+       CVO_B200_ERR_UNSUPPORTED = -4 }; /* a branch of the reference that is not built  */
 
 enum { CVO_B200_MODE_CVO = 0,     /* cvo::compute_flow   (src/cvo.cpp:164-210)          */
        CVO_B200_MODE_ACVO = 1 };  /* acvo::compute_flow  (src/adaptive_cvo.cpp:154-272) */
@@ -121,6 +122,29 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs,
  * the slot's moving cloud becomes its fixed cloud (pointer swap on the device) and a new moving cloud
  * is uploaded, so a sequence uploads each frame once. */
 int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n);
+
+/* Image front door.  Replaces pcd_generator::load_image + create_pointcloud
+ * (src/pcd_generator.cpp:384-420: cv::cvtColor to gray / HSV, the 3-level gradient pyramid, DSO's PixelSelector2
+ * with num_want = 3000, pinhole back-projection with the intrinsics of `dataset_seq` (:241-302), the 5-D features
+ * of `feature_type` 0 = HSV/[180,255,255] + gradient*2/255 (acvo) or 1 = raw channels + raw gradient (cvo)) and the
+ * tail of set_pcd() (src/cvo.cpp:319-357), entirely on the device: the image and depth are copied once and the
+ * cloud is written straight into the slot's packed planes.
+ *  img3   height x width x 3, 8-bit, as cv::imread returns it;  depth  height x width, 16-bit.
+ *  width and height must be multiples of 32 (TUM: 640 x 480).
+ * The first call on a fresh slot creates the FIXED cloud (src/cvo.cpp:326-334); every later call makes the slot's
+ * moving cloud its fixed cloud (:417) and creates the new moving cloud.  *num_points receives the cloud size.
+ * Synchronous.  CVO_B200_ERR_UNSUPPORTED: a low-texture frame for which the reference would add Canny edges
+ * (src/pcd_generator.cpp:135-163) -- not built; the slot is left unchanged. */
+int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
+                               int width, int height, int dataset_seq, int feature_type, int* num_points);
+/* The cloud the last cvo_b200_push_frame_images generated, in the reference's (raster) order: xyz n x 3,
+ * feat n x 5 row-major (parity hook; valid until the next upload of any kind). */
+int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n);
+/* Forgets the clouds of a slot (start of a new sequence). */
+int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot);
+/* Test hook: the byte sequence `rand() & 0xFF` of glibc after srand(seed), as used for the selector's
+ * randomPattern (thirdparty/PixelSelector2.cpp:36-38), produced without touching the C library's state. */
+int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out);
 
 /* One pass of transform_pcd + se_kernel + compute_flow + compute_step_size at a given state
  * (src/cvo.cpp:368-377) without updating anything: fills one record (R,T echo the input). */

@@ -9,9 +9,10 @@
 //   Q4  R, T are never reset between pairs; ell is never re-armed in cvo but is in acvo (src/adaptive_cvo.cpp:476-478)
 //   Q5  `iter` is only assigned when a stop test fired (src/cvo.cpp:381,403)
 // The reference's image overload set_pcd(dataset_seq, cv::Mat RGB, cv::Mat depth, ...) runs the image
-// front-end (pcd_generator, out of scope here); this header offers the raw-array
-// overload that front-end's OUTPUT feeds: N x 3 positions and N x 5 features.  INTEGRATION.md shows the
-// three-line change that routes the reference's own set_pcd()/align() through this library.
+// front end (pcd_generator + DSO PixelSelector2); this header offers both an
+// image overload on plain pointers (the front end then runs on the device, cvo_b200_push_frame_images) and the
+// raw-array overload that front end's OUTPUT feeds: N x 3 positions and N x 5 features.  INTEGRATION.md shows
+// the three-line change that routes the reference's own set_pcd()/align() through this library.
 //
 // Header-only; needs only libcvo_b200.so.  No Eigen / OpenCV / PCL / TBB.
 #ifndef CVO_B200_FRONTEND_HPP
@@ -103,6 +104,28 @@ class registration {
         have_moving_ = true;
     }
     void set_pcd(const point_cloud& pc) { set_pcd(pc.positions.data(), pc.features.data(), pc.num_points); }
+
+    // set_pcd(dataset_seq, RGB, depth, ...) (src/cvo.cpp:319-357) with the image front end on the device
+    // (pcd_generator::load_image + create_pointcloud: feature type 1 for cvo, src/cvo.cpp:329, 0 for acvo,
+    // src/adaptive_cvo.cpp:451).  img3: height x width x 3 8-bit as cv::imread returns it (cv::Mat::data of a
+    // continuous CV_8UC3), depth: height x width 16-bit (CV_16UC1).  Returns the number of points.
+    int set_pcd(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
+        int n = 0;
+        check(cvo_b200_push_frame_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
+        if (!init) {
+            init = true;
+            return n;
+        }
+        pair_bound_ = true;
+        if (adaptive_) ell_ = params_.ell_init;  // src/adaptive_cvo.cpp:476-478
+        have_moving_ = true;
+        return n;
+    }
+    void run_cvo(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
+        const bool first = !init;  // src/cvo.cpp:422-435
+        set_pcd(dataset_seq, img3, depth, width, height);
+        if (!first) align();
+    }
 
     // align (src/cvo.cpp:361-420)
     void align() {

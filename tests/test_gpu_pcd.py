@@ -1,0 +1,108 @@
+"""GPU parity tests of the image front end: cvo_b200_push_frame_images against the CPU
+restatement of pcd_generator + DSO PixelSelector2 (oracle/pcd_oracle.cpp).  The bar is BIT-EXACT: the path is
+integer / byte / index work plus a handful of individually rounded float operations."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import pose_diff
+from cvo_rgbd_b200 import capi, frontend, synth
+from oracle import pcd_oracle as P
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pcd_golden.json")
+
+
+@pytest.fixture(scope="module")
+def img_ctx():
+    ctx = capi.Context(0, max_points=4096, max_slots=4)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,texture,dataset_seq,feature_type", [(1, 1.0, 1, 1), (2, 1.0, 1, 0), (3, 0.3, 2, 1),
+                                                                   (4, 0.05, 3, 0), (5, 3.0, 0, 1), (21, 1.0, 4, 1),
+                                                                   (22, 0.6, 5, 0), (23, 2.0, 1, 1)])
+def test_generated_cloud_equals_the_oracle_bit_for_bit(img_ctx, seed, texture, dataset_seq, feature_type):
+    """Covers no re-selection (potential 3 only), re-selection with a larger potential (too many picks) and with a
+    smaller one (too few), every camera model of src/pcd_generator.cpp:241-302 and both feature types."""
+    img, dep = synth.make_frame(seed, texture=texture)
+    want = P.create_pointcloud(img, dep, dataset_seq, feature_type)
+    img_ctx.reset_slot(0)
+    n = img_ctx.push_frame_images(0, img, dep, dataset_seq, feature_type)
+    xyz, feat = img_ctx.last_generated_cloud()
+    assert n == len(want["xyz"]) == len(xyz)
+    assert np.array_equal(xyz, want["xyz"])
+    assert np.array_equal(feat, want["feat"])
+
+
+def test_golden_fingerprints(img_ctx):
+    import hashlib
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for case in json.load(open(GOLD)):
+        img, dep = synth.make_frame(case["seed"], texture=case["texture"])
+        img_ctx.reset_slot(0)
+        assert img_ctx.push_frame_images(0, img, dep, case["dataset_seq"], case["feature_type"]) == case["n"]
+        xyz, feat = img_ctx.last_generated_cloud()
+        assert sha(xyz) == case["xyz_sha"] and sha(feat) == case["feat_sha"]
+
+
+def test_other_image_sizes_and_refused_sizes(img_ctx):
+    img, dep = synth.make_frame(31, w=320, h=256)
+    want = P.create_pointcloud(img, dep, 1, 1)
+    img_ctx.reset_slot(1)
+    assert img_ctx.push_frame_images(1, img, dep, 1, 1) == len(want["xyz"])
+    xyz, feat = img_ctx.last_generated_cloud()
+    assert np.array_equal(xyz, want["xyz"]) and np.array_equal(feat, want["feat"])
+    with pytest.raises(capi.CvoB200Error) as e:
+        img_ctx.push_frame_images(1, np.zeros((100, 100, 3), np.uint8), np.ones((100, 100), np.uint16))
+    assert e.value.code == capi.ERR_ARG
+
+
+def test_low_texture_frame_is_reported_not_processed_differently(img_ctx):
+    """The reference adds Canny edges when the selector keeps fewer than num_want/3 pixels
+    (src/pcd_generator.cpp:135-163); that branch is not built: the call fails and the slot is unchanged."""
+    img, dep = synth.make_frame(12, texture=0.0)
+    img[:] = (img.astype(np.int32) // 8 * 8).astype(np.uint8)
+    assert P.create_pointcloud(img, dep, 1, 1)["canny"]
+    img_ctx.reset_slot(2)
+    good = synth.make_frame(1)
+    n0 = img_ctx.push_frame_images(2, good[0], good[1], 1, 1)
+    with pytest.raises(capi.CvoB200Error) as e:
+        img_ctx.push_frame_images(2, img, dep, 1, 1)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    n1 = img_ctx.push_frame_images(2, *synth.make_frame(2), 1, 1)  # still the second frame of the sequence
+    assert n0 > 0 and n1 > 0
+    r = img_ctx.align(np.array([2]), _few_iters(capi.default_params("cvo")))
+    assert np.isfinite(r["transform"]).all()
+
+
+def _few_iters(p):
+    p.fixed_iters = 3
+    return p
+
+
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_image_sequence_through_the_frontend_equals_the_array_path(kind):
+    """run_cvo on images (device front end) == run_cvo on the clouds the oracle extracts from the same images."""
+    frames = []
+    base_img, base_dep = synth.make_frame(41)
+    for k in range(3):  # a camera panning over a static scene: shift the image and the depth by a few pixels
+        frames.append((np.roll(base_img, 3 * k, axis=1), np.roll(base_dep, 3 * k, axis=1)))
+    cls = frontend.cvo if kind == "cvo" else frontend.acvo
+    a, b = cls(max_points=4096), cls(max_points=4096)
+    try:
+        for img, dep in frames:
+            a.run_cvo_images(1, img, dep)
+            o = P.create_pointcloud(img, dep, 1, 1 if kind == "cvo" else 0)
+            b.run_cvo(o["xyz"], o["feat"])
+            assert np.array_equal(a.transform, b.transform) and np.array_equal(a.accum_transform, b.accum_transform)
+            assert a.iter == b.iter
+        assert np.linalg.norm(a.accum_transform[:3, 3]) > 1e-4  # it registered a motion
+        rot, tr = pose_diff(a.accum_transform, b.accum_transform)
+        assert rot == 0 and tr == 0
+    finally:
+        a.close()
+        b.close()
