@@ -26,6 +26,7 @@ EXPORTS = [
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
+    "cvo_b200_last_frame_used_canny",
 ]
 
 
@@ -109,6 +110,7 @@ def load():
                                                C.c_int, C.c_int, ip]
     lib.cvo_b200_last_generated_cloud.argtypes = [vp, fp, fp, C.c_int, ip]
     lib.cvo_b200_reset_slot.argtypes = [vp, C.c_int]
+    lib.cvo_b200_last_frame_used_canny.argtypes = [vp]
     lib.cvo_b200_selftest_rand_bytes.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_ubyte)]
     lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
     lib.cvo_b200_last_list_builds.argtypes = [vp]
@@ -226,6 +228,10 @@ class Context:
         xyz, feat = np.zeros((n.value, 3), np.float32), np.zeros((n.value, 5), np.float32)
         self._check(self._lib.cvo_b200_last_generated_cloud(self._h, _fp(xyz), _fp(feat), n.value, C.byref(n)))
         return xyz, feat
+
+    @property
+    def last_frame_used_canny(self):
+        return bool(self._lib.cvo_b200_last_frame_used_canny(self._h))
 
     def reset_slot(self, slot):
         self._check(self._lib.cvo_b200_reset_slot(self._h, slot))

@@ -81,6 +81,7 @@ struct cvo_b200_ctx {
         bool tables = false;
     } pipe;
     int last_gen_n = 0;
+    int last_gen_canny = 0;
     double* h_inner = nullptr;  // pinned
 
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
@@ -810,6 +811,19 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
         pcd_decide_kernel<<<1, 1, 0, st>>>(B, stage);
     }
     pcd_subsample_kernel<<<1, 1024, 0, st>>>(B);
+    {   // low-texture top-up (src/pcd_generator.cpp:135-163): decided on the device, a few empty launches otherwise.
+        // Its scratch re-uses level 1 of the pyramid, which nothing reads after the selection.
+        CannyScratch cs;
+        cs.blurred = reinterpret_cast<uint8_t*>(B.I[1]);
+        cs.mag = reinterpret_cast<uint16_t*>(B.dx[1]);  // spans dx[1] + dy[1]
+        cs.cls = reinterpret_cast<uint8_t*>(B.g2[1]);
+        pcd_blur_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, cs);
+        pcd_sobel_mag_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, cs);
+        pcd_nms_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, cs);
+        pcd_hysteresis_kernel<<<1, 1024, 0, st>>>(B, cs);
+        pcd_topup_kernel<<<((w / 8) * (h / 8) + T - 1) / T, T, 0, st>>>(B, cs);
+        pcd_topup_done_kernel<<<1, 1, 0, st>>>(B);
+    }
     PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, target), slot_f(ctx, slot, target),
                    slot_f4(ctx, slot, target), 0, 0};
     CK(cudaMemcpyAsync(ctx->d_jobs, &job, sizeof(PackJob), cudaMemcpyHostToDevice, st));
@@ -817,17 +831,13 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
                                          ctx->max_points, &ctx->d_jobs->n);
     pack_sort_kernel<<<1, kPackThreads, ctx->pack_smem_max, st>>>(ctx->d_jobs, ctx->sort_points);
     CK(cudaGetLastError());
-    ctx->launches += 14;
+    ctx->launches += 20;
     CK(cudaMemcpyAsync(P.h_ctl, P.d_ctl, sizeof(SelCtl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const SelCtl& c = *P.h_ctl;
     ctx->last_gen_n = c.num_points < ctx->max_points ? c.num_points : ctx->max_points;
     if (num_points) *num_points = c.num_points;
-    if (c.status == PCD_STATUS_NEEDS_CANNY) {
-        ctx->err = "low-texture frame: the selector kept fewer than num_want/3 pixels and the reference would add Canny "
-                   "edges (src/pcd_generator.cpp:135-163); that top-up is not built";
-        return CVO_B200_ERR_UNSUPPORTED;
-    }
+    ctx->last_gen_canny = c.canny_used;
     if (c.status == PCD_STATUS_TOO_MANY_POINTS) return fail_arg(ctx, "the frame yields more points than max_points");
     if (c.num_points <= 0) {
         ctx->err = "empty cloud";
@@ -851,6 +861,8 @@ int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, in
     CK(cudaStreamSynchronize(ctx->stream));
     return CVO_B200_OK;
 }
+
+int cvo_b200_last_frame_used_canny(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_gen_canny : 0; }
 
 int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot) {
     if (!ctx) return CVO_B200_ERR_ARG;

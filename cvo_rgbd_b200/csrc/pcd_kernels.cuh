@@ -18,8 +18,9 @@
 // reference (the random sub-sampling, PixelSelector2.cpp:226-243, indexed by the RANK of a selected pixel, and the
 // point / feature emission) are exclusive scans over the pixel flags.
 //
-// Not built: the Canny top-up for low-texture frames (src/pcd_generator.cpp:135-163, cv::blur + cv::Canny); such a
-// frame is reported (PCD_STATUS_NEEDS_CANNY) instead of being processed differently from the reference.
+// The Canny top-up for low-texture frames (src/pcd_generator.cpp:135-163: cv::blur 3x3 + cv::Canny(0, 25, 3), then
+// one extra pixel per 8 x 8 block) is decided and executed on the device as well: its five kernels are always
+// enqueued and return at once unless the selector kept fewer than num_want/3 pixels.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -44,6 +45,7 @@ struct SelCtl {
     int num_points;   // selected pixels with a depth reading: the cloud size
     int status;
     int num_want;
+    int canny_used;   // the low-texture top-up ran for this frame
 };
 
 struct PcdBuffers {
@@ -89,6 +91,7 @@ __global__ void pcd_gray_kernel(PcdBuffers b, int num_want) {
         for (int s = 0; s < 2; ++s) c.n[s][0] = c.n[s][1] = c.n[s][2] = 0;
         c.quotia = 0.f; c.num_have = 0; c.num_selected = 0; c.num_points = 0; c.status = PCD_STATUS_OK;
         c.num_want = num_want;
+        c.canny_used = 0;
     }
     if (i >= b.w * b.h) return;
     b.I[0][i] = (float)rgb2gray_u8(b.img3[3 * i], b.img3[3 * i + 1], b.img3[3 * i + 2]);
@@ -336,6 +339,143 @@ __global__ void __launch_bounds__(1024) pcd_subsample_kernel(PcdBuffers b) {
     if (threadIdx.x == 0) {
         c.num_selected = num;
         if (num < c.num_want / 3) c.status = PCD_STATUS_NEEDS_CANNY;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Canny top-up (src/pcd_generator.cpp:135-163).  cv::blur and cv::Canny restated from OpenCV's algorithm
+// (modules/imgproc/src/canny.cpp); every kernel returns unless the selection raised PCD_STATUS_NEEDS_CANNY.
+// ---------------------------------------------------------------------------------------------------------
+struct CannyScratch {
+    uint8_t* blurred;  // w * h
+    uint16_t* mag;     // w * h: |dx| + |dy| of the 3 x 3 Sobel (<= 2040)
+    uint8_t* cls;      // w * h: 0 no edge, 1 candidate (local maximum above the low threshold), 2 edge
+};
+
+// cv::blur(intensity, edge, Size(3,3)): BORDER_REFLECT_101, rounded mean (sum / 9 never ends in .5)
+__global__ void pcd_blur_kernel(PcdBuffers b, CannyScratch cs) {
+    if (b.ctl->status != PCD_STATUS_NEEDS_CANNY) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, w = b.w, h = b.h;
+    if (i >= w * h) return;
+    const int x = i % w, y = i / w;
+    int sum = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        int yy = y + dy;
+        yy = yy < 0 ? -yy : (yy >= h ? 2 * h - 2 - yy : yy);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            int xx = x + dx;
+            xx = xx < 0 ? -xx : (xx >= w ? 2 * w - 2 - xx : xx);
+            sum += (int)b.I[0][yy * w + xx];  // level 0 of the pyramid holds the 8-bit intensity exactly
+        }
+    }
+    cs.blurred[i] = (uint8_t)((sum + 4) / 9);
+}
+
+__device__ __forceinline__ void sobel3(const uint8_t* img, int w, int h, int x, int y, int& dx, int& dy) {
+    const int xm = max(x - 1, 0), xp = min(x + 1, w - 1), ym = max(y - 1, 0), yp = min(y + 1, h - 1);  // BORDER_REPLICATE
+    const int a = img[ym * w + xm], bb = img[ym * w + x], c = img[ym * w + xp];
+    const int d = img[y * w + xm], f = img[y * w + xp];
+    const int g = img[yp * w + xm], hh = img[yp * w + x], k = img[yp * w + xp];
+    dx = (c + 2 * f + k) - (a + 2 * d + g);
+    dy = (g + 2 * hh + k) - (a + 2 * bb + c);
+}
+
+__global__ void pcd_sobel_mag_kernel(PcdBuffers b, CannyScratch cs) {
+    if (b.ctl->status != PCD_STATUS_NEEDS_CANNY) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, w = b.w, h = b.h;
+    if (i >= w * h) return;
+    int dx, dy;
+    sobel3(cs.blurred, w, h, i % w, i / w, dx, dy);
+    cs.mag[i] = (uint16_t)(abs(dx) + abs(dy));  // L2gradient = false
+}
+
+// non-maximum suppression with the 15-bit tan(22.5 deg) sector test and its asymmetric comparisons; low = 0, high = 25
+__global__ void pcd_nms_kernel(PcdBuffers b, CannyScratch cs) {
+    if (b.ctl->status != PCD_STATUS_NEEDS_CANNY) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, w = b.w, h = b.h;
+    if (i >= w * h) return;
+    const int x = i % w, y = i / w;
+    auto M = [&](int xx, int yy) { return (xx < 0 || yy < 0 || xx >= w || yy >= h) ? 0 : (int)cs.mag[yy * w + xx]; };
+    const int v = cs.mag[i];
+    uint8_t c = 0;
+    if (v > 0) {
+        int xs, ys;
+        sobel3(cs.blurred, w, h, x, y, xs, ys);
+        const long long TG22 = 13573;  // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+        const long long ax = abs(xs), ay = (long long)abs(ys) << 15;
+        const long long tg22x = ax * TG22, tg67x = tg22x + (ax << 16);
+        bool ismax;
+        if (ay < tg22x) ismax = v > M(x - 1, y) && v >= M(x + 1, y);
+        else if (ay > tg67x) ismax = v > M(x, y - 1) && v >= M(x, y + 1);
+        else {
+            const int sgn = (xs ^ ys) < 0 ? -1 : 1;
+            ismax = v > M(x - sgn, y - 1) && v > M(x + sgn, y + 1);
+        }
+        if (ismax) c = v > 25 ? 2 : 1;
+    }
+    cs.cls[i] = c;
+}
+
+// 8-connected hysteresis: candidates touching an edge become edges, to the fixed point (which is unique, so the
+// races between threads reading and promoting neighbours do not matter).  One CTA; thread t owns a contiguous
+// pixel range and sweeps it forwards and backwards, so that chains along the raster order close in one pass.
+__global__ void __launch_bounds__(1024) pcd_hysteresis_kernel(PcdBuffers b, CannyScratch cs) {
+    if (b.ctl->status != PCD_STATUS_NEEDS_CANNY) return;
+    __shared__ int changed;
+    const int w = b.w, h = b.h, npix = w * h, per = (npix + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, npix), hi = min(lo + per, npix);
+    volatile uint8_t* cls = cs.cls;
+    auto promote = [&](int i) {
+        if (cls[i] != 1) return 0;
+        const int x = i % w, y = i / w;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || yy < 0 || xx >= w || yy >= h) continue;
+                if (cls[yy * w + xx] == 2) {
+                    cls[i] = 2;
+                    return 1;
+                }
+            }
+        return 0;
+    };
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        int any = 0;
+        for (int i = lo; i < hi; ++i) any |= promote(i);
+        for (int i = hi - 1; i >= lo; --i) any |= promote(i);
+        if (any) changed = 1;
+        __threadfence_block();
+        __syncthreads();
+        if (!changed) break;
+    }
+}
+
+// the top-up itself: in every 8 x 8 block the first edge pixel (rows outer, columns inner) that is not selected yet
+// becomes a selected pixel (src/pcd_generator.cpp:144-162).  Clears the condition: the frame proceeds normally.
+__global__ void pcd_topup_kernel(PcdBuffers b, CannyScratch cs) {
+    if (b.ctl->status != PCD_STATUS_NEEDS_CANNY) return;
+    const int w = b.w, h = b.h, nbx = w / 8, nby = h / 8;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbx * nby) return;
+    const int x0 = (t % nbx) * 8, y0 = (t / nbx) * 8;
+    for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 8; ++i) {
+            const int p = (y0 + j) * w + x0 + i;
+            if (cs.cls[p] == 2 && b.map[p] == 0) {
+                b.map[p] = 1;
+                return;
+            }
+        }
+}
+__global__ void pcd_topup_done_kernel(PcdBuffers b) {
+    if (b.ctl->status == PCD_STATUS_NEEDS_CANNY) {
+        b.ctl->status = PCD_STATUS_OK;
+        b.ctl->canny_used = 1;
     }
 }
 

@@ -133,13 +133,16 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
  *  width and height must be multiples of 32 (TUM: 640 x 480).
  * The first call on a fresh slot creates the FIXED cloud (src/cvo.cpp:326-334); every later call makes the slot's
  * moving cloud its fixed cloud (:417) and creates the new moving cloud.  *num_points receives the cloud size.
- * Synchronous.  CVO_B200_ERR_UNSUPPORTED: a low-texture frame for which the reference would add Canny edges
- * (src/pcd_generator.cpp:135-163) -- not built; the slot is left unchanged. */
+ * A low-texture frame (fewer than num_want/3 pixels selected) gets the reference's Canny top-up
+ * (src/pcd_generator.cpp:135-163: cv::blur 3x3, cv::Canny(0, 25, 3), one extra pixel per 8 x 8 block), also on the
+ * device.  Synchronous.  On an error the slot is left unchanged. */
 int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
                                int width, int height, int dataset_seq, int feature_type, int* num_points);
 /* The cloud the last cvo_b200_push_frame_images generated, in the reference's (raster) order: xyz n x 3,
  * feat n x 5 row-major (parity hook; valid until the next upload of any kind). */
 int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n);
+/* Whether the last cvo_b200_push_frame_images took the Canny top-up branch. */
+int cvo_b200_last_frame_used_canny(const cvo_b200_ctx* ctx);
 /* Forgets the clouds of a slot (start of a new sequence). */
 int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot);
 /* Test hook: the byte sequence `rand() & 0xFF` of glibc after srand(seed), as used for the selector's

@@ -8,7 +8,7 @@
 //   dso::PixelSelector::makeHists        thirdparty/PixelSelector2.cpp:71-136
 //   dso::PixelSelector::makeMaps         thirdparty/PixelSelector2.cpp:137-282
 //   dso::PixelSelector::select           thirdparty/PixelSelector2.cpp:286-435
-//   pcd_generator::select_point          src/pcd_generator.cpp:122-164   (Canny top-up: done by the Python wrapper with cv2)
+//   pcd_generator::select_point          src/pcd_generator.cpp:122-164   (incl. the Canny top-up, cv::blur + cv::Canny restated)
 //   pcd_generator::get_points_from_pixels src/pcd_generator.cpp:233-327
 //   pcd_generator::get_features          src/pcd_generator.cpp:329-382
 // Only tests/, __graft_entry__.smoke() and bench.py's CPU arm may load this library; the product path never does.
@@ -16,7 +16,10 @@
 // OpenCV is a third-party dependency of the reference that is absent from /root/reference and unpinned ("OpenCV >= 3",
 // CMakeLists.txt:46).  The two colour conversions are restated here from OpenCV 4.x's published 8-bit fixed-point
 // formulas (modules/imgproc/src/color_rgb / color_hsv: 15-bit luma weights 9798/19235/3735; HSV with hsv_shift = 12
-// and the sdiv / hdiv180 tables) and PINNED against the cv2 4.13 of this image in tests/test_pcd_oracle.py.
+// and the sdiv / hdiv180 tables), cv::blur(3x3) and cv::Canny(0, 25, aperture 3, L1 gradient) from OpenCV's published
+// algorithm (modules/imgproc/src/canny.cpp: Sobel with replicated border, 15-bit tan(22.5 deg) sector test with its
+// asymmetric > / >= comparisons, 8-connected hysteresis); all four are PINNED against the cv2 4.13 of this image in
+// tests/test_pcd_oracle.py.
 //
 // Two reads of uninitialised heap memory in the reference are given a defined value here (and in the CUDA path):
 //   U1  abs_squared_grad[l] is `new float[]` and its first and last image rows are never written
@@ -284,6 +287,89 @@ void pcd_oracle_rgb2hsv(const uint8_t* img3, int n, uint8_t* hsv3) {
         hsv3[3 * i + 1] = (uint8_t)s;
         hsv3[3 * i + 2] = (uint8_t)v;
     }
+}
+
+// cv::blur(src, dst, Size(3,3)) on 8-bit (BORDER_REFLECT_101, rounded mean; sum/9 never ends in .5) followed by
+// cv::Canny(dst, dst, 0, 25, 3) (L2gradient = false).  edge: w*h bytes, 0 or 255.
+void pcd_oracle_blur_canny(const uint8_t* gray, int w, int h, uint8_t* blurred, uint8_t* edge) {
+    auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int sum = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) sum += gray[refl(y + dy, h) * w + refl(x + dx, w)];
+            blurred[y * w + x] = (uint8_t)((sum + 4) / 9);
+        }
+    auto clampi = [](int i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); };
+    std::vector<int> gx((size_t)w * h), gy((size_t)w * h), mag((size_t)(w + 2) * (h + 2), 0);
+    auto B = [&](int x, int y) { return (int)blurred[clampi(y, h) * w + clampi(x, w)]; };
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int dx = (B(x + 1, y - 1) + 2 * B(x + 1, y) + B(x + 1, y + 1)) - (B(x - 1, y - 1) + 2 * B(x - 1, y) + B(x - 1, y + 1));
+            const int dy = (B(x - 1, y + 1) + 2 * B(x, y + 1) + B(x + 1, y + 1)) - (B(x - 1, y - 1) + 2 * B(x, y - 1) + B(x + 1, y - 1));
+            gx[y * w + x] = dx;
+            gy[y * w + x] = dy;
+            mag[(y + 1) * (w + 2) + x + 1] = std::abs(dx) + std::abs(dy);
+        }
+    const int low = 0, high = 25;
+    const long long TG22 = (long long)(0.4142135623730950488016887242097 * (1 << 15) + 0.5);
+    std::vector<uint8_t> cls((size_t)w * h, 0);  // 0 no edge, 1 candidate, 2 edge
+    std::vector<int> stack;
+    const int ms = w + 2;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const int* m = &mag[(y + 1) * ms + x + 1];
+            const int v = *m;
+            if (!(v > low)) continue;
+            const int xs = gx[y * w + x], ys = gy[y * w + x];
+            const long long ax = std::abs(xs), ay = (long long)std::abs(ys) << 15;
+            const long long tg22x = ax * TG22, tg67x = tg22x + (ax << 16);
+            bool ismax;
+            if (ay < tg22x) ismax = v > m[-1] && v >= m[1];
+            else if (ay > tg67x) ismax = v > m[-ms] && v >= m[ms];
+            else {
+                const int sgn = (xs ^ ys) < 0 ? -1 : 1;
+                ismax = v > m[-ms - sgn] && v > m[ms + sgn];
+            }
+            if (!ismax) continue;
+            if (v > high) { cls[y * w + x] = 2; stack.push_back(y * w + x); }
+            else cls[y * w + x] = 1;
+        }
+    while (!stack.empty()) {  // 8-connected hysteresis
+        const int i = stack.back();
+        stack.pop_back();
+        const int x = i % w, y = i / w;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || yy < 0 || xx >= w || yy >= h) continue;
+                if (cls[yy * w + xx] == 1) { cls[yy * w + xx] = 2; stack.push_back(yy * w + xx); }
+            }
+    }
+    for (int i = 0; i < w * h; ++i) edge[i] = cls[i] == 2 ? 255 : 0;
+}
+
+// the Canny top-up of select_point (src/pcd_generator.cpp:135-163): in every 8 x 8 block the first edge pixel (rows
+// outer, columns inner) that is not selected yet becomes a selected pixel.  Returns 1 if it ran.
+int pcd_oracle_canny_topup(const uint8_t* gray, int w, int h, int num_want, int num_selected, float* map) {
+    if (!(num_selected < num_want / 3)) return 0;
+    std::vector<uint8_t> blurred((size_t)w * h), edge((size_t)w * h);
+    pcd_oracle_blur_canny(gray, w, h, blurred.data(), edge.data());
+    const int block_size = 8;
+    for (int y = 0; y < h; y += block_size)
+        for (int x = 0; x < w; x += block_size) {
+            bool point_got = false;
+            for (int j = 0; j < block_size; ++j) {
+                for (int i = 0; i < block_size; ++i)
+                    if (edge[(y + j) * w + x + i] != 0 && map[(y + j) * w + x + i] == 0) {
+                        map[(y + j) * w + x + i] = 1;
+                        point_got = true;
+                        break;
+                    }
+                if (point_got) break;
+            }
+        }
+    return 1;
 }
 
 // select_point up to (not including) the Canny top-up: map_out (w*h floats, 0 / 1 / 2 / 4), returns num_selected.

@@ -2,9 +2,9 @@
 (pcd_generator + DSO PixelSelector2; see the header of pcd_oracle.cpp for the file:line map).
 TEST INFRASTRUCTURE ONLY -- the product path never imports this.
 
-The two OpenCV colour conversions are restated in C (pcd_oracle.cpp) and pinned against cv2 by
-tests/test_pcd_oracle.py; the Canny top-up of select_point (src/pcd_generator.cpp:135-163), which the reference
-delegates to cv::blur + cv::Canny, is delegated to cv2 here as well (the same third-party library)."""
+What the reference delegates to OpenCV -- the two colour conversions, cv::blur and cv::Canny of the low-texture
+top-up (src/pcd_generator.cpp:135-163) -- is restated in C (pcd_oracle.cpp) and pinned against cv2 by
+tests/test_pcd_oracle.py."""
 import ctypes as C
 import os
 import subprocess
@@ -27,6 +27,8 @@ def load():
     lib.pcd_oracle_rgb2gray.argtypes = [u8, C.c_int, u8]
     lib.pcd_oracle_rgb2hsv.argtypes = [u8, C.c_int, u8]
     lib.pcd_oracle_select.argtypes = [u8, C.c_int, C.c_int, C.c_int, fp, fp, fp, ip, ip]
+    lib.pcd_oracle_blur_canny.argtypes = [u8, C.c_int, C.c_int, u8, u8]
+    lib.pcd_oracle_canny_topup.argtypes = [u8, C.c_int, C.c_int, C.c_int, C.c_int, fp]
     lib.pcd_oracle_points.argtypes = [fp, u16, u8, u8, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]
     _lib = lib
     return lib
@@ -50,26 +52,20 @@ def rgb2hsv(img3):
     return out
 
 
+def blur_canny(gray):
+    """(cv::blur(gray, 3x3), cv::Canny(blurred, 0, 25, 3)) restated."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    blurred, edge = np.empty_like(gray), np.empty_like(gray)
+    load().pcd_oracle_blur_canny(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], _p(blurred, C.c_uint8), _p(edge, C.c_uint8))
+    return blurred, edge
+
+
 def canny_top_up(gray, sel_map, num_want, num_selected):
     """select_point's fallback for low-texture frames (src/pcd_generator.cpp:135-163). Returns True if it ran."""
-    if not num_selected < num_want // 3:
-        return False
-    import cv2
-    h, w = gray.shape
-    edge = cv2.blur(gray, (3, 3))
-    edge = cv2.Canny(edge, 0, 25, apertureSize=3)
-    for y in range(0, h, 8):
-        for x in range(0, w, 8):
-            got = False
-            for j in range(8):
-                for i in range(8):
-                    if edge[y + j, x + i] != 0 and sel_map[y + j, x + i] == 0:
-                        sel_map[y + j, x + i] = 1
-                        got = True
-                        break
-                if got:
-                    break
-    return True
+    gray = np.ascontiguousarray(gray, np.uint8)
+    assert sel_map.dtype == np.float32 and sel_map.flags["C_CONTIGUOUS"]
+    return bool(load().pcd_oracle_canny_topup(_p(gray, C.c_uint8), gray.shape[1], gray.shape[0], num_want, num_selected,
+                                              _p(sel_map, C.c_float)))
 
 
 def create_pointcloud(img3, depth, dataset_seq=1, feature_type=1, num_want=3000, allow_canny=True):

@@ -61,20 +61,21 @@ def test_other_image_sizes_and_refused_sizes(img_ctx):
     assert e.value.code == capi.ERR_ARG
 
 
-def test_low_texture_frame_is_reported_not_processed_differently(img_ctx):
+def test_low_texture_frames_take_the_canny_top_up_on_the_device(img_ctx):
     """The reference adds Canny edges when the selector keeps fewer than num_want/3 pixels
-    (src/pcd_generator.cpp:135-163); that branch is not built: the call fails and the slot is unchanged."""
-    img, dep = synth.make_frame(12, texture=0.0)
-    img[:] = (img.astype(np.int32) // 8 * 8).astype(np.uint8)
-    assert P.create_pointcloud(img, dep, 1, 1)["canny"]
-    img_ctx.reset_slot(2)
-    good = synth.make_frame(1)
-    n0 = img_ctx.push_frame_images(2, good[0], good[1], 1, 1)
-    with pytest.raises(capi.CvoB200Error) as e:
-        img_ctx.push_frame_images(2, img, dep, 1, 1)
-    assert e.value.code == capi.ERR_UNSUPPORTED
-    n1 = img_ctx.push_frame_images(2, *synth.make_frame(2), 1, 1)  # still the second frame of the sequence
-    assert n0 > 0 and n1 > 0
+    (src/pcd_generator.cpp:135-163): cv::blur + cv::Canny + one extra pixel per 8 x 8 block, bit-exact here too."""
+    for seed, quant in ((12, 8), (13, 4), (14, 16)):
+        img, dep = synth.make_frame(seed, texture=0.0)
+        img[:] = (img.astype(np.int32) // quant * quant).astype(np.uint8)
+        want = P.create_pointcloud(img, dep, 1, 1)
+        img_ctx.reset_slot(2)
+        n = img_ctx.push_frame_images(2, img, dep, 1, 1)
+        assert img_ctx.last_frame_used_canny == want["canny"]
+        xyz, feat = img_ctx.last_generated_cloud()
+        assert n == len(want["xyz"]) and np.array_equal(xyz, want["xyz"]) and np.array_equal(feat, want["feat"])
+    assert want["canny"] or seed != 12
+    n1 = img_ctx.push_frame_images(2, *synth.make_frame(2), 1, 1)  # a textured second frame: no top-up
+    assert n1 > 2000 and not img_ctx.last_frame_used_canny
     r = img_ctx.align(np.array([2]), _few_iters(capi.default_params("cvo")))
     assert np.isfinite(r["transform"]).all()
 

@@ -82,8 +82,26 @@ def test_oracle_structure():
     assert np.allclose(r0["feat"][:, 3:], r["feat"][:, 3:] * 2 / 255.0, rtol=1e-6)
 
 
+def test_blur_and_canny_restatements_equal_opencv():
+    """cv::blur(3x3) and cv::Canny(0, 25, 3) of the low-texture top-up (src/pcd_generator.cpp:141-142)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    for trial in range(5):
+        g = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+        if trial >= 1:
+            g = cv2.GaussianBlur(g, (0, 0), 1 + trial)
+        if trial == 4:
+            g = (g // 4 * 4).astype(np.uint8)
+        b, e = P.blur_canny(g)
+        wb = cv2.blur(g, (3, 3))
+        assert np.array_equal(b, wb) and np.array_equal(e, cv2.Canny(wb, 0, 25, apertureSize=3))
+    img, _ = synth.make_frame(7)
+    gray = P.rgb2gray(img)
+    b, e = P.blur_canny(gray)
+    assert np.array_equal(e, cv2.Canny(cv2.blur(gray, (3, 3)), 0, 25, apertureSize=3)) and (e != 0).sum() > 1000
+
+
 def test_low_texture_frame_takes_the_canny_branch():
-    pytest.importorskip("cv2")
     img, dep = synth.make_frame(12, texture=0.0)
     img[:] = (img.astype(np.int32) // 8 * 8).astype(np.uint8)  # flatten the noise: almost no gradient anywhere
     with pytest.raises(RuntimeError):
