@@ -76,6 +76,7 @@ struct cvo_b200_ctx {
         float* d_ths = nullptr;      // ths | thsSmoothed
         uint8_t* d_map = nullptr;
         uint8_t* d_rnd = nullptr;    // the selector's randomPattern
+        int* d_blockcnt = nullptr;   // flagged pixels per 1024-pixel block (raster-order ranks)
         SelCtl* d_ctl = nullptr;
         SelCtl* h_ctl = nullptr;     // pinned
         bool tables = false;
@@ -312,7 +313,7 @@ CamInfo camera_info(int dataset_seq) {  // src/pcd_generator.cpp:241-302
 
 void free_image_pipe(cvo_b200_ctx* ctx) {
     cvo_b200_ctx::ImagePipe& P = ctx->pipe;
-    cudaFree(P.d_img3); cudaFree(P.d_depth); cudaFree(P.d_pyr); cudaFree(P.d_ths); cudaFree(P.d_map); cudaFree(P.d_rnd);
+    cudaFree(P.d_img3); cudaFree(P.d_depth); cudaFree(P.d_pyr); cudaFree(P.d_ths); cudaFree(P.d_map); cudaFree(P.d_rnd); cudaFree(P.d_blockcnt);
     cudaFree(P.d_ctl);
     if (P.h_ctl) cudaFreeHost(P.h_ctl);
     P = cvo_b200_ctx::ImagePipe();
@@ -340,6 +341,7 @@ int ensure_image_pipe(cvo_b200_ctx* ctx, int w, int h) {
     CK(cudaMalloc(&P.d_ths, (size_t)(w / 32) * (h / 32) * 2 * sizeof(float)));
     CK(cudaMalloc(&P.d_map, wh));
     CK(cudaMalloc(&P.d_rnd, wh));
+    CK(cudaMalloc(&P.d_blockcnt, ((wh + 1023) / 1024) * sizeof(int)));
     CK(cudaMalloc(&P.d_ctl, sizeof(SelCtl)));
     CK(cudaMallocHost(&P.h_ctl, sizeof(SelCtl)));
     std::vector<uint8_t> rnd(wh);
@@ -807,10 +809,13 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
     const int max_blocks = ((w + 3) / 4) * ((h + 3) / 4);  // potential 1: 4 x 4 blocks
     for (int stage = 0; stage < 2; ++stage) {
         pcd_clear_map_kernel<<<(wh + T - 1) / T, T, 0, st>>>(B, stage);
-        pcd_select_kernel<<<(max_blocks + T - 1) / T, T, 0, st>>>(B, stage);
+        pcd_select_kernel<<<(max_blocks * 16 + T - 1) / T, T, 0, st>>>(B, stage);  // one thread per pot x pot cell
         pcd_decide_kernel<<<1, 1, 0, st>>>(B, stage);
     }
-    pcd_subsample_kernel<<<1, 1024, 0, st>>>(B);
+    const int nblk = (wh + 1023) / 1024;
+    pcd_count_kernel<FLAG_SELECTED><<<nblk, 1024, 0, st>>>(B, P.d_blockcnt);
+    pcd_subsample_kernel<<<nblk, 1024, 0, st>>>(B, P.d_blockcnt);
+    pcd_after_subsample_kernel<<<1, 1, 0, st>>>(B);
     {   // low-texture top-up (src/pcd_generator.cpp:135-163): decided on the device, a few empty launches otherwise.
         // Its scratch re-uses level 1 of the pyramid, which nothing reads after the selection.
         CannyScratch cs;
@@ -827,11 +832,12 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
     PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, target), slot_f(ctx, slot, target),
                    slot_f4(ctx, slot, target), 0, 0};
     CK(cudaMemcpyAsync(ctx->d_jobs, &job, sizeof(PackJob), cudaMemcpyHostToDevice, st));
-    pcd_points_kernel<<<1, 1024, 0, st>>>(B, camera_info(dataset_seq), feature_type, ctx->d_raw_xyz, ctx->d_raw_feat,
-                                         ctx->max_points, &ctx->d_jobs->n);
+    pcd_count_kernel<FLAG_POINT><<<nblk, 1024, 0, st>>>(B, P.d_blockcnt);
+    pcd_points_kernel<<<nblk, 1024, 0, st>>>(B, P.d_blockcnt, camera_info(dataset_seq), feature_type, ctx->d_raw_xyz,
+                                            ctx->d_raw_feat, ctx->max_points, &ctx->d_jobs->n);
     pack_sort_kernel<<<1, kPackThreads, ctx->pack_smem_max, st>>>(ctx->d_jobs, ctx->sort_points);
     CK(cudaGetLastError());
-    ctx->launches += 20;
+    ctx->launches += 23;
     CK(cudaMemcpyAsync(P.h_ctl, P.d_ctl, sizeof(SelCtl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const SelCtl& c = *P.h_ctl;

@@ -46,6 +46,7 @@ struct SelCtl {
     int status;
     int num_want;
     int canny_used;   // the low-texture top-up ran for this frame
+    int num_dropped;  // pixels the random sub-sampling removed
 };
 
 struct PcdBuffers {
@@ -92,6 +93,7 @@ __global__ void pcd_gray_kernel(PcdBuffers b, int num_want) {
         c.quotia = 0.f; c.num_have = 0; c.num_selected = 0; c.num_points = 0; c.status = PCD_STATUS_OK;
         c.num_want = num_want;
         c.canny_used = 0;
+        c.num_dropped = 0;
     }
     if (i >= b.w * b.h) return;
     b.I[0][i] = (float)rgb2gray_u8(b.img3[3 * i], b.img3[3 * i + 1], b.img3[3 * i + 2]);
@@ -183,71 +185,99 @@ __global__ void pcd_clear_map_kernel(PcdBuffers b, int s) {
     if (i < b.w * b.h) b.map[i] = 0;
 }
 
-// select() (PixelSelector2.cpp:286-435): one thread = one 4pot x 4pot block, the reference's loop nest.
-__global__ void pcd_select_kernel(PcdBuffers b, int s) {
+// select() (PixelSelector2.cpp:286-435).  The reference walks every 4pot x 4pot block with one loop nest whose
+// early-outs (bestIdx3 / bestIdx4 == -2) make the result equivalent to:
+//   level 1  every pot x pot cell picks its pixel of largest ag0 among those above the block threshold;
+//   level 2  a 2pot x 2pot group WITHOUT any level-1 pass picks its pixel of largest ag1 among those above th1;
+//   level 3  a block without any level-1 or level-2 pass picks its pixel of largest ag2 among those above th2;
+// ties go to the pixel that comes first in the loop order (strict >).  One thread evaluates one cell; the 4 cells
+// of a group and the 16 cells of a block sit in adjacent lanes (in loop order) and are combined with shuffles.
+struct SelCand {
+    float val;  // < 0: none
+    int idx;
+    int ord;    // position in the loop order, for ties
+};
+__device__ __forceinline__ SelCand sel_better(const SelCand& a, const SelCand& b) {
+    if (b.val > a.val || (b.val == a.val && b.ord < a.ord)) return b;
+    return a;
+}
+__device__ __forceinline__ SelCand sel_shfl_xor(const SelCand& c, int m) {
+    SelCand r;
+    r.val = __shfl_xor_sync(0xffffffffu, c.val, m);
+    r.idx = __shfl_xor_sync(0xffffffffu, c.idx, m);
+    r.ord = __shfl_xor_sync(0xffffffffu, c.ord, m);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) pcd_select_kernel(PcdBuffers b, int s) {
     SelCtl& c = *b.ctl;
     if (!c.run[s]) return;
     const int pot = c.pot[s];
     const int w = b.w, h = b.h, w1 = w / 2, w2 = w / 4, w32 = w / 32;
     const int nbx = (w + 4 * pot - 1) / (4 * pot), nby = (h + 4 * pot - 1) / (4 * pot);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbx * nby) return;
-    const int x4 = (t % nbx) * 4 * pot, y4 = (t / nbx) * 4 * pot;
+    const int blk = t >> 4, sub = t & 15;
+    const bool in_grid = blk < nbx * nby;  // (whole 16-lane groups are in or out together)
+    const int x4 = (blk % nbx) * 4 * pot, y4 = (blk / nbx) * 4 * pot;
+    const int grp = sub >> 2, cell = sub & 3;
+    const int x234 = x4 + (grp & 1) * 2 * pot + (cell & 1) * pot, y234 = y4 + (grp >> 1) * 2 * pot + (cell >> 1) * pot;
     const float* mapmax0 = b.g2[0];
     const float* mapmax1 = b.g2[1];
     const float* mapmax2 = b.g2[2];
     const float dw1 = 0.75f, dw2 = __fmul_rn(dw1, dw1);  // setting_gradDownweightPerLevel
     const float thFactor = 1.f;
-    int n2 = 0, n3 = 0, n4 = 0;
-    const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
-    int bestIdx4 = -1;
-    float bestVal4 = 0.f;
-    for (int y3 = 0; y3 < my3; y3 += 2 * pot)
-        for (int x3 = 0; x3 < mx3; x3 += 2 * pot) {
-            const int x34 = x3 + x4, y34 = y3 + y4;
-            const int my2 = min(2 * pot, h - y34), mx2 = min(2 * pot, w - x34);
-            int bestIdx3 = -1;
-            float bestVal3 = 0.f;
-            for (int y2 = 0; y2 < my2; y2 += pot)
-                for (int x2 = 0; x2 < mx2; x2 += pot) {
-                    const int x234 = x2 + x34, y234 = y2 + y34;
-                    const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
-                    int bestIdx2 = -1;
-                    float bestVal2 = 0.f;
-                    for (int y1 = 0; y1 < my1; ++y1)
-                        for (int x1 = 0; x1 < mx1; ++x1) {
-                            const int xf = x1 + x234, yf = y1 + y234;
-                            const int idx = xf + w * yf;
-                            if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
-                            const float pixelTH0 = b.thsSmoothed[(xf >> 5) + (yf >> 5) * w32];
-                            const float pixelTH1 = __fmul_rn(pixelTH0, dw1);
-                            const float pixelTH2 = __fmul_rn(pixelTH1, dw2);
-                            const float ag0 = mapmax0[idx];
-                            if (ag0 > __fmul_rn(pixelTH0, thFactor)) {
-                                if (ag0 > bestVal2) { bestVal2 = ag0; bestIdx2 = idx; bestIdx3 = -2; bestIdx4 = -2; }
-                            }
-                            if (bestIdx3 == -2) continue;
-                            const float ag1 = mapmax1[(int)__fadd_rn(__fmul_rn((float)xf, 0.5f), 0.25f) +
-                                                      (int)__fadd_rn(__fmul_rn((float)yf, 0.5f), 0.25f) * w1];
-                            if (ag1 > __fmul_rn(pixelTH1, thFactor)) {
-                                if (ag1 > bestVal3) { bestVal3 = ag1; bestIdx3 = idx; bestIdx4 = -2; }
-                            }
-                            if (bestIdx4 == -2) continue;
-                            // (int)(xf*0.25f+0.125): the literal 0.125 is a double there; exact either way
-                            const float ag2 = mapmax2[(int)((double)__fmul_rn((float)xf, 0.25f) + 0.125) +
-                                                      (int)((double)__fmul_rn((float)yf, 0.25f) + 0.125) * w2];
-                            if (ag2 > __fmul_rn(pixelTH2, thFactor)) {
-                                if (ag2 > bestVal4) { bestVal4 = ag2; bestIdx4 = idx; }
-                            }
-                        }
-                    if (bestIdx2 > 0) { b.map[bestIdx2] = 1; bestVal3 = 1e10f; n2++; }
-                }
-            if (bestIdx3 > 0) { b.map[bestIdx3] = 2; bestVal4 = 1e10f; n3++; }
-        }
-    if (bestIdx4 > 0) { b.map[bestIdx4] = 4; n4++; }
-    if (n2) atomicAdd(&c.n[s][0], n2);
-    if (n3) atomicAdd(&c.n[s][1], n3);
-    if (n4) atomicAdd(&c.n[s][2], n4);
+    SelCand c1 = {-1.f, -1, sub}, c2 = {-1.f, -1, sub}, c3 = {-1.f, -1, sub};
+    if (in_grid && x234 < w && y234 < h) {
+        const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
+        for (int y1 = 0; y1 < my1; ++y1)
+            for (int x1 = 0; x1 < mx1; ++x1) {
+                const int xf = x1 + x234, yf = y1 + y234;
+                const int idx = xf + w * yf;
+                if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
+                const float pixelTH0 = b.thsSmoothed[(xf >> 5) + (yf >> 5) * w32];
+                const float pixelTH1 = __fmul_rn(pixelTH0, dw1);
+                const float pixelTH2 = __fmul_rn(pixelTH1, dw2);
+                const float ag0 = mapmax0[idx];
+                if (ag0 > __fmul_rn(pixelTH0, thFactor) && ag0 > c1.val && ag0 > 0.f) { c1.val = ag0; c1.idx = idx; }
+                const float ag1 = mapmax1[(int)__fadd_rn(__fmul_rn((float)xf, 0.5f), 0.25f) +
+                                          (int)__fadd_rn(__fmul_rn((float)yf, 0.5f), 0.25f) * w1];
+                if (ag1 > __fmul_rn(pixelTH1, thFactor) && ag1 > c2.val && ag1 > 0.f) { c2.val = ag1; c2.idx = idx; }
+                // (int)(xf*0.25f+0.125): the literal 0.125 is a double there; exact either way
+                const float ag2 = mapmax2[(int)((double)__fmul_rn((float)xf, 0.25f) + 0.125) +
+                                          (int)((double)__fmul_rn((float)yf, 0.25f) + 0.125) * w2];
+                if (ag2 > __fmul_rn(pixelTH2, thFactor) && ag2 > c3.val && ag2 > 0.f) { c3.val = ag2; c3.idx = idx; }
+            }
+    }
+    // level 1: this cell's pick (bestIdx2 > 0)
+    const bool p1 = c1.idx > 0;
+    if (p1) b.map[c1.idx] = 1;
+    // level 2: the group's pick, if no cell of the group has a level-1 pass
+    bool g1 = c1.idx >= 0;  // "a pixel passed level 1" (idx 0 cannot pass: it lies in the excluded border)
+    g1 |= __shfl_xor_sync(0xffffffffu, g1, 1);
+    g1 |= __shfl_xor_sync(0xffffffffu, g1, 2);
+    SelCand gc = c2;
+    gc = sel_better(gc, sel_shfl_xor(gc, 1));
+    gc = sel_better(gc, sel_shfl_xor(gc, 2));
+    const bool p2 = cell == 0 && !g1 && gc.idx > 0;
+    if (p2) b.map[gc.idx] = 2;
+    // level 3: the block's pick, if no pixel of the block passed level 1 or level 2
+    bool b12 = g1 || (c2.idx >= 0);
+    b12 |= __shfl_xor_sync(0xffffffffu, b12, 1);
+    b12 |= __shfl_xor_sync(0xffffffffu, b12, 2);
+    b12 |= __shfl_xor_sync(0xffffffffu, b12, 4);
+    b12 |= __shfl_xor_sync(0xffffffffu, b12, 8);
+    SelCand bc = c3;
+#pragma unroll
+    for (int m = 1; m < 16; m <<= 1) bc = sel_better(bc, sel_shfl_xor(bc, m));
+    const bool p3 = sub == 0 && !b12 && bc.idx > 0;
+    if (p3) b.map[bc.idx] = 4;
+    const int n2 = __popc(__ballot_sync(0xffffffffu, p1)), n3 = __popc(__ballot_sync(0xffffffffu, p2)),
+              n4 = __popc(__ballot_sync(0xffffffffu, p3));
+    if ((threadIdx.x & 31) == 0) {
+        if (n2) atomicAdd(&c.n[s][0], n2);
+        if (n3) atomicAdd(&c.n[s][1], n3);
+        if (n4) atomicAdd(&c.n[s][2], n4);
+    }
 }
 
 // makeMaps' decisions after a select() (PixelSelector2.cpp:181-224), one thread.  Stage 0 may schedule ONE
@@ -277,69 +307,89 @@ __global__ void pcd_decide_kernel(PcdBuffers b, int s) {
     }
 }
 
-// exclusive scan over one flag per pixel in raster order, single CTA: thread t owns the contiguous pixel range
-// [t * per, (t + 1) * per).  Returns this thread's exclusive prefix; *total = number of flagged pixels.
-template <class F>
-__device__ __forceinline__ int raster_rank(int npix, int per, F flag, int* total) {
-    __shared__ int wsum[32];
-    __shared__ int stotal;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int lo = min(t * per, npix), hi = min(lo + per, npix);
-    int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += flag(i) ? 1 : 0;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) wsum[warp] = incl;
+// Raster-order rank of the flagged pixels, spread over ceil(npix / 1024) CTAs: a counting kernel leaves one count
+// per 1024-pixel block; the consuming kernel's CTA sums the counts of the blocks before it (<= a few hundred ints)
+// and ranks its own pixels with warp ballots.  Pixel i is handled by thread i % 1024 of CTA i / 1024: coalesced.
+__device__ __forceinline__ int block_count_flags(bool flag) {  // total over the CTA, valid in every thread
+    __shared__ int wcnt[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wcnt[warp] = __popc(bal);
     __syncthreads();
+    int v = wcnt[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    return v;
+}
+// rank of this thread's pixel among the flagged pixels of the whole image (only meaningful where flag is set);
+// *block_total / *before = flagged pixels in this CTA / in the CTAs before it
+__device__ __forceinline__ int raster_rank(bool flag, const int* blockCnt, int* before, int* block_total) {
+    __shared__ int wbase[32];
+    __shared__ int sbefore;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wbase[warp] = __popc(bal);
+    int part = 0;  // counts of the blocks before this one
+    for (int bidx = threadIdx.x; bidx < (int)blockIdx.x; bidx += blockDim.x) part += blockCnt[bidx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (threadIdx.x == 0) sbefore = 0;
+    __syncthreads();
+    if (lane == 0 && part) atomicAdd(&sbefore, part);
     if (warp == 0) {
-        int v = wsum[lane], iv = v;
+        const int v = wbase[lane];
+        int iv = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, iv, o);
             if (lane >= o) iv += u;
         }
-        wsum[lane] = iv - v;
-        if (lane == 31) stotal = iv;
+        wbase[lane] = iv - v;
+        if (lane == 31) *block_total = iv;  // caller passes a __shared__ int
     }
     __syncthreads();
-    *total = stotal;
-    return wsum[warp] + incl - cnt;
+    *before = sbefore;
+    return sbefore + wbase[warp] + __popc(bal & ((1u << lane) - 1u));
+}
+
+enum { FLAG_SELECTED = 0, FLAG_POINT = 1 };
+template <int WHAT>
+__global__ void __launch_bounds__(1024) pcd_count_kernel(PcdBuffers b, int* blockCnt) {
+    if (WHAT == FLAG_SELECTED && !((double)b.ctl->quotia < 0.95)) return;  // no sub-sampling: nobody reads the counts
+    const int i = blockIdx.x * 1024 + threadIdx.x, npix = b.w * b.h;
+    bool flag = false;
+    if (i < npix) flag = (WHAT == FLAG_SELECTED) ? b.map[i] != 0 : (b.map[i] != 0 && b.depth[i] != 0);
+    const int c = block_count_flags(flag);
+    if (threadIdx.x == 0) blockCnt[blockIdx.x] = c;
 }
 
 // the random sub-sampling of makeMaps (PixelSelector2.cpp:226-243): the rn-th selected pixel in raster order is
-// dropped if randomPattern[rn] > 255 * quotia.  Also raises the Canny condition of select_point (:135).
-__global__ void __launch_bounds__(1024) pcd_subsample_kernel(PcdBuffers b) {
+// dropped if randomPattern[rn] > 255 * quotia
+__global__ void __launch_bounds__(1024) pcd_subsample_kernel(PcdBuffers b, const int* blockCnt) {
     SelCtl& c = *b.ctl;
-    const int npix = b.w * b.h, per = (npix + 1023) / 1024;
     const float quotia = c.quotia;
-    int num = c.num_have;
-    if ((double)quotia < 0.95) {  // float against the double literal, as there
-        int total;
-        uint8_t* map = b.map;
-        int rn = raster_rank(npix, per, [map](int i) { return map[i] != 0; }, &total);
-        const unsigned char charTH = (unsigned char)__fmul_rn(255.f, quotia);
-        const int lo = min((int)threadIdx.x * per, npix), hi = min(lo + per, npix);
-        int dropped = 0;
-        for (int i = lo; i < hi; ++i)
-            if (map[i] != 0) {
-                if (b.randomPattern[rn] > charTH) { map[i] = 0; ++dropped; }
-                ++rn;
-            }
-        __shared__ int sdrop;
-        if (threadIdx.x == 0) sdrop = 0;
-        __syncthreads();
-        if (dropped) atomicAdd(&sdrop, dropped);
-        __syncthreads();
-        num -= sdrop;
-    }
-    if (threadIdx.x == 0) {
-        c.num_selected = num;
-        if (num < c.num_want / 3) c.status = PCD_STATUS_NEEDS_CANNY;
-    }
+    if (!((double)quotia < 0.95)) return;  // float against the double literal, as there
+    __shared__ int stotal, sdrop;
+    const int i = blockIdx.x * 1024 + threadIdx.x, npix = b.w * b.h;
+    const bool flag = i < npix && b.map[i] != 0;
+    int before;
+    if (threadIdx.x == 0) sdrop = 0;
+    const int rn = raster_rank(flag, blockCnt, &before, &stotal);
+    const unsigned char charTH = (unsigned char)__fmul_rn(255.f, quotia);
+    const bool drop = flag && b.randomPattern[rn] > charTH;
+    if (drop) b.map[i] = 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, drop);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&sdrop, __popc(bal));
+    __syncthreads();
+    if (threadIdx.x == 0 && sdrop) atomicAdd(&c.num_dropped, sdrop);
+}
+
+// makeMaps' return value and the Canny condition of select_point (src/pcd_generator.cpp:135)
+__global__ void pcd_after_subsample_kernel(PcdBuffers b) {
+    SelCtl& c = *b.ctl;
+    c.num_selected = c.num_have - c.num_dropped;
+    if (c.num_selected < c.num_want / 3) c.status = PCD_STATUS_NEEDS_CANNY;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -481,43 +531,39 @@ __global__ void pcd_topup_done_kernel(PcdBuffers b) {
 
 // get_points_from_pixels + get_features (src/pcd_generator.cpp:304-381): the selected pixels with a depth reading,
 // in raster order, as n x 3 positions and n x 5 features (row-major), plus the point count for the pack job.
-__global__ void __launch_bounds__(1024) pcd_points_kernel(PcdBuffers b, CamInfo cam, int feature_type, float* xyz, float* feat,
-                                                          int max_points, int* job_n) {
+__global__ void __launch_bounds__(1024) pcd_points_kernel(PcdBuffers b, const int* blockCnt, CamInfo cam, int feature_type,
+                                                          float* xyz, float* feat, int max_points, int* job_n) {
     SelCtl& c = *b.ctl;
-    const int npix = b.w * b.h, per = (npix + 1023) / 1024, w = b.w;
-    const uint8_t* map = b.map;
-    const uint16_t* depth = b.depth;
-    int total;
-    int idx = raster_rank(npix, per, [map, depth](int i) { return map[i] != 0 && depth[i] != 0; }, &total);
-    const int lo = min((int)threadIdx.x * per, npix), hi = min(lo + per, npix);
-    for (int i = lo; i < hi; ++i) {
-        if (!(map[i] != 0 && depth[i] != 0)) continue;
-        if (idx < max_points) {
-            const int x = i % w, y = i / w;
-            const float z = __fdiv_rn((float)depth[i], cam.scaling_factor);
-            xyz[3 * idx + 2] = z;
-            xyz[3 * idx + 0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, cam.cx), z), cam.fx);
-            xyz[3 * idx + 1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)y, cam.cy), z), cam.fy);
-            const int c0 = b.img3[3 * i], c1 = b.img3[3 * i + 1], c2 = b.img3[3 * i + 2];
-            if (feature_type == 0) {  // HSV / [180, 255, 255] and gradient * 2 / 255, evaluated in double (:336-358)
-                int hh, s, v;
-                rgb2hsv_u8(c0, c1, c2, hh, s, v);
-                feat[5 * idx + 0] = (float)((double)hh / 180.0);
-                feat[5 * idx + 1] = (float)((double)s / 255.0);
-                feat[5 * idx + 2] = (float)((double)v / 255.0);
-                feat[5 * idx + 3] = (float)((double)b.dx[0][i] / 255.0 * 2.0);
-                feat[5 * idx + 4] = (float)((double)b.dy[0][i] / 255.0 * 2.0);
-            } else {  // raw channels and raw gradient (:359-381)
-                feat[5 * idx + 0] = (float)c0;
-                feat[5 * idx + 1] = (float)c1;
-                feat[5 * idx + 2] = (float)c2;
-                feat[5 * idx + 3] = b.dx[0][i];
-                feat[5 * idx + 4] = b.dy[0][i];
-            }
+    __shared__ int stotal;
+    const int i = blockIdx.x * 1024 + threadIdx.x, npix = b.w * b.h, w = b.w;
+    const bool flag = i < npix && b.map[i] != 0 && b.depth[i] != 0;
+    int before;
+    const int idx = raster_rank(flag, blockCnt, &before, &stotal);
+    if (flag && idx < max_points) {
+        const int x = i % w, y = i / w;
+        const float z = __fdiv_rn((float)b.depth[i], cam.scaling_factor);
+        xyz[3 * idx + 2] = z;
+        xyz[3 * idx + 0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, cam.cx), z), cam.fx);
+        xyz[3 * idx + 1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)y, cam.cy), z), cam.fy);
+        const int c0 = b.img3[3 * i], c1 = b.img3[3 * i + 1], c2 = b.img3[3 * i + 2];
+        if (feature_type == 0) {  // HSV / [180, 255, 255] and gradient * 2 / 255, evaluated in double (:336-358)
+            int hh, s, v;
+            rgb2hsv_u8(c0, c1, c2, hh, s, v);
+            feat[5 * idx + 0] = (float)((double)hh / 180.0);
+            feat[5 * idx + 1] = (float)((double)s / 255.0);
+            feat[5 * idx + 2] = (float)((double)v / 255.0);
+            feat[5 * idx + 3] = (float)((double)b.dx[0][i] / 255.0 * 2.0);
+            feat[5 * idx + 4] = (float)((double)b.dy[0][i] / 255.0 * 2.0);
+        } else {  // raw channels and raw gradient (:359-381)
+            feat[5 * idx + 0] = (float)c0;
+            feat[5 * idx + 1] = (float)c1;
+            feat[5 * idx + 2] = (float)c2;
+            feat[5 * idx + 3] = b.dx[0][i];
+            feat[5 * idx + 4] = b.dy[0][i];
         }
-        ++idx;
     }
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {  // the last block sees the total
+        const int total = before + stotal;
         c.num_points = total;
         if (total > max_points) c.status = PCD_STATUS_TOO_MANY_POINTS;
         *job_n = total > max_points ? max_points : total;
