@@ -195,7 +195,7 @@ __device__ __forceinline__ bool tag_is(const StageTag& t, const float4* g, int f
 }
 
 struct ListRef {
-    uint2* entries;  // the flat list: (row << 12 | col within the round's chunks, bits of the colour exponent t_c)
+    uint2* entries;  // the flat list: (row * 16 << 16 | col * 16 within the round's chunks, bits of the colour exponent t_c)
     uint2* staging;  // build scratch of the CTA (shared by its three lists): per-unit regions before compaction
     unsigned cap;
 };
@@ -879,16 +879,16 @@ __device__ __forceinline__ HotConsts hot_consts(const IterConsts& ic) {
 template <int KIND>
 __device__ __forceinline__ void list_body(const Smem& sm, const HotConsts& hc, const KParams& kp, uint32_t ent, float t_c,
                                           int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
-    const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
-    const float4 xg = sm.u.ls.rowG[row];
-    const float4 yg = sm.colG[col];
+    const uint32_t rowb = ent >> 16, colb = ent & 0xffffu;  // byte offsets into the row / column stages
+    const float4 xg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.rowG) + rowb);
+    const float4 yg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.colG) + colb);
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     bool near;
     float a = kernel_a(hc, kp, d2, t_c, near);
     if (near) {
         const IterConsts& ic = sm.ic;
-        const int ri = src.row_base + row, ci = src.col_base + col;
+        const int ri = src.row_base + (int)(rowb >> 4), ci = src.col_base + (int)(colb >> 4);
         a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
                                __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     }
@@ -896,7 +896,8 @@ __device__ __forceinline__ void list_body(const Smem& sm, const HotConsts& hc, c
     const bool ok = (a > kp.sp_thres) && (d2 < hc.d2_thres);
     a = ok ? a : 0.f;
     if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
-        const float4 z1 = sm.u.ls.ss.colZ1[col], z2 = sm.u.ls.ss.colZ2[col];
+        const float4 z1 = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.ss.colZ1) + colb);
+        const float4 z2 = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.ss.colZ2) + colb);
         StepCol c;
         c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
         c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
@@ -1122,8 +1123,8 @@ struct PassGeom {
 __device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, int G) {
     PassGeom pg;
     const int total_rt = (rows_n + kTile - 1) / kTile;
-    pg.t_begin = (int)(((long long)total_rt * rank) / G);
-    const int t_end = (int)(((long long)total_rt * (rank + 1)) / G);
+    pg.t_begin = (total_rt * rank) / G;  // total_rt <= 512, G <= 16
+    const int t_end = (total_rt * (rank + 1)) / G;
     pg.my_tiles = t_end - pg.t_begin;
     pg.total_ct = (cols_n + kTile - 1) / kTile;
     // split every row tile's column range into S segments so that there are >= ~4 units per warp
@@ -1183,7 +1184,8 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // --------------------------------------------------------------------------------------------
 // neighbour candidate lists
 // --------------------------------------------------------------------------------------------
-// A list entry is (row | col, t_c): the index pair and its pose-independent colour exponent
+// A list entry is (row * 16 << 16 | col * 16, t_c): the index pair (as byte offsets into the staged rows / columns
+// of its round) and its pose-independent colour exponent
 // t_c = |f_i - g_j|^2 log2(e) / (2 c_ell^2).  With T = log2(s2 c_sigma^2 / sp_thres) the gate a > sp_thres reads
 // d2 log2(e)/(2 l^2) + t_c < T, i.e. every pair has its OWN ball radius r_e = sqrt((T - t_c) 2 l^2 / log2 e) <= r
 // (equal colours: r_e = r, the ell-ball; a colour mismatch shrinks it; t_c >= T or a failed colour gate: never a
@@ -1319,8 +1321,9 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
     // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
-    if (keep && cursor + kTile <= limit)
-        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), make_uint2(ent + (row_off << 12), __float_as_uint(t_c)));
+    if (keep && cursor + kTile <= limit)  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
+        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)),
+               make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c)));
     cursor += __popc(b);
 }
 
@@ -1702,13 +1705,13 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             __syncthreads();
         }
 
+        if (threadIdx.x == 0) {  // iteration 0: update_tf (src/cvo.cpp:368) + which lists to build
+            sm.serial += 1;
+            prepare_iter(sm, kp, kp.d2c_thres);
+            if (use_lists) list_policy(sm, acvo, args.list_skin);
+        }
+        __syncthreads();
         for (int k = 0; k < max_iter; ++k) {
-            if (threadIdx.x == 0) {
-                sm.serial += 1;
-                prepare_iter(sm, kp, kp.d2c_thres);  // update_tf, src/cvo.cpp:368
-                if (use_lists) list_policy(sm, acvo, args.list_skin);
-            }
-            __syncthreads();
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             if (use_lists && sm.lst[LIST_XY].need) build_list(sm, kp, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
@@ -1743,6 +1746,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 cvo_b200_iter_rec* rec = nullptr;
                 if (args.trace && pi == 0 && rank == 0 && k < args.trace_cap) rec = args.trace + k;
                 update_state(sm, kp, k, rec);
+                if (!sm.done && k + 1 < max_iter) {  // the next iteration's update_tf + list decisions, same serial section
+                    sm.serial += 1;
+                    prepare_iter(sm, kp, kp.d2c_thres);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin);
+                }
             }
             __syncthreads();
             if (sm.done) break;
