@@ -1458,7 +1458,12 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 const uint2* src = lr.staging + sm.u.of.bu.off[u];
                 uint2* dst = lr.entries + sm.lst_base + sm.u.of.bu.pos[u];
                 const int c = sm.u.of.bu.act[u];
-                for (int i = lane; i < c; i += 32) __stcg(dst + i, __ldcg(src + i));
+                int i = lane;
+                for (; i + 96 < c; i += 128) {  // four loads in flight per lane
+                    const uint2 v0 = __ldcg(src + i), v1 = __ldcg(src + i + 32), v2 = __ldcg(src + i + 64), v3 = __ldcg(src + i + 96);
+                    __stcg(dst + i, v0); __stcg(dst + i + 32, v1); __stcg(dst + i + 64, v2); __stcg(dst + i + 96, v3);
+                }
+                for (; i < c; i += 32) __stcg(dst + i, __ldcg(src + i));
             }
         }
     }
