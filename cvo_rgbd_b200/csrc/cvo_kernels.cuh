@@ -786,12 +786,25 @@ __device__ __forceinline__ void step_accumulate(const IC& ic, const StepCol& c, 
     const float gamma = -ic.temp_coef * (c.nrm + 2.f * ((c.z2x * rx + c.z2y * ry) + c.z2z * rz));  // :264
     const float delta = ic.p2t * (c.pdt - ((z3x * rx + z3y * ry) + z3z * rz));                     // :267
     const float epsil = -ic.temp_coef * (c.ecn + 2.f * ((z4x * rx + z4y * ry) + z4z * rz));        // :270
+#ifdef CVO_STEP_F32_PRODUCTS
+    // the reference's own mix of f32 products and f64 sums (src/cvo.cpp:275-279), term by term
     const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
     acc[0] += (double)(a * beta);                                                                  // :275
     acc[1] += ad * (gd + (double)(beta * beta) * 0.5);                                             // :276
     acc[2] += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0));  // :277
     acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
                     (1.0 / 24.0) * (bd * bd) * (bd * bd));                                         // :278-279
+#else
+    // B..E of src/cvo.cpp:275-279 with the five f32 quantities promoted once and the polynomial evaluated in f64
+    // (the reference forms a*beta, beta^2, beta*gamma, beta^3, beta*delta in f32 first: a 6e-8 relative rounding per
+    // term that is not reproduced; three fewer f32->f64 conversions, which share the MUFU pipe)
+    const double bd = (double)beta, gd = (double)gamma, dd = (double)delta, ed = (double)epsil, ad = (double)a;
+    const double b2 = bd * bd;
+    acc[0] = fma(ad, bd, acc[0]);                                                          // :275
+    acc[1] = fma(ad, fma(0.5, b2, gd), acc[1]);                                            // :276
+    acc[2] = fma(ad, fma(b2 * bd, 1.0 / 6.0, fma(bd, gd, dd)), acc[2]);                    // :277
+    acc[3] = fma(ad, fma(b2 * b2, 1.0 / 24.0, fma(0.5, gd * (b2 + gd), fma(bd, dd, ed))), acc[3]);  // :278-279
+#endif
 }
 
 // Accumulation tail of a candidate whose kernel value a is known (a = 0 for a rejected one, which then adds +0
