@@ -91,6 +91,7 @@ struct cvo_b200_ctx {
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
     float list_skin = 0.08f;
+    float list_shrink = 0.7f;
     long long last_list_builds = 0;
 
     float last_ms = 0.f;
@@ -419,6 +420,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
+    args.list_shrink = ctx->list_shrink;
     CK(cudaMemcpyAsync(ctx->d_pairs, ctx->h_pairs, sizeof(PairDev) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_states, ctx->h_states, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
@@ -572,6 +574,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     if (env && env[0] == '1') ctx->sort_points = 0;
     env = getenv("CVO_B200_NO_LISTS");  // tuning / A-B switch; cvo_b200_set_neighbor_lists is the API
     if (env && env[0] == '1') ctx->lists_enabled = false;
+    env = getenv("CVO_B200_LIST_SHRINK");  // tuning knob
+    if (env && atof(env) > 0.0 && atof(env) <= 1.0) ctx->list_shrink = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN");
     if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin = (float)atof(env);
 #undef CKC

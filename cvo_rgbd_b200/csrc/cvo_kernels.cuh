@@ -247,6 +247,7 @@ struct AlignArgs {
     uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
     unsigned list_cap;
     float list_skin;
+    float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius
 };
 
 struct InnerArgs {
@@ -1209,7 +1210,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // disp = max_j |(M1 - M0) y_j + (t1 - t0)|.  Since r_e <= r0, the list covers everything that can pass as long as
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
-__device__ void list_policy(Smem& sm, bool acvo, float skin) {
+__device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
     const int nk = acvo ? LIST_KINDS : 1;
@@ -1237,9 +1238,9 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin) {
                 }
                 if (!(disp == disp)) disp = 1.0e30;  // NaN state: never trust an old list
             }
-            // rebuild when something that can pass may be missing, or when ell has shrunk the ball by > 10 % (a
+            // rebuild when something that can pass may be missing, or when ell has shrunk the ball a lot (shrink < 0.7 by default: a
             // list that is much too wide costs more in every pass than one rebuild)
-            need = !(fmax(0.0, r_now - (double)L.r0) + disp <= (double)L.slack) || (r_now < 0.9 * (double)L.r0);
+            need = !(fmax(0.0, r_now - (double)L.r0) + disp <= (double)L.slack) || (r_now < (double)shrink * (double)L.r0);
         }
         L.need = need ? 1 : 0;
         if (need) {
@@ -1726,7 +1727,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         if (threadIdx.x == 0) {  // iteration 0: update_tf (src/cvo.cpp:368) + which lists to build
             sm.serial += 1;
             prepare_iter(sm, kp, kp.d2c_thres);
-            if (use_lists) list_policy(sm, acvo, args.list_skin);
+            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
         }
         __syncthreads();
         for (int k = 0; k < max_iter; ++k) {
@@ -1767,7 +1768,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 if (!sm.done && k + 1 < max_iter) {  // the next iteration's update_tf + list decisions, same serial section
                     sm.serial += 1;
                     prepare_iter(sm, kp, kp.d2c_thres);
-                    if (use_lists) list_policy(sm, acvo, args.list_skin);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
                 }
             }
             __syncthreads();
