@@ -725,19 +725,18 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
 // se_kernel's value and gates in the reference's own arithmetic (src/cvo.cpp:146-152): colour distance summed left
 // to right, exp() in f64 narrowed to f32, a = ck * k in f32.  Deliberately not inlined: it runs for about one
 // candidate in a million (see kernel_a) and must not cost the hot loops registers.
-__device__ __noinline__ float kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
-                                                 float4 xf, float xf4, float4 yf, float yf4, float d2) {
-    const float e0 = xf.x - yf.x, e1 = xf.y - yf.y, e2 = xf.z - yf.z, e3 = xf.w - yf.w, e4 = xf4 - yf4;
-    float d2e = __fmul_rn(e0, e0);
-    d2e = __fadd_rn(d2e, __fmul_rn(e1, e1));
-    d2e = __fadd_rn(d2e, __fmul_rn(e2, e2));
-    d2e = __fadd_rn(d2e, __fmul_rn(e3, e3));
-    d2e = __fadd_rn(d2e, __fmul_rn(e4, e4));
+__device__ __noinline__ float kernel_value_exact_d(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
+                                                   float d2c, float d2) {
     const double l = (double)ell, cl = (double)c_ell;
     const float k = (float)((double)s2 * exp(-(double)d2 / (2.0 * l * l)));
-    const float ck = (float)((double)cs2 * exp(-(double)d2e / (2.0 * cl * cl)));
+    const float ck = (float)((double)cs2 * exp(-(double)d2c / (2.0 * cl * cl)));
     const float a = __fmul_rn(ck, k);
-    return ((d2e < d2c_thres) && (a > sp_thres)) ? a : 0.f;  // a > sp_thres > 0 when accepted
+    return ((d2c < d2c_thres) && (a > sp_thres)) ? a : 0.f;  // a > sp_thres > 0 when accepted
+}
+__device__ __forceinline__ float colour_d2(const float4& xf, float xf4, const float4& yf, float yf4);
+__device__ __forceinline__ float kernel_value_exact(float ell, float d2c_thres, float s2, float cs2, float c_ell, float sp_thres,
+                                                    float4 xf, float xf4, float4 yf, float yf4, float d2) {
+    return kernel_value_exact_d(ell, d2c_thres, s2, cs2, c_ell, sp_thres, colour_d2(xf, xf4, yf, yf4), d2);
 }
 
 // (feature_x - feature_y).squaredNorm() summed left to right (src/cvo.cpp:145-146); pose-independent.
@@ -1318,8 +1317,15 @@ __device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile
 // Build, per candidate: exact distance at the build pose, colour gate and colour exponent (pose-independent,
 // src/cvo.cpp:145-148), and the pair's own radius + slack.  Survivors are appended to the unit's staging region with
 // their row index made relative to the round (`row_off` = 32 * the unit's row tile within the round).
+// SELF = 0: an (x, y) list entry (byte offsets of the pair, colour exponent).  SELF = 1 / 2: the (x, x) / (y, y) list of
+// acvo, whose distances never change (x is never transformed, rigid motion preserves |y_i - y_j|): the entry IS the
+// pair of invariants (d2, colour d2), and a pass over it touches no point data at all.  For (y, y) the sign bit of the
+// colour distance marks the rows that contribute to the length-scale gradient (always for (x, x); for (y, y) quirk Q1:
+// original index >= num_fixed).
+template <int SELF>
 __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
-                                           uint32_t ent, bool live, uint32_t row_off, uint2* out, int limit, int& cursor) {
+                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2* out, int limit,
+                                           int& cursor) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
@@ -1335,17 +1341,25 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
     // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
-    if (keep && cursor + kTile <= limit)  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
-        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)),
-               make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c)));
+    if (keep && cursor + kTile <= limit) {
+        uint2 e;
+        if (SELF == 0) {  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
+            e = make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c));
+        } else {
+            const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
+            e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
+        }
+        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
+    }
     cursor += __popc(b);
 }
 
+template <int SELF>
 __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
-                                                const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int ct_begin,
-                                                int ct_end, uint2* out, int limit) {
+                                                const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int yy_row_min,
+                                                int ct_begin, int ct_end, uint2* out, int limit) {
     const int lane = threadIdx.x & 31;
-    const RowTile rt = load_row_tile<true, false, true>(sm, ws, rows, row_tf, tile);
+    const RowTile rt = load_row_tile<true, SELF == 2, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = L.thr_build * 1.0001f;
     uint32_t* q = sm_queue(sm);
     int qn = 0, cursor = 0;
@@ -1363,12 +1377,12 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
             __syncwarp();
             while (qn >= 32) {
                 qn -= 32;
-                build_eval(sm, ws, kp, L, q[qn + lane], true, row_off, out, limit, cursor);
+                build_eval<SELF>(sm, ws, kp, L, q[qn + lane], true, row_off, yy_row_min, out, limit, cursor);
             }
             __syncwarp();
         }
     }
-    if (qn > 0) build_eval(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, out, limit, cursor);
+    if (qn > 0) build_eval<SELF>(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, yy_row_min, out, limit, cursor);
     __syncwarp();
     return cursor;
 }
@@ -1388,8 +1402,9 @@ __device__ __forceinline__ int next_unit(Smem& sm) {
 //             pass ((row 0, col 0) are real points, t_c = +inf gives a = 0).
 // Which warp evaluated which unit does not matter: the flat list is a pure function of the inputs.  On return
 // sm.lst[kind].valid is 1, or -1 if a scratch area was too small.
+template <int SELF>
 __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
-                           int rank, int G, uint32_t& tma_phase, int kind, const ListRef& lr) {
+                           int rank, int G, int yy_row_min, uint32_t& tma_phase, int kind, const ListRef& lr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     const ListState& L = sm.lst[kind];
@@ -1425,8 +1440,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 if (u >= nunits) break;
                 const int t = u / pg.S, sg = u - t * pg.S;
                 const int c_begin = (int)(((long long)nct * sg) / pg.S), c_end = (int)(((long long)nct * (sg + 1)) / pg.S);
-                const int c = build_unit_write(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile), c_begin,
-                                               c_end, stage + wcur, seg - wcur);
+                const int c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile),
+                                                     yy_row_min, c_begin, c_end, stage + wcur, seg - wcur);
                 if (lane == 0) {
                     sm.u.of.bu.off[u] = warp * seg + wcur;
                     sm.u.of.bu.act[u] = c;
@@ -1447,8 +1462,9 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 const int padded = (base + kListTrip - 1) / kListTrip * kListTrip;
                 const int at = sm.lst_used;
                 const bool fits = !sm.lst_ovf && (unsigned)(at + padded) <= lr.cap;
-                if (fits)
-                    for (int i = base + lane; i < padded; i += 32) __stcg(lr.entries + at + i, make_uint2(0u, 0x7f800000u));
+                if (fits)  // padding: t_c = +inf (pair list) / d2 = 1e30, colour d2 = +inf (self lists) => a = 0, finite terms
+                    for (int i = base + lane; i < padded; i += 32)
+                        __stcg(lr.entries + at + i, make_uint2(SELF ? __float_as_uint(1.0e30f) : 0u, 0x7f800000u));
                 __syncwarp();
                 if (lane == 0) {
                     if (fits) {
@@ -1628,6 +1644,97 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
     __syncthreads();
 }
 
+// A pass over the (x, x) or (y, y) list of acvo (src/adaptive_cvo.cpp:159-160,205-231,243-265): the entries are the
+// pose-independent pairs (d2, colour d2), so nothing is staged and no point is touched -- the list streams through the
+// warps (same trips, same two register sets as run_pass_list) and every entry costs a dozen instructions.
+//   acc[0] = nnz, acc[1] = sum a * d2 / ell^3 (for (y, y): only the rows quirk Q1 lets through)
+__device__ __forceinline__ void self_body(const IterConsts& ic, const KParams& kp, float c1, float d2_thres, float inv_ell3,
+                                          uint32_t d2_bits, uint32_t d2c_bits, float& pdl, int& cnt) {
+    const float d2 = __uint_as_float(d2_bits);
+    const float d2c = __uint_as_float(d2c_bits & 0x7fffffffu);
+    const bool q1 = (d2c_bits >> 31) != 0;
+    bool near;
+    HotConsts h;  // only c1 is read by kernel_a
+    h.c1 = c1;
+    float a = kernel_a(h, kp, d2, __fmul_rn(d2c, kp.c2), near);
+    if (near) a = kernel_value_exact_d(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, d2c, d2);
+    const bool ok = (a > kp.sp_thres) && (d2 < d2_thres);
+    a = ok ? a : 0.f;
+    pdl = fmaf(inv_ell3 * (q1 ? a : 0.f), d2, pdl);  // src/adaptive_cvo.cpp:210,231 / :256,259
+    cnt += ok ? 1 : 0;
+}
+
+template <int KIND>  // PASS_XX or PASS_YY
+__device__ void run_pass_self(Smem& sm, const KParams& kp, const CloudDev& rows, const CloudDev& cols, int rank, int G, int kind,
+                              const ListRef& lr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    const float c1 = sm.ic.c1, d2_thres = sm.ic.d2_thres, inv_ell3 = sm.ic.inv_ell3;
+    float pdl = 0.f;
+    int cnt = 0;
+    double acc[2] = {0.0, 0.0};
+    int round = 0;
+    for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round)
+        for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
+            const uint2 rd = sm.lround[kind][round];
+            const int ntrip = (int)rd.y / kListTrip;
+            const uint2* e0 = lr.entries + rd.x;
+            const uint2* e = e0 + lane;
+            uint2 a0, a1, a2, a3, b0, b1, b2, b3;
+#define CVO_LOAD_TRIP(x0, x1, x2, x3, tt)                                                        \
+    {                                                                                            \
+        const uint2* q = e + (size_t)min((tt), ntrip - 1) * kListTrip;                           \
+        x0 = __ldcg(q); x1 = __ldcg(q + kTile); x2 = __ldcg(q + 2 * kTile); x3 = __ldcg(q + 3 * kTile); \
+        if (lane < 8) {                                                                          \
+            const uint2* f = e0 + (size_t)min((tt) + kPrefetchTrips * kWarps, ntrip - 1) * kListTrip + lane * 16; \
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(f));                                   \
+        }                                                                                        \
+    }
+#define CVO_RUN_TRIP(x0, x1, x2, x3)                                                             \
+    {                                                                                            \
+        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x0.x, x0.y, pdl, cnt);                      \
+        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x1.x, x1.y, pdl, cnt);                      \
+        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x2.x, x2.y, pdl, cnt);                      \
+        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x3.x, x3.y, pdl, cnt);                      \
+        acc[1] += (double)pdl;  /* <= 4 terms per f32 partial */                                 \
+        pdl = 0.f;                                                                               \
+    }
+            int t = warp;
+            if (t < ntrip) {
+                CVO_LOAD_TRIP(a0, a1, a2, a3, t)
+#pragma unroll 1
+                while (true) {
+                    CVO_LOAD_TRIP(b0, b1, b2, b3, t + kWarps)
+                    CVO_RUN_TRIP(a0, a1, a2, a3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(a0, a1, a2, a3, t + kWarps)
+                    CVO_RUN_TRIP(b0, b1, b2, b3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                }
+            }
+#undef CVO_LOAD_TRIP
+#undef CVO_RUN_TRIP
+        }
+    acc[0] = (double)cnt;
+    __syncthreads();  // the previous pass is done with the warp totals
+    acc[0] = warp_sum(acc[0]);
+    acc[1] = warp_sum(acc[1]);
+    if (lane == 0) {
+        sm.u.ls.warpTot[warp][0] = acc[0];
+        sm.u.ls.warpTot[warp][1] = acc[1];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumAcc) {  // fixed-order sum over the warps
+        double t = 0.0;
+        if (threadIdx.x < 2)
+            for (int w = 0; w < kWarps; ++w) t += sm.u.ls.warpTot[w][threadIdx.x];
+        sm.blockTot[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 // All-gather of the per-CTA totals through distributed shared memory; every CTA of the cluster ends with
 // identical cluster totals in sm.sum[dst_off ...] (summed in rank order).
 template <int NV>
@@ -1732,21 +1839,21 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         __syncthreads();
         for (int k = 0; k < max_iter; ++k) {
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
-            if (use_lists && sm.lst[LIST_XY].need) build_list(sm, kp, pair.x, false, pair.y, true, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (use_lists && sm.lst[LIST_XY].need) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
             if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else if (list_xy) run_pass_list<PASS_FLOW_CVO>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                if (use_lists && sm.lst[LIST_XX].need) build_list(sm, kp, pair.x, false, pair.x, false, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
+                if (use_lists && sm.lst[LIST_XX].need) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
                 if (use_lists && sm.lst[LIST_XX].valid > 0)
-                    run_pass_list<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
+                    run_pass_self<PASS_XX>(sm, kp, pair.x, pair.x, rank, G, LIST_XX, lref[LIST_XX]);
                 else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                if (use_lists && sm.lst[LIST_YY].need) build_list(sm, kp, pair.y, true, pair.y, true, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
+                if (use_lists && sm.lst[LIST_YY].need) build_list<2>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
                 if (use_lists && sm.lst[LIST_YY].valid > 0)
-                    run_pass_list<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
+                    run_pass_self<PASS_YY>(sm, kp, pair.y, pair.y, rank, G, LIST_YY, lref[LIST_YY]);
                 else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZYY + threadIdx.x] = sm.blockTot[threadIdx.x];
             }
