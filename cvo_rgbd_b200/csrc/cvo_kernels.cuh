@@ -38,6 +38,9 @@ namespace cg = cooperative_groups;
 #endif
 constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;
+// The on-the-fly passes and the list builds keep per-warp queues and row tiles in shared memory: at most 16 warps
+// take part in them (with more threads per CTA the others only help with staging and wait at the barriers).
+constexpr int kWorkWarps = kWarps < 16 ? kWarps : 16;
 constexpr int kTile = 32;
 constexpr int kColChunk = 3072;                 // moving-cloud points resident in shared memory per pass
 constexpr int kColTiles = kColChunk / kTile;
@@ -148,7 +151,7 @@ struct WarpScratch {
 struct FeatStage {
     float4 colF[kColChunk];             // {f0, f1, f2, f3}
     float colF4[kColChunk];             // f4
-    uint32_t queue[kWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
+    uint32_t queue[kWorkWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
 };
 struct StepStage {
     float4 colZ1[kColChunk];  // {xi z + v, |xi z + v|^2}                       (src/cvo.cpp:226-228,235)
@@ -161,7 +164,7 @@ struct BuildUnits {  // neighbour-list build, per unit of the round:
 };
 struct OnTheFlyStage {
     FeatStage fs;
-    WarpScratch ws[kWarps];
+    WarpScratch ws[kWorkWarps];
     union {
         double unitPart[kMaxUnits][kUnitAcc];  // on-the-fly pass: one fixed slot per work unit => scheduling-independent sums
         BuildUnits bu;                         // list build
@@ -1143,7 +1146,7 @@ __device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, 
     // split every row tile's column range into S segments so that there are >= ~4 units per warp
     int S = 1;
     if (pg.my_tiles > 0) {
-        S = (CVO_UNITS_PER_WARP * kWarps + pg.my_tiles - 1) / pg.my_tiles;
+        S = (CVO_UNITS_PER_WARP * kWorkWarps + pg.my_tiles - 1) / pg.my_tiles;
         const int s_max = max(1, min(pg.total_ct, kColTiles) / 8);
         S = max(1, min(min(S, s_max), kMaxUnits));
     }
@@ -1174,7 +1177,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
             stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
             __syncthreads();
-            while (true) {
+            while ((threadIdx.x >> 5) < kWorkWarps) {
                 int u = 0;
                 if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
                 u = __shfl_sync(0xffffffffu, u, 0);
@@ -1408,8 +1411,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     const ListState& L = sm.lst[kind];
-    WarpScratch& ws = sm.u.of.ws[warp];
-    const int seg = (int)(lr.cap / kWarps) & ~3;  // this warp's staging segment
+    WarpScratch& ws = sm.u.of.ws[warp < kWorkWarps ? warp : 0];
+    const int seg = (int)(lr.cap / kWorkWarps) & ~3;  // this warp's staging segment
     uint2* const stage = lr.staging + (size_t)warp * seg;
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
@@ -1435,7 +1438,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 break;
             }
             int wcur = 0;  // entries this warp has staged in this round
-            while (true) {  // evaluate
+            while (warp < kWorkWarps) {  // evaluate
                 const int u = next_unit(sm);
                 if (u >= nunits) break;
                 const int t = u / pg.S, sg = u - t * pg.S;
