@@ -883,6 +883,17 @@ int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot) {
     return CVO_B200_OK;
 }
 
+#ifdef CVO_PHASE_CLOCKS
+int cvo_b200_phase_clocks(unsigned long long* out16, int reset) {
+    cudaMemcpyFromSymbol(out16, g_phase_clocks, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out) {
     if (n < 0 || !out) return CVO_B200_ERR_ARG;
     glibc_rand_bytes(seed, (size_t)n, out);

@@ -36,6 +36,9 @@ namespace cg = cooperative_groups;
 #ifndef CVO_GROUP
 #define CVO_GROUP 2
 #endif
+#ifndef CVO_BUILD_SEGMENTS
+#define CVO_BUILD_SEGMENTS 4
+#endif
 constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;
 // The on-the-fly passes and the list builds keep per-warp queues and row tiles in shared memory: at most 16 warps
@@ -419,7 +422,11 @@ __device__ void finalize_flow(Smem& sm) {
 
 // poly_solver + root selection (src/cvo.cpp:53-69,291-307): smallest positive real root of
 // 4E t^3 + 3D t^2 + 2C t + B, f64 closed form on the f32-normalised coefficients.
+// Called by ALL lanes of one warp with the same arguments: lane i % 3 evaluates and polishes root i (the f64 cbrt /
+// acos / cos and the Newton steps are the longest dependent chain of the per-iteration serial section), then the
+// smallest positive root is taken across the lanes.  Every lane returns the same step.
 __device__ float step_from_coeffs(double B, double C, double D, double E, float min_step, float max_step) {
+    const int which = (threadIdx.x & 31) % 3;
     const float p0 = (float)(4.0 * (double)(float)E);
     const float p1 = (float)(3.0 * (double)(float)D);
     const float p2 = (float)(2.0 * (double)(float)C);
@@ -432,29 +439,32 @@ __device__ float step_from_coeffs(double B, double C, double D, double E, float 
         const double q = (3.0 * a1 - a2 * a2) * (1.0 / 9.0);
         const double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) * (1.0 / 54.0);
         const double disc = q * q * q + r * r;
-        double roots[3];
-        int n = 0;
         const double shift = a2 * (1.0 / 3.0);
-        if (disc > 0.0) {
-            const double sd = sqrt(disc);
-            roots[n++] = cbrt(r + sd) + cbrt(r - sd) - shift;
-        } else if (disc == 0.0) {
-            const double s = cbrt(r);
-            roots[n++] = 2.0 * s - shift;
-            roots[n++] = -s - shift;
-        } else {
+        double x = 0.0;
+        bool have = false;
+        if (disc > 0.0) {  // one real root
+            if (which == 0) {
+                const double sd = sqrt(disc);
+                x = cbrt(r + sd) + cbrt(r - sd) - shift;
+                have = true;
+            }
+        } else if (disc == 0.0) {  // a double root
+            if (which < 2) {
+                const double sr = cbrt(r);
+                x = (which == 0 ? 2.0 * sr : -sr) - shift;
+                have = true;
+            }
+        } else {  // three real roots
             double cth = r / sqrt(-q * q * q);
             cth = fmin(1.0, fmax(-1.0, cth));
             const double th = acos(cth);
             const double m = 2.0 * sqrt(-q);
             const double kTwoPi = 6.283185307179586476925286766559;
-            roots[n++] = m * cos(th * (1.0 / 3.0)) - shift;
-            roots[n++] = m * cos((th + kTwoPi) * (1.0 / 3.0)) - shift;
-            roots[n++] = m * cos((th + 2.0 * kTwoPi) * (1.0 / 3.0)) - shift;
+            x = m * cos((th + (double)which * kTwoPi) * (1.0 / 3.0)) - shift;
+            have = true;
         }
-        for (int i = 0; i < n; ++i) {
-            double x = roots[i];
-            for (int it = 0; it < 3; ++it) {
+        if (have) {
+            for (int it = 0; it < 3; ++it) {  // Newton polish
                 const double f = ((x + a2) * x + a1) * x + a0;
                 const double fp = (3.0 * x + 2.0 * a2) * x + a1;
                 if (fp == 0.0 || !isfinite(f)) break;
@@ -463,9 +473,10 @@ __device__ float step_from_coeffs(double B, double C, double D, double E, float 
                 x = xn;
             }
             const float xr = (float)x;
-            if (xr > 0.f && xr < best) best = xr;
+            if (xr > 0.f) best = xr;
         }
     }
+    best = warp_min(best);
     float step = (best == kNone) ? min_step : best;
     return step > max_step ? max_step : step;
 }
@@ -497,11 +508,13 @@ __device__ void exp_sek3(const float* w, const float* v, float dt, float* dR, fl
 }
 
 // Body of align() after compute_step_size (src/cvo.cpp:379-410, src/adaptive_cvo.cpp:508-545)
+// Called by all lanes of warp 0; lane 0 applies the update.
 __device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_rec* rec) {
     IterConsts& ic = sm.ic;
     PairState& st = sm.st;
     const double B = sm.sum[0], C = sm.sum[1], D = sm.sum[2], E = sm.sum[3];
     const float step = step_from_coeffs(B, C, D, E, kp.min_step, kp.max_step);
+    if ((threadIdx.x & 31) != 0) return;
     const bool stops = !(kp.fixed_iters > 0);
     const float ell_used = st.ell;
     bool stop = false;
@@ -1197,6 +1210,19 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
     __syncthreads();
 }
 
+#ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles CTA 0
+__device__ unsigned long long g_phase_clocks[16];  // spends per phase
+__device__ long long g_phase_t0;
+#define CVO_PHASE(i)                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+        const long long now = clock64();                                     \
+        g_phase_clocks[i] += (unsigned long long)(now - g_phase_t0);         \
+        g_phase_t0 = now;                                                    \
+    }
+#else
+#define CVO_PHASE(i)
+#endif
+
 // --------------------------------------------------------------------------------------------
 // neighbour candidate lists
 // --------------------------------------------------------------------------------------------
@@ -1212,7 +1238,29 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // disp = max_j |(M1 - M0) y_j + (t1 - t0)|.  Since r_e <= r0, the list covers everything that can pass as long as
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
+// Called by all lanes of warp 0 (after lane 0 ran prepare_iter and a __syncwarp): the 8 box corners go to 8 lanes.
 __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
+    const int lane = threadIdx.x & 31;
+    double disp_xy = 0.0;
+    if (sm.lst[LIST_XY].valid > 0) {
+        // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is attained at
+        // one of the 8 corners
+        const ListState& L = sm.lst[LIST_XY];
+        const int c = lane & 7;
+        double dm[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)L.tf[i];
+        const double px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
+        const double ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
+        const double ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
+        const double ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
+        double d = sqrt(ex * ex + ey * ey + ez * ez);
+        if (!(d == d)) d = 1.0e30;  // NaN state: never trust an old list
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+        disp_xy = d;
+    }
+    if (lane != 0) return;
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
     const int nk = acvo ? LIST_KINDS : 1;
@@ -1224,24 +1272,9 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
         }
         bool need = L.valid == 0;
         if (!need) {
-            double disp = 0.0;
-            if (kind == LIST_XY) {
-                // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is
-                // attained at one of the 8 corners
-                double dm[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)L.tf[i];
-                for (int c = 0; c < 8; ++c) {
-                    const double px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
-                    const double ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
-                    const double ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
-                    const double ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
-                    disp = fmax(disp, sqrt(ex * ex + ey * ey + ez * ez));
-                }
-                if (!(disp == disp)) disp = 1.0e30;  // NaN state: never trust an old list
-            }
-            // rebuild when something that can pass may be missing, or when ell has shrunk the ball a lot (shrink < 0.7 by default: a
-            // list that is much too wide costs more in every pass than one rebuild)
+            const double disp = kind == LIST_XY ? disp_xy : 0.0;
+            // rebuild when something that can pass may be missing, or when ell has shrunk the ball a lot (a list that
+            // is much too wide costs more in every pass than one rebuild)
             need = !(fmax(0.0, r_now - (double)L.r0) + disp <= (double)L.slack) || (r_now < (double)shrink * (double)L.r0);
         }
         L.need = need ? 1 : 0;
@@ -1423,9 +1456,12 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     bool stop = false;
     for (int rb = 0; rb < pg.my_tiles && !stop; rb += pg.tiles_per_round) {
         const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
-        const int nunits = ntile * pg.S;
         for (int cb = 0; cb < pg.total_ct && !stop; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
+            // the build's own unit decomposition (the list passes do not use units): enough column segments per row
+            // tile that the 16 warps end together -- the evaluation cost per unit varies a lot
+            const int Sb = max(1, min(min(kMaxUnits / ntile, CVO_BUILD_SEGMENTS), nct / 8));
+            const int nunits = ntile * Sb;
             __syncthreads();
             stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) {
@@ -1437,12 +1473,13 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 stop = true;
                 break;
             }
+            CVO_PHASE(6)
             int wcur = 0;  // entries this warp has staged in this round
             while (warp < kWorkWarps) {  // evaluate
                 const int u = next_unit(sm);
                 if (u >= nunits) break;
-                const int t = u / pg.S, sg = u - t * pg.S;
-                const int c_begin = (int)(((long long)nct * sg) / pg.S), c_end = (int)(((long long)nct * (sg + 1)) / pg.S);
+                const int t = u / Sb, sg = u - t * Sb;
+                const int c_begin = (nct * sg) / Sb, c_end = (nct * (sg + 1)) / Sb;
                 const int c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile),
                                                      yy_row_min, c_begin, c_end, stage + wcur, seg - wcur);
                 if (lane == 0) {
@@ -1453,6 +1490,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 wcur = min(wcur + c, seg);
             }
             __syncthreads();
+            CVO_PHASE(7)
             if (warp == 0) {  // places in the flat list: exclusive scan of the unit counts in unit order
                 int base = 0;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
@@ -1485,6 +1523,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 stop = true;
                 break;
             }
+            CVO_PHASE(8)
             while (true) {  // compaction: staging segments -> flat list
                 const int u = next_unit(sm);
                 if (u >= nunits) break;
@@ -1501,6 +1540,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
         }
     }
     __syncthreads();  // the list (global memory) is complete and visible to the whole CTA
+    CVO_PHASE(9)
     if (threadIdx.x == 0) sm.lst[kind].valid = sm.lst_ovf ? -1 : 1;
     __syncthreads();
 }
@@ -1763,6 +1803,7 @@ __device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& c
 // --------------------------------------------------------------------------------------------
 // the persistent align kernel
 // --------------------------------------------------------------------------------------------
+
 __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -1834,19 +1875,28 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             __syncthreads();
         }
 
-        if (threadIdx.x == 0) {  // iteration 0: update_tf (src/cvo.cpp:368) + which lists to build
-            sm.serial += 1;
-            prepare_iter(sm, kp, kp.d2c_thres);
+        if (threadIdx.x < 32) {  // iteration 0: update_tf (src/cvo.cpp:368) + which lists to build
+            if (threadIdx.x == 0) {
+                sm.serial += 1;
+                prepare_iter(sm, kp, kp.d2c_thres);
+            }
+            __syncwarp();
             if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
         }
         __syncthreads();
+#ifdef CVO_PHASE_CLOCKS
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_t0 = clock64();
+#endif
         for (int k = 0; k < max_iter; ++k) {
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
+            CVO_PHASE(0)
             if (use_lists && sm.lst[LIST_XY].need) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            CVO_PHASE(1)
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
             if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else if (list_xy) run_pass_list<PASS_FLOW_CVO>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
+            CVO_PHASE(2)
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
                 if (use_lists && sm.lst[LIST_XX].need) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
@@ -1864,24 +1914,31 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             cluster_allreduce<ACC_FLOW_COUNT>(sm, cluster, sm.flowTot, 0, kFlowOff);
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
+            CVO_PHASE(3)
             // compute_step_size (src/cvo.cpp:377)
             if (list_xy) run_pass_list<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
+            CVO_PHASE(4)
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 32) {  // the serial section of the iteration, on warp 0 (its parallel parts use the lanes)
                 // remember the transform used by this iteration: it is what the reference multiplies
                 // into accum_transform when the loop exits here (quirk Q3, src/cvo.cpp:413-414)
-                write_tf44(sm.ic.tf, sm.st.prev_tf);
+                if (threadIdx.x == 0) write_tf44(sm.ic.tf, sm.st.prev_tf);
                 cvo_b200_iter_rec* rec = nullptr;
                 if (args.trace && pi == 0 && rank == 0 && k < args.trace_cap) rec = args.trace + k;
                 update_state(sm, kp, k, rec);
+                __syncwarp();
                 if (!sm.done && k + 1 < max_iter) {  // the next iteration's update_tf + list decisions, same serial section
-                    sm.serial += 1;
-                    prepare_iter(sm, kp, kp.d2c_thres);
+                    if (threadIdx.x == 0) {
+                        sm.serial += 1;
+                        prepare_iter(sm, kp, kp.d2c_thres);
+                    }
+                    __syncwarp();
                     if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
                 }
             }
             __syncthreads();
+            CVO_PHASE(5)
             if (sm.done) break;
         }
         if (threadIdx.x == 0 && rank == 0) {

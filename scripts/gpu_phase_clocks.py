@@ -1,0 +1,21 @@
+"""Scratch: per-phase cycle split of CTA 0 (needs the CVO_PHASE_CLOCKS variant: build_variants.py clk:CVO_PHASE_CLOCKS)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from cvo_rgbd_b200 import capi, synth
+lib = capi.load()
+ctx = capi.Context(0, max_points=3072, max_slots=296)
+for s in range(296):
+    pr = synth.config_pair(2, s)
+    ctx.set_pair(s, pr['x_pos'], pr['x_feat'], pr['y_pos'], pr['y_feat'])
+gp = capi.default_params('cvo'); gp.ell_policy = capi.ELL_FIXED; gp.ell_init = 0.10; gp.fixed_iters = 100
+ctx.align(list(range(296)), gp)
+out = (C.c_ulonglong * 16)()
+lib.cvo_b200_phase_clocks(out, 1)
+ctx.align(list(range(296)), gp)
+lib.cvo_b200_phase_clocks(out, 1)
+v = np.array(out[:10], float)
+names = ["(loop top)", "list build: rest", "FLOW pass", "allreduce + finalize_flow", "STEP pass", "allreduce + update_state + prepare_iter", "build: stage", "build: evaluate sweep", "build: scan", "build: compaction copy"]
+print("kernel_ms", ctx.last_kernel_ms, "total Mcycles on CTA 0:", v.sum() / 1e6)
+for n, x in zip(names, v):
+    print("%-45s %8.2f Mcycles  %5.1f %%" % (n, x / 1e6, 100 * x / v.sum()))
