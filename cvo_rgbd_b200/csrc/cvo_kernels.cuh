@@ -1260,6 +1260,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
         for (int o = 4; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
         disp_xy = d;
     }
+    __syncwarp();  // every lane has read the build transform before lane 0 may replace it
     if (lane != 0) return;
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
@@ -1828,6 +1829,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         lref[i].cap = args.list_cap;
     }
 
+    cluster.sync();  // every CTA of the cluster runs before anyone writes into its shared memory
+
     while (true) {
         if (rank == 0 && threadIdx.x == 0) {
             const int idx = atomicAdd(args.counter, 1);
@@ -1965,7 +1968,7 @@ __global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerA
         sm.st.ell = args.ell;
         prepare_iter(sm, args.kp, args.kp.d2c_thres);
     }
-    __syncthreads();
+    cluster.sync();  // (also: every CTA of the cluster runs before the all-reduce writes into its shared memory)
     run_pass<PASS_INNER>(sm, args.kp, args.pair.x, false, args.pair.y, false, rank, G, 0, tma_phase);
     cluster_allreduce<2>(sm, cluster, sm.blockTot, 0, 0);
     if (rank == 0 && threadIdx.x == 0) {
