@@ -905,24 +905,30 @@ __device__ __forceinline__ HotConsts hot_consts(const IterConsts& ic) {
     return h;
 }
 
-template <int KIND>
-__device__ __forceinline__ void list_body(const Smem& sm, const HotConsts& hc, const KParams& kp, uint32_t ent, float t_c,
+// EXACT = false: the branch-free body of the hot loop.  A candidate whose fast kernel value lies within a few ulp of
+// sp_thres (`near`, about one in a million) contributes NOTHING here and is reported to the caller, which re-runs it
+// with EXACT = true once the trip's bodies are done: no branch sits between the bodies, so the compiler interleaves
+// them, and membership in A still agrees with the CPU path bit for bit.
+template <int KIND, bool EXACT>
+__device__ __forceinline__ bool list_body(const Smem& sm, const HotConsts& hc, const KParams& kp, uint32_t ent, float t_c,
                                           int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
     const uint32_t rowb = ent >> 16, colb = ent & 0xffffu;  // byte offsets into the row / column stages
     const float4 xg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.rowG) + rowb);
     const float4 yg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.colG) + colb);
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
-    bool near;
-    float a = kernel_a(hc, kp, d2, t_c, near);
-    if (near) {
+    bool near = false;
+    float a;
+    if (EXACT) {
         const IterConsts& ic = sm.ic;
         const int ri = src.row_base + (int)(rowb >> 4), ci = src.col_base + (int)(colb >> 4);
         a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
                                __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
+    } else {
+        a = kernel_a(hc, kp, d2, t_c, near);
     }
     // src/cvo.cpp:152 and the exact strict ball test (thirdparty/nanoflann.hpp:249-253)
-    const bool ok = (a > kp.sp_thres) && (d2 < hc.d2_thres);
+    const bool ok = !near && (a > kp.sp_thres) && (d2 < hc.d2_thres);
     a = ok ? a : 0.f;
     if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
         const float4 z1 = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.ss.colZ1) + colb);
@@ -937,6 +943,7 @@ __device__ __forceinline__ void list_body(const Smem& sm, const HotConsts& hc, c
         const bool q1 = (KIND == PASS_YY) ? (__float_as_int(xg.w) >= yy_row_min) : true;
         accumulate_terms<KIND>(hc, kp, xg, yg, dx, dy, dz, a, ok, q1, fp, acc);
     }
+    return near;
 }
 
 template <int KIND>
@@ -1641,10 +1648,16 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
     }
 #define CVO_RUN_TRIP(x0, x1, x2, x3)                                                             \
     {                                                                                            \
-        list_body<KIND>(sm, hc, kp, x0.x, __uint_as_float(x0.y), yy_row_min, src, fp, acc);      \
-        list_body<KIND>(sm, hc, kp, x1.x, __uint_as_float(x1.y), yy_row_min, src, fp, acc);      \
-        list_body<KIND>(sm, hc, kp, x2.x, __uint_as_float(x2.y), yy_row_min, src, fp, acc);      \
-        list_body<KIND>(sm, hc, kp, x3.x, __uint_as_float(x3.y), yy_row_min, src, fp, acc);      \
+        const bool n0 = list_body<KIND, false>(sm, hc, kp, x0.x, __uint_as_float(x0.y), yy_row_min, src, fp, acc); \
+        const bool n1 = list_body<KIND, false>(sm, hc, kp, x1.x, __uint_as_float(x1.y), yy_row_min, src, fp, acc); \
+        const bool n2 = list_body<KIND, false>(sm, hc, kp, x2.x, __uint_as_float(x2.y), yy_row_min, src, fp, acc); \
+        const bool n3 = list_body<KIND, false>(sm, hc, kp, x3.x, __uint_as_float(x3.y), yy_row_min, src, fp, acc); \
+        if (__any_sync(0xffffffffu, n0 | n1 | n2 | n3)) { /* about one trip in ten thousand */    \
+            if (n0) list_body<KIND, true>(sm, hc, kp, x0.x, 0.f, yy_row_min, src, fp, acc);       \
+            if (n1) list_body<KIND, true>(sm, hc, kp, x1.x, 0.f, yy_row_min, src, fp, acc);       \
+            if (n2) list_body<KIND, true>(sm, hc, kp, x2.x, 0.f, yy_row_min, src, fp, acc);       \
+            if (n3) list_body<KIND, true>(sm, hc, kp, x3.x, 0.f, yy_row_min, src, fp, acc);       \
+        }                                                                                        \
     }
             int t = warp;
             if (t < ntrip) {
@@ -1692,20 +1705,26 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
 // pose-independent pairs (d2, colour d2), so nothing is staged and no point is touched -- the list streams through the
 // warps (same trips, same two register sets as run_pass_list) and every entry costs a dozen instructions.
 //   acc[0] = nnz, acc[1] = sum a * d2 / ell^3 (for (y, y): only the rows quirk Q1 lets through)
-__device__ __forceinline__ void self_body(const IterConsts& ic, const KParams& kp, float c1, float d2_thres, float inv_ell3,
+template <bool EXACT>
+__device__ __forceinline__ bool self_body(const IterConsts& ic, const KParams& kp, float c1, float d2_thres, float inv_ell3,
                                           uint32_t d2_bits, uint32_t d2c_bits, float& pdl, int& cnt) {
     const float d2 = __uint_as_float(d2_bits);
     const float d2c = __uint_as_float(d2c_bits & 0x7fffffffu);
     const bool q1 = (d2c_bits >> 31) != 0;
-    bool near;
-    HotConsts h;  // only c1 is read by kernel_a
-    h.c1 = c1;
-    float a = kernel_a(h, kp, d2, __fmul_rn(d2c, kp.c2), near);
-    if (near) a = kernel_value_exact_d(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, d2c, d2);
-    const bool ok = (a > kp.sp_thres) && (d2 < d2_thres);
+    bool near = false;
+    float a;
+    if (EXACT) {
+        a = kernel_value_exact_d(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, d2c, d2);
+    } else {
+        HotConsts h;  // only c1 is read by kernel_a
+        h.c1 = c1;
+        a = kernel_a(h, kp, d2, __fmul_rn(d2c, kp.c2), near);
+    }
+    const bool ok = !near && (a > kp.sp_thres) && (d2 < d2_thres);
     a = ok ? a : 0.f;
     pdl = fmaf(inv_ell3 * (q1 ? a : 0.f), d2, pdl);  // src/adaptive_cvo.cpp:210,231 / :256,259
     cnt += ok ? 1 : 0;
+    return near;
 }
 
 template <int KIND>  // PASS_XX or PASS_YY
@@ -1736,10 +1755,16 @@ __device__ void run_pass_self(Smem& sm, const KParams& kp, const CloudDev& rows,
     }
 #define CVO_RUN_TRIP(x0, x1, x2, x3)                                                             \
     {                                                                                            \
-        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x0.x, x0.y, pdl, cnt);                      \
-        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x1.x, x1.y, pdl, cnt);                      \
-        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x2.x, x2.y, pdl, cnt);                      \
-        self_body(sm.ic, kp, c1, d2_thres, inv_ell3, x3.x, x3.y, pdl, cnt);                      \
+        const bool n0 = self_body<false>(sm.ic, kp, c1, d2_thres, inv_ell3, x0.x, x0.y, pdl, cnt); \
+        const bool n1 = self_body<false>(sm.ic, kp, c1, d2_thres, inv_ell3, x1.x, x1.y, pdl, cnt); \
+        const bool n2 = self_body<false>(sm.ic, kp, c1, d2_thres, inv_ell3, x2.x, x2.y, pdl, cnt); \
+        const bool n3 = self_body<false>(sm.ic, kp, c1, d2_thres, inv_ell3, x3.x, x3.y, pdl, cnt); \
+        if (__any_sync(0xffffffffu, n0 | n1 | n2 | n3)) {                                        \
+            if (n0) self_body<true>(sm.ic, kp, c1, d2_thres, inv_ell3, x0.x, x0.y, pdl, cnt);    \
+            if (n1) self_body<true>(sm.ic, kp, c1, d2_thres, inv_ell3, x1.x, x1.y, pdl, cnt);    \
+            if (n2) self_body<true>(sm.ic, kp, c1, d2_thres, inv_ell3, x2.x, x2.y, pdl, cnt);    \
+            if (n3) self_body<true>(sm.ic, kp, c1, d2_thres, inv_ell3, x3.x, x3.y, pdl, cnt);    \
+        }                                                                                        \
         acc[1] += (double)pdl;  /* <= 4 terms per f32 partial */                                 \
         pdl = 0.f;                                                                               \
     }
