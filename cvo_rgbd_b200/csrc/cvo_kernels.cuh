@@ -36,6 +36,12 @@ namespace cg = cooperative_groups;
 #ifndef CVO_GROUP
 #define CVO_GROUP 2
 #endif
+#ifndef CVO_LIST_SETS
+#define CVO_LIST_SETS 3
+#endif
+#ifndef CVO_SELF_SETS
+#define CVO_SELF_SETS 3
+#endif
 #ifndef CVO_BUILD_SEGMENTS
 #define CVO_BUILD_SEGMENTS 4
 #endif
@@ -1631,9 +1637,9 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             const int ntrip = (int)rd.y / kListTrip;
             const uint2* e0 = lr.entries + rd.x;
             const uint2* e = e0 + lane;
-            // Two register sets (A, B) alternate between "being processed" and "being loaded" without ever being
-            // copied: a copy would have to wait for the load it copies.  Loads past the warp's last trip are clamped
-            // to it (always readable, never a branch).
+            // Register sets (A, B, C) rotate between "being processed" and "being loaded" without ever being copied: a
+            // copy would have to wait for the load it copies.  Loads past the warp's last trip are clamped to it
+            // (always readable, never a branch).
             uint2 a0, a1, a2, a3, b0, b1, b2, b3;
             // The lists stream from HBM (they are larger than this SM's share of L2): an L2 prefetch a few trips
             // ahead (8 lines of 128 B per trip, one per lane 0..7) leaves the register loads only L2 latency to cover.
@@ -1661,6 +1667,29 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
     }
             int t = warp;
             if (t < ntrip) {
+#if CVO_LIST_SETS == 3
+                // three register sets: the loads run TWO trips ahead of the arithmetic (a trip of interleaved bodies is
+                // shorter than the latency of a list line that misses L2)
+                uint2 c0, c1, c2, c3;
+                CVO_LOAD_TRIP(a0, a1, a2, a3, t)
+                CVO_LOAD_TRIP(b0, b1, b2, b3, t + kWarps)
+#pragma unroll 1
+                while (true) {
+                    CVO_LOAD_TRIP(c0, c1, c2, c3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(a0, a1, a2, a3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(a0, a1, a2, a3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(b0, b1, b2, b3)
+                    flush_partial<KIND>(fp, acc);  // <= 12 terms per f32 partial, like a short row of A
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(b0, b1, b2, b3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(c0, c1, c2, c3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                }
+#else
                 CVO_LOAD_TRIP(a0, a1, a2, a3, t)
 #pragma unroll 1
                 while (true) {
@@ -1674,6 +1703,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
                     t += kWarps;
                     if (t >= ntrip) break;
                 }
+#endif
             }
 #undef CVO_LOAD_TRIP
 #undef CVO_RUN_TRIP
@@ -1770,6 +1800,26 @@ __device__ void run_pass_self(Smem& sm, const KParams& kp, const CloudDev& rows,
     }
             int t = warp;
             if (t < ntrip) {
+#if CVO_SELF_SETS == 3  // three register sets, loads two trips ahead (see run_pass_list)
+                uint2 g0, g1, g2, g3;
+                CVO_LOAD_TRIP(a0, a1, a2, a3, t)
+                CVO_LOAD_TRIP(b0, b1, b2, b3, t + kWarps)
+#pragma unroll 1
+                while (true) {
+                    CVO_LOAD_TRIP(g0, g1, g2, g3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(a0, a1, a2, a3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(a0, a1, a2, a3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(b0, b1, b2, b3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                    CVO_LOAD_TRIP(b0, b1, b2, b3, t + 2 * kWarps)
+                    CVO_RUN_TRIP(g0, g1, g2, g3)
+                    t += kWarps;
+                    if (t >= ntrip) break;
+                }
+#else
                 CVO_LOAD_TRIP(a0, a1, a2, a3, t)
 #pragma unroll 1
                 while (true) {
@@ -1782,6 +1832,7 @@ __device__ void run_pass_self(Smem& sm, const KParams& kp, const CloudDev& rows,
                     t += kWarps;
                     if (t >= ntrip) break;
                 }
+#endif
             }
 #undef CVO_LOAD_TRIP
 #undef CVO_RUN_TRIP
