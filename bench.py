@@ -51,9 +51,11 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, device):
-        self.device, self.proc, self.path = device, None, None
+        self.device, self.proc, self.path, self.skip = device, None, None, 0
 
     def start(self):
+        """Starts `nvidia-smi -lms 20` and returns once its first sample has arrived (it takes ~0.1-0.5 s to come up:
+        without the wait a short timed region could end before the first sample)."""
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -63,6 +65,10 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 3.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.01)
+            self.skip = sum(1 for _ in open(self.path))  # samples taken before the timed region
         except Exception:
             self.proc = None
 
@@ -77,7 +83,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            lines = open(self.path).read().splitlines()
+            if len(lines) > self.skip + 1:
+                lines = lines[self.skip:]  # only what was sampled under load
+            for line in lines:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
