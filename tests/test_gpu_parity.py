@@ -402,3 +402,38 @@ def test_maximum_cloud_size(oracle):
     _check_eval(g, o, False)
     with pytest.raises(capi.CvoB200Error):
         capi.Context(0, max_points=16385, max_slots=1)
+
+
+def test_degenerate_inputs_terminate_with_finite_or_flagged_results(gpu_ctx, oracle):
+    """All points identical (every pair is a neighbour, zero-size bounding box), duplicated points, and NaN / Inf
+    coordinates: no hang, no crash; NaN / Inf points are never neighbours of anything."""
+    gp = capi.default_params("cvo")
+    gp.fixed_iters = 4
+    pr = synth.make_pair(75, 300, 280, "cvo")
+    # (1) all points identical
+    x = np.tile(pr["x_pos"][:1], (300, 1))
+    y = np.tile(pr["x_pos"][:1], (280, 1))
+    gpu_ctx.set_pair(0, x, pr["x_feat"], y, pr["y_feat"])
+    e = gpu_ctx.eval(0, np.eye(3), np.zeros(3), 0.1, gp)
+    o = oracle.evaluate(x, pr["x_feat"], y, pr["y_feat"], np.eye(3), np.zeros(3), 0.1, oracle.default_params("cvo"))
+    assert e["nnz"] == o["nnz"] and np.isfinite(e["omega"]).all()
+    r = gpu_ctx.align(np.array([0]), gp)
+    assert np.isfinite(r["transform"]).all()
+    # (2) every point twice
+    x2, f2 = np.repeat(pr["x_pos"], 2, axis=0), np.repeat(pr["x_feat"], 2, axis=0)
+    gpu_ctx.set_pair(0, x2, f2, pr["y_pos"], pr["y_feat"])
+    e = gpu_ctx.eval(0, R0, T0, 0.1, gp)
+    o = oracle.evaluate(x2, f2, pr["y_pos"], pr["y_feat"], R0, T0, 0.1, oracle.default_params("cvo"))
+    _check_eval(e, o, False)
+    # (3) some NaN / Inf coordinates: those points drop out, the rest is unchanged
+    xn = pr["x_pos"].copy()
+    xn[::7] = np.nan
+    xn[3::11] = np.inf
+    keep = np.isfinite(xn).all(axis=1)
+    gpu_ctx.set_pair(0, xn, pr["x_feat"], pr["y_pos"], pr["y_feat"])
+    a = gpu_ctx.eval(0, R0, T0, 0.1, gp)
+    gpu_ctx.set_pair(0, pr["x_pos"][keep], pr["x_feat"][keep], pr["y_pos"], pr["y_feat"])
+    b = gpu_ctx.eval(0, R0, T0, 0.1, gp)
+    assert a["nnz"] == b["nnz"] and rel_err(a["omega"], b["omega"]) < 1e-6 and rel_err(a["B"], b["B"]) < 1e-6
+    r = gpu_ctx.align(np.array([0]), gp)
+    assert r["status"][0] in (capi.STATUS_MAX_ITER, capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE, capi.STATUS_NAN)
