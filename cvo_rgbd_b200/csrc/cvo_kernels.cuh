@@ -708,14 +708,16 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
     const float* tf12 = sm.ic.tf;
     for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
         const int p = base + i;
-        const bool valid = p < c.n;
+        bool valid = p < c.n;
         float4 g;
         if (valid) {
             g = __ldg(c.g + p);
             if (tf) apply_tf(tf12, g.x, g.y, g.z);
-        } else {
-            g = make_float4(sentinel, sentinel, sentinel, 0.f);
+            // a point with a NaN / Inf coordinate is nobody's neighbour (d2 < thr is false): move it far away so that
+            // the branch-free bodies only ever multiply their zero weights with finite numbers
+            valid = isfinite(g.x) && isfinite(g.y) && isfinite(g.z);
         }
+        if (!valid) g = make_float4(sentinel, sentinel, sentinel, 0.f);
         if (MODE == STAGE_FULL) {
             const float c2 = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
             sm.colG[i] = make_float4(g.x, g.y, g.z, c2);
@@ -1085,8 +1087,8 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
     const float inf = __int_as_float(0x7f800000);
     // stage the row tile: registers for the mask phase, warp-private shared memory for the survivor body
     const int p = tile * kTile + lane;
-    const bool valid = p < rows.n;
-    float4 xg, xf;
+    bool valid = p < rows.n;
+    float4 xg = make_float4(0.f, 0.f, 0.f, 0.f), xf = make_float4(0.f, 0.f, 0.f, 0.f);
     int orig = -1;
     if (valid) {
         xg = __ldg(rows.g + p);
@@ -1094,10 +1096,9 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
         orig = __float_as_int(xg.w);
         xg.w = __ldg(rows.f4 + p);
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
-    } else {
-        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
-        xf = make_float4(0.f, 0.f, 0.f, 0.f);
+        valid = isfinite(xg.x) && isfinite(xg.y) && isfinite(xg.z);  // (see stage_tiles)
     }
+    if (!valid) xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, xg.w);
     __syncwarp();  // the previous unit's body reads are done
     ws.rowG[lane] = xg;
     ws.rowF[lane] = xf;
@@ -1318,7 +1319,7 @@ __device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
     const int p = tile * kTile + lane;
-    const bool valid = p < rows.n;
+    bool valid = p < rows.n;
     float4 xg, xf = make_float4(0.f, 0.f, 0.f, 0.f);
     int orig = -1;
     if (valid) {
@@ -1330,9 +1331,9 @@ __device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws
             xg.w = __ldg(rows.f4 + p);
         }
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
-    } else {
-        xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, 0.f);
+        valid = isfinite(xg.x) && isfinite(xg.y) && isfinite(xg.z);  // (see stage_tiles)
     }
+    if (!valid) xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, xg.w);
     __syncwarp();  // the previous unit's reads of the warp scratch are done
     ws.rowG[lane] = xg;
     if (NEED_FEAT) ws.rowF[lane] = xf;
@@ -1575,12 +1576,11 @@ __device__ __forceinline__ void stage_step_terms(Smem& sm, int n) {
 __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int first, int n, bool tf) {
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const int p = first + i;
-        float4 g;
+        float4 g = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, __int_as_float(-1));
         if (p < c.n) {
-            g = __ldg(c.g + p);
-            if (tf) apply_tf(sm.ic.tf, g.x, g.y, g.z);
-        } else {
-            g = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, __int_as_float(-1));
+            float4 q = __ldg(c.g + p);
+            if (tf) apply_tf(sm.ic.tf, q.x, q.y, q.z);
+            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) g = q;  // (see stage_tiles)
         }
         sm.u.ls.rowG[i] = g;
     }
@@ -1933,6 +1933,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
             for (int i = threadIdx.x; i < pair.y.n; i += kThreads) {
                 const float4 g = __ldg(pair.y.g + i);
+                if (!(isfinite(g.x) && isfinite(g.y) && isfinite(g.z))) continue;  // such a point is never staged as is
                 lo[0] = fminf(lo[0], g.x); lo[1] = fminf(lo[1], g.y); lo[2] = fminf(lo[2], g.z);
                 hi[0] = fmaxf(hi[0], g.x); hi[1] = fmaxf(hi[1], g.y); hi[2] = fmaxf(hi[2], g.z);
             }
@@ -2087,6 +2088,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_sort_kernel(const PackJo
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const float v = job.xyz[3 * i + a];
+            if (!isfinite(v)) continue;  // keeps the Morton grid of the finite points intact
             lo[a] = fminf(lo[a], v);
             hi[a] = fmaxf(hi[a], v);
         }
