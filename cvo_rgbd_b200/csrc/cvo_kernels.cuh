@@ -335,6 +335,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// all three finite <=> the sum of the magnitudes is finite (NaN and Inf both fail the comparison)
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+    return (fabsf(x) + fabsf(y)) + fabsf(z) < __int_as_float(0x7f800000);
+}
+
 __device__ __forceinline__ float exp2f_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -715,7 +720,7 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
             if (tf) apply_tf(tf12, g.x, g.y, g.z);
             // a point with a NaN / Inf coordinate is nobody's neighbour (d2 < thr is false): move it far away so that
             // the branch-free bodies only ever multiply their zero weights with finite numbers
-            valid = isfinite(g.x) && isfinite(g.y) && isfinite(g.z);
+            valid = finite3(g.x, g.y, g.z);
         }
         if (!valid) g = make_float4(sentinel, sentinel, sentinel, 0.f);
         if (MODE == STAGE_FULL) {
@@ -1096,7 +1101,7 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
         orig = __float_as_int(xg.w);
         xg.w = __ldg(rows.f4 + p);
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
-        valid = isfinite(xg.x) && isfinite(xg.y) && isfinite(xg.z);  // (see stage_tiles)
+        valid = finite3(xg.x, xg.y, xg.z);  // (see stage_tiles)
     }
     if (!valid) xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, xg.w);
     __syncwarp();  // the previous unit's body reads are done
@@ -1331,7 +1336,7 @@ __device__ __forceinline__ RowTile load_row_tile(const Smem& sm, WarpScratch& ws
             xg.w = __ldg(rows.f4 + p);
         }
         if (row_tf) apply_tf(sm.ic.tf, xg.x, xg.y, xg.z);
-        valid = isfinite(xg.x) && isfinite(xg.y) && isfinite(xg.z);  // (see stage_tiles)
+        valid = finite3(xg.x, xg.y, xg.z);  // (see stage_tiles)
     }
     if (!valid) xg = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, xg.w);
     __syncwarp();  // the previous unit's reads of the warp scratch are done
@@ -1580,7 +1585,7 @@ __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int firs
         if (p < c.n) {
             float4 q = __ldg(c.g + p);
             if (tf) apply_tf(sm.ic.tf, q.x, q.y, q.z);
-            if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z)) g = q;  // (see stage_tiles)
+            if (finite3(q.x, q.y, q.z)) g = q;  // (see stage_tiles)
         }
         sm.u.ls.rowG[i] = g;
     }
@@ -1933,7 +1938,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
             for (int i = threadIdx.x; i < pair.y.n; i += kThreads) {
                 const float4 g = __ldg(pair.y.g + i);
-                if (!(isfinite(g.x) && isfinite(g.y) && isfinite(g.z))) continue;  // such a point is never staged as is
+                if (!finite3(g.x, g.y, g.z)) continue;  // such a point is never staged as is
                 lo[0] = fminf(lo[0], g.x); lo[1] = fminf(lo[1], g.y); lo[2] = fminf(lo[2], g.z);
                 hi[0] = fmaxf(hi[0], g.x); hi[1] = fmaxf(hi[1], g.y); hi[2] = fmaxf(hi[2], g.z);
             }
