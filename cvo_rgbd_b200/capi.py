@@ -24,7 +24,7 @@ EXPORTS = [
     "cvo_b200_align_trace", "cvo_b200_inner_product", "cvo_b200_sync", "cvo_b200_last_kernel_ms",
     "cvo_b200_kernel_launches", "cvo_b200_last_cluster_size", "cvo_b200_last_num_clusters",
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
-    "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds",
+    "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny",
 ]
@@ -115,6 +115,8 @@ def load():
     lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
     lib.cvo_b200_last_list_builds.argtypes = [vp]
     lib.cvo_b200_last_list_builds.restype = C.c_longlong
+    lib.cvo_b200_last_list_refines.argtypes = [vp]
+    lib.cvo_b200_last_list_refines.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -295,6 +297,10 @@ class Context:
     @property
     def last_list_builds(self):
         return int(self._lib.cvo_b200_last_list_builds(self._h))
+
+    @property
+    def last_list_refines(self):
+        return int(self._lib.cvo_b200_last_list_refines(self._h))
 
     @property
     def last_kernel_ms(self):

@@ -92,7 +92,8 @@ struct cvo_b200_ctx {
     bool lists_alloc_failed = false;
     float list_skin = 0.08f;
     float list_shrink = 0.7f;
-    long long last_list_builds = 0;
+    float list_refine_min = 1.0f;
+    long long last_list_builds = 0, last_list_refines = 0;
 
     float last_ms = 0.f;
     long long launches = 0;
@@ -421,6 +422,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
     args.list_shrink = ctx->list_shrink;
+    args.list_refine_min = ctx->list_refine_min;
     // The pair descriptors and states live in pinned host memory that the kernel reads and writes directly (unified
     // addressing: 272 B per pair, once at its start and once at its end).  No host->device copy sits in the launch
     // path: a small copy would queue behind the upload of the NEXT batch on the copy engine (measured: 0.8 ms).
@@ -442,11 +444,12 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_G = G;
     ctx->last_nclusters = ncl;
-    long long total = 0, builds = 0;
+    long long total = 0, builds = 0, refines = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const PairState& st = ctx->h_states[i];
         total += st.n_run;
         builds += st.n_builds;
+        refines += st.n_refines;
         if (RT_io) {
             memcpy(RT_io + (size_t)i * 12, st.R, sizeof(float) * 9);
             memcpy(RT_io + (size_t)i * 12 + 9, st.T, sizeof(float) * 3);
@@ -459,6 +462,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     }
     ctx->last_total_iters = total;
     ctx->last_list_builds = builds;
+    ctx->last_list_refines = refines;
     if (args.trace) {
         const int n = ctx->h_states[0].n_run < args.trace_cap ? ctx->h_states[0].n_run : args.trace_cap;
         memcpy(trace, ctx->h_trace, sizeof(cvo_b200_iter_rec) * n);
@@ -576,6 +580,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     if (env && env[0] == '1') ctx->lists_enabled = false;
     env = getenv("CVO_B200_LIST_SHRINK");  // tuning knob
     if (env && atof(env) > 0.0 && atof(env) <= 1.0) ctx->list_shrink = (float)atof(env);
+    env = getenv("CVO_B200_LIST_REFINE_MIN");
+    if (env && atof(env) > 0.0) ctx->list_refine_min = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN");
     if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin = (float)atof(env);
 #undef CKC
@@ -979,6 +985,7 @@ int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
 }
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_total_iters : 0; }
 long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_builds : 0; }
+long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_refines : 0; }
 int cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (!(skin >= 0.f && skin <= 1.f)) return fail_arg(ctx, "skin must be in [0, 1]");

@@ -112,6 +112,7 @@ struct PairState {
     int status;
     int n_run;
     int n_builds;  // neighbour-list (re)builds of the (x, y) list during this align()
+    int n_refines;  // ... and how often one of the pair's lists was narrowed in place instead (refine_list)
     float tf[16];
     float prev_tf[16];
 };
@@ -224,6 +225,7 @@ struct Smem {
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
     uint2 lround[LIST_KINDS][kMaxListRounds];  // (offset, entries) of every round of a list; entries % kListTrip == 0
     int lst_base;
+    int refineCnt[kWarps], refinePos[kWarps];  // refine_list: entries every warp kept / where they go
     StageTag colTag, rowTag;  // what the column / row stages of the list passes currently hold
     int serial;               // running iteration number of this CTA: identifies "transformed with this iteration's pose"
     float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
@@ -260,6 +262,7 @@ struct AlignArgs {
     unsigned list_cap;
     float list_skin;
     float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius
+    float list_refine_min;  // ... by filtering the old list if it has at least this fraction of a fresh skin to spare
 };
 
 struct InnerArgs {
@@ -1258,7 +1261,7 @@ __device__ long long g_phase_t0;
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
 // Called by all lanes of warp 0 (after lane 0 ran prepare_iter and a __syncwarp): the 8 box corners go to 8 lanes.
-__device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
+__device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink, float refine_min) {
     const int lane = threadIdx.x & 31;
     double disp_xy = 0.0;
     if (sm.lst[LIST_XY].valid > 0) {
@@ -1299,9 +1302,20 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
         }
         L.need = need ? 1 : 0;
         if (need) {
-            const double s = (double)skin * r_now;
+            double s = (double)skin * r_now;
+            if (L.valid > 0 && r_now <= (double)L.r0) {
+                // The ball has shrunk and the old list still covers the pose with room to spare: everything the new
+                // list must hold (|x_i - T1 y_j| < r_e1 + s1, r_e1 <= r_e0) is in the old one as long as
+                // s1 + disp <= s0, so the new list is a FILTER of the old one (refine_list) -- no all-pairs sweep.
+                const double disp = kind == LIST_XY ? disp_xy : 0.0;
+                const double left = (double)L.slack - disp - margin;
+                if (left >= (double)refine_min * s) {
+                    s = fmin(s, left);
+                    L.need = 2;
+                }
+            }
             const double rb = r_now + s + margin;
-            L.valid = 0;
+            if (L.need == 1) L.valid = 0;
             L.r0 = (float)r_now;
             L.slack = (float)(s * (1.0 - 1.0e-6));            // rounded DOWN: what the validity test may assume
             L.s_build = (float)((s + margin) * (1.0 + 1.0e-6));  // rounded UP: what the build adds to r_e
@@ -1309,7 +1323,8 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink) {
             L.inv_c1 = (float)(2.0 * (double)sm.st.ell * (double)sm.st.ell / 1.4426950408889634 * (1.0 + 1.0e-6));
 #pragma unroll
             for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i];
-            if (kind == LIST_XY) sm.st.n_builds += 1;
+            if (L.need == 2) sm.st.n_refines += 1;
+            else if (kind == LIST_XY) sm.st.n_builds += 1;
         }
     }
 }
@@ -1589,6 +1604,105 @@ __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int firs
         }
         sm.u.ls.rowG[i] = g;
     }
+}
+
+// Narrows a valid list in place after ell has shrunk (list_policy, need == 2): the new list -- every pair within
+// r_e + s of the CURRENT pose and length-scale -- is a filter of the old one, so one streaming pass over the old
+// entries replaces the all-pairs sweep of a rebuild.  Per round: every warp filters a contiguous range of trips into the
+// same range of the staging area (order kept, so the list stays a pure function of the inputs), the 16 counts are
+// scanned, the ranges are copied back behind one another and the round is padded to a whole trip.  The narrowed
+// rounds only ever move towards the front of the list area, behind the read position.
+//   SELF == 0: entries (row, col, t_c); the distance is measured on the staged rows / transformed columns.
+//   SELF != 0: entries (d2, colour d2 | Q1 flag): d2 is pose-independent, nothing is staged.
+template <int SELF>
+__device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const CloudDev& rows, const CloudDev& cols, int rank, int G,
+                            uint32_t& tma_phase, int kind, const ListRef& lr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    const ListState& L = sm.lst[kind];
+    const float t_lim = kp.t_lim, inv_c1 = L.inv_c1, s_build = L.s_build, c2 = kp.c2;
+    if (threadIdx.x == 0) sm.lst_used = 0;
+    int round = 0;
+    for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round) {
+        const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
+        for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
+            const int nct = min(kColTiles, pg.total_ct - cb);
+            __syncthreads();
+            if (SELF == 0) {  // the stages of a list pass (run_pass_list finds them afterwards)
+                const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
+                const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, sm.serial);
+                const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, -1);
+                if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase);
+                if (!have_rows) stage_rows(sm, rows, row_first, ntile * kTile, false);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = sm.serial;
+                    sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = -1;
+                }
+            }
+            const uint2 rd = sm.lround[kind][round];
+            const int ntrip = (int)rd.y / kListTrip;
+            const int t_begin = (ntrip * warp) / kWarps, t_end = (ntrip * (warp + 1)) / kWarps;
+            const uint2* src = lr.entries + rd.x + lane;
+            uint2* const dst = lr.staging + (size_t)t_begin * kListTrip;
+            int cursor = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const uint2* q = src + (size_t)t * kListTrip;
+                uint2 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __ldcg(q + j * kTile);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float d2, t_c;
+                    if (SELF == 0) {
+                        const float4 xg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.rowG) + (v[j].x >> 16));
+                        const float4 yg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.colG) + (v[j].x & 0xffffu));
+                        d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
+                        t_c = __uint_as_float(v[j].y);
+                    } else {
+                        d2 = __uint_as_float(v[j].x);
+                        t_c = __fmul_rn(__uint_as_float(v[j].y & 0x7fffffffu), c2);
+                    }
+                    const float re2 = (t_lim - t_c) * inv_c1;  // (padding: t_c = +inf, never kept)
+                    const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + s_build;
+                    const bool keep = (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
+                    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+                    if (keep) __stcg(dst + cursor + __popc(b & ((1u << lane) - 1u)), v[j]);
+                    cursor += __popc(b);
+                }
+            }
+            if (lane == 0) sm.refineCnt[warp] = cursor;
+            __syncthreads();
+            if (warp == 0) {
+                const int c = lane < kWarps ? sm.refineCnt[lane] : 0;
+                int excl, total;
+                warp_scan_count(c, lane, excl, total);
+                if (lane < kWarps) sm.refinePos[lane] = excl;
+                const int padded = (total + kListTrip - 1) / kListTrip * kListTrip;
+                const int at = sm.lst_used;
+                for (int i = total + lane; i < padded; i += 32)
+                    __stcg(lr.entries + at + i, make_uint2(SELF ? __float_as_uint(1.0e30f) : 0u, 0x7f800000u));
+                __syncwarp();
+                if (lane == 0) {
+                    sm.lround[kind][round] = make_uint2((unsigned)at, (unsigned)padded);
+                    sm.lst_base = at;
+                    sm.lst_used = at + padded;
+                }
+            }
+            __syncthreads();
+            {
+                const uint2* from = dst;
+                uint2* to = lr.entries + sm.lst_base + sm.refinePos[warp];
+                int i = lane;
+                for (; i + 96 < cursor; i += 128) {
+                    const uint2 v0 = __ldcg(from + i), v1 = __ldcg(from + i + 32), v2 = __ldcg(from + i + 64), v3 = __ldcg(from + i + 96);
+                    __stcg(to + i, v0); __stcg(to + i + 32, v1); __stcg(to + i + 64, v2); __stcg(to + i + 96, v3);
+                }
+                for (; i < cursor; i += 32) __stcg(to + i, __ldcg(from + i));
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // One all-pairs pass over a valid neighbour list.  Rows and columns of the round are staged once; the round's flat
@@ -1927,6 +2041,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             sm.st.status = CVO_B200_STATUS_MAX_ITER;
             sm.st.n_run = 0;
             sm.st.n_builds = 0;
+            sm.st.n_refines = 0;
             sm.done = 0;
             sm.colTag.serial = sm.rowTag.serial = -2;
 #pragma unroll
@@ -1966,7 +2081,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 prepare_iter(sm, kp, kp.d2c_thres);
             }
             __syncwarp();
-            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
+            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink, args.list_refine_min);
         }
         __syncthreads();
 #ifdef CVO_PHASE_CLOCKS
@@ -1975,7 +2090,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         for (int k = 0; k < max_iter; ++k) {
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             CVO_PHASE(0)
-            if (use_lists && sm.lst[LIST_XY].need) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (use_lists && sm.lst[LIST_XY].need == 1) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            else if (use_lists && sm.lst[LIST_XY].need == 2) refine_list<0>(sm, kp, pair.x, pair.y, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             CVO_PHASE(1)
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
             if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
@@ -1984,12 +2100,14 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             CVO_PHASE(2)
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                if (use_lists && sm.lst[LIST_XX].need) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
+                if (use_lists && sm.lst[LIST_XX].need == 1) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
+                else if (use_lists && sm.lst[LIST_XX].need == 2) refine_list<1>(sm, kp, pair.x, pair.x, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
                 if (use_lists && sm.lst[LIST_XX].valid > 0)
                     run_pass_self<PASS_XX>(sm, kp, pair.x, pair.x, rank, G, LIST_XX, lref[LIST_XX]);
                 else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                if (use_lists && sm.lst[LIST_YY].need) build_list<2>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
+                if (use_lists && sm.lst[LIST_YY].need == 1) build_list<2>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
+                else if (use_lists && sm.lst[LIST_YY].need == 2) refine_list<2>(sm, kp, pair.y, pair.y, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
                 if (use_lists && sm.lst[LIST_YY].valid > 0)
                     run_pass_self<PASS_YY>(sm, kp, pair.y, pair.y, rank, G, LIST_YY, lref[LIST_YY]);
                 else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
@@ -2019,7 +2137,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                         prepare_iter(sm, kp, kp.d2c_thres);
                     }
                     __syncwarp();
-                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink, args.list_refine_min);
                 }
             }
             __syncthreads();

@@ -204,6 +204,9 @@ long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
 int       cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin);
 /* Sum over the pairs of the last align call of (x, y) list builds. */
 long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx);
+/* ... and of the times one of the pair's lists ((x, y), or acvo's (x, x) / (y, y)) was narrowed in place after ell
+ * shrank: a filter of the old list instead of an all-pairs sweep. */
+long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx);
 int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
 
 #ifdef __cplusplus

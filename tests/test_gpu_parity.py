@@ -218,6 +218,40 @@ def test_neighbor_lists_agree_with_on_the_fly_passes(gpu_ctx, kind, cfg):
         gpu_ctx.set_neighbor_lists(True)
 
 
+@pytest.mark.parametrize("kind,cfg,refine_min", [("cvo", 2, 0.05), ("acvo", 3, 0.05), ("acvo", 3, None)])
+def test_lists_narrowed_in_place_agree_with_on_the_fly_passes(kind, cfg, refine_min, monkeypatch):
+    """When ell shrinks, a list with slack to spare is FILTERED down to the new ball instead of being rebuilt
+    (refine_list).  The narrowed list must still cover every pair that can pass: per-iteration counts equal the
+    on-the-fly passes' on one CTA (several rounds) and on a cluster.  refine_min = 0.05 forces the (x, y) list through
+    it at every ell step; the default only narrows when a whole fresh skin fits (acvo's pose-independent lists)."""
+    if refine_min is not None:
+        monkeypatch.setenv("CVO_B200_LIST_REFINE_MIN", str(refine_min))
+    pr = synth.config_pair(cfg)
+    gp = capi.default_params(kind)
+    ctx = capi.Context(0, max_points=4096, max_slots=1)
+    try:
+        _set(ctx, 0, pr)
+        ctx.set_neighbor_lists(False)
+        ref = ctx.align_trace(0, gp, trace_cap=40)
+        ctx.set_neighbor_lists(True)
+        for g in (1, 8):
+            ctx.set_cluster_size(g)
+            got = ctx.align_trace(0, gp, trace_cap=40)
+            assert ctx.last_list_refines >= 1, g
+            a, b = got["trace"][0], ref["trace"][0]
+            assert (a["nnz"], a["nnz_xx"], a["nnz_yy"]) == (b["nnz"], b["nnz_xx"], b["nnz_yy"])
+            for k in range(1, 12):  # across the ell steps (cvo: k = 3...; acvo: every iteration)
+                a, b = got["trace"][k], ref["trace"][k]
+                assert abs(a["nnz"] - b["nnz"]) <= 3, (g, k)
+                assert abs(a["nnz_xx"] - b["nnz_xx"]) <= 3 and abs(a["nnz_yy"] - b["nnz_yy"]) <= 3, (g, k)
+                if k < 8:  # (later the two runs' states have drifted apart by rounding: only the counts stay comparable)
+                    assert rel_err(a["omega"], b["omega"]) < 1e-4 and rel_err(a["v"], b["v"]) < 1e-4, (g, k)
+            rot, tr = pose_diff(got["transform"], ref["transform"])
+            assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (g, rot, tr)
+    finally:
+        ctx.close()
+
+
 def test_neighbor_list_survives_large_motion_and_cluster_sizes(gpu_ctx, oracle):
     """Large initial misalignment (many rebuilds while the pose moves by much more than the skin) on every
     cluster size, checked against the oracle's trajectory."""
