@@ -807,36 +807,54 @@ struct FlowPartial {
 };
 
 // One nonzero of A in compute_step_size (src/cvo.cpp:260-279): beta, gamma, delta, epsilon from the column's
-// step-size terms and r = x_i - y_j, and the f64 accumulation of B, C, D, E.
+// step-size terms and r = x_i - y_j, and this nonzero's terms of B, C, D, E.
+//   The higher powers need no per-entry cross products: with z1 = omega x y + v,
+//     xi^3 z = Omega^2 z1 = omega (omega . z1) - |omega|^2 z1,   omega . z1 = omega . v   (omega . (omega x y) = 0)
+//     xi^4 z = Omega^3 z1 = -|omega|^2 (omega x z1) = -|omega|^2 z2                       (Omega^3 = -|omega|^2 Omega)
+//   so z3 . r = (omega . v)(omega . r) - |omega|^2 (z1 . r) and z4 . r = -|omega|^2 (z2 . r): three dot products per
+//   entry instead of four dot products and two cross products.  (The reference forms the powers as matrix products,
+//   src/cvo.cpp:229-234: either way the result is the same to f32 rounding.)
+struct StepTerms {
+    float tB, tC, tD, tE;
+};
+template <class IC>
+__device__ __forceinline__ StepTerms step_terms(const IC& ic, const StepCol& c, float rx, float ry, float rz, float a) {
+    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+    const float ww = (w0 * w0 + w1 * w1) + w2 * w2;                       // loop invariants: the compiler hoists them
+    const float wv = (w0 * ic.v[0] + w1 * ic.v[1]) + w2 * ic.v[2];
+    const float p1 = (c.z1x * rx + c.z1y * ry) + c.z1z * rz;
+    const float p2 = (c.z2x * rx + c.z2y * ry) + c.z2z * rz;
+    const float pw = (w0 * rx + w1 * ry) + w2 * rz;
+    const float p3 = wv * pw - ww * p1;                                   // z3 . r
+    const float beta = ic.m2t * p1;                                       // :262
+    const float gamma = -ic.temp_coef * (c.nrm + 2.f * p2);               // :264
+    const float delta = ic.p2t * (c.pdt - p3);                            // :267
+    const float epsil = -ic.temp_coef * (c.ecn - 2.f * (ww * p2));        // :270
+    StepTerms t;
+#ifdef CVO_STEP_F32_PRODUCTS
+    // the reference's own mix of f32 products and f64 sums inside a term (src/cvo.cpp:275-279)
+    const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
+    t.tB = a * beta;
+    t.tC = (float)(ad * (gd + (double)(beta * beta) * 0.5));
+    t.tD = (float)(ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0)));
+    t.tE = (float)(ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd + (1.0 / 24.0) * (bd * bd) * (bd * bd)));
+#else
+    // The terms are f32 in the reference too (its `double(A_ij * (...))` promotes a finished f32-by-f64 expression of
+    // f32 inputs); here the whole polynomial is f32 FMAs.
+    const float b2 = beta * beta;
+    t.tB = a * beta;                                                                                      // :275
+    t.tC = a * fmaf(0.5f, b2, gamma);                                                                     // :276
+    t.tD = a * fmaf(b2 * beta, 1.f / 6.f, fmaf(beta, gamma, delta));                                      // :277
+    t.tE = a * fmaf(b2 * b2, 1.f / 24.f, fmaf(0.5f, gamma * (b2 + gamma), fmaf(beta, delta, epsil)));    // :278-279
+#endif
+    return t;
+}
+// on-the-fly passes: every nonzero is promoted and summed in f64 (src/cvo.cpp:275-279)
 template <class IC>
 __device__ __forceinline__ void step_accumulate(const IC& ic, const StepCol& c, float rx, float ry, float rz, float a,
                                                 double* acc) {
-    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
-    const float z3x = w1 * c.z2z - w2 * c.z2y, z3y = w2 * c.z2x - w0 * c.z2z, z3z = w0 * c.z2y - w1 * c.z2x;
-    const float z4x = w1 * z3z - w2 * z3y, z4y = w2 * z3x - w0 * z3z, z4z = w0 * z3y - w1 * z3x;
-    const float beta = ic.m2t * ((c.z1x * rx + c.z1y * ry) + c.z1z * rz);                          // :262
-    const float gamma = -ic.temp_coef * (c.nrm + 2.f * ((c.z2x * rx + c.z2y * ry) + c.z2z * rz));  // :264
-    const float delta = ic.p2t * (c.pdt - ((z3x * rx + z3y * ry) + z3z * rz));                     // :267
-    const float epsil = -ic.temp_coef * (c.ecn + 2.f * ((z4x * rx + z4y * ry) + z4z * rz));        // :270
-#ifdef CVO_STEP_F32_PRODUCTS
-    // the reference's own mix of f32 products and f64 sums (src/cvo.cpp:275-279), term by term
-    const double bd = (double)beta, gd = (double)gamma, ad = (double)a;
-    acc[0] += (double)(a * beta);                                                                  // :275
-    acc[1] += ad * (gd + (double)(beta * beta) * 0.5);                                             // :276
-    acc[2] += ad * ((double)(delta + beta * gamma) + (double)(beta * beta * beta) * (1.0 / 6.0));  // :277
-    acc[3] += ad * ((double)(epsil + beta * delta) + 0.5 * bd * bd * gd + 0.5 * gd * gd +
-                    (1.0 / 24.0) * (bd * bd) * (bd * bd));                                         // :278-279
-#else
-    // B..E of src/cvo.cpp:275-279 with the five f32 quantities promoted once and the polynomial evaluated in f64
-    // (the reference forms a*beta, beta^2, beta*gamma, beta^3, beta*delta in f32 first: a 6e-8 relative rounding per
-    // term that is not reproduced; three fewer f32->f64 conversions, which share the MUFU pipe)
-    const double bd = (double)beta, gd = (double)gamma, dd = (double)delta, ed = (double)epsil, ad = (double)a;
-    const double b2 = bd * bd;
-    acc[0] = fma(ad, bd, acc[0]);                                                          // :275
-    acc[1] = fma(ad, fma(0.5, b2, gd), acc[1]);                                            // :276
-    acc[2] = fma(ad, fma(b2 * bd, 1.0 / 6.0, fma(bd, gd, dd)), acc[2]);                    // :277
-    acc[3] = fma(ad, fma(b2 * b2, 1.0 / 24.0, fma(0.5, gd * (b2 + gd), fma(bd, dd, ed))), acc[3]);  // :278-279
-#endif
+    const StepTerms t = step_terms(ic, c, rx, ry, rz, a);
+    acc[0] += (double)t.tB; acc[1] += (double)t.tC; acc[2] += (double)t.tD; acc[3] += (double)t.tE;
 }
 
 // Accumulation tail of a candidate whose kernel value a is known (a = 0 for a rejected one, which then adds +0
@@ -953,7 +971,9 @@ __device__ __forceinline__ bool list_body(const Smem& sm, const HotConsts& hc, c
         c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
         c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
         c.ecn = yg.w;
-        step_accumulate(hc, c, -dx, -dy, -dz, a, acc);
+        // list passes: the four entries a lane handles in one trip are summed in f32, then promoted (flush_partial)
+        const StepTerms t = step_terms(hc, c, -dx, -dy, -dz, a);
+        fp.po0 += t.tB; fp.po1 += t.tC; fp.pv0 += t.tD; fp.pv1 += t.tE;
     } else {
         // quirk Q1 is defined on the ORIGINAL row index, carried in the w lane of the staged row
         const bool q1 = (KIND == PASS_YY) ? (__float_as_int(xg.w) >= yy_row_min) : true;
@@ -964,7 +984,11 @@ __device__ __forceinline__ bool list_body(const Smem& sm, const HotConsts& hc, c
 
 template <int KIND>
 __device__ __forceinline__ void flush_partial(FlowPartial& fp, double* acc) {
-    if (KIND == PASS_STEP) return;
+    if (KIND == PASS_STEP) {  // B, C, D, E: one trip's four entries per lane (list passes only)
+        acc[0] += (double)fp.po0; acc[1] += (double)fp.po1; acc[2] += (double)fp.pv0; acc[3] += (double)fp.pv1;
+        fp.po0 = fp.po1 = fp.pv0 = fp.pv1 = 0.f;
+        return;
+    }
     if (fp.cnt) {
         if (KIND == PASS_FLOW || KIND == PASS_FLOW_CVO) {
             acc[ACC_W0] += (double)fp.po0; acc[ACC_W0 + 1] += (double)fp.po1; acc[ACC_W0 + 2] += (double)fp.po2;
@@ -1783,6 +1807,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
             if (n2) list_body<KIND, true>(sm, hc, kp, x2.x, 0.f, yy_row_min, src, fp, acc);       \
             if (n3) list_body<KIND, true>(sm, hc, kp, x3.x, 0.f, yy_row_min, src, fp, acc);       \
         }                                                                                        \
+        if (KIND == PASS_STEP) flush_partial<KIND>(fp, acc);                                     \
     }
             int t = warp;
             if (t < ntrip) {
@@ -1800,7 +1825,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
                     if (t >= ntrip) break;
                     CVO_LOAD_TRIP(a0, a1, a2, a3, t + 2 * kWarps)
                     CVO_RUN_TRIP(b0, b1, b2, b3)
-                    flush_partial<KIND>(fp, acc);  // <= 12 terms per f32 partial, like a short row of A
+                    if (KIND != PASS_STEP) flush_partial<KIND>(fp, acc);  // <= 12 terms per f32 partial, like a short row of A
                     t += kWarps;
                     if (t >= ntrip) break;
                     CVO_LOAD_TRIP(b0, b1, b2, b3, t + 2 * kWarps)
@@ -1818,7 +1843,7 @@ __device__ void run_pass_list(Smem& sm, const KParams& kp, const CloudDev& rows,
                     if (t >= ntrip) break;
                     CVO_LOAD_TRIP(a0, a1, a2, a3, t + kWarps)
                     CVO_RUN_TRIP(b0, b1, b2, b3)
-                    flush_partial<KIND>(fp, acc);  // <= 8 terms per f32 partial, like a short row of A
+                    if (KIND != PASS_STEP) flush_partial<KIND>(fp, acc);  // <= 8 terms per f32 partial, like a short row of A
                     t += kWarps;
                     if (t >= ntrip) break;
                 }
