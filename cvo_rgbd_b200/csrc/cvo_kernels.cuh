@@ -343,6 +343,12 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) {
     return (fabsf(x) + fabsf(y)) + fabsf(z) < __int_as_float(0x7f800000);
 }
 
+// sqrt to 2 ulp in one MUFU (the list builds use it inside bounds that carry their own safety factor)
+__device__ __forceinline__ float sqrtf_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float exp2f_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -1432,7 +1438,7 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const float d2c = colour_d2(xf, xg.w, yf, yf4);
     const float t_c = __fmul_rn(d2c, kp.c2);
     const float re2 = (kp.t_lim - t_c) * L.inv_c1;  // the pair's own squared ball radius (rounded up)
-    const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + L.s_build;
+    const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + L.s_build;
     const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
     // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
@@ -1590,7 +1596,14 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 uint2* dst = lr.entries + sm.lst_base + sm.u.of.bu.pos[u];
                 const int c = sm.u.of.bu.act[u];
                 int i = lane;
-                for (; i + 96 < c; i += 128) {  // four loads in flight per lane
+                for (; i + 224 < c; i += 256) {  // eight loads in flight per lane
+                    uint2 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + i + 32 * j);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg(dst + i + 32 * j, v[j]);
+                }
+                for (; i + 96 < c; i += 128) {
                     const uint2 v0 = __ldcg(src + i), v1 = __ldcg(src + i + 32), v2 = __ldcg(src + i + 64), v3 = __ldcg(src + i + 96);
                     __stcg(dst + i, v0); __stcg(dst + i + 32, v1); __stcg(dst + i + 64, v2); __stcg(dst + i + 96, v3);
                 }
@@ -1688,7 +1701,7 @@ __device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const Clou
                         t_c = __fmul_rn(__uint_as_float(v[j].y & 0x7fffffffu), c2);
                     }
                     const float re2 = (t_lim - t_c) * inv_c1;  // (padding: t_c = +inf, never kept)
-                    const float lim = sqrtf(fmaxf(re2, 0.f)) * 1.000001f + s_build;
+                    const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + s_build;
                     const bool keep = (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
                     const uint32_t b = __ballot_sync(0xffffffffu, keep);
                     if (keep) __stcg(dst + cursor + __popc(b & ((1u << lane) - 1u)), v[j]);
