@@ -1424,10 +1424,8 @@ __device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile
 // colour distance marks the rows that contribute to the length-scale gradient (always for (x, x); for (y, y) quirk Q1:
 // original index >= num_fixed).
 template <int SELF>
-__device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
-                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2* out, int limit,
-                                           int& cursor) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2& e) {
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
@@ -1439,20 +1437,40 @@ __device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws
     const float t_c = __fmul_rn(d2c, kp.c2);
     const float re2 = (kp.t_lim - t_c) * L.inv_c1;  // the pair's own squared ball radius (rounded up)
     const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + L.s_build;
-    const bool keep = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
-    const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
-    if (keep && cursor + kTile <= limit) {
-        uint2 e;
-        if (SELF == 0) {  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
-            e = make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c));
-        } else {
-            const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
-            e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
-        }
-        __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
+    if (SELF == 0) {  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
+        e = make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c));
+    } else {
+        const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
+        e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
     }
+    return live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
+}
+// appends the kept candidates of one warp-wide batch in lane order
+// (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
+__device__ __forceinline__ void build_append(bool keep, const uint2& e, uint2* out, int limit, int& cursor) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (keep && cursor + kTile <= limit) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
     cursor += __popc(b);
+}
+template <int SELF>
+__device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2* out, int limit,
+                                           int& cursor) {
+    uint2 e;
+    const bool keep = build_test<SELF>(sm, ws, kp, L, ent, live, row_off, yy_row_min, e);
+    build_append(keep, e, out, limit, cursor);
+}
+// two batches at once: their loads and arithmetic interleave (the evaluation is latency-bound on one batch)
+template <int SELF>
+__device__ __forceinline__ void build_eval2(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+                                            uint32_t ent0, uint32_t ent1, uint32_t row_off, int yy_row_min, uint2* out,
+                                            int limit, int& cursor) {
+    uint2 e0, e1;
+    const bool k0 = build_test<SELF>(sm, ws, kp, L, ent0, true, row_off, yy_row_min, e0);
+    const bool k1 = build_test<SELF>(sm, ws, kp, L, ent1, true, row_off, yy_row_min, e1);
+    build_append(k0, e0, out, limit, cursor);
+    build_append(k1, e1, out, limit, cursor);
 }
 
 template <int SELF>
@@ -1476,7 +1494,11 @@ __device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws,
             push_mask(q, qn + excl, mask, ((uint32_t)lane << 12) | (uint32_t)((c0 + j) * kTile));
             qn += total;
             __syncwarp();
-            while (qn >= 32) {
+            while (qn >= 64) {
+                qn -= 64;
+                build_eval2<SELF>(sm, ws, kp, L, q[qn + 32 + lane], q[qn + lane], row_off, yy_row_min, out, limit, cursor);
+            }
+            if (qn >= 32) {
                 qn -= 32;
                 build_eval<SELF>(sm, ws, kp, L, q[qn + lane], true, row_off, yy_row_min, out, limit, cursor);
             }
