@@ -144,7 +144,6 @@ struct IterConsts {
     float c1;  // log2(e)/(2 ell^2)
     float ell;
     float omega[3], v[3];
-    float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
     float temp_coef, m2t, p2t;
 };
 
@@ -207,8 +206,20 @@ __device__ __forceinline__ bool tag_is(const StageTag& t, const float4* g, int f
     return t.g == g && t.first == first && t.n == n && t.serial == serial;
 }
 
+// The passes over a neighbour list keep their stages as PLANES (structure of arrays: x[], y[], z[], w[] of kColChunk
+// floats each, in the memory of the float4 arrays named below): the 32 entries a warp handles at a time address a few
+// consecutive rows and columns of one 32-column tile, so 4-byte gathers from a plane hit 32 different banks (equal
+// indices broadcast), while 16-byte gathers of {x, y, z, w} records replay on every pair of indices that agree mod 8
+// and move the unused w lane.  An entry holds the BYTE offsets of its row and column inside a plane.
+constexpr uint32_t kPlaneBytes = (uint32_t)kColChunk * 4u;
+template <int PLANE>
+__device__ __forceinline__ float plane_ld(const void* base, uint32_t byte_off) {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + PLANE * kPlaneBytes + byte_off);
+}
+__device__ __forceinline__ float* plane_of(void* base, int plane) { return reinterpret_cast<float*>(base) + plane * kColChunk; }
+
 struct ListRef {
-    uint2* entries;  // the flat list: (row * 16 << 16 | col * 16 within the round's chunks, bits of the colour exponent t_c)
+    uint2* entries;  // the flat list: (row * 4 << 16 | col * 4 within the round's chunks, bits of the colour exponent t_c)
     uint2* staging;  // build scratch of the CTA (shared by its three lists): per-unit regions before compaction
     unsigned cap;
 };
@@ -426,14 +437,6 @@ __device__ void finalize_flow(Smem& sm) {
         ic.omega[t] = (float)sm.sum[kFlowOff + ACC_W0 + t];
         ic.v[t] = (float)sm.sum[kFlowOff + ACC_V0 + t];
     }
-    float W[9];
-    skew3(ic.omega, W);
-    mat3_mul(W, W, ic.W2);
-    mat3_mul(ic.W2, W, ic.W3);
-    mat3_mul(ic.W3, W, ic.W4);
-    mat3_vec(W, ic.v, ic.Wv);
-    mat3_vec(ic.W2, ic.v, ic.W2v);
-    mat3_vec(ic.W3, ic.v, ic.W3v);
     const double l = (double)sm.st.ell;
     ic.temp_coef = (float)(1.0 / (2.0 * l * l));  // src/cvo.cpp:241
     ic.m2t = (float)(-2.0 * (double)ic.temp_coef);
@@ -742,13 +745,16 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
                 float* b = sm.colBox[i >> 5];
                 b[0] = lx; b[1] = ly; b[2] = lz; b[3] = hx; b[4] = hy; b[5] = hz; b[6] = c2m;
             }
-        } else if (MODE == STAGE_GEOM) {
-            sm.colG[i] = make_float4(g.x, g.y, g.z, 0.f);
-        } else {
-            const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
-            sm.colG[i] = make_float4(g.x, g.y, g.z, sc.ecn);
-            sm.u.ls.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
-            sm.u.ls.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
+        } else {  // list passes: planes
+            plane_of(sm.colG, 0)[i] = g.x; plane_of(sm.colG, 1)[i] = g.y; plane_of(sm.colG, 2)[i] = g.z;
+            if (MODE == STAGE_STEP) {
+                const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
+                plane_of(sm.colG, 3)[i] = sc.ecn;
+                float* z1 = plane_of(sm.u.ls.ss.colZ1, 0);
+                float* z2 = plane_of(sm.u.ls.ss.colZ2, 0);
+                z1[i] = sc.z1x; z1[i + kColChunk] = sc.z1y; z1[i + 2 * kColChunk] = sc.z1z; z1[i + 3 * kColChunk] = sc.nrm;
+                z2[i] = sc.z2x; z2[i + kColChunk] = sc.z2y; z2[i + 2 * kColChunk] = sc.z2z; z2[i + 3 * kColChunk] = sc.pdt;
+            }
         }
     }
     if (MODE == STAGE_FULL) {
@@ -952,16 +958,18 @@ __device__ __forceinline__ HotConsts hot_consts(const IterConsts& ic) {
 template <int KIND, bool EXACT>
 __device__ __forceinline__ bool list_body(const Smem& sm, const HotConsts& hc, const KParams& kp, uint32_t ent, float t_c,
                                           int yy_row_min, const ListSrc& src, FlowPartial& fp, double* acc) {
-    const uint32_t rowb = ent >> 16, colb = ent & 0xffffu;  // byte offsets into the row / column stages
-    const float4 xg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.rowG) + rowb);
-    const float4 yg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.colG) + colb);
+    const uint32_t rowb = ent >> 16, colb = ent & 0xffffu;  // byte offsets into the row / column planes
+    float4 xg, yg;
+    xg.x = plane_ld<0>(sm.u.ls.rowG, rowb); xg.y = plane_ld<1>(sm.u.ls.rowG, rowb); xg.z = plane_ld<2>(sm.u.ls.rowG, rowb);
+    yg.x = plane_ld<0>(sm.colG, colb); yg.y = plane_ld<1>(sm.colG, colb); yg.z = plane_ld<2>(sm.colG, colb);
+    xg.w = yg.w = 0.f;
     const float dx = yg.x - xg.x, dy = yg.y - xg.y, dz = yg.z - xg.z;  // diff_yx, src/cvo.cpp:192
     const float d2 = dist2(dx, dy, dz);
     bool near = false;
     float a;
     if (EXACT) {
         const IterConsts& ic = sm.ic;
-        const int ri = src.row_base + (int)(rowb >> 4), ci = src.col_base + (int)(colb >> 4);
+        const int ri = src.row_base + (int)(rowb >> 2), ci = src.col_base + (int)(colb >> 2);
         a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri),
                                __ldg(src.rows->f4 + ri), __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     } else {
@@ -971,12 +979,12 @@ __device__ __forceinline__ bool list_body(const Smem& sm, const HotConsts& hc, c
     const bool ok = !near && (a > kp.sp_thres) && (d2 < hc.d2_thres);
     a = ok ? a : 0.f;
     if (KIND == PASS_STEP) {  // the column's step-size terms were computed once, when the chunk was staged
-        const float4 z1 = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.ss.colZ1) + colb);
-        const float4 z2 = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.ss.colZ2) + colb);
         StepCol c;
-        c.z1x = z1.x; c.z1y = z1.y; c.z1z = z1.z; c.nrm = z1.w;
-        c.z2x = z2.x; c.z2y = z2.y; c.z2z = z2.z; c.pdt = z2.w;
-        c.ecn = yg.w;
+        c.z1x = plane_ld<0>(sm.u.ls.ss.colZ1, colb); c.z1y = plane_ld<1>(sm.u.ls.ss.colZ1, colb);
+        c.z1z = plane_ld<2>(sm.u.ls.ss.colZ1, colb); c.nrm = plane_ld<3>(sm.u.ls.ss.colZ1, colb);
+        c.z2x = plane_ld<0>(sm.u.ls.ss.colZ2, colb); c.z2y = plane_ld<1>(sm.u.ls.ss.colZ2, colb);
+        c.z2z = plane_ld<2>(sm.u.ls.ss.colZ2, colb); c.pdt = plane_ld<3>(sm.u.ls.ss.colZ2, colb);
+        c.ecn = plane_ld<3>(sm.colG, colb);
         // list passes: the four entries a lane handles in one trip are summed in f32, then promoted (flush_partial)
         const StepTerms t = step_terms(hc, c, -dx, -dy, -dz, a);
         fp.po0 += t.tB; fp.po1 += t.tC; fp.pv0 += t.tD; fp.pv1 += t.tE;
@@ -1437,8 +1445,8 @@ __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws
     const float t_c = __fmul_rn(d2c, kp.c2);
     const float re2 = (kp.t_lim - t_c) * L.inv_c1;  // the pair's own squared ball radius (rounded up)
     const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + L.s_build;
-    if (SELF == 0) {  // the flat list addresses its stages in bytes: (row * 16) << 16 | col * 16
-        e = make_uint2((((uint32_t)row + row_off) << 20) | ((uint32_t)col << 4), __float_as_uint(t_c));
+    if (SELF == 0) {  // the flat list addresses its stages in bytes within a plane: (row * 4) << 16 | col * 4
+        e = make_uint2((((uint32_t)row + row_off) << 18) | ((uint32_t)col << 2), __float_as_uint(t_c));
     } else {
         const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
         e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
@@ -1642,11 +1650,12 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
 // STEP pass over a list right after a pass that staged the same transformed columns: only the step-size terms are new.
 __device__ __forceinline__ void stage_step_terms(Smem& sm, int n) {
     for (int i = threadIdx.x; i < n; i += kThreads) {
-        const float4 g = sm.colG[i];
-        const StepCol sc = step_col(sm.ic, g.x, g.y, g.z);
-        sm.colG[i].w = sc.ecn;
-        sm.u.ls.ss.colZ1[i] = make_float4(sc.z1x, sc.z1y, sc.z1z, sc.nrm);
-        sm.u.ls.ss.colZ2[i] = make_float4(sc.z2x, sc.z2y, sc.z2z, sc.pdt);
+        const StepCol sc = step_col(sm.ic, plane_of(sm.colG, 0)[i], plane_of(sm.colG, 1)[i], plane_of(sm.colG, 2)[i]);
+        plane_of(sm.colG, 3)[i] = sc.ecn;
+        float* z1 = plane_of(sm.u.ls.ss.colZ1, 0);
+        float* z2 = plane_of(sm.u.ls.ss.colZ2, 0);
+        z1[i] = sc.z1x; z1[i + kColChunk] = sc.z1y; z1[i + 2 * kColChunk] = sc.z1z; z1[i + 3 * kColChunk] = sc.nrm;
+        z2[i] = sc.z2x; z2[i + kColChunk] = sc.z2y; z2[i + 2 * kColChunk] = sc.z2z; z2[i + 3 * kColChunk] = sc.pdt;
     }
 }
 
@@ -1661,7 +1670,7 @@ __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int firs
             if (tf) apply_tf(sm.ic.tf, q.x, q.y, q.z);
             if (finite3(q.x, q.y, q.z)) g = q;  // (see stage_tiles)
         }
-        sm.u.ls.rowG[i] = g;
+        plane_of(sm.u.ls.rowG, 0)[i] = g.x; plane_of(sm.u.ls.rowG, 1)[i] = g.y; plane_of(sm.u.ls.rowG, 2)[i] = g.z;
     }
 }
 
@@ -1714,9 +1723,10 @@ __device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const Clou
                 for (int j = 0; j < 4; ++j) {
                     float d2, t_c;
                     if (SELF == 0) {
-                        const float4 xg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.u.ls.rowG) + (v[j].x >> 16));
-                        const float4 yg = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sm.colG) + (v[j].x & 0xffffu));
-                        d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
+                        const uint32_t rowb = v[j].x >> 16, colb = v[j].x & 0xffffu;
+                        d2 = dist2(plane_ld<0>(sm.colG, colb) - plane_ld<0>(sm.u.ls.rowG, rowb),
+                                   plane_ld<1>(sm.colG, colb) - plane_ld<1>(sm.u.ls.rowG, rowb),
+                                   plane_ld<2>(sm.colG, colb) - plane_ld<2>(sm.u.ls.rowG, rowb));
                         t_c = __uint_as_float(v[j].y);
                     } else {
                         d2 = __uint_as_float(v[j].x);
@@ -2047,7 +2057,8 @@ __device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& c
             *dst = v;
         }
     }
-    cluster.sync();
+    if (G == 1) __syncthreads();  // one CTA per pair: no need for the (slower) hardware cluster barrier
+    else cluster.sync();
     if (threadIdx.x < NV) {
         double t = 0.0;
         for (int r = 0; r < G; ++r) t += sm.xchg[buf][r][threadIdx.x];
