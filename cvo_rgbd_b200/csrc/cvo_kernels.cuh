@@ -676,7 +676,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phas
 // Step-size terms of one (transformed) moving point z (src/cvo.cpp:226-237) through z_{k+1} = omega x z_k
 // (= Omega^k y + Omega^(k-1) v): z1 = xi z + v, z2 = xi^2 z + xi v, |z1|^2, -z1.z2, |z2|^2 + 2 z1.z3.
 struct StepCol {
-    float z1x, z1y, z1z, nrm;
+    float z1x, z1y, z1z, nrm;  // nrm, pdt, ecn: scaled by -t, 2t, -t (t = 1/(2 l^2)), see step_col
     float z2x, z2y, z2z, pdt;
     float ecn;
 };
@@ -689,9 +689,13 @@ __device__ __forceinline__ StepCol step_col(const IC& ic, float yx, float yy, fl
     c.z1z = (w0 * yy - w1 * yx) + ic.v[2];
     c.z2x = w1 * c.z1z - w2 * c.z1y; c.z2y = w2 * c.z1x - w0 * c.z1z; c.z2z = w0 * c.z1y - w1 * c.z1x;
     const float z3x = w1 * c.z2z - w2 * c.z2y, z3y = w2 * c.z2x - w0 * c.z2z, z3z = w0 * c.z2y - w1 * c.z2x;
-    c.nrm = (c.z1x * c.z1x + c.z1y * c.z1y) + c.z1z * c.z1z;                                       // normxiz2, :235
-    c.pdt = -((c.z1x * c.z2x + c.z1y * c.z2y) + c.z1z * c.z2z);                                    // xiz_dot_xi2z, :236
-    c.ecn = ((c.z2x * c.z2x + c.z2y * c.z2y) + c.z2z * c.z2z) + 2.f * ((c.z1x * z3x + c.z1y * z3y) + c.z1z * z3z);  // :237
+    const float nrm = (c.z1x * c.z1x + c.z1y * c.z1y) + c.z1z * c.z1z;                                   // normxiz2, :235
+    const float pdt = -((c.z1x * c.z2x + c.z1y * c.z2y) + c.z1z * c.z2z);                                // xiz_dot_xi2z, :236
+    const float ecn = ((c.z2x * c.z2x + c.z2y * c.z2y) + c.z2z * c.z2z) + 2.f * ((c.z1x * z3x + c.z1y * z3y) + c.z1z * z3z);  // :237
+    // stored with the coefficients gamma / delta / epsilon multiply them by (src/cvo.cpp:264-270): one FMA per term per entry
+    c.nrm = -ic.temp_coef * nrm;
+    c.pdt = ic.p2t * pdt;
+    c.ecn = -ic.temp_coef * ecn;
     return c;
 }
 
@@ -837,11 +841,13 @@ __device__ __forceinline__ StepTerms step_terms(const IC& ic, const StepCol& c, 
     const float p1 = (c.z1x * rx + c.z1y * ry) + c.z1z * rz;
     const float p2 = (c.z2x * rx + c.z2y * ry) + c.z2z * rz;
     const float pw = (w0 * rx + w1 * ry) + w2 * rz;
-    const float p3 = wv * pw - ww * p1;                                   // z3 . r
+    // gamma = -t (nrm + 2 p2), delta = 2t (pdt - z3 . r), epsil = -t (ecn + 2 z4 . r) with t = temp_coef, the
+    // column's nrm / pdt / ecn already scaled (step_col) and the rest folded into per-iteration constants
+    const float kG = -2.f * ic.temp_coef, kDw = -ic.p2t * wv, kD1 = ic.p2t * ww, kE = 2.f * ic.temp_coef * ww;
     const float beta = ic.m2t * p1;                                       // :262
-    const float gamma = -ic.temp_coef * (c.nrm + 2.f * p2);               // :264
-    const float delta = ic.p2t * (c.pdt - p3);                            // :267
-    const float epsil = -ic.temp_coef * (c.ecn - 2.f * (ww * p2));        // :270
+    const float gamma = fmaf(kG, p2, c.nrm);                              // :264
+    const float delta = fmaf(kDw, pw, fmaf(kD1, p1, c.pdt));              // :267
+    const float epsil = fmaf(kE, p2, c.ecn);                              // :270
     StepTerms t;
 #ifdef CVO_STEP_F32_PRODUCTS
     // the reference's own mix of f32 products and f64 sums inside a term (src/cvo.cpp:275-279)
