@@ -19,14 +19,14 @@ ctx.set_cluster_size(0)
 gp = capi.default_params('cvo')
 for rep in range(2):
     r = ctx.align(list(range(296)), gp)
-print(f"[{tag}] cvo stock P=296 kernel_ms={ctx.last_kernel_ms:.3f} pairs/s={296/ctx.last_kernel_ms*1e3:.1f} iters mean={r['iters'].mean():.1f} builds/pair={ctx.last_list_builds/len(r["iters"]):.1f} refines/pair={ctx.last_list_refines/len(r["iters"]):.1f}")
+print(f"[{tag}] cvo stock P=296 kernel_ms={ctx.last_kernel_ms:.3f} pairs/s={296/ctx.last_kernel_ms*1e3:.1f} iters mean={r["iters"].mean():.1f} max={r["iters"].max()} builds/pair={ctx.last_list_builds/len(r["iters"]):.1f} refines/pair={ctx.last_list_refines/len(r["iters"]):.1f}")
 prs = [synth.config_pair(3, i) for i in range(148)]
 for s, pr in enumerate(prs):
     ctx.set_pair(s, pr['x_pos'], pr['x_feat'], pr['y_pos'], pr['y_feat'])
 gp = capi.default_params('acvo')
 for rep in range(2):
     r = ctx.align(list(range(148)), gp)
-print(f"[{tag}] acvo stock P=148 kernel_ms={ctx.last_kernel_ms:.3f} pairs/s={148/ctx.last_kernel_ms*1e3:.1f} iters mean={r['iters'].mean():.1f} builds/pair={ctx.last_list_builds/len(r["iters"]):.1f} refines/pair={ctx.last_list_refines/len(r["iters"]):.1f}")
+print(f"[{tag}] acvo stock P=148 kernel_ms={ctx.last_kernel_ms:.3f} pairs/s={148/ctx.last_kernel_ms*1e3:.1f} iters mean={r["iters"].mean():.1f} max={r["iters"].max()} builds/pair={ctx.last_list_builds/len(r["iters"]):.1f} refines/pair={ctx.last_list_refines/len(r["iters"]):.1f}")
 pr = synth.config_pair(5)
 ctx.set_pair(0, pr['x_pos'], pr['x_feat'], pr['y_pos'], pr['y_feat'])
 gp = capi.default_params('cvo'); gp.ell_policy = capi.ELL_FIXED; gp.ell_init = 0.10; gp.fixed_iters = 20
