@@ -2169,6 +2169,12 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             CVO_PHASE(0)
             if (use_lists && sm.lst[LIST_XY].need == 1) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
             else if (use_lists && sm.lst[LIST_XY].need == 2) refine_list<0>(sm, kp, pair.x, pair.y, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (use_lists && acvo) {  // all builds come before the first pass: the stages the FLOW pass fills survive to the STEP pass
+                if (sm.lst[LIST_XX].need == 1) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
+                else if (sm.lst[LIST_XX].need == 2) refine_list<1>(sm, kp, pair.x, pair.x, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
+                if (sm.lst[LIST_YY].need == 1) build_list<2>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
+                else if (sm.lst[LIST_YY].need == 2) refine_list<2>(sm, kp, pair.y, pair.y, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
+            }
             CVO_PHASE(1)
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
             if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
@@ -2177,14 +2183,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             CVO_PHASE(2)
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
             if (acvo) {  // Axx, Ayy (src/adaptive_cvo.cpp:159-160)
-                if (use_lists && sm.lst[LIST_XX].need == 1) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
-                else if (use_lists && sm.lst[LIST_XX].need == 2) refine_list<1>(sm, kp, pair.x, pair.x, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
                 if (use_lists && sm.lst[LIST_XX].valid > 0)
                     run_pass_self<PASS_XX>(sm, kp, pair.x, pair.x, rank, G, LIST_XX, lref[LIST_XX]);
                 else run_pass<PASS_XX>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase);
                 if (threadIdx.x < 2) sm.flowTot[ACC_NNZXX + threadIdx.x] = sm.blockTot[threadIdx.x];
-                if (use_lists && sm.lst[LIST_YY].need == 1) build_list<2>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase, LIST_YY, lref[LIST_YY]);
-                else if (use_lists && sm.lst[LIST_YY].need == 2) refine_list<2>(sm, kp, pair.y, pair.y, rank, G, tma_phase, LIST_YY, lref[LIST_YY]);
                 if (use_lists && sm.lst[LIST_YY].valid > 0)
                     run_pass_self<PASS_YY>(sm, kp, pair.y, pair.y, rank, G, LIST_YY, lref[LIST_YY]);
                 else run_pass<PASS_YY>(sm, kp, pair.y, true, pair.y, true, rank, G, pair.x.n, tma_phase);
