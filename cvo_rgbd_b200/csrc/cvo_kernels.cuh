@@ -401,6 +401,19 @@ __device__ __forceinline__ float dot3f(const float* a, const float* b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
 }
 
+#ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles CTA 0
+__device__ unsigned long long g_phase_clocks[16];  // spends per phase
+__device__ long long g_phase_t0;
+#define CVO_PHASE(i)                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+        const long long now = clock64();                                     \
+        g_phase_clocks[i] += (unsigned long long)(now - g_phase_t0);         \
+        g_phase_t0 = now;                                                    \
+    }
+#else
+#define CVO_PHASE(i)
+#endif
+
 // --------------------------------------------------------------------------------------------
 // scalar epilogue pieces (one thread per CTA; every CTA of a cluster computes the same values)
 // --------------------------------------------------------------------------------------------
@@ -444,9 +457,8 @@ __device__ void finalize_flow(Smem& sm) {
 }
 
 // poly_solver + root selection (src/cvo.cpp:53-69,291-307): smallest positive real root of
-// 4E t^3 + 3D t^2 + 2C t + B, f64 closed form on the f32-normalised coefficients.
-// Called by ALL lanes of one warp with the same arguments: lane i % 3 evaluates and polishes root i (the f64 cbrt /
-// acos / cos and the Newton steps are the longest dependent chain of the per-iteration serial section), then the
+// 4E t^3 + 3D t^2 + 2C t + B: closed form on the f32-normalised coefficients, polished to the f64 root by Newton.
+// Called by ALL lanes of one warp with the same arguments: lane i % 3 evaluates and polishes root i, then the
 // smallest positive root is taken across the lanes.  Every lane returns the same step.
 __device__ float step_from_coeffs(double B, double C, double D, double E, float min_step, float max_step) {
     const int which = (threadIdx.x & 31) % 3;
@@ -463,37 +475,55 @@ __device__ float step_from_coeffs(double B, double C, double D, double E, float 
         const double r = (9.0 * a2 * a1 - 27.0 * a0 - 2.0 * a2 * a2 * a2) * (1.0 / 54.0);
         const double disc = q * q * q + r * r;
         const double shift = a2 * (1.0 / 3.0);
-        double x = 0.0;
+        // Closed form in f32 as the starting point (the f64 cbrt / acos / cos were the longest dependent chain of the
+        // serial section), Newton in f64 to convergence: the root is the f64 root either way.  Which formula applies is
+        // decided by the f64 discriminant.
+        const float qf = (float)q, rf = (float)r, shiftf = (float)shift;
+        float g = 0.f;
         bool have = false;
         if (disc > 0.0) {  // one real root
             if (which == 0) {
-                const double sd = sqrt(disc);
-                x = cbrt(r + sd) + cbrt(r - sd) - shift;
+                const float sd = sqrtf((float)disc);
+                g = cbrtf(rf + sd) + cbrtf(rf - sd) - shiftf;
                 have = true;
             }
         } else if (disc == 0.0) {  // a double root
             if (which < 2) {
-                const double sr = cbrt(r);
-                x = (which == 0 ? 2.0 * sr : -sr) - shift;
+                const float sr = cbrtf(rf);
+                g = (which == 0 ? 2.f * sr : -sr) - shiftf;
                 have = true;
             }
         } else {  // three real roots
-            double cth = r / sqrt(-q * q * q);
-            cth = fmin(1.0, fmax(-1.0, cth));
-            const double th = acos(cth);
-            const double m = 2.0 * sqrt(-q);
-            const double kTwoPi = 6.283185307179586476925286766559;
-            x = m * cos((th + (double)which * kTwoPi) * (1.0 / 3.0)) - shift;
+            float cth = rf * rsqrtf(-qf * qf * qf);
+            cth = fminf(1.f, fmaxf(-1.f, cth));
+            const float th = acosf(cth);
+            g = 2.f * sqrtf(-qf) * cosf((th + (float)which * 6.2831853f) * (1.f / 3.f)) - shiftf;
             have = true;
         }
+        double x = (double)g;
+        if (have && !isfinite(g)) {  // coefficients outside the f32 range: the same formulas in f64
+            if (disc > 0.0) {
+                const double sd = sqrt(disc);
+                x = cbrt(r + sd) + cbrt(r - sd) - shift;
+            } else if (disc == 0.0) {
+                const double sr = cbrt(r);
+                x = (which == 0 ? 2.0 * sr : -sr) - shift;
+            } else {
+                double cth = r / sqrt(-q * q * q);
+                cth = fmin(1.0, fmax(-1.0, cth));
+                x = 2.0 * sqrt(-q) * cos((acos(cth) + (double)which * 6.283185307179586476925286766559) * (1.0 / 3.0)) - shift;
+            }
+        }
         if (have) {
-            for (int it = 0; it < 3; ++it) {  // Newton polish
+            for (int it = 0; it < 8; ++it) {  // Newton: two or three steps from an f32-accurate start
                 const double f = ((x + a2) * x + a1) * x + a0;
                 const double fp = (3.0 * x + 2.0 * a2) * x + a1;
                 if (fp == 0.0 || !isfinite(f)) break;
-                const double xn = x - f / fp;
+                const double dx = f / fp;
+                const double xn = x - dx;
                 if (!isfinite(xn)) break;
                 x = xn;
+                if (fabs(dx) <= 1.0e-13 * fabs(x)) break;
             }
             const float xr = (float)x;
             if (xr > 0.f) best = xr;
@@ -537,6 +567,7 @@ __device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_r
     PairState& st = sm.st;
     const double B = sm.sum[0], C = sm.sum[1], D = sm.sum[2], E = sm.sum[3];
     const float step = step_from_coeffs(B, C, D, E, kp.min_step, kp.max_step);
+    CVO_PHASE(14)
     if ((threadIdx.x & 31) != 0) return;
     const bool stops = !(kp.fixed_iters > 0);
     const float ell_used = st.ell;
@@ -1276,18 +1307,6 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
     __syncthreads();
 }
 
-#ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles CTA 0
-__device__ unsigned long long g_phase_clocks[16];  // spends per phase
-__device__ long long g_phase_t0;
-#define CVO_PHASE(i)                                                         \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
-        const long long now = clock64();                                     \
-        g_phase_clocks[i] += (unsigned long long)(now - g_phase_t0);         \
-        g_phase_t0 = now;                                                    \
-    }
-#else
-#define CVO_PHASE(i)
-#endif
 
 // --------------------------------------------------------------------------------------------
 // neighbour candidate lists
@@ -2202,6 +2221,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             CVO_PHASE(4)
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
+            CVO_PHASE(10)
             if (threadIdx.x < 32) {  // the serial section of the iteration, on warp 0 (its parallel parts use the lanes)
                 // remember the transform used by this iteration: it is what the reference multiplies
                 // into accum_transform when the loop exits here (quirk Q3, src/cvo.cpp:413-414)
@@ -2210,13 +2230,16 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 if (args.trace && pi == 0 && rank == 0 && k < args.trace_cap) rec = args.trace + k;
                 update_state(sm, kp, k, rec);
                 __syncwarp();
+                CVO_PHASE(11)
                 if (!sm.done && k + 1 < max_iter) {  // the next iteration's update_tf + list decisions, same serial section
                     if (threadIdx.x == 0) {
                         sm.serial += 1;
                         prepare_iter(sm, kp, kp.d2c_thres);
                     }
                     __syncwarp();
+                    CVO_PHASE(12)
                     if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink, args.list_refine_min);
+                    CVO_PHASE(13)
                 }
             }
             __syncthreads();
