@@ -163,6 +163,7 @@ struct FeatStage {
     uint32_t queue[kWorkWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
 };
 struct StepStage {
+    // (list passes: four planes of kColChunk floats each, see plane_ld; nrm and pdt pre-scaled, see step_col)
     float4 colZ1[kColChunk];  // {xi z + v, |xi z + v|^2}                       (src/cvo.cpp:226-228,235)
     float4 colZ2[kColChunk];  // {xi^2 z + xi v, -(xi z + v).(xi^2 z + xi v)}   (src/cvo.cpp:229-230,236)
 };
@@ -180,7 +181,7 @@ struct OnTheFlyStage {
     };
 };
 struct ListStage {
-    float4 rowG[kColChunk];  // {x, y, z, bits of the original index} of the round's (transformed) rows
+    float4 rowG[kColChunk];  // planes x[], y[], z[] (kColChunk floats each) of the round's (transformed) rows
     StepStage ss;
     double warpTot[kWarps][kNumAcc];  // one total per warp, summed in warp order
 };
@@ -225,8 +226,9 @@ struct ListRef {
 };
 
 struct Smem {
-    float4 colG[kColChunk];   // {x, y, z, w} of the staged (transformed) column points; w = |c|^2 for the prefilter,
-                              // or the step-size term of src/cvo.cpp:237 in the STEP pass over a list
+    float4 colG[kColChunk];   // on-the-fly passes / list builds: {x, y, z, |c|^2} records of the staged (transformed) columns;
+                              // list passes: planes x[], y[], z[], w[] of kColChunk floats each (see plane_ld), w = the
+                              // (scaled) step-size term of src/cvo.cpp:237 in the STEP pass
     union {
         OnTheFlyStage of;
         ListStage ls;
@@ -1311,7 +1313,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // --------------------------------------------------------------------------------------------
 // neighbour candidate lists
 // --------------------------------------------------------------------------------------------
-// A list entry is (row * 16 << 16 | col * 16, t_c): the index pair (as byte offsets into the staged rows / columns
+// A list entry is (row * 4 << 16 | col * 4, t_c): the index pair (as byte offsets into the planes of the staged rows / columns
 // of its round) and its pose-independent colour exponent
 // t_c = |f_i - g_j|^2 log2(e) / (2 c_ell^2).  With T = log2(s2 c_sigma^2 / sp_thres) the gate a > sp_thres reads
 // d2 log2(e)/(2 l^2) + t_c < T, i.e. every pair has its OWN ball radius r_e = sqrt((T - t_c) 2 l^2 / log2 e) <= r
