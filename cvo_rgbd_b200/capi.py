@@ -26,7 +26,7 @@ EXPORTS = [
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
-    "cvo_b200_last_frame_used_canny",
+    "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size",
 ]
 
 
@@ -112,6 +112,7 @@ def load():
     lib.cvo_b200_reset_slot.argtypes = [vp, C.c_int]
     lib.cvo_b200_last_frame_used_canny.argtypes = [vp]
     lib.cvo_b200_selftest_rand_bytes.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_ubyte)]
+    lib.cvo_b200_selftest_step_size.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_float, C.c_float, fp]
     lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
     lib.cvo_b200_last_list_builds.argtypes = [vp]
     lib.cvo_b200_last_list_builds.restype = C.c_longlong
@@ -297,6 +298,15 @@ class Context:
     @property
     def last_list_builds(self):
         return int(self._lib.cvo_b200_last_list_builds(self._h))
+
+    def selftest_step_size(self, bcde, min_step=0.2, max_step=0.8):
+        """The device's line search (src/cvo.cpp:53-69,291-307) on rows {B, C, D, E} of `bcde` (test hook)."""
+        bcde = np.ascontiguousarray(bcde, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros(len(bcde), np.float32)
+        self._check(self._lib.cvo_b200_selftest_step_size(self._h, bcde.ctypes.data_as(C.POINTER(C.c_double)), len(bcde),
+                                                          C.c_float(min_step), C.c_float(max_step),
+                                                          out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     @property
     def last_list_refines(self):

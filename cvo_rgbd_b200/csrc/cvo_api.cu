@@ -898,6 +898,39 @@ int cvo_b200_phase_clocks(unsigned long long* out16, int reset) {
 }
 #endif
 
+namespace {
+// one warp per problem: the device's step_from_coeffs is warp-cooperative
+__global__ void selftest_step_kernel(const double* bcde, int n, float min_step, float max_step, float* out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const float s = step_from_coeffs(bcde[4 * i], bcde[4 * i + 1], bcde[4 * i + 2], bcde[4 * i + 3], min_step, max_step);
+    if (threadIdx.x == 0) out[i] = s;
+}
+}  // namespace
+
+int cvo_b200_selftest_step_size(cvo_b200_ctx* ctx, const double* bcde, int n, float min_step, float max_step, float* out) {
+    if (!ctx || !bcde || !out || n < 0) return CVO_B200_ERR_ARG;
+    if (n == 0) return CVO_B200_OK;
+    double* d_in = nullptr;
+    float* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, sizeof(double) * 4 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, bcde, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        selftest_step_kernel<<<n, 32, 0, ctx->stream>>>(d_in, n, min_step, max_step, d_out);
+        ctx->launches += 1;
+        e = cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("selftest_step_size: ") + cudaGetErrorString(e);
+        return CVO_B200_ERR_CUDA;
+    }
+    return CVO_B200_OK;
+}
+
 int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out) {
     if (n < 0 || !out) return CVO_B200_ERR_ARG;
     glibc_rand_bytes(seed, (size_t)n, out);

@@ -148,6 +148,9 @@ int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot);
 /* Test hook: the byte sequence `rand() & 0xFF` of glibc after srand(seed), as used for the selector's
  * randomPattern (thirdparty/PixelSelector2.cpp:36-38), produced without touching the C library's state. */
 int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out);
+/* Test hook: the device's line search on n coefficient sets {B, C, D, E} (poly_solver + root selection,
+ * src/cvo.cpp:53-69,291-307), one result per set. */
+int cvo_b200_selftest_step_size(cvo_b200_ctx* ctx, const double* bcde, int n, float min_step, float max_step, float* out);
 
 /* One pass of transform_pcd + se_kernel + compute_flow + compute_step_size at a given state
  * (src/cvo.cpp:368-377) without updating anything: fills one record (R,T echo the input). */

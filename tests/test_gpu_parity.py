@@ -471,3 +471,29 @@ def test_degenerate_inputs_terminate_with_finite_or_flagged_results(gpu_ctx, ora
     assert a["nnz"] == b["nnz"] and rel_err(a["omega"], b["omega"]) < 1e-6 and rel_err(a["B"], b["B"]) < 1e-6
     r = gpu_ctx.align(np.array([0]), gp)
     assert r["status"][0] in (capi.STATUS_MAX_ITER, capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE, capi.STATUS_NAN)
+
+
+def test_device_line_search_matches_the_oracle_root_selection(gpu_ctx, oracle):
+    """poly_solver + root selection (src/cvo.cpp:53-69,291-307) on the device (f64 discriminant, f32 closed form as the
+    start, Newton in f64) against the oracle's f64 closed form: one / three real roots, negative-only roots (-> min_step),
+    roots past max_step (-> clamp), E = 0 (quirk Q7 -> min_step), and coefficient sets of real runs."""
+    rng = np.random.default_rng(42)
+    cases = [(-1.0, 0.5, 0.1, 0.05), (1.0, 1.0, 1.0, 1.0), (0.0, 0.0, 0.0, 0.0), (-1.0, 0.0, 0.0, 1e-12),
+             (-2.0e3, 1.5e3, 40.0, 900.0), (-3.1e2, 9.0e2, -2.0e2, 6.0e2), (-6.0, 11.0, -6.0, 1.0), (-0.006, 0.011, -0.006, 0.001)]
+    for _ in range(400):  # t = root of 4E t^3 + 3D t^2 + 2C t + B with the roots where the line search lives
+        roots = rng.uniform(-1.5, 1.5, size=3) if rng.random() < 0.6 else np.array([rng.uniform(0.05, 1.2), np.nan, np.nan])
+        e4 = 10 ** rng.uniform(-2, 4) * rng.choice([-1.0, 1.0])
+        if np.isnan(roots[1]):  # one real root r0 and a complex pair: (t - r0)(t^2 + p t + q), p^2 < 4 q
+            p_, q_ = rng.uniform(-1, 1), rng.uniform(0.3, 2.0)
+            poly = np.convolve([1.0, -roots[0]], [1.0, p_, q_])
+        else:
+            if min(abs(roots[0] - roots[1]), abs(roots[0] - roots[2]), abs(roots[1] - roots[2])) < 0.05:
+                continue  # nearly multiple roots are ill-conditioned in the reference's f32 solver as well
+            poly = np.poly(roots)
+        c3, c2, c1, c0 = e4 * poly
+        cases.append((c0, c1 / 2.0, c2 / 3.0, c3 / 4.0))
+    bcde = np.array(cases, dtype=np.float64)
+    got = gpu_ctx.selftest_step_size(bcde)
+    for (B, C_, D, E), g in zip(cases, got):
+        want = oracle.step_from_coeffs(B, C_, D, E)
+        assert abs(float(g) - want) <= 2e-6 * max(want, 1e-3), (B, C_, D, E, float(g), want)
