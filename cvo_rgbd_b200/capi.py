@@ -26,7 +26,7 @@ EXPORTS = [
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
-    "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size",
+    "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.cvo_b200_last_frame_used_canny.argtypes = [vp]
     lib.cvo_b200_selftest_rand_bytes.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_ubyte)]
     lib.cvo_b200_selftest_step_size.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_float, C.c_float, fp]
+    lib.cvo_b200_selftest_exp_sek3.argtypes = [vp, fp, C.c_int, fp]
     lib.cvo_b200_set_neighbor_lists.argtypes = [vp, C.c_int, C.c_float]
     lib.cvo_b200_last_list_builds.argtypes = [vp]
     lib.cvo_b200_last_list_builds.restype = C.c_longlong
@@ -307,6 +308,14 @@ class Context:
                                                           C.c_float(min_step), C.c_float(max_step),
                                                           out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def selftest_exp_sek3(self, omega_v_dt):
+        """The device's Exp_SEK3 (src/LieGroup.cpp:159-186) on rows {omega, v, dt}; returns (dR [n,3,3], dT [n,3])."""
+        rows = np.ascontiguousarray(omega_v_dt, dtype=np.float32).reshape(-1, 7)
+        out = np.zeros((len(rows), 12), np.float32)
+        self._check(self._lib.cvo_b200_selftest_exp_sek3(self._h, rows.ctypes.data_as(C.POINTER(C.c_float)), len(rows),
+                                                         out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out[:, :9].reshape(-1, 3, 3), out[:, 9:]
 
     @property
     def last_list_refines(self):

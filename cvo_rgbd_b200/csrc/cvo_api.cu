@@ -908,6 +908,36 @@ __global__ void selftest_step_kernel(const double* bcde, int n, float min_step, 
 }
 }  // namespace
 
+namespace {
+__global__ void selftest_exp_kernel(const float* wvs, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    exp_sek3(wvs + 7 * i, wvs + 7 * i + 3, wvs[7 * i + 6], out + 12 * i, out + 12 * i + 9);
+}
+}  // namespace
+
+int cvo_b200_selftest_exp_sek3(cvo_b200_ctx* ctx, const float* omega_v_dt, int n, float* dR_dT) {
+    if (!ctx || !omega_v_dt || !dR_dT || n < 0) return CVO_B200_ERR_ARG;
+    if (n == 0) return CVO_B200_OK;
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, sizeof(float) * 7 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * 12 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, omega_v_dt, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        selftest_exp_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(d_in, n, d_out);
+        ctx->launches += 1;
+        e = cudaMemcpyAsync(dR_dT, d_out, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("selftest_exp_sek3: ") + cudaGetErrorString(e);
+        return CVO_B200_ERR_CUDA;
+    }
+    return CVO_B200_OK;
+}
+
 int cvo_b200_selftest_step_size(cvo_b200_ctx* ctx, const double* bcde, int n, float min_step, float max_step, float* out) {
     if (!ctx || !bcde || !out || n < 0) return CVO_B200_ERR_ARG;
     if (n == 0) return CVO_B200_OK;

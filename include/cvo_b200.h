@@ -151,6 +151,9 @@ int cvo_b200_selftest_rand_bytes(unsigned seed, int n, unsigned char* out);
 /* Test hook: the device's line search on n coefficient sets {B, C, D, E} (poly_solver + root selection,
  * src/cvo.cpp:53-69,291-307), one result per set. */
 int cvo_b200_selftest_step_size(cvo_b200_ctx* ctx, const double* bcde, int n, float min_step, float max_step, float* out);
+/* Test hook: the device's Exp_SEK3 (src/LieGroup.cpp:159-186, incl. the small-angle quirk) on n rows
+ * {omega[3], v[3], dt}; out: n rows {dR row-major [9], dT[3]}. */
+int cvo_b200_selftest_exp_sek3(cvo_b200_ctx* ctx, const float* omega_v_dt, int n, float* dR_dT);
 
 /* One pass of transform_pcd + se_kernel + compute_flow + compute_step_size at a given state
  * (src/cvo.cpp:368-377) without updating anything: fills one record (R,T echo the input). */

@@ -497,3 +497,24 @@ def test_device_line_search_matches_the_oracle_root_selection(gpu_ctx, oracle):
     for (B, C_, D, E), g in zip(cases, got):
         want = oracle.step_from_coeffs(B, C_, D, E)
         assert abs(float(g) - want) <= 2e-6 * max(want, 1e-3), (B, C_, D, E, float(g), want)
+
+
+def test_device_exp_sek3_matches_the_oracle_including_the_small_angle_quirk(gpu_ctx, oracle):
+    """Exp_SEK3 with K = 1 (src/LieGroup.cpp:159-186) on the device against the oracle: twists and steps of the size the
+    line search produces, and theta < 1e-6 where the reference sets Jl = I, i.e. dT = v unscaled by dt (quirk Q2)."""
+    rng = np.random.default_rng(5)
+    rows = []
+    for _ in range(300):
+        w = rng.normal(size=3) * 10 ** rng.uniform(-5, -0.5)
+        v = rng.normal(size=3) * 10 ** rng.uniform(-5, -0.5)
+        rows.append(np.concatenate([w, v, [rng.uniform(0.2, 0.8)]]))
+    rows += [np.array([1e-8, 0, 0, 0.3, -0.2, 0.1, 0.25]), np.array([0, 0, 0, 0.01, 0.02, -0.03, 0.8]),
+             np.array([0, 9.9e-7, 0, 1.0, 0.0, 0.0, 0.2]), np.array([0, 1.01e-6, 0, 1.0, 0.0, 0.0, 0.2])]
+    rows = np.array(rows, dtype=np.float32)
+    dR, dT = gpu_ctx.selftest_exp_sek3(rows)
+    for r, gR, gT in zip(rows, dR, dT):
+        wR, wT = oracle.exp_sek3(r[:3], r[3:6], float(r[6]))
+        assert np.abs(gR - wR).max() <= 3e-7, r            # entries of a rotation: <= 1 in size, a few f32 ulp
+        assert np.abs(gT - wT).max() <= 3e-7 * max(1.0, np.abs(wT).max()) + 1e-6 * np.abs(wT).max(), r
+    small = rows[-4]  # theta = 1e-8: dR = I, dT = v (not dt * v)
+    assert np.array_equal(dR[-4], np.eye(3, dtype=np.float32)) and np.allclose(dT[-4], small[3:6], rtol=0, atol=0)
