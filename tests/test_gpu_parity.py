@@ -497,6 +497,12 @@ def test_device_line_search_matches_the_oracle_root_selection(gpu_ctx, oracle):
     for (B, C_, D, E), g in zip(cases, got):
         want = oracle.step_from_coeffs(B, C_, D, E)
         assert abs(float(g) - want) <= 2e-6 * max(want, 1e-3), (B, C_, D, E, float(g), want)
+    # coefficient sets far outside anything a registration produces (the f32 start overflows: f64 formulas take over;
+    # non-finite inputs): whatever the roots, the step is a finite number in (0, max_step]
+    wild = [(-1.0, 1.0, 1.0, 1e-20), (1e30, -1e30, 1e30, -1e30), (-1e-30, 1e-30, 1e-30, 1e-30), (np.nan, 1.0, 1.0, 1.0),
+            (-1.0, np.inf, 1.0, 1.0), (0.0, 0.0, 0.0, 1.0), (-1.0, 1.0, 1.0, -1e-25)]
+    for g in gpu_ctx.selftest_step_size(np.array(wild, dtype=np.float64)):
+        assert np.isfinite(g) and 0.0 < float(g) <= 0.8 + 1e-7
 
 
 def test_device_exp_sek3_matches_the_oracle_including_the_small_angle_quirk(gpu_ctx, oracle):
