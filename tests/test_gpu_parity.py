@@ -252,6 +252,34 @@ def test_lists_narrowed_in_place_agree_with_on_the_fly_passes(kind, cfg, refine_
         ctx.close()
 
 
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_multi_round_lists_narrowed_in_place_on_one_cta(kind, monkeypatch):
+    """refine_list over SEVERAL rounds (4000 x 4200 points on one CTA: 2 row chunks x 2 column chunks): the narrowed
+    rounds move towards the front of the list area behind the read position.  Counts against the on-the-fly passes."""
+    monkeypatch.setenv("CVO_B200_LIST_REFINE_MIN", "0.05")
+    pr = synth.make_pair(4242, 4000, 4200, kind)
+    gp = capi.default_params(kind)
+    ctx = capi.Context(0, max_points=4352, max_slots=1)
+    try:
+        _set(ctx, 0, pr)
+        ctx.set_cluster_size(1)
+        ctx.set_neighbor_lists(False)
+        ref = ctx.align_trace(0, gp, trace_cap=16)
+        ctx.set_neighbor_lists(True)
+        got = ctx.align_trace(0, gp, trace_cap=16)
+        assert ctx.last_list_refines >= 1
+        a, b = got["trace"][0], ref["trace"][0]
+        assert (a["nnz"], a["nnz_xx"], a["nnz_yy"]) == (b["nnz"], b["nnz_xx"], b["nnz_yy"])
+        for k in range(1, min(12, got["n_iterations_run"], ref["n_iterations_run"])):
+            a, b = got["trace"][k], ref["trace"][k]
+            assert abs(a["nnz"] - b["nnz"]) <= 4, k
+            assert abs(a["nnz_xx"] - b["nnz_xx"]) <= 4 and abs(a["nnz_yy"] - b["nnz_yy"]) <= 4, k
+        rot, tr = pose_diff(got["transform"], ref["transform"])
+        assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (rot, tr)
+    finally:
+        ctx.close()
+
+
 def test_neighbor_list_survives_large_motion_and_cluster_sizes(gpu_ctx, oracle):
     """Large initial misalignment (many rebuilds while the pose moves by much more than the skin) on every
     cluster size, checked against the oracle's trajectory."""
