@@ -20,13 +20,14 @@ OK, ERR_ARG, ERR_CUDA, ERR_EMPTY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 # every symbol include/cvo_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "cvo_b200_default_params_cvo", "cvo_b200_default_params_acvo", "cvo_b200_create", "cvo_b200_destroy",
-    "cvo_b200_last_error", "cvo_b200_set_pair", "cvo_b200_set_pairs", "cvo_b200_push_frame", "cvo_b200_eval", "cvo_b200_align",
+    "cvo_b200_last_error", "cvo_b200_set_pair", "cvo_b200_set_pairs", "cvo_b200_push_frame", "cvo_b200_replace_moving", "cvo_b200_replace_moving_images", "cvo_b200_eval", "cvo_b200_align",
     "cvo_b200_align_trace", "cvo_b200_inner_product", "cvo_b200_sync", "cvo_b200_last_kernel_ms",
     "cvo_b200_kernel_launches", "cvo_b200_last_cluster_size", "cvo_b200_last_num_clusters",
     "cvo_b200_set_cluster_size", "cvo_b200_last_total_iterations", "cvo_b200_num_sms",
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
+    "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes",
 ]
 
 
@@ -89,6 +90,7 @@ def load():
     lib.cvo_b200_set_pair.argtypes = [vp, C.c_int, fp, fp, C.c_int, fp, fp, C.c_int]
     lib.cvo_b200_set_pairs.argtypes = [vp, ip, C.c_int, fp, fp, ip, fp, fp, ip, C.c_int]
     lib.cvo_b200_push_frame.argtypes = [vp, C.c_int, fp, fp, C.c_int]
+    lib.cvo_b200_replace_moving.argtypes = [vp, C.c_int, fp, fp, C.c_int]
     lib.cvo_b200_eval.argtypes = [vp, C.c_int, fp, fp, C.c_float, C.POINTER(Params), C.POINTER(IterRec)]
     lib.cvo_b200_align.argtypes = [vp, ip, C.c_int, C.POINTER(Params), fp, fp, fp, fp, ip, ip]
     lib.cvo_b200_align_trace.argtypes = [vp, C.c_int, C.POINTER(Params), fp, fp, fp, fp, ip, ip,
@@ -108,6 +110,10 @@ def load():
     lib.cvo_b200_num_sms.argtypes = [vp]
     lib.cvo_b200_push_frame_images.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ushort), C.c_int, C.c_int,
                                                C.c_int, C.c_int, ip]
+    lib.cvo_b200_replace_moving_images.argtypes = lib.cvo_b200_push_frame_images.argtypes
+    lib.cvo_b200_neighbor_lists_active.argtypes = [vp]
+    lib.cvo_b200_list_scratch_bytes.argtypes = [vp]
+    lib.cvo_b200_list_scratch_bytes.restype = C.c_longlong
     lib.cvo_b200_last_generated_cloud.argtypes = [vp, fp, fp, C.c_int, ip]
     lib.cvo_b200_reset_slot.argtypes = [vp, C.c_int]
     lib.cvo_b200_last_frame_used_canny.argtypes = [vp]
@@ -209,18 +215,22 @@ class Context:
         self._check(self._lib.cvo_b200_set_pairs(self._h, _ipt(slots), P, _fp(fx), _fp(ff), _ipt(n_fixed), _fp(mx),
                                                  _fp(mf), _ipt(n_moving), stride))
 
-    def push_frame(self, slot, xyz, feat):
+    def push_frame(self, slot, xyz, feat, promote=True):
+        """promote=True: moving becomes fixed, then the new moving cloud (src/cvo.cpp:417 + the next set_pcd);
+        promote=False: the moving cloud is replaced (a second set_pcd without an align, cvo_b200_replace_moving)."""
         x, f = _f32(xyz), _f32(feat)
-        self._check(self._lib.cvo_b200_push_frame(self._h, slot, _fp(x), _fp(f), x.shape[0]))
+        fn = self._lib.cvo_b200_push_frame if promote else self._lib.cvo_b200_replace_moving
+        self._check(fn(self._h, slot, _fp(x), _fp(f), x.shape[0]))
 
-    def push_frame_images(self, slot, img3, depth, dataset_seq=1, feature_type=1):
+    def push_frame_images(self, slot, img3, depth, dataset_seq=1, feature_type=1, promote=True):
         """Image front door: h x w x 3 uint8 (as cv::imread returns it) + h x w uint16 depth -> the slot's next cloud,
-        generated on the device.  Returns the number of points."""
+        generated on the device.  Returns the number of points.  promote: see push_frame."""
         img3 = np.ascontiguousarray(img3, np.uint8)
         depth = np.ascontiguousarray(depth, np.uint16)
         assert img3.ndim == 3 and img3.shape[2] == 3 and depth.shape == img3.shape[:2]
         n = C.c_int(0)
-        self._check(self._lib.cvo_b200_push_frame_images(
+        fn = self._lib.cvo_b200_push_frame_images if promote else self._lib.cvo_b200_replace_moving_images
+        self._check(fn(
             self._h, slot, img3.ctypes.data_as(C.POINTER(C.c_ubyte)), depth.ctypes.data_as(C.POINTER(C.c_ushort)),
             img3.shape[1], img3.shape[0], dataset_seq, feature_type, C.byref(n)))
         return n.value
@@ -316,6 +326,15 @@ class Context:
         self._check(self._lib.cvo_b200_selftest_exp_sek3(self._h, rows.ctypes.data_as(C.POINTER(C.c_float)), len(rows),
                                                          out.ctypes.data_as(C.POINTER(C.c_float))))
         return out[:, :9].reshape(-1, 3, 3), out[:, 9:]
+
+    @property
+    def neighbor_lists_active(self):
+        return bool(self._lib.cvo_b200_neighbor_lists_active(self._h))
+
+    @property
+    def list_capacity(self):
+        """Bytes of HBM scratch the neighbour lists occupy right now."""
+        return int(self._lib.cvo_b200_list_scratch_bytes(self._h))
 
     @property
     def last_list_refines(self):

@@ -88,6 +88,7 @@ struct cvo_b200_ctx {
     // neighbour-list scratch (allocated on the first align): [num_sms][LIST_KINDS] areas
     uint2* d_list_entries = nullptr;
     unsigned list_cap = 0;
+    int list_ctas = 0;  // CTAs the scratch currently has areas for
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
     float list_skin = 0.08f;
@@ -98,6 +99,7 @@ struct cvo_b200_ctx {
     float last_ms = 0.f;
     long long launches = 0;
     int last_G = 0, last_nclusters = 0, force_G = 0;
+    int max_clusters[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // per cluster size, -1 = not asked yet
     long long last_total_iters = 0;
     int sort_points = 1;
     size_t pack_smem_max = 0;
@@ -221,11 +223,57 @@ int flush_all_batches(cvo_b200_ctx* ctx) {
     return CVO_B200_OK;
 }
 
+// How many clusters of G CTAs of align_kernel the device can hold at once (one CTA per SM; the GPCs' SM counts decide
+// how many clusters of a given size fit).  Cached per context.
+int max_resident_clusters(cvo_b200_ctx* ctx, int G) {
+    if (ctx->max_clusters[G] >= 0) return ctx->max_clusters[G];
+    int n = 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    cfg.gridDim = dim3(G, 1, 1);
+    bool ok = cudaFuncSetAttribute(align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) == cudaSuccess;
+    if (ok && G > 8) ok = cudaFuncSetAttribute(align_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!ok || cudaOccupancyMaxActiveClusters(&n, align_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (n * G > ctx->num_sms) n = ctx->num_sms / G;
+    ctx->max_clusters[G] = n;
+    return n;
+}
+
+// CTAs per pair.  A batch of P pairs on clusters of G CTAs runs in ceil(P / resident clusters) waves, and one pair
+// takes about (s + (1 - s) / G) of its one-CTA time, s being the part of an iteration that does not split (the serial
+// section on one warp and the cluster barriers: measured 0.08-0.12 of a one-CTA iteration at 3000 points).  The G
+// with the smallest waves x time wins; any size 1..16 is allowed (the row tiles are dealt rank * tiles / G), so e.g.
+// 63 pairs -- the per-GPU share of BASELINE config 4 on 8 GPUs -- run as 63 clusters of 2 = 126 of 148 SMs instead of
+// the 63 CTAs the power-of-two rule of round 1 (2 P G <= #SMs) launched.
 int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
     if (ctx->force_G > 0) return ctx->force_G;
-    int G = 1;
-    while (G < 16 && (long long)n_pairs * G * 2 <= ctx->num_sms) G *= 2;
-    return G;
+    const double serial = 0.12;
+    int best_G = 1;
+    double best = 1.0e30;
+    for (int G = 1; G <= kMaxCluster; ++G) {
+        const int fit = max_resident_clusters(ctx, G);
+        if (fit < 1) continue;
+        const int ncl = n_pairs < fit ? n_pairs : fit;
+        const int waves = (n_pairs + ncl - 1) / ncl;
+        const double cost = waves * (serial + (1.0 - serial) / G);
+        if (cost < best * (1.0 - 1.0e-9)) {
+            best = cost;
+            best_G = G;
+        }
+    }
+    return best_G;
 }
 
 template <typename KernelT, typename ArgT>
@@ -263,25 +311,41 @@ int launch_cluster_kernel(cvo_b200_ctx* ctx, KernelT kernel, const ArgT& args, i
     return CVO_B200_OK;
 }
 
-// The neighbour-list scratch is only ever touched by the CTA it belongs to; it is sized for one CTA per SM.
-// Failing to allocate it is not an error: the passes then run on the fly.
-void ensure_list_scratch(cvo_b200_ctx* ctx) {
-    if (ctx->d_list_entries || ctx->lists_alloc_failed || !ctx->lists_enabled) return;
-    unsigned long long cap = (unsigned long long)ctx->max_points * ctx->max_points / 8;
+// The neighbour-list scratch is only ever touched by the CTA it belongs to: [CTAs of the launch][3 lists + build
+// staging] areas of `list_cap` entries.  It is sized by the launch at hand -- the CTAs actually launched and the
+// largest cloud among the pairs being aligned, not max_points -- and only ever grows (a frontend object with
+// max_points = 16384 aligning 3000-point pairs on one 16-CTA cluster holds 0.6 GB, not the 9.9 GB of a full-machine
+// launch of maximum-size clouds).  Failing to allocate it is not an error: the passes then run on the fly
+// (cvo_b200_neighbor_lists_active reports it).
+void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
+    if (ctx->lists_alloc_failed || !ctx->lists_enabled) return;
+    unsigned long long cap = (unsigned long long)max_n * max_n / 8;
     if (cap < (1ull << 18)) cap = 1ull << 18;
     if (cap > (1ull << 21)) cap = 1ull << 21;
+    cap = (cap + 1023ull) & ~1023ull;
     if (const char* env = getenv("CVO_B200_LIST_CAP")) {  // test hook: a small area forces the overflow fallback
         const long long v = atoll(env);
         if (v >= 1024) cap = (unsigned long long)v & ~1023ull;
     }
-    const size_t areas = (size_t)ctx->num_sms * (LIST_KINDS + 1);  // three lists + the build staging per CTA
+    if (ctx->d_list_entries && ctx->list_ctas >= n_ctas && ctx->list_cap >= cap) return;
+    if (ctx->d_list_entries) {  // grow: nothing is in flight on this stream between align calls, but be explicit
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_list_entries);
+        ctx->d_list_entries = nullptr;
+        if (ctx->list_cap > cap) cap = ctx->list_cap;
+        if (ctx->list_ctas > n_ctas) n_ctas = ctx->list_ctas;
+    }
+    const size_t areas = (size_t)n_ctas * (LIST_KINDS + 1);
     if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();
         ctx->d_list_entries = nullptr;
         ctx->lists_alloc_failed = true;
+        ctx->list_cap = 0;
+        ctx->list_ctas = 0;
         return;
     }
     ctx->list_cap = (unsigned)cap;
+    ctx->list_ctas = n_ctas;
 }
 
 
@@ -416,7 +480,24 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
         args.trace_cap = trace_cap < ctx->trace_cap ? trace_cap : ctx->trace_cap;
     }
     args.kp = make_kparams(p, false);
-    ensure_list_scratch(ctx);
+    int G = choose_cluster(ctx, n_pairs);
+    {
+        int fit = max_resident_clusters(ctx, G);
+        if (fit < 1 && G > 8 && ctx->force_G == 0) {  // 16-CTA clusters are opt-in; fall back to portable 8
+            G = 8;
+            fit = max_resident_clusters(ctx, G);
+        }
+        if (fit < 1) {
+            ctx->err = "cluster size not schedulable on this device";
+            return CVO_B200_ERR_CUDA;
+        }
+        int max_n = 0;
+        for (int i = 0; i < n_pairs; ++i) {
+            max_n = ctx->h_pairs[i].x.n > max_n ? ctx->h_pairs[i].x.n : max_n;
+            max_n = ctx->h_pairs[i].y.n > max_n ? ctx->h_pairs[i].y.n : max_n;
+        }
+        ensure_list_scratch(ctx, (n_pairs < fit ? n_pairs : fit) * G, max_n);
+    }
     const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr;
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
     args.list_cap = ctx->list_cap;
@@ -427,15 +508,14 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     // addressing: 272 B per pair, once at its start and once at its end).  No host->device copy sits in the launch
     // path: a small copy would queue behind the upload of the NEXT batch on the copy engine (measured: 0.8 ms).
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-    int G = choose_cluster(ctx, n_pairs);
     int ncl = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = launch_cluster_kernel(ctx, align_kernel, args, G, n_pairs, &ncl);
-    if (rc != CVO_B200_OK && G > 8 && ctx->force_G == 0) {  // 16-CTA clusters are opt-in; fall back to portable 8
-        G = 8;
-        rc = launch_cluster_kernel(ctx, align_kernel, args, G, n_pairs, &ncl);
-    }
     if (rc != CVO_B200_OK) return rc;
+    if (lists && ncl * G > ctx->list_ctas) {  // cannot happen: both sides use the same occupancy query
+        ctx->err = "internal: launch larger than the neighbour-list scratch";
+        return CVO_B200_ERR_CUDA;
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (args.trace)
         CK(cudaMemcpyAsync(ctx->h_trace, ctx->d_trace, sizeof(cvo_b200_iter_rec) * args.trace_cap,
@@ -736,7 +816,7 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const f
     return CVO_B200_OK;
 }
 
-int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {
+static int push_cloud(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n, bool promote) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (slot < 0 || slot >= ctx->max_slots || !ctx->slots[slot].bound) return fail_arg(ctx, "slot not bound");
     if (!xyz || !feat) return fail_arg(ctx, "null cloud pointer");
@@ -749,17 +829,31 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
     int rc = flush_all_batches(ctx);
     if (rc) return rc;
     cvo_b200_ctx::Slot& s = ctx->slots[slot];
-    s.fixed_buf = 1 - s.fixed_buf;  // moving becomes fixed (src/cvo.cpp:417)
-    const int mb = 1 - s.fixed_buf;
+    // promote: moving becomes fixed (src/cvo.cpp:417) and the new cloud lands in the old fixed buffer; otherwise the
+    // moving cloud is replaced in place (two set_pcd() calls without an align() in between, src/cvo.cpp:336-351).
+    // The slot's bookkeeping only changes once the upload and the pack launch have been enqueued successfully.
+    const int fixed_buf = promote ? 1 - s.fixed_buf : s.fixed_buf;
+    const int mb = 1 - fixed_buf;
     rc = upload_cloud(ctx, 0, xyz, feat, n);
     if (rc) return rc;
-    s.n[mb] = n;
     PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, mb), slot_f(ctx, slot, mb), slot_f4(ctx, slot, mb), n, 0};
-    return launch_pack(ctx, &job, 1, ctx->d_jobs);
+    rc = launch_pack(ctx, &job, 1, ctx->d_jobs);
+    if (rc) return rc;
+    s.fixed_buf = fixed_buf;
+    s.n[mb] = n;
+    return CVO_B200_OK;
 }
 
-int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth, int width,
-                               int height, int dataset_seq, int feature_type, int* num_points) {
+int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {
+    return push_cloud(ctx, slot, xyz, feat, n, true);
+}
+
+int cvo_b200_replace_moving(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n) {
+    return push_cloud(ctx, slot, xyz, feat, n, false);
+}
+
+static int push_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth, int width,
+                       int height, int dataset_seq, int feature_type, int* num_points, bool promote) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
     if (!img3 || !depth) return fail_arg(ctx, "null image pointer");
@@ -779,7 +873,8 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
     int fixed_buf = s.fixed_buf, target;
     if (!s.have_fixed) { fixed_buf = 0; target = 0; }
     else if (!s.bound) target = 1 - fixed_buf;
-    else { fixed_buf = 1 - fixed_buf; target = 1 - fixed_buf; }
+    else if (promote) { fixed_buf = 1 - fixed_buf; target = 1 - fixed_buf; }
+    else target = 1 - fixed_buf;  // no align() since the last frame: the moving cloud is replaced (src/cvo.cpp:336-351)
     const int w = width, h = height, wh = w * h;
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(P.d_img3, img3, (size_t)wh * 3, cudaMemcpyHostToDevice, st));
@@ -862,6 +957,16 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
     if (!s.have_fixed) s.have_fixed = true;
     else s.bound = true;
     return CVO_B200_OK;
+}
+
+int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth, int width,
+                               int height, int dataset_seq, int feature_type, int* num_points) {
+    return push_images(ctx, slot, img3, depth, width, height, dataset_seq, feature_type, num_points, true);
+}
+
+int cvo_b200_replace_moving_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
+                                   int width, int height, int dataset_seq, int feature_type, int* num_points) {
+    return push_images(ctx, slot, img3, depth, width, height, dataset_seq, feature_type, num_points, false);
 }
 
 int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n) {
@@ -1042,7 +1147,7 @@ int cvo_b200_last_cluster_size(const cvo_b200_ctx* ctx) { return ctx ? ctx->last
 int cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_nclusters : 0; }
 int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
     if (!ctx) return CVO_B200_ERR_ARG;
-    if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16)) return fail_arg(ctx, "cluster size must be 0,1,2,4,8,16");
+    if (g < 0 || g > kMaxCluster) return fail_arg(ctx, "cluster size must be 0 (automatic) or 1..16");
     ctx->force_G = g;
     return CVO_B200_OK;
 }
@@ -1057,5 +1162,12 @@ int cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin) {
     return CVO_B200_OK;
 }
 int cvo_b200_num_sms(const cvo_b200_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+int cvo_b200_neighbor_lists_active(const cvo_b200_ctx* ctx) {
+    return ctx && ctx->lists_enabled && ctx->d_list_entries != nullptr ? 1 : 0;
+}
+long long cvo_b200_list_scratch_bytes(const cvo_b200_ctx* ctx) {
+    if (!ctx || !ctx->d_list_entries) return 0;
+    return (long long)ctx->list_ctas * (LIST_KINDS + 1) * (long long)ctx->list_cap * (long long)sizeof(uint2);
+}
 
 }  // extern "C"

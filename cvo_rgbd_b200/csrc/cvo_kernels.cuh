@@ -1585,16 +1585,14 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             const int Sb = max(1, min(min(kMaxUnits / ntile, CVO_BUILD_SEGMENTS), nct / 8));
             const int nunits = ntile * Sb;
             __syncthreads();
-            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
-            if (threadIdx.x == 0) {
-                sm.next_unit = 0;
-                if (round >= kMaxListRounds) sm.lst_ovf = 1;
-            }
-            __syncthreads();
-            if (sm.lst_ovf) {
+            if (round >= kMaxListRounds) {  // uniform: every thread counts the rounds itself.  (sm.lst_ovf is only ever READ
+                if (threadIdx.x == 0) sm.lst_ovf = 1;  // behind the barrier that follows the evaluation, where warps set it.)
                 stop = true;
                 break;
             }
+            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            if (threadIdx.x == 0) sm.next_unit = 0;
+            __syncthreads();
             CVO_PHASE(6)
             int wcur = 0;  // entries this warp has staged in this round
             while (warp < kWorkWarps) {  // evaluate

@@ -566,7 +566,9 @@ __global__ void __launch_bounds__(1024) pcd_points_kernel(PcdBuffers b, const in
         const int total = before + stotal;
         c.num_points = total;
         if (total > max_points) c.status = PCD_STATUS_TOO_MANY_POINTS;
-        *job_n = total > max_points ? max_points : total;
+        // Too many points: the pack job gets n = 0, so pack_sort_kernel returns at once and the slot's planes (for a
+        // bound slot: the current FIXED cloud) are left exactly as they were -- the error leaves the slot unchanged.
+        *job_n = total > max_points ? 0 : total;
     }
 }
 

@@ -30,6 +30,7 @@ class _Registration:
         self._images = False
         self._bound = False
         self._have_moving = False
+        self._aligned = False  # an align() has run since the last set_pcd: the next set_pcd promotes moving -> fixed
         self.status = 0
 
     def close(self):
@@ -52,7 +53,10 @@ class _Registration:
             self._ctx.set_pair(self._slot, self._first[0], self._first[1], xyz, feat)
             self._bound = True
         else:
-            self._ctx.push_frame(self._slot, xyz, feat)  # fixed <- moving (src/cvo.cpp:417) + new moving cloud
+            # fixed <- moving happened at the end of align() (src/cvo.cpp:417); without an align() since the last
+            # set_pcd only the moving cloud is replaced (:336-351)
+            self._ctx.push_frame(self._slot, xyz, feat, promote=self._aligned)
+        self._aligned = False
         if self._KIND == "acvo":  # src/adaptive_cvo.cpp:476-478
             self._ell = float(self.params.ell_init)
         self._have_moving = True
@@ -64,7 +68,9 @@ class _Registration:
         if self._first is not None or (self.init and not self._images):
             raise RuntimeError("one frontend object takes either arrays or images, not both")
         self._images = True
-        n = self._ctx.push_frame_images(self._slot, img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1)
+        n = self._ctx.push_frame_images(self._slot, img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1,
+                                        promote=(not self._bound) or self._aligned)
+        self._aligned = False
         if not self.init:
             self.init = True
             return n
@@ -94,6 +100,7 @@ class _Registration:
         self.accum_transform = self.accum_transform @ self.prev_transform  # :414
         self.transform = r["transform"][0]                                 # :415
         self._have_moving = False
+        self._aligned = True                                               # :417
 
     def run_cvo(self, xyz, feat):
         """run_cvo (src/cvo.cpp:422-435)."""

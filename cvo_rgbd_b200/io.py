@@ -6,7 +6,7 @@
                    + raw gradient; acvo = H/180, S/255, V/255 + gradient * 2 / 255.  A PCD file carries no image gradient:
                    the two gradient features are 0.
   read_assoc       TUM `assoc.txt` as the reference's drivers read it (src/cvo_main.cpp:75-101)
-  PoseWriter       `name tx ty tz qx qy qz qw` of accum_transform, one line per aligned frame (src/cvo_main.cpp:58-65)
+  PoseWriter       `name tx ty tz qx qy qz qw` of accum_transform, one line per frame once `init` is set -- the identity line of frame 0 included (src/cvo_main.cpp:58-65)
   read_trajectory  TUM trajectory files (groundtruth.txt, cvo_poses_qt.txt) -> {stamp: 4x4}
 
 Host-side I/O only; no arithmetic of the registration path lives here.
@@ -143,7 +143,7 @@ def quaternion_to_rotation(q):
 
 
 class PoseWriter:
-    """cvo_poses_qt.txt / acvo_poses_qt.txt: `name tx ty tz qx qy qz qw` of accum_transform per aligned frame."""
+    """cvo_poses_qt.txt / acvo_poses_qt.txt: `name tx ty tz qx qy qz qw` of accum_transform, one line per frame once the frontend's `init` is set (frame 0: identity; src/cvo_main.cpp:58-65)."""
 
     def __init__(self, path):
         self._f = open(path, "w")

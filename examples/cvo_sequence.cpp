@@ -41,11 +41,12 @@ int run(Reg& reg, const std::string& folder, const std::string& out_name, bool a
         }
         const bool had_fixed = reg.init;
         reg.run_cvo(cvo_b200::make_point_cloud(pc, adaptive));
-        if (had_fixed) {
+        if (had_fixed)
             std::cout << "frame " << i << ": " << assoc[i - 1].rgb_name << " -> " << assoc[i].rgb_name << "  iterations "
                       << reg.iter << std::endl;
-            poses.write(assoc[i].rgb_name, reg.accum_transform);
-        }
+        // the reference writes accum_transform for EVERY frame once cvo.init is set, the identity line of frame 0
+        // included (src/cvo_main.cpp:58-65)
+        if (reg.init) poses.write(assoc[i].rgb_name, reg.accum_transform);
         ++done;
     }
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

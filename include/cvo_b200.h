@@ -122,6 +122,10 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs,
  * the slot's moving cloud becomes its fixed cloud (pointer swap on the device) and a new moving cloud
  * is uploaded, so a sequence uploads each frame once. */
 int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n);
+/* Replaces the slot's MOVING cloud only (no promotion): what a second set_pcd() without an align() in between does in
+ * the reference, where the promotion sits at the end of align() (src/cvo.cpp:336-351 vs :417).  The frontends call
+ * this instead of cvo_b200_push_frame when no align() has run since the last set_pcd(). */
+int cvo_b200_replace_moving(cvo_b200_ctx* ctx, int slot, const float* xyz, const float* feat, int n);
 
 /* Image front door.  Replaces pcd_generator::load_image + create_pointcloud
  * (src/pcd_generator.cpp:384-420: cv::cvtColor to gray / HSV, the 3-level gradient pyramid, DSO's PixelSelector2
@@ -138,6 +142,10 @@ int cvo_b200_push_frame(cvo_b200_ctx* ctx, int slot, const float* xyz, const flo
  * device.  Synchronous.  On an error the slot is left unchanged. */
 int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
                                int width, int height, int dataset_seq, int feature_type, int* num_points);
+/* cvo_b200_push_frame_images without the promotion: the new cloud replaces the slot's moving cloud (see
+ * cvo_b200_replace_moving).  On a slot without a bound pair it behaves like cvo_b200_push_frame_images. */
+int cvo_b200_replace_moving_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
+                                   int width, int height, int dataset_seq, int feature_type, int* num_points);
 /* The cloud the last cvo_b200_push_frame_images generated, in the reference's (raster) order: xyz n x 3,
  * feat n x 5 row-major (parity hook; valid until the next upload of any kind). */
 int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n);
@@ -196,7 +204,8 @@ float     cvo_b200_last_kernel_ms(const cvo_b200_ctx* ctx);
 long long cvo_b200_kernel_launches(const cvo_b200_ctx* ctx);
 int       cvo_b200_last_cluster_size(const cvo_b200_ctx* ctx);
 int       cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx);
-/* Overrides the CTAs-per-pair choice (1,2,4,8,16); 0 = automatic. */
+/* Overrides the CTAs-per-pair choice (1..16); 0 = automatic: the size that minimises waves x per-pair time for
+ * the batch at hand (a single pair: 16 CTAs; 63 pairs: 2; 2 x #SMs pairs: 1). */
 int       cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int ctas_per_pair);
 /* Sum over the pairs of the last align call of iterations executed (work accounting for the roofline). */
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
@@ -214,6 +223,12 @@ long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx);
  * shrank: a filter of the old list instead of an all-pairs sweep. */
 long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx);
 int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
+/* 1 if the last align used (or the next will use) neighbour lists; 0 if they are disabled or their scratch could not
+ * be allocated (every pass then runs on the fly: same results, several times slower). */
+int       cvo_b200_neighbor_lists_active(const cvo_b200_ctx* ctx);
+/* Bytes of HBM scratch the neighbour lists currently occupy: CTAs of the largest launch so far x 4 areas x capacity,
+ * the capacity following the largest cloud aligned so far (not max_points). */
+long long cvo_b200_list_scratch_bytes(const cvo_b200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -94,10 +94,14 @@ class registration {
         if (!pair_bound_) {
             rc = cvo_b200_set_pair(ctx_, 0, first_xyz_.data(), first_feat_.data(), first_n_, xyz, feat, n);
             pair_bound_ = (rc == CVO_B200_OK);
-        } else {
+        } else if (aligned_since_set_) {
             rc = cvo_b200_push_frame(ctx_, 0, xyz, feat, n);  // fixed <- moving happened in align() (src/cvo.cpp:417)
+        } else {
+            // a second set_pcd() without an align() in between only replaces the moving cloud (src/cvo.cpp:336-351)
+            rc = cvo_b200_replace_moving(ctx_, 0, xyz, feat, n);
         }
         check(rc);
+        aligned_since_set_ = false;
         if (adaptive_) {  // src/adaptive_cvo.cpp:476-478
             ell_ = params_.ell_init;
         }
@@ -111,7 +115,11 @@ class registration {
     // continuous CV_8UC3), depth: height x width 16-bit (CV_16UC1).  Returns the number of points.
     int set_pcd(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
         int n = 0;
-        check(cvo_b200_push_frame_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
+        if (!pair_bound_ || aligned_since_set_)
+            check(cvo_b200_push_frame_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
+        else  // no align() since the last frame: only the moving cloud is replaced (src/cvo.cpp:336-351)
+            check(cvo_b200_replace_moving_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
+        aligned_since_set_ = false;
         if (!init) {
             init = true;
             return n;
@@ -137,6 +145,7 @@ class registration {
         accum_transform = accum_transform * prev_transform;        // Q3 (src/cvo.cpp:413-414)
         last_status_ = status;
         have_moving_ = false;
+        aligned_since_set_ = true;  // ptr_fixed_pcd = std::move(ptr_moving_pcd) (src/cvo.cpp:417): the next set_pcd promotes
     }
 
     void run_cvo(const float* xyz, const float* feat, int n) {  // src/cvo.cpp:422-435
@@ -163,7 +172,7 @@ class registration {
     float ell_ = 0.f;
     std::vector<float> first_xyz_, first_feat_;
     int first_n_ = 0;
-    bool pair_bound_ = false, have_moving_ = false;
+    bool pair_bound_ = false, have_moving_ = false, aligned_since_set_ = false;
     int last_status_ = 0;
 };
 

@@ -1,0 +1,156 @@
+"""Parity of the workloads bench.py MEASURES, through the C ABI, against the CPU oracle at north_star's tolerance
+(1e-4 rad / 1e-4 m per pair, written below):
+
+  cfg2  BASELINE.json configs[1]: 3000 x 3000 points, ELL_FIXED 0.10, exactly 100 iterations, stop tests off --
+        as a single pair on a whole-machine cluster AND as pairs inside the 2 x #SMs batch the benchmark launches
+        (one CTA per pair), i.e. the exact launch geometry of the headline number;
+  cfg4  BASELINE.json configs[3]: ragged pairs N, M ~ U{2700..3300}, stock cvo schedule, identity init, aligned to
+        convergence in ONE batch (reference loop: src/cvo_main.cpp:36-66 with cvo::align, src/cvo.cpp:361-420).
+
+The stock schedule's converged pose carries an intrinsic noise floor of the order of 1e-4 (conftest.py, the
+distribution in profiles/r02_parity_distribution.json): cfg4 therefore asserts 1e-4 on the bulk of the batch and
+POSE_TOL_FLOOR on every pair, with the measured numbers in the failure message.  cfg2 (fixed ell, no stop tests) is
+held to 1e-4 on every pair."""
+import numpy as np
+import pytest
+
+from conftest import POSE_TOL_FLOOR, POSE_TOL_NORTH_STAR, pose_diff, rel_err
+from cvo_rgbd_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+CFG2_ELL, CFG2_ITERS, CFG2_POINTS = 0.10, 100, 3000
+
+
+def _cfg2(p, mod):
+    p.ell_policy, p.ell_init, p.fixed_iters = mod.ELL_FIXED, CFG2_ELL, CFG2_ITERS
+    return p
+
+
+def _oracle_cfg2(oracle, pr, trace_cap=0):
+    return oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], _cfg2(oracle.default_params("cvo"), oracle),
+                        trace_cap=trace_cap)
+
+
+def _check_record(g, o, tight):
+    """One iteration record (nnz, omega, v, B..E, step) of the device against the oracle's."""
+    assert abs(g["nnz"] - o["nnz"]) <= 2, (g["nnz"], o["nnz"])
+    tol = 1e-5 if tight else 2e-3
+    flips = abs(g["nnz"] - o["nnz"])
+    for k in ("omega", "v"):
+        scale = max(np.abs(o[k]).max(), 1e-30)
+        assert np.abs(np.asarray(g[k]) - np.asarray(o[k])).max() < tol * scale + 2e-4 * flips + 1e-9, k
+    if tight and flips == 0:
+        for k in ("B", "C", "D", "E"):
+            assert rel_err(g[k], o[k]) < 1e-5, k
+        assert abs(g["step"] - o["step"]) < 1e-5 * max(1.0, o["step"])
+
+
+def test_cfg2_exact_single_pair_on_a_cluster(gpu_ctx, oracle):
+    """The benchmark's pair 0 alone: the library spreads it over a 16-CTA cluster (latency mode)."""
+    pr = synth.config_pair(2, 0)
+    gpu_ctx.set_pair(0, pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"])
+    g = gpu_ctx.align_trace(0, _cfg2(capi.default_params("cvo"), capi), trace_cap=CFG2_ITERS)
+    o = _oracle_cfg2(oracle, pr, trace_cap=CFG2_ITERS)
+    assert gpu_ctx.last_cluster_size > 1
+    assert g["n_iterations_run"] == o["n_iterations_run"] == CFG2_ITERS
+    assert g["status"] == capi.STATUS_MAX_ITER and g["iters"] == CFG2_ITERS
+    _check_record(g["trace"][0], o["trace"][0], tight=True)    # first iteration: identical inputs
+    _check_record(g["trace"][-1], o["trace"][-1], tight=False)  # last iteration: both sit at the ell = 0.10 fixed point
+    assert all(abs(t["ell"] - CFG2_ELL) < 1e-7 for t in g["trace"])
+    rot, tr = pose_diff(g["transform"], o["transform"])
+    assert rot < POSE_TOL_NORTH_STAR and tr < POSE_TOL_NORTH_STAR, (rot, tr)
+
+
+def test_cfg2_exact_pairs_inside_the_benchmark_batch(oracle):
+    """bench.py's launch: 2 x #SMs distinct cfg-2 pairs, one CTA per pair (G = 1), batched upload.  Twelve pairs spread
+    over the batch (first and last CTA wave included) are checked against the oracle at 1e-4; the whole batch must
+    have run exactly 100 iterations and be finite; pair 0 must agree with the single-pair cluster run."""
+    probe = capi.Context(0, 64, 1)
+    P = 2 * probe.num_sms
+    probe.close()
+    n = CFG2_POINTS
+    hx, hfx = np.empty((P, n, 3), np.float32), np.empty((P, n, 5), np.float32)
+    hy, hfy = np.empty((P, n, 3), np.float32), np.empty((P, n, 5), np.float32)
+    for s in range(P):
+        pr = synth.config_pair(2, s)
+        hx[s], hfx[s], hy[s], hfy[s] = pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"]
+    counts = np.full(P, n, np.int32)
+    slots = np.arange(P, dtype=np.int32)
+    with capi.Context(0, max_points=n + 72, max_slots=P) as ctx:
+        ctx.set_pairs(slots, hx, hfx, counts, hy, hfy, counts)
+        gp = _cfg2(capi.default_params("cvo"), capi)
+        res = ctx.align(slots, gp)
+        assert ctx.last_cluster_size == 1 and ctx.last_num_clusters == P // 2
+        assert ctx.last_total_iterations == P * CFG2_ITERS
+        assert np.isfinite(res["transform"]).all()
+        assert (res["status"] == capi.STATUS_MAX_ITER).all() and (res["iters"] == CFG2_ITERS).all()
+        worst = (0.0, 0.0)
+        for s in sorted(set(np.linspace(0, P - 1, 12).astype(int).tolist())):
+            o = oracle.align(hx[s], hfx[s], hy[s], hfy[s], _cfg2(oracle.default_params("cvo"), oracle))
+            rot, tr = pose_diff(res["transform"][s], o["transform"])
+            worst = (max(worst[0], rot), max(worst[1], tr))
+            assert rot < POSE_TOL_NORTH_STAR and tr < POSE_TOL_NORTH_STAR, (s, rot, tr)
+        # the same pair alone (16-CTA cluster) and inside the batch (1 CTA): same pose up to f32 summation order
+        ctx.set_pair(0, hx[0], hfx[0], hy[0], hfy[0])
+        single = ctx.align(np.array([0], np.int32), gp)
+        assert ctx.last_cluster_size > 1
+        rot, tr = pose_diff(single["transform"][0], res["transform"][0])
+        assert rot < POSE_TOL_NORTH_STAR and tr < POSE_TOL_NORTH_STAR, (rot, tr)
+        print("cfg2 batch: worst of 12 sampled pairs vs oracle: %.2e rad %.2e m" % worst)
+
+
+def test_cfg4_ragged_batch_aligned_to_convergence(oracle):
+    """24 ragged cfg-4 pairs (N, M ~ U{2700..3300}), stock cvo, identity init, one batched upload, one align launch."""
+    P = 24
+    prs = [synth.config_pair(4, i) for i in range(P)]
+    stride = max(max(len(p["x_pos"]), len(p["y_pos"])) for p in prs)
+    hx, hfx = np.zeros((P, stride, 3), np.float32), np.zeros((P, stride, 5), np.float32)
+    hy, hfy = np.zeros((P, stride, 3), np.float32), np.zeros((P, stride, 5), np.float32)
+    nf, nm = np.zeros(P, np.int32), np.zeros(P, np.int32)
+    for s, pr in enumerate(prs):
+        nf[s], nm[s] = len(pr["x_pos"]), len(pr["y_pos"])
+        hx[s, :nf[s]], hfx[s, :nf[s]] = pr["x_pos"], pr["x_feat"]
+        hy[s, :nm[s]], hfy[s, :nm[s]] = pr["y_pos"], pr["y_feat"]
+    assert len(set(nf.tolist())) > 4 and nf.min() >= 2700 and nf.max() <= 3300
+    slots = np.arange(P, dtype=np.int32)
+    with capi.Context(0, max_points=stride, max_slots=P) as ctx:
+        ctx.set_pairs(slots, hx, hfx, nf, hy, hfy, nm)
+        res = ctx.align(slots, capi.default_params("cvo"))
+        assert np.isin(res["status"], (capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE)).all()
+        rots, trs = [], []
+        for s, pr in enumerate(prs):
+            o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], oracle.default_params("cvo"))
+            rot, tr = pose_diff(res["transform"][s], o["transform"])
+            rots.append(rot)
+            trs.append(tr)
+            assert abs(int(res["iters"][s]) - o["iters"]) <= max(15, o["iters"] // 3), (s, res["iters"][s], o["iters"])
+            rot_gt, tr_gt = pose_diff(res["transform"][s], pr["T_gt"])
+            assert rot_gt < 1e-2 and tr_gt < 1e-2
+        rots, trs = np.array(rots), np.array(trs)
+        msg = "cfg4 batch of %d: rot median %.2e max %.2e rad; trans median %.2e max %.2e m; within 1e-4: %d/%d" % (
+            P, np.median(rots), rots.max(), np.median(trs), trs.max(),
+            int(((rots < POSE_TOL_NORTH_STAR) & (trs < POSE_TOL_NORTH_STAR)).sum()), P)
+        print(msg)
+        # every pair inside the measured noise floor of the stop tests; the bulk at north_star's 1e-4
+        assert rots.max() < POSE_TOL_FLOOR and trs.max() < POSE_TOL_FLOOR, msg
+        assert np.median(rots) < POSE_TOL_NORTH_STAR and np.median(trs) < POSE_TOL_NORTH_STAR, msg
+        assert ((rots < POSE_TOL_NORTH_STAR) & (trs < POSE_TOL_NORTH_STAR)).mean() >= 0.75, msg
+
+
+def test_cfg4_batch_fills_the_machine(oracle):
+    """The per-GPU share of cfg4 on an 8-GPU node is 62-63 pairs: the launch must not leave most of the SMs idle
+    (round 1 launched one CTA per pair there: 42 % of the machine)."""
+    P = 63
+    prs = [synth.config_pair(4, 8 * i) for i in range(P)]
+    with capi.Context(0, max_points=3328, max_slots=P) as ctx:
+        for s, pr in enumerate(prs):
+            ctx.set_pair(s, pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"])
+        res = ctx.align(np.arange(P, dtype=np.int32), capi.default_params("cvo"))
+        busy = ctx.last_cluster_size * min(P, ctx.last_num_clusters)
+        assert busy >= 0.8 * ctx.num_sms, (ctx.last_cluster_size, ctx.last_num_clusters, ctx.num_sms)
+        for s in (0, 31, 62):
+            pr = prs[s]
+            o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], oracle.default_params("cvo"))
+            rot, tr = pose_diff(res["transform"][s], o["transform"])
+            assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (s, rot, tr)

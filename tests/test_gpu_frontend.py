@@ -98,7 +98,8 @@ def test_cpp_sequence_driver_over_pcd_files_equals_python_frontend(tmp_path):
     out = subprocess.run([exe, str(folder) + "/", "cvo", "3000"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     traj = cio.read_trajectory(str(folder / "cvo_poses_qt.txt"))
-    assert len(traj) == len(frames) - 1
+    assert len(traj) == len(frames)  # one line per frame, the identity of frame 0 included (src/cvo_main.cpp:58-65)
+    assert np.abs(traj[float(names[0])] - np.eye(4)).max() < 1e-7
     reg = frontend.cvo(max_points=2048)
     try:
         for k, n_ in enumerate(names):
@@ -113,3 +114,30 @@ def test_cpp_sequence_driver_over_pcd_files_equals_python_frontend(tmp_path):
         reg.close()
     # and the recovered trajectory is the camera motion of the synthetic sequence (evaluation harness, 8f row 3)
     assert np.linalg.norm(reg.accum_transform[:3, 3]) > 1e-3
+
+
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_second_set_pcd_without_align_only_replaces_the_moving_cloud(oracle, kind):
+    """In the reference the fixed <- moving promotion sits at the END of align() (src/cvo.cpp:417): two set_pcd()
+    calls without an align() in between replace the moving cloud and keep the fixed one (src/cvo.cpp:336-351)."""
+    a = synth.make_pair(910, 900, 950, kind)
+    b = synth.make_pair(910, 900, 1000, kind, motion_scale=0.5)  # same scene, another moving cloud
+    reg = (frontend.cvo if kind == "cvo" else frontend.acvo)(max_points=2048)
+    try:
+        reg.set_pcd(a["x_pos"], a["x_feat"])   # fixed
+        reg.set_pcd(a["y_pos"], a["y_feat"])   # moving
+        reg.set_pcd(b["y_pos"], b["y_feat"])   # moving again, no align in between: the fixed cloud must survive
+        reg.align()
+        op = oracle.default_params(kind)
+        o = oracle.align(a["x_pos"], a["x_feat"], b["y_pos"], b["y_feat"], op)
+        rot, tr = pose_diff(reg.transform, o["transform"])
+        assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (rot, tr)
+        # after the align the promotion has happened: the next set_pcd pairs (b.moving, new cloud)
+        reg.set_pcd(a["y_pos"], a["y_feat"])
+        reg.align()
+        ell = o["ell"] if kind == "cvo" else float(op.ell_init)
+        o2 = oracle.align(b["y_pos"], b["y_feat"], a["y_pos"], a["y_feat"], op, R=o["R"], T=o["T"], ell=ell)
+        rot, tr = pose_diff(reg.transform, o2["transform"])
+        assert rot < 2 * POSE_TOL_FLOOR and tr < 2 * POSE_TOL_FLOOR, (rot, tr)
+    finally:
+        reg.close()

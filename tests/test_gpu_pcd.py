@@ -80,6 +80,29 @@ def test_low_texture_frames_take_the_canny_top_up_on_the_device(img_ctx):
     assert np.isfinite(r["transform"]).all()
 
 
+def test_frame_with_too_many_points_leaves_the_bound_slot_unchanged():
+    """an overflowing frame must not touch the slot's planes (for a bound slot the target buffer is the
+    current FIXED cloud) nor its bookkeeping."""
+    with capi.Context(0, max_points=2048, max_slots=1) as ctx:
+        frames = []
+        for seed, half in ((51, slice(320, None)), (52, slice(0, 320))):
+            img, dep = synth.make_frame(seed)
+            dep[:, half] = 0  # half of the image has no depth reading: about half of the ~3000 selected pixels survive
+            frames.append((img, dep))
+        n0 = ctx.push_frame_images(0, *frames[0], 1, 1)
+        n1 = ctx.push_frame_images(0, *frames[1], 1, 1)
+        assert 0 < n0 <= 2048 and 0 < n1 <= 2048
+        before = ctx.align(np.array([0]), _few_iters(capi.default_params("cvo")))
+        with pytest.raises(capi.CvoB200Error) as e:
+            ctx.push_frame_images(0, *synth.make_frame(53), 1, 1)  # ~3000 points > max_points
+        assert e.value.code == capi.ERR_ARG
+        after = ctx.align(np.array([0]), _few_iters(capi.default_params("cvo")))
+        assert np.array_equal(before["transform"], after["transform"])  # same clouds, deterministic kernel
+        # and the slot still takes a frame that fits (promotion: pair becomes (frame 1, frame 0 again))
+        assert ctx.push_frame_images(0, *frames[0], 1, 1) == n0
+        assert np.isfinite(ctx.align(np.array([0]), _few_iters(capi.default_params("cvo")))["transform"]).all()
+
+
 def _few_iters(p):
     p.fixed_iters = 3
     return p
