@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY: see ../opencv.hpp.
+#include "../opencv.hpp"

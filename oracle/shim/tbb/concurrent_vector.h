@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY: see tbb.h in this directory.
+#include "tbb.h"
