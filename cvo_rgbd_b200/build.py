@@ -4,7 +4,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "cvo_api.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "cvo_kernels.cuh"), os.path.join(_HERE, "csrc", "pcd_kernels.cuh"),
+DEPS = [SRC, os.path.join(_HERE, "csrc", "cvo_kernels.cuh"), os.path.join(_HERE, "csrc", "cvo_quads.cuh"), os.path.join(_HERE, "csrc", "pcd_kernels.cuh"),
         os.path.join(_HERE, "..", "include", "cvo_b200.h")]
 OUT = os.path.join(_HERE, "libcvo_b200.so")
 

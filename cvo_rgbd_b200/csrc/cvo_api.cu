@@ -499,7 +499,8 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
         }
         ensure_list_scratch(ctx, (n_pairs < fit ? n_pairs : fit) * G, max_n);
     }
-    const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr;
+    // the list passes rely on a > sp_thres implying the ell-ball test, which holds for c_sigma^2 <= 1 (cvo_quads.cuh)
+    const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr && args.kp.cs2 <= 1.0f;
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;

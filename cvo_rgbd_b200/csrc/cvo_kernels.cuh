@@ -157,11 +157,23 @@ struct WarpScratch {
 // What sits beside the column geometry depends on the pass.  On-the-fly passes and list builds need the column
 // features, the warps' survivor queues and row tiles, and the per-unit partial sums; a pass over a neighbour list
 // needs this CTA's rows (geometry only) and, for the STEP pass, the per-column step-size terms.
+// Row-sorted compaction of a freshly built (x, y) list (build_list<0>, "quads"): per row of the round how many entries
+// it has, where its first quad sits inside its row tile, and a running cursor; per row tile the first quad.
+struct QuadBuild {
+    int rowCnt[kColChunk];
+    int rowQ[kColChunk];
+    int rowCur[kColChunk];
+    int tileQ[kColTiles + 1];
+};
 struct FeatStage {
     float4 colF[kColChunk];             // {f0, f1, f2, f3}
     float colF4[kColChunk];             // f4
-    uint32_t queue[kWorkWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
+    union {
+        uint32_t queue[kWorkWarps][kQueueCap];  // per warp: in-ball (row, col) pairs waiting for the survivor body
+        QuadBuild qb;                           // after the evaluation of a round: the compaction's counters
+    };
 };
+static_assert(sizeof(QuadBuild) <= sizeof(uint32_t) * kWorkWarps * kQueueCap, "the compaction counters live in the queues' memory");
 struct StepStage {
     // (list passes: four planes of kColChunk floats each, see plane_ld; nrm and pdt pre-scaled, see step_col)
     float4 colZ1[kColChunk];  // {xi z + v, |xi z + v|^2}                       (src/cvo.cpp:226-228,235)
@@ -1368,7 +1380,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink, float
         L.need = need ? 1 : 0;
         if (need) {
             double s = (double)skin * r_now;
-            if (L.valid > 0 && r_now <= (double)L.r0) {
+            if (kind != LIST_XY && L.valid > 0 && r_now <= (double)L.r0) {  // (the (x, y) list is rebuilt: its quads are row-sorted)
                 // The ball has shrunk and the old list still covers the pose with room to spare: everything the new
                 // list must hold (|x_i - T1 y_j| < r_e1 + s1, r_e1 <= r_e0) is in the old one as long as
                 // s1 + disp <= s0, so the new list is a FILTER of the old one (refine_list) -- no all-pairs sweep.
@@ -1561,6 +1573,9 @@ __device__ __forceinline__ int next_unit(Smem& sm) {
 // Which warp evaluated which unit does not matter: the flat list is a pure function of the inputs.  On return
 // sm.lst[kind].valid is 1, or -1 if a scratch area was too small.
 template <int SELF>
+__device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int kind, int round, int ntile, int Sb);
+
+template <int SELF>
 __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
                            int rank, int G, int yy_row_min, uint32_t& tma_phase, int kind, const ListRef& lr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1611,6 +1626,13 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             }
             __syncthreads();
             CVO_PHASE(7)
+            if (SELF == 0) {  // the (x, y) list: row-sorted quads (see compact_quads)
+                if (!compact_quads<SELF>(sm, lr, kind, round, ntile, Sb)) {
+                    stop = true;
+                    break;
+                }
+                continue;
+            }
             if (warp == 0) {  // places in the flat list: exclusive scan of the unit counts in unit order
                 int base = 0;
                 for (int i0 = 0; i0 < nunits; i0 += 32) {
@@ -2069,6 +2091,8 @@ __device__ void run_pass_self(Smem& sm, const KParams& kp, const CloudDev& rows,
     __syncthreads();
 }
 
+#include "cvo_quads.cuh"
+
 // All-gather of the per-CTA totals through distributed shared memory; every CTA of the cluster ends with
 // identical cluster totals in sm.sum[dst_off ...] (summed in rank order).
 template <int NV>
@@ -2187,7 +2211,6 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             CVO_PHASE(0)
             if (use_lists && sm.lst[LIST_XY].need == 1) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
-            else if (use_lists && sm.lst[LIST_XY].need == 2) refine_list<0>(sm, kp, pair.x, pair.y, rank, G, tma_phase, LIST_XY, lref[LIST_XY]);
             if (use_lists && acvo) {  // all builds come before the first pass: the stages the FLOW pass fills survive to the STEP pass
                 if (sm.lst[LIST_XX].need == 1) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
                 else if (sm.lst[LIST_XX].need == 2) refine_list<1>(sm, kp, pair.x, pair.x, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
@@ -2196,8 +2219,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             }
             CVO_PHASE(1)
             const bool list_xy = use_lists && sm.lst[LIST_XY].valid > 0;
-            if (list_xy && acvo) run_pass_list<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
-            else if (list_xy) run_pass_list<PASS_FLOW_CVO>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            // nnz(A) / sum(A) are only observable through the trace of pair 0 (and, for acvo, through dl)
+            const bool stats = args.trace != nullptr && pi == 0;
+            if (list_xy && acvo) run_pass_quads<PASS_FLOW, true>(sm, kp, pair.x, pair.y, rank, G, tma_phase, lref[LIST_XY]);
+            else if (list_xy && stats) run_pass_quads<PASS_FLOW_CVO, true>(sm, kp, pair.x, pair.y, rank, G, tma_phase, lref[LIST_XY]);
+            else if (list_xy) run_pass_quads<PASS_FLOW_CVO, false>(sm, kp, pair.x, pair.y, rank, G, tma_phase, lref[LIST_XY]);
             else run_pass<PASS_FLOW>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             CVO_PHASE(2)
             if (threadIdx.x < ACC_FLOW_COUNT) sm.flowTot[threadIdx.x] = threadIdx.x < 9 ? sm.blockTot[threadIdx.x] : 0.0;
@@ -2217,7 +2243,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             __syncthreads();
             CVO_PHASE(3)
             // compute_step_size (src/cvo.cpp:377)
-            if (list_xy) run_pass_list<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            if (list_xy) run_pass_quads<PASS_STEP, false>(sm, kp, pair.x, pair.y, rank, G, tma_phase, lref[LIST_XY]);
             else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             CVO_PHASE(4)
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);

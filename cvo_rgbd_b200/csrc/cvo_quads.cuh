@@ -1,0 +1,486 @@
+// cvo_quads.cuh -- the (x, y) neighbour list as ROW-SORTED QUADS and the two passes over it (included by
+// cvo_kernels.cuh inside namespace cvo_b200).
+//
+// Layout.  The candidates of one round (row chunk x column chunk) are sorted by row; every row's run is padded to a
+// multiple of four, so the list is a sequence of QUADS: four candidates of ONE row.  A quad is stored as three
+// parallel arrays (structure of arrays, 26 B per quad = 6.5 B per candidate; 8 B before):
+//     ntc  float4   the four NEGATED colour exponents -t_c (padding: -inf  =>  a = 0)
+//     cols 4 x u16  byte offsets of the four columns inside a plane of the staged column chunk
+//     row  u16      byte offset of the row inside a plane of the staged row chunk
+// and a round is padded to a whole TRIP of 32 quads: lane l of a warp takes quad l of the trip with one LDG.128, one
+// LDG.64 and one LDG.U16, all three coalesced.
+//
+// Why rows.  With d = y_j - x_i (diff_yx, src/cvo.cpp:192) the flow of a row factors:
+//     sum_j a_ij (x_i x y_j) = x_i x sum_j a_ij d_ij        (x_i x x_i = 0)        src/cvo.cpp:191,197
+//     sum_j a_ij (y_j - x_i) =       sum_j a_ij d_ij                                 src/cvo.cpp:192,198
+// so a candidate costs three FMAs (a d) instead of a cross product and six, and the cross product is taken once per
+// quad -- the reference's own order of operations (per-row f32 sums `Ai*cross_xy`, `Ai*diff_yx`, then f64 across rows).
+// The step-size terms (src/cvo.cpp:226-279) factor the same way: with the ROW vectors u_i = omega x x_i + v and
+// w_i = omega x u_i,
+//     xi z_j       = z1 = u_i + omega x d                 z1 . r = -u_i . d                        (r = x_i - y_j = -d)
+//     xi^2 z_j     = z2 = w_i + omega (omega . d) - |omega|^2 d
+//     S           := |omega x d|^2 = |omega|^2 |d|^2 - (omega . d)^2
+//     z2 . r       = S - w_i . d                          |z1|^2 = |u_i|^2 + S - 2 w_i . d
+//     |z2|^2       = |w_i|^2 + |omega|^2 (S - 2 w_i . d)
+//     -z1 . z2     = 0                                    (z2 = omega x z1: the reference's xiz_dot_xi2z, :236, is pure
+//                                                          f32 rounding noise around 0; its effect on D is < 1e-9 relative)
+//     |z2|^2 + 2 z1 . z3 = -|z2|^2                        (z3 = omega x z2: the reference's epsil_const, :237)
+//   with Q := 3 S - 4 w_i . d:
+//     beta = 2t u_i . d     gamma = -t (|u_i|^2 + Q)     delta = 2t ((omega . v)(omega . d) - |omega|^2 u_i . d)
+//     epsil = t (|w_i|^2 + |omega|^2 Q)                                                            (t = 1 / (2 l^2))
+// Three dot products per candidate (u.d, w.d, omega.d), nothing per COLUMN: the eight per-column planes the STEP pass
+// used to stage and gather (nine shared loads per candidate) are gone; eight per-ROW terms are staged instead and read
+// once per quad.
+//
+// Packed arithmetic.  A lane holds its quad as two PAIRS of candidates and evaluates them with the packed f32x2
+// instructions of sm_100 (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.rn.f32x2): one issue slot per two candidates for all of
+// the geometry, the kernel exponent and the polynomial.  The kernel is issue-bound, so this is
+// where the time goes down; every operation is the same correctly rounded f32 operation as before.
+//
+// Gates.  a > sp_thres implies the strict ell-ball test d2 < d2_thres whenever c_sigma^2 <= 1 (k = a / ck >= a) and a
+// is not within the re-decision band of sp_thres, so the fast path tests only a; candidates inside the band (about one
+// in a million) are re-decided per candidate by kernel_value_exact + the exact ball test, as before.  (With
+// c_sigma > 1 -- neither reference class -- the host keeps the passes on the fly.)
+#pragma once
+
+namespace quads {
+
+constexpr int kQuadTrip = 32;            // quads per trip (one per lane)
+constexpr int kQuadBytes = 26;           // 16 (ntc) + 8 (cols) + 2 (row)
+
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float hsum(float2 a) { return a.x + a.y; }
+
+struct Round {  // one round's arrays inside the CTA's list area
+    const float4* ntc;
+    const uint2* cols;
+    const unsigned short* row;
+    int ntrip;
+    const char* pf_base;  // this lane's share of the L2 prefetch of a trip: first line and bytes per trip (lanes 0..6)
+    int pf_stride;
+};
+__device__ __forceinline__ Round round_ref(const ListRef& lr, uint2 rd, int lane) {
+    const char* base = reinterpret_cast<const char*>(lr.entries) + (size_t)rd.x * 16u;
+    Round r;
+    r.ntc = reinterpret_cast<const float4*>(base);
+    r.cols = reinterpret_cast<const uint2*>(base + (size_t)rd.y * 16u);
+    r.row = reinterpret_cast<const unsigned short*>(base + (size_t)rd.y * 24u);
+    r.ntrip = (int)rd.y / kQuadTrip;
+    // a trip is 512 B of ntc (4 lines), 256 B of cols (2 lines), 64 B of rows (half a line)
+    r.pf_base = lane < 4 ? reinterpret_cast<const char*>(r.ntc) + lane * 128
+                : lane < 6 ? reinterpret_cast<const char*>(r.cols) + (lane - 4) * 128 : reinterpret_cast<const char*>(r.row);
+    r.pf_stride = lane < 4 ? 512 : lane < 6 ? 256 : 64;
+    return r;
+}
+
+struct Quad {
+    float4 ntc;
+    uint2 cols;
+    uint32_t row;
+};
+__device__ __forceinline__ Quad load_quad(const Round& r, int trip, int lane) {
+    const int q = min(trip, r.ntrip - 1) * kQuadTrip + lane;  // loads past the warp's last trip are clamped to it
+    Quad v;
+    v.ntc = __ldcg(r.ntc + q);
+    v.cols = __ldcg(r.cols + q);
+    v.row = (uint32_t)__ldcg(r.row + q);
+    return v;
+}
+// the lines of a trip a few trips ahead -> L2
+__device__ __forceinline__ void prefetch_trip(const Round& r, int trip, int lane) {
+    if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.pf_base + (size_t)min(trip, r.ntrip - 1) * r.pf_stride));
+}
+
+// Geometry and gated kernel values of one quad.
+struct QuadGeom {
+    float xr, yr, zr;              // the row
+    float2 dxa, dya, dza, d2a;     // candidates 0, 1: d = y - x, |d|^2 (nanoflann's accumulation order, see dist2)
+    float2 dxb, dyb, dzb, d2b;     // candidates 2, 3
+    float2 aa, ab;                 // a (0 where a gate failed)
+};
+
+// `near`: some candidate of the quad has its fast kernel value inside the re-decision band around sp_thres.
+__device__ __forceinline__ bool quad_geom(const Smem& sm, const HotConsts& hc, const KParams& kp, const Quad& q, QuadGeom& g) {
+    const void* rp = sm.u.ls.rowG;
+    const void* cp = sm.colG;
+    g.xr = plane_ld<0>(rp, q.row); g.yr = plane_ld<1>(rp, q.row); g.zr = plane_ld<2>(rp, q.row);
+    const uint32_t c0 = q.cols.x & 0xffffu, c1 = q.cols.x >> 16, c2 = q.cols.y & 0xffffu, c3 = q.cols.y >> 16;
+    g.dxa = __fadd2_rn(make_float2(plane_ld<0>(cp, c0), plane_ld<0>(cp, c1)), bc(-g.xr));
+    g.dya = __fadd2_rn(make_float2(plane_ld<1>(cp, c0), plane_ld<1>(cp, c1)), bc(-g.yr));
+    g.dza = __fadd2_rn(make_float2(plane_ld<2>(cp, c0), plane_ld<2>(cp, c1)), bc(-g.zr));
+    g.dxb = __fadd2_rn(make_float2(plane_ld<0>(cp, c2), plane_ld<0>(cp, c3)), bc(-g.xr));
+    g.dyb = __fadd2_rn(make_float2(plane_ld<1>(cp, c2), plane_ld<1>(cp, c3)), bc(-g.yr));
+    g.dzb = __fadd2_rn(make_float2(plane_ld<2>(cp, c2), plane_ld<2>(cp, c3)), bc(-g.zr));
+    g.d2a = __ffma2_rn(g.dza, g.dza, __ffma2_rn(g.dya, g.dya, __fmul2_rn(g.dxa, g.dxa)));
+    g.d2b = __ffma2_rn(g.dzb, g.dzb, __ffma2_rn(g.dyb, g.dyb, __fmul2_rn(g.dxb, g.dxb)));
+    // a = s2 c_sigma^2 2^-(d2 c1 + t_c)  (kernel_a; -(d2 c1 + t_c) = fma(d2, -c1, -t_c) bit for bit)
+    const float2 ea = __ffma2_rn(g.d2a, bc(-hc.c1), make_float2(q.ntc.x, q.ntc.y));
+    const float2 eb = __ffma2_rn(g.d2b, bc(-hc.c1), make_float2(q.ntc.z, q.ntc.w));
+    const float2 fa = __fmul2_rn(bc(kp.s2cs2), make_float2(exp2f_approx(ea.x), exp2f_approx(ea.y)));
+    const float2 fb = __fmul2_rn(bc(kp.s2cs2), make_float2(exp2f_approx(eb.x), exp2f_approx(eb.y)));
+    const float2 ma = __fadd2_rn(fa, bc(-kp.sp_thres)), mb = __fadd2_rn(fb, bc(-kp.sp_thres));  // a - sp_thres: same sign as (a > sp_thres)
+    const float m = fminf(fminf(fabsf(ma.x), fabsf(ma.y)), fminf(fabsf(mb.x), fabsf(mb.y)));
+    g.aa = make_float2(ma.x > 0.f ? fa.x : 0.f, ma.y > 0.f ? fa.y : 0.f);  // src/cvo.cpp:152
+    g.ab = make_float2(mb.x > 0.f ? fb.x : 0.f, mb.y > 0.f ? fb.y : 0.f);
+    return m < kp.sp_band;
+}
+
+// The re-decision of a quad that has a candidate inside the band: every candidate's value and gates in the reference's
+// own arithmetic (kernel_value_exact: features from global memory) and the exact strict ball test.  About one trip in
+// ten thousand gets here; not inlined so that it costs the hot loop no registers.
+__device__ __noinline__ float quad_exact1(const Smem& sm, const KParams& kp, const ListSrc& src, uint32_t rowb, uint32_t colb, float d2) {
+    const IterConsts& ic = sm.ic;
+    const int ri = src.row_base + (int)(rowb >> 2), ci = src.col_base + (int)(colb >> 2);
+    float a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri), __ldg(src.rows->f4 + ri),
+                                 __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
+    if (!(d2 < ic.d2_thres)) a = 0.f;  // thirdparty/nanoflann.hpp:249-253
+    return a;
+}
+__device__ __forceinline__ void redecide(const Smem& sm, const KParams& kp, const ListSrc& src, const Quad& q, bool near, QuadGeom& g) {
+    if (__any_sync(0xffffffffu, near)) {
+        if (near) {  // padding candidates (-t_c = -inf) stay at a = 0
+            const float ninf = -__int_as_float(0x7f800000);
+            g.aa.x = q.ntc.x > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.x & 0xffffu, g.d2a.x) : 0.f;
+            g.aa.y = q.ntc.y > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.x >> 16, g.d2a.y) : 0.f;
+            g.ab.x = q.ntc.z > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.y & 0xffffu, g.d2b.x) : 0.f;
+            g.ab.y = q.ntc.w > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.y >> 16, g.d2b.y) : 0.f;
+        }
+    }
+}
+
+// ---- FLOW (src/cvo.cpp:164-210; acvo: + the (x, y) term of the length-scale gradient, src/adaptive_cvo.cpp:202,228) ----
+// STATS: nnz(A) and sum(A) are wanted (acvo always: nnz enters dl; cvo only for the trace / eval hook).
+template <int KIND, bool STATS>
+__device__ __forceinline__ void flow_quad(const HotConsts& hc, const KParams& kp, const QuadGeom& g, FlowPartial& fp) {
+    const float sx = hsum(__ffma2_rn(g.ab, g.dxb, __fmul2_rn(g.aa, g.dxa)));  // sum_j a_ij d_ij over the quad, f32 like
+    const float sy = hsum(__ffma2_rn(g.ab, g.dyb, __fmul2_rn(g.aa, g.dya)));  // the reference's per-row Ai*diff_yx
+    const float sz = hsum(__ffma2_rn(g.ab, g.dzb, __fmul2_rn(g.aa, g.dza)));
+    fp.po0 = fmaf(kp.inv_c, g.yr * sz - g.zr * sy, fp.po0);  // (1/c) x_i x sum a d
+    fp.po1 = fmaf(kp.inv_c, g.zr * sx - g.xr * sz, fp.po1);
+    fp.po2 = fmaf(kp.inv_c, g.xr * sy - g.yr * sx, fp.po2);
+    fp.pv0 = fmaf(kp.inv_d, sx, fp.pv0);
+    fp.pv1 = fmaf(kp.inv_d, sy, fp.pv1);
+    fp.pv2 = fmaf(kp.inv_d, sz, fp.pv2);
+    if (KIND == PASS_FLOW) fp.pdl = fmaf(hc.inv_ell3, hsum(__ffma2_rn(g.ab, g.d2b, __fmul2_rn(g.aa, g.d2a))), fp.pdl);
+    if (STATS) {
+        fp.psum += hsum(__fadd2_rn(g.aa, g.ab));
+        fp.cnt += (g.aa.x > 0.f) + (g.aa.y > 0.f) + (g.ab.x > 0.f) + (g.ab.y > 0.f);
+    }
+}
+// per-lane f32 partials (a few quads) -> f64 (src/cvo.cpp:202-203)
+template <int KIND, bool STATS>
+__device__ __forceinline__ void flush_flow(FlowPartial& fp, double* acc) {
+    acc[ACC_W0] += (double)fp.po0; acc[ACC_W0 + 1] += (double)fp.po1; acc[ACC_W0 + 2] += (double)fp.po2;
+    acc[ACC_V0] += (double)fp.pv0; acc[ACC_V0 + 1] += (double)fp.pv1; acc[ACC_V0 + 2] += (double)fp.pv2;
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = 0.f;
+    if (KIND == PASS_FLOW) {
+        acc[ACC_DLXY] += (double)fp.pdl;
+        fp.pdl = 0.f;
+    }
+    if (STATS) {
+        acc[ACC_SUMA] += (double)fp.psum;
+        acc[ACC_NNZ] += (double)fp.cnt;
+        fp.psum = 0.f;
+        fp.cnt = 0;
+    }
+}
+
+// ---- STEP (src/cvo.cpp:213-289): this quad's terms of B, C, D, E ----
+struct StepRow {  // the row's staged terms, see stage_row_step_terms
+    float ux, uy, uz, wx, wy, wz, guu, ew2;
+};
+struct StepConsts {  // per-iteration scalars of the row-factored form
+    float w0, w1, w2;   // omega
+    float ww;           // |omega|^2
+    float b2t;          // 2t                     beta  = b2t u.d
+    float mt;           // -t                     gamma = guu + mt Q            (guu = -t |u|^2)
+    float dk1, dk2;     // 2t (omega.v), -2t |omega|^2      delta = dk1 omega.d + dk2 u.d
+    float etw;          // t |omega|^2            epsil = ew2 + etw Q           (ew2 = t |w|^2)
+};
+__device__ __forceinline__ StepConsts step_consts(const HotConsts& hc) {
+    StepConsts s;
+    s.w0 = hc.omega[0]; s.w1 = hc.omega[1]; s.w2 = hc.omega[2];
+    s.ww = (s.w0 * s.w0 + s.w1 * s.w1) + s.w2 * s.w2;
+    const float wv = (s.w0 * hc.v[0] + s.w1 * hc.v[1]) + s.w2 * hc.v[2];
+    s.b2t = hc.p2t;
+    s.mt = -hc.temp_coef;
+    s.dk1 = hc.p2t * wv;
+    s.dk2 = -hc.p2t * s.ww;
+    s.etw = hc.temp_coef * s.ww;
+    return s;
+}
+__device__ __forceinline__ float2 step_pair(const StepConsts& sc, const StepRow& r, float2 dx, float2 dy, float2 dz, float2 d2, float2 a,
+                                            float2& tC, float2& tD, float2& tE) {
+    const float2 pu = __ffma2_rn(bc(r.uz), dz, __ffma2_rn(bc(r.uy), dy, __fmul2_rn(bc(r.ux), dx)));  // u_i . d
+    const float2 pw = __ffma2_rn(bc(r.wz), dz, __ffma2_rn(bc(r.wy), dy, __fmul2_rn(bc(r.wx), dx)));  // w_i . d
+    const float2 po = __ffma2_rn(bc(sc.w2), dz, __ffma2_rn(bc(sc.w1), dy, __fmul2_rn(bc(sc.w0), dx)));  // omega . d
+    const float2 S = __ffma2_rn(make_float2(-po.x, -po.y), po, __fmul2_rn(bc(sc.ww), d2));           // |omega x d|^2
+    const float2 Q = __ffma2_rn(bc(3.f), S, __fmul2_rn(bc(-4.f), pw));
+    const float2 beta = __fmul2_rn(bc(sc.b2t), pu);                                   // src/cvo.cpp:262
+    const float2 gamma = __ffma2_rn(bc(sc.mt), Q, bc(r.guu));                         // :264
+    const float2 delta = __ffma2_rn(bc(sc.dk1), po, __fmul2_rn(bc(sc.dk2), pu));     // :267
+    const float2 epsil = __ffma2_rn(bc(sc.etw), Q, bc(r.ew2));                       // :270
+    const float2 b2 = __fmul2_rn(beta, beta);
+    const float2 tB = __fmul2_rn(a, beta);                                            // :275
+    tC = __fmul2_rn(a, __ffma2_rn(bc(0.5f), b2, gamma));                              // :276
+    tD = __fmul2_rn(a, __ffma2_rn(__fmul2_rn(b2, beta), bc(1.f / 6.f), __ffma2_rn(beta, gamma, delta)));  // :277
+    tE = __fmul2_rn(a, __ffma2_rn(__fmul2_rn(b2, b2), bc(1.f / 24.f),
+                                  __ffma2_rn(bc(0.5f), __fmul2_rn(gamma, __fadd2_rn(b2, gamma)), __ffma2_rn(beta, delta, epsil))));  // :278-279
+    return tB;
+}
+__device__ __forceinline__ void step_quad(const Smem& sm, const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {
+    const void* z1 = sm.u.ls.ss.colZ1;  // the step stage holds the ROW terms here: planes ux, uy, uz, guu | wx, wy, wz, ew2
+    const void* z2 = sm.u.ls.ss.colZ2;
+    StepRow r;
+    r.ux = plane_ld<0>(z1, rowb); r.uy = plane_ld<1>(z1, rowb); r.uz = plane_ld<2>(z1, rowb); r.guu = plane_ld<3>(z1, rowb);
+    r.wx = plane_ld<0>(z2, rowb); r.wy = plane_ld<1>(z2, rowb); r.wz = plane_ld<2>(z2, rowb); r.ew2 = plane_ld<3>(z2, rowb);
+    float2 cA, dA, eA, cB, dB, eB;
+    const float2 bA = step_pair(sc, r, g.dxa, g.dya, g.dza, g.d2a, g.aa, cA, dA, eA);
+    const float2 bB = step_pair(sc, r, g.dxb, g.dyb, g.dzb, g.d2b, g.ab, cB, dB, eB);
+    // the quad's four terms are summed in f32, then promoted (the reference promotes every term, src/cvo.cpp:275-279)
+    acc[0] += (double)hsum(__fadd2_rn(bA, bB));
+    acc[1] += (double)hsum(__fadd2_rn(cA, cB));
+    acc[2] += (double)hsum(__fadd2_rn(dA, dB));
+    acc[3] += (double)hsum(__fadd2_rn(eA, eB));
+}
+
+}  // namespace quads
+
+// Per-ROW step-size terms of the round's staged rows (untransformed fixed cloud): u = omega x x + v, w = omega x u,
+// -t |u|^2, t |w|^2 (t = 1 / (2 l^2)); see the header of this file.  Runs once per iteration, n <= kColChunk rows.
+__device__ __forceinline__ void stage_row_step_terms(Smem& sm, int n) {
+    const IterConsts& ic = sm.ic;
+    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+    float* z1 = plane_of(sm.u.ls.ss.colZ1, 0);
+    float* z2 = plane_of(sm.u.ls.ss.colZ2, 0);
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float x = plane_of(sm.u.ls.rowG, 0)[i], y = plane_of(sm.u.ls.rowG, 1)[i], z = plane_of(sm.u.ls.rowG, 2)[i];
+        const float ux = (w1 * z - w2 * y) + ic.v[0], uy = (w2 * x - w0 * z) + ic.v[1], uz = (w0 * y - w1 * x) + ic.v[2];
+        const float wx = w1 * uz - w2 * uy, wy = w2 * ux - w0 * uz, wz = w0 * uy - w1 * ux;
+        z1[i] = ux; z1[i + kColChunk] = uy; z1[i + 2 * kColChunk] = uz;
+        z1[i + 3 * kColChunk] = -ic.temp_coef * ((ux * ux + uy * uy) + uz * uz);
+        z2[i] = wx; z2[i + kColChunk] = wy; z2[i + 2 * kColChunk] = wz;
+        z2[i + 3 * kColChunk] = ic.temp_coef * ((wx * wx + wy * wy) + wz * wz);
+    }
+}
+
+// Row-sorted compaction of the round that build_list<0> has just evaluated: the units' staged candidates
+// ((row, col) byte offsets, t_c), unit by unit, become the round's quads.
+//   count    every row tile is taken by ONE warp, which walks the tile's units in unit order and counts the candidates of
+//            each of its 32 rows (the lanes of a batch that hold the same row are found with match.any);
+//   place    quads per row -> exclusive scan inside the tile -> exclusive scan over the tiles -> the round's region in
+//            the list area (ntc | cols | row arrays, padded to a whole trip with quads that can never pass);
+//   scatter  the same warp walks the same units in the same order: a candidate's slot is its row's cursor plus its rank
+//            among the batch's lanes with that row.  Rows are private to the warp, so no atomics are involved and the
+//            list is a pure function of the inputs, whichever warp evaluated which unit.
+// Returns false (and sets sm.lst_ovf) if the region does not fit the list area.
+template <int SELF>
+__device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int kind, int round, int ntile, int Sb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    QuadBuild& qb = sm.u.of.fs.qb;
+    const BuildUnits& bu = sm.u.of.bu;
+    const float ninf = -__int_as_float(0x7f800000);
+    if (sm.lst_ovf) return false;  // a unit outgrew its staging segment: its tail was never stored (stable since the barrier)
+    // ---- count
+    for (int t = warp; t < ntile; t += kWarps) {
+        qb.rowCnt[t * kTile + lane] = 0;
+        __syncwarp();
+        for (int sg = 0; sg < Sb; ++sg) {
+            const int u = t * Sb + sg, c = bu.act[u];
+            const uint2* src = lr.staging + bu.off[u];
+            for (int i0 = 0; i0 < c; i0 += 32) {
+                const bool have = i0 + lane < c;
+                const int r = have ? (int)(__ldcg(src + i0 + lane).x >> 18) - t * kTile : kTile + lane;  // idle lanes: singletons
+                const unsigned m = __match_any_sync(0xffffffffu, r);
+                if (have && lane == __ffs(m) - 1) qb.rowCnt[t * kTile + r] += __popc(m);
+                __syncwarp();
+            }
+        }
+        const int q = (qb.rowCnt[t * kTile + lane] + 3) >> 2;
+        int excl, total;
+        warp_scan_count(q, lane, excl, total);
+        qb.rowQ[t * kTile + lane] = excl;
+        if (lane == 0) qb.tileQ[t] = total;
+    }
+    __syncthreads();
+    // ---- place
+    if (warp == 0) {
+        int base = 0;
+        for (int i0 = 0; i0 < ntile; i0 += 32) {
+            const int c = (i0 + lane < ntile) ? qb.tileQ[i0 + lane] : 0;
+            int excl, total;
+            warp_scan_count(c, lane, excl, total);
+            __syncwarp();
+            if (i0 + lane < ntile) qb.tileQ[i0 + lane] = base + excl;
+            base += total;
+        }
+        const int nq = (base + quads::kQuadTrip - 1) / quads::kQuadTrip * quads::kQuadTrip;
+        const unsigned units16 = ((unsigned)nq * quads::kQuadBytes + 15u) / 16u;  // the region, in 16-byte units
+        const unsigned at = (unsigned)sm.lst_used;
+        const bool fits = !sm.lst_ovf && (unsigned long long)(at + units16) * 16ull <= (unsigned long long)lr.cap * 8ull;
+        if (fits) {  // the quads behind the last row: never pass (-t_c = -inf), address row 0 / column 0
+            char* rb = reinterpret_cast<char*>(lr.entries) + (size_t)at * 16u;
+            for (int q = base + lane; q < nq; q += 32) {
+                __stcg(reinterpret_cast<float4*>(rb) + q, make_float4(ninf, ninf, ninf, ninf));
+                __stcg(reinterpret_cast<uint2*>(rb + (size_t)nq * 16u) + q, make_uint2(0u, 0u));
+                reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u)[q] = 0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (fits) {
+                sm.lround[kind][round] = make_uint2(at, (unsigned)nq);
+                sm.lst_base = (int)at;
+                sm.lst_used = (int)(at + units16);
+            } else {
+                sm.lst_ovf = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (sm.lst_ovf) return false;
+    // ---- scatter
+    {
+        const unsigned nq = sm.lround[kind][round].y;
+        char* rb = reinterpret_cast<char*>(lr.entries) + (size_t)sm.lst_base * 16u;
+        float* ntc = reinterpret_cast<float*>(rb);
+        unsigned short* cols = reinterpret_cast<unsigned short*>(rb + (size_t)nq * 16u);
+        unsigned short* rowq = reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u);
+        for (int t = warp; t < ntile; t += kWarps) {
+            qb.rowCur[t * kTile + lane] = 0;
+            __syncwarp();
+            const int tile_q = qb.tileQ[t];
+            for (int sg = 0; sg < Sb; ++sg) {
+                const int u = t * Sb + sg, c = bu.act[u];
+                const uint2* src = lr.staging + bu.off[u];
+                for (int i0 = 0; i0 < c; i0 += 32) {
+                    const bool have = i0 + lane < c;
+                    const uint2 e = have ? __ldcg(src + i0 + lane) : make_uint2(0u, 0u);
+                    const int r = have ? (int)(e.x >> 18) - t * kTile : kTile + lane;
+                    const unsigned m = __match_any_sync(0xffffffffu, r);
+                    const int cur = have ? qb.rowCur[t * kTile + r] : 0;
+                    __syncwarp();
+                    if (have && lane == __ffs(m) - 1) qb.rowCur[t * kTile + r] = cur + __popc(m);
+                    __syncwarp();
+                    if (have) {
+                        const int pos = cur + __popc(m & ((1u << lane) - 1u));
+                        const int q = tile_q + qb.rowQ[t * kTile + r] + (pos >> 2), slot = pos & 3;
+                        ntc[q * 4 + slot] = -__uint_as_float(e.y);
+                        cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
+                        if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
+                    }
+                }
+            }
+            // the tail of every row's last quad
+            const int cnt = qb.rowCnt[t * kTile + lane];
+            for (int pos = cnt; pos < ((cnt + 3) & ~3); ++pos) {
+                const int q = tile_q + qb.rowQ[t * kTile + lane] + (pos >> 2), slot = pos & 3;
+                ntc[q * 4 + slot] = ninf;
+                cols[q * 4 + slot] = 0;
+            }
+        }
+    }
+    return true;
+}
+
+// One pass over the (x, y) list in quad form; same staging rules, trips, rotating register sets and fixed-order
+// reduction as run_pass_list.  KIND: PASS_FLOW (acvo), PASS_FLOW_CVO, PASS_STEP.
+template <int KIND, bool STATS>
+__device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows, const CloudDev& cols, int rank, int G,
+                               uint32_t& tma_phase, const ListRef& lr) {
+    constexpr int NV = PassTraits<KIND>::NV;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
+    ListSrc src;
+    src.rows = &rows;
+    src.cols = &cols;
+    const HotConsts hc = hot_consts(sm.ic);
+    const quads::StepConsts sc = quads::step_consts(hc);
+    FlowPartial fp;
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
+    fp.cnt = 0;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    int round = 0;
+    for (int rb = 0; rb < pg.my_tiles; rb += pg.tiles_per_round) {
+        const int ntile = min(pg.tiles_per_round, pg.my_tiles - rb);
+        for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
+            const int nct = min(kColTiles, pg.total_ct - cb);
+            __syncthreads();  // everyone is done with the previous round's stage (and its tags are written)
+            // Stage only what is not there already: the fixed cloud's rows survive from pass to pass and from iteration to
+            // iteration, the STEP pass finds the columns the FLOW pass transformed and adds the per-row step-size terms.
+            const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
+            const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, sm.serial);
+            const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, -1);
+            if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase);
+            if (!have_rows) stage_rows(sm, rows, row_first, ntile * kTile, false);
+            if (KIND == PASS_STEP) {
+                if (!have_rows) __syncthreads();
+                stage_row_step_terms(sm, ntile * kTile);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {  // read again only after the next barrier
+                sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = sm.serial;
+                sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = -1;
+            }
+            src.row_base = row_first;
+            src.col_base = col_first;
+            const quads::Round rd = quads::round_ref(lr, sm.lround[LIST_XY][round], lane);
+            int t = warp;
+            if (t < rd.ntrip) {
+                // three register sets rotate between "being processed" and "being loaded" (never copied): the loads run two
+                // trips ahead of the arithmetic, the L2 prefetch a few trips ahead of the loads
+                quads::Quad qa = quads::load_quad(rd, t, lane), qb2 = quads::load_quad(rd, t + kWarps, lane), qc;
+#define CVO_QUAD_TRIP(q)                                                                     \
+    {                                                                                        \
+        quads::QuadGeom g;                                                                   \
+        const bool near = quads::quad_geom(sm, hc, kp, q, g);                                \
+        quads::redecide(sm, kp, src, q, near, g);                                            \
+        if (KIND == PASS_STEP) quads::step_quad(sm, sc, q.row, g, acc);                      \
+        else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                   \
+    }
+#pragma unroll 1
+                while (true) {
+                    qc = quads::load_quad(rd, t + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qa)
+                    t += kWarps;
+                    if (t >= rd.ntrip) break;
+                    qa = quads::load_quad(rd, t + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qb2)
+                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 2 quads (one or two rows) per f32 partial
+                    t += kWarps;
+                    if (t >= rd.ntrip) break;
+                    qb2 = quads::load_quad(rd, t + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qc)
+                    t += kWarps;
+                    if (t >= rd.ntrip) break;
+                }
+#undef CVO_QUAD_TRIP
+            }
+            if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
+        }
+    }
+    warp_sum_multi<NV>(acc, lane);
+    if (NV >= 8) {
+        if ((lane & 3) == 0) sm.u.ls.warpTot[warp][multi_value_index(lane)] = acc[0];
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 8; i < NV; ++i) sm.u.ls.warpTot[warp][i] = acc[i];
+        }
+    } else if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sm.u.ls.warpTot[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumAcc) {  // fixed-order sum over the warps
+        double tt = 0.0;
+        if (threadIdx.x < NV)
+            for (int w = 0; w < kWarps; ++w) tt += sm.u.ls.warpTot[w][threadIdx.x];
+        sm.blockTot[threadIdx.x] = tt;
+    }
+    __syncthreads();
+}

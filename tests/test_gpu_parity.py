@@ -218,12 +218,13 @@ def test_neighbor_lists_agree_with_on_the_fly_passes(gpu_ctx, kind, cfg):
         gpu_ctx.set_neighbor_lists(True)
 
 
-@pytest.mark.parametrize("kind,cfg,refine_min", [("cvo", 2, 0.05), ("acvo", 3, 0.05), ("acvo", 3, None)])
+@pytest.mark.parametrize("kind,cfg,refine_min", [("acvo", 3, 0.05), ("acvo", 3, None)])
 def test_lists_narrowed_in_place_agree_with_on_the_fly_passes(kind, cfg, refine_min, monkeypatch):
     """When ell shrinks, a list with slack to spare is FILTERED down to the new ball instead of being rebuilt
     (refine_list).  The narrowed list must still cover every pair that can pass: per-iteration counts equal the
-    on-the-fly passes' on one CTA (several rounds) and on a cluster.  refine_min = 0.05 forces the (x, y) list through
-    it at every ell step; the default only narrows when a whole fresh skin fits (acvo's pose-independent lists)."""
+    on-the-fly passes' on one CTA (several rounds) and on a cluster.  Only acvo's pose-independent (x, x) / (y, y) lists
+    are narrowed: the (x, y) list is kept as row-sorted quads since round 2 and is rebuilt instead (it was narrowed 0.9
+    times per 59 iterations).  refine_min = 0.05 narrows at every ell step; the default only when a whole fresh skin fits."""
     if refine_min is not None:
         monkeypatch.setenv("CVO_B200_LIST_REFINE_MIN", str(refine_min))
     pr = synth.config_pair(cfg)
@@ -267,7 +268,7 @@ def test_multi_round_lists_narrowed_in_place_on_one_cta(kind, monkeypatch):
         ref = ctx.align_trace(0, gp, trace_cap=16)
         ctx.set_neighbor_lists(True)
         got = ctx.align_trace(0, gp, trace_cap=16)
-        assert ctx.last_list_refines >= 1
+        assert ctx.last_list_refines >= 1 or kind == "cvo"  # cvo has only the (x, y) list, which is rebuilt, not narrowed
         a, b = got["trace"][0], ref["trace"][0]
         assert (a["nnz"], a["nnz_xx"], a["nnz_yy"]) == (b["nnz"], b["nnz_xx"], b["nnz_yy"])
         for k in range(1, min(12, got["n_iterations_run"], ref["n_iterations_run"])):
