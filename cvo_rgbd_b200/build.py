@@ -26,7 +26,7 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     return out
 
 
-def _build_example(name, extra_deps=()):
+def _build_example(name, extra_deps=(), cuda_runtime=False):
     root = os.path.dirname(_HERE)
     src = os.path.join(root, "examples", name + ".cpp")
     out = os.path.join(root, "examples", name)
@@ -35,8 +35,10 @@ def _build_example(name, extra_deps=()):
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + _HERE, "-lcvo_b200",
-                    "-Wl,-rpath,$ORIGIN/../cvo_rgbd_b200"], check=True)
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-o", out, src, "-L" + _HERE, "-lcvo_b200", "-Wl,-rpath,$ORIGIN/../cvo_rgbd_b200"]
+    if cuda_runtime:  # the example itself asks the runtime how many devices there are
+        cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True)
     return out
 
 
@@ -48,6 +50,11 @@ def build_frontend_example():
 def build_sequence_driver():
     """Compiles examples/cvo_sequence.cpp: the reference's sequence driver (src/cvo_main.cpp) over PCD files."""
     return _build_example("cvo_sequence", ("cvo_b200_io.hpp",))
+
+
+def build_multi_gpu_example():
+    """Compiles examples/cvo_batch_multi_gpu.cpp: one context per GPU + cvo_b200_align_multi (BASELINE config 4)."""
+    return _build_example("cvo_batch_multi_gpu", cuda_runtime=True)
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@ EXPORTS = [
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
-    "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes",
+    "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes", "cvo_b200_align_multi",
 ]
 
 
@@ -111,6 +111,8 @@ def load():
     lib.cvo_b200_push_frame_images.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ushort), C.c_int, C.c_int,
                                                C.c_int, C.c_int, ip]
     lib.cvo_b200_replace_moving_images.argtypes = lib.cvo_b200_push_frame_images.argtypes
+    lib.cvo_b200_align_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, fp, fp, ip, fp, fp, ip, C.c_int, C.POINTER(Params), fp, ip,
+                                         ip, fp]
     lib.cvo_b200_neighbor_lists_active.argtypes = [vp]
     lib.cvo_b200_list_scratch_bytes.argtypes = [vp]
     lib.cvo_b200_list_scratch_bytes.restype = C.c_longlong
@@ -127,6 +129,26 @@ def load():
     lib.cvo_b200_last_list_refines.restype = C.c_longlong
     _lib = lib
     return lib
+
+
+def align_multi(contexts, fx, ff, n_fixed, mx, mf, n_moving, params):
+    """cvo_b200_align_multi: pairs q -> contexts[q mod len(contexts)], one host thread per context (= per GPU).
+    fx/mx: [P, stride, 3], ff/mf: [P, stride, 5] C-contiguous float32.  Returns dict(transform, iters, status, kernel_ms)."""
+    lib = load()
+    n_fixed = np.ascontiguousarray(n_fixed, dtype=np.int32)
+    n_moving = np.ascontiguousarray(n_moving, dtype=np.int32)
+    P, stride = fx.shape[0], fx.shape[1]
+    for a, w in ((fx, 3), (ff, 5), (mx, 3), (mf, 5)):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.shape == (P, stride, w)
+    hs = (C.c_void_p * len(contexts))(*[c._h.value for c in contexts])
+    tf = np.zeros((P, 4, 4), np.float32)
+    iters, status = np.zeros(P, np.int32), np.zeros(P, np.int32)
+    ms = np.zeros(len(contexts), np.float32)
+    rc = lib.cvo_b200_align_multi(hs, len(contexts), P, _fp(fx), _fp(ff), _ipt(n_fixed), _fp(mx), _fp(mf), _ipt(n_moving), stride,
+                                  C.byref(params), _fp(tf), _ipt(iters), _ipt(status), _fp(ms))
+    if rc != OK:
+        raise CvoB200Error("cvo_b200_align_multi failed: %d (%s)" % (rc, "; ".join(lib.cvo_b200_last_error(c._h).decode() for c in contexts)), rc)
+    return dict(transform=tf, iters=iters, status=status, kernel_ms=ms)
 
 
 def selftest_rand_bytes(seed, n):

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cvo_kernels.cuh"
@@ -737,22 +738,25 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot, const float* fixed_xyz, const
     return launch_pack(ctx, jobs, 2, ctx->d_jobs);
 }
 
-int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const float* fixed_xyz,
-                       const float* fixed_feat, const int* n_fixed, const float* moving_xyz, const float* moving_feat,
-                       const int* n_moving, int stride_points) {
+// cvo_b200_set_pairs with the batch's pairs `pair_step` pairs apart in the caller's arrays (1: contiguous; W: every
+// W-th pair, the share of one of W devices in cvo_b200_align_multi).  The counts are indexed the same way.
+static int set_pairs_strided(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const float* fixed_xyz,
+                             const float* fixed_feat, const int* n_fixed, const float* moving_xyz, const float* moving_feat,
+                             const int* n_moving, int stride_points, int pair_step) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (!slots || !fixed_xyz || !fixed_feat || !moving_xyz || !moving_feat || !n_fixed || !n_moving)
         return fail_arg(ctx, "null pointer");
     if (n_pairs <= 0 || n_pairs > ctx->max_slots) return fail_arg(ctx, "bad pair count");
     if (stride_points <= 0) return fail_arg(ctx, "bad stride");
+    if (pair_step < 1) return fail_arg(ctx, "bad pair step");
     for (int i = 0; i < n_pairs; ++i) {
+        const int nf = n_fixed[(size_t)i * pair_step], nm = n_moving[(size_t)i * pair_step];
         if (slots[i] < 0 || slots[i] >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
-        if (n_fixed[i] <= 0 || n_moving[i] <= 0) {
+        if (nf <= 0 || nm <= 0) {
             ctx->err = "empty cloud";
             return CVO_B200_ERR_EMPTY;
         }
-        if (n_fixed[i] > ctx->max_points || n_moving[i] > ctx->max_points || n_fixed[i] > stride_points ||
-            n_moving[i] > stride_points)
+        if (nf > ctx->max_points || nm > ctx->max_points || nf > stride_points || nm > stride_points)
             return fail_arg(ctx, "cloud larger than max_points / stride");
     }
     CK(cudaSetDevice(ctx->device));
@@ -791,26 +795,35 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const f
             const int rc = flush_batch(ctx, s.pending_batch);
             if (rc) return rc;
         }
+        const int nf = n_fixed[(size_t)i * pair_step], nm = n_moving[(size_t)i * pair_step];
         s.fixed_buf = 0;
-        s.n[0] = n_fixed[i];
-        s.n[1] = n_moving[i];
+        s.n[0] = nf;
+        s.n[1] = nm;
         s.bound = true;
         s.have_fixed = true;
         s.pending_batch = b;
         B.h_jobs[2 * i] = {d_fx + i * cloud3, d_ff + i * cloud5, slot_g(ctx, slot, 0), slot_f(ctx, slot, 0),
-                           slot_f4(ctx, slot, 0), n_fixed[i], 0};
+                           slot_f4(ctx, slot, 0), nf, 0};
         B.h_jobs[2 * i + 1] = {d_mx + i * cloud3, d_mf + i * cloud5, slot_g(ctx, slot, 1), slot_f(ctx, slot, 1),
-                               slot_f4(ctx, slot, 1), n_moving[i], 0};
-        if ((size_t)n_fixed[i] * sizeof(unsigned long long) > ctx->pack_smem_max ||
-            (size_t)n_moving[i] * sizeof(unsigned long long) > ctx->pack_smem_max)
+                               slot_f4(ctx, slot, 1), nm, 0};
+        if ((size_t)nf * sizeof(unsigned long long) > ctx->pack_smem_max ||
+            (size_t)nm * sizeof(unsigned long long) > ctx->pack_smem_max)
             return fail_arg(ctx, "cloud too large for the single-CTA sort");
     }
     B.njobs = 2 * n_pairs;
     cudaStream_t cs = ctx->copy_stream;
-    CK(cudaMemcpyAsync(d_fx, fixed_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(d_ff, fixed_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(d_mx, moving_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(d_mf, moving_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
+    if (pair_step == 1) {
+        CK(cudaMemcpyAsync(d_fx, fixed_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(d_ff, fixed_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(d_mx, moving_xyz, sizeof(float) * n_pairs * cloud3, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(d_mf, moving_feat, sizeof(float) * n_pairs * cloud5, cudaMemcpyHostToDevice, cs));
+    } else {  // every pair_step-th cloud: a 2-D copy, one row per pair
+        const size_t w3 = sizeof(float) * cloud3, w5 = sizeof(float) * cloud5;
+        CK(cudaMemcpy2DAsync(d_fx, w3, fixed_xyz, w3 * pair_step, w3, n_pairs, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpy2DAsync(d_ff, w5, fixed_feat, w5 * pair_step, w5, n_pairs, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpy2DAsync(d_mx, w3, moving_xyz, w3 * pair_step, w3, n_pairs, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpy2DAsync(d_mf, w5, moving_feat, w5 * pair_step, w5, n_pairs, cudaMemcpyHostToDevice, cs));
+    }
     CK(cudaMemcpyAsync(B.d_jobs, B.h_jobs, sizeof(PackJob) * B.njobs, cudaMemcpyHostToDevice, cs));
     CK(cudaEventRecord(B.copied, cs));
     B.pending = true;
@@ -843,6 +856,65 @@ static int push_cloud(cvo_b200_ctx* ctx, int slot, const float* xyz, const float
     if (rc) return rc;
     s.fixed_buf = fixed_buf;
     s.n[mb] = n;
+    return CVO_B200_OK;
+}
+
+int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const float* fixed_xyz,
+                       const float* fixed_feat, const int* n_fixed, const float* moving_xyz, const float* moving_feat,
+                       const int* n_moving, int stride_points) {
+    return set_pairs_strided(ctx, slots, n_pairs, fixed_xyz, fixed_feat, n_fixed, moving_xyz, moving_feat, n_moving, stride_points, 1);
+}
+
+int cvo_b200_align_multi(cvo_b200_ctx* const* ctxs, int n_ctx, int n_pairs, const float* fixed_xyz, const float* fixed_feat,
+                         const int* n_fixed, const float* moving_xyz, const float* moving_feat, const int* n_moving,
+                         int stride_points, const cvo_b200_params* p, float* transform, int* iters, int* status,
+                         float* kernel_ms) {
+    if (!ctxs || n_ctx <= 0 || n_pairs <= 0 || !p || !transform) return CVO_B200_ERR_ARG;
+    for (int c = 0; c < n_ctx; ++c)
+        if (!ctxs[c]) return CVO_B200_ERR_ARG;
+    std::vector<int> rc(n_ctx, CVO_B200_OK);
+    // pair q -> context q mod n_ctx; every context works through its share in chunks of its slot count on its own
+    // host thread (one ctx = one caller thread); results go straight to index q of the caller's arrays: that is the
+    // gather (one process holds all devices, so no collective is involved; across processes see sharding.py).
+    auto work = [&](int c) {
+        cvo_b200_ctx* ctx = ctxs[c];
+        const int mine = (n_pairs - c + n_ctx - 1) / n_ctx;
+        std::vector<int> slots(ctx->max_slots);
+        for (int i = 0; i < ctx->max_slots; ++i) slots[i] = i;
+        std::vector<float> tf;
+        std::vector<int> it, st;
+        float ms = 0.f;
+        for (int done = 0; done < mine && rc[c] == CVO_B200_OK; done += ctx->max_slots) {
+            const int n = mine - done < ctx->max_slots ? mine - done : ctx->max_slots;
+            const size_t first = (size_t)c + (size_t)done * n_ctx;  // global index of the chunk's first pair
+            const size_t c3 = (size_t)stride_points * 3, c5 = (size_t)stride_points * 5;
+            rc[c] = set_pairs_strided(ctx, slots.data(), n, fixed_xyz + first * c3, fixed_feat + first * c5, n_fixed + first,
+                                      moving_xyz + first * c3, moving_feat + first * c5, n_moving + first, stride_points, n_ctx);
+            if (rc[c] != CVO_B200_OK) break;
+            tf.resize((size_t)n * 16);
+            it.resize(n);
+            st.resize(n);
+            rc[c] = cvo_b200_align(ctx, slots.data(), n, p, nullptr, nullptr, tf.data(), nullptr, it.data(), st.data());
+            if (rc[c] != CVO_B200_OK) break;
+            ms += ctx->last_ms;
+            for (int i = 0; i < n; ++i) {
+                const size_t q = first + (size_t)i * n_ctx;
+                memcpy(transform + q * 16, tf.data() + (size_t)i * 16, sizeof(float) * 16);
+                if (iters) iters[q] = it[i];
+                if (status) status[q] = st[i];
+            }
+        }
+        if (kernel_ms) kernel_ms[c] = ms;
+    };
+    if (n_ctx == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int c = 0; c < n_ctx; ++c) th.emplace_back(work, c);
+        for (auto& t : th) t.join();
+    }
+    for (int c = 0; c < n_ctx; ++c)
+        if (rc[c] != CVO_B200_OK) return rc[c];
     return CVO_B200_OK;
 }
 

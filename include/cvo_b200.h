@@ -118,6 +118,19 @@ int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs,
                        const float* moving_xyz, const float* moving_feat, const int* n_moving,
                        int stride_points);
 
+/* The multi-GPU batch driver (BASELINE config 4; the reference's driver loop src/cvo_main.cpp:36-66 over INDEPENDENT
+ * pairs, each started from the identity): `n_pairs` frame pairs laid out as for cvo_b200_set_pairs are dealt round-robin
+ * to `n_ctx` contexts -- one per GPU, pair q -> ctxs[q mod n_ctx] -- and every context uploads and aligns its share on a
+ * host thread of its own, in chunks of its slot count.  No data-path collective: the pairs are independent; the 4x4
+ * `transform`s (n_pairs x 16), `iters` and `status` (n_pairs, may be NULL) are written at index q, which is the gather.
+ * kernel_ms (n_ctx, may be NULL) receives each context's summed align-kernel time.  One process, all devices; a
+ * one-process-per-GPU job shards with the same rule and gathers with one NCCL all-gather (cvo_rgbd_b200/sharding.py). */
+int cvo_b200_align_multi(cvo_b200_ctx* const* ctxs, int n_ctx, int n_pairs,
+                         const float* fixed_xyz, const float* fixed_feat, const int* n_fixed,
+                         const float* moving_xyz, const float* moving_feat, const int* n_moving,
+                         int stride_points, const cvo_b200_params* p,
+                         float* transform, int* iters, int* status, float* kernel_ms);
+
 /* Replaces `ptr_fixed_pcd = std::move(ptr_moving_pcd)` (src/cvo.cpp:417) + the next set_pcd():
  * the slot's moving cloud becomes its fixed cloud (pointer swap on the device) and a new moving cloud
  * is uploaded, so a sequence uploads each frame once. */

@@ -183,3 +183,36 @@ def test_cfg4_batch_fills_the_machine(oracle):
             o = oracle.align(pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"], oracle.default_params("cvo"))
             rot, tr = pose_diff(res["transform"][s], o["transform"])
             assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (s, rot, tr)
+
+
+def test_align_multi_deals_pairs_over_contexts_and_gathers_in_pair_order():
+    """cvo_b200_align_multi, the native multi-GPU batch driver (BASELINE config 4): pair q -> context q mod W, a host
+    thread per context, chunks of the context's slot count, results at index q.  Two contexts on ONE device exercise the
+    same code path as two GPUs; the result must equal the single-context batch bit for bit (same launch geometry per
+    pair is not guaranteed -- cluster sizes differ with the batch size -- so poses are compared at f32 summation noise)."""
+    P = 11
+    prs = [synth.config_pair(4, 100 + i) for i in range(P)]
+    stride = max(max(len(p["x_pos"]), len(p["y_pos"])) for p in prs)
+    hx, hfx = np.zeros((P, stride, 3), np.float32), np.zeros((P, stride, 5), np.float32)
+    hy, hfy = np.zeros((P, stride, 3), np.float32), np.zeros((P, stride, 5), np.float32)
+    nf, nm = np.zeros(P, np.int32), np.zeros(P, np.int32)
+    for s, pr in enumerate(prs):
+        nf[s], nm[s] = len(pr["x_pos"]), len(pr["y_pos"])
+        hx[s, :nf[s]], hfx[s, :nf[s]] = pr["x_pos"], pr["x_feat"]
+        hy[s, :nm[s]], hfy[s, :nm[s]] = pr["y_pos"], pr["y_feat"]
+    gp = capi.default_params("cvo")
+    a, b = capi.Context(0, max_points=stride, max_slots=2), capi.Context(0, max_points=stride, max_slots=3)
+    one = capi.Context(0, max_points=stride, max_slots=P)
+    try:
+        multi = capi.align_multi([a, b], hx, hfx, nf, hy, hfy, nm, gp)
+        one.set_pairs(np.arange(P, dtype=np.int32), hx, hfx, nf, hy, hfy, nm)
+        ref = one.align(np.arange(P, dtype=np.int32), gp)
+        assert (multi["kernel_ms"] > 0).all()
+        assert np.isin(multi["status"], (capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE)).all()
+        for q in range(P):
+            rot, tr = pose_diff(multi["transform"][q], ref["transform"][q])
+            assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (q, rot, tr)
+            rot_gt, tr_gt = pose_diff(multi["transform"][q], prs[q]["T_gt"])
+            assert rot_gt < 1e-2 and tr_gt < 1e-2, q  # every pair landed at ITS OWN index
+    finally:
+        a.close(); b.close(); one.close()

@@ -141,3 +141,12 @@ def test_second_set_pcd_without_align_only_replaces_the_moving_cloud(oracle, kin
         assert rot < 2 * POSE_TOL_FLOOR and tr < 2 * POSE_TOL_FLOOR, (rot, tr)
     finally:
         reg.close()
+
+
+def test_compiled_multi_gpu_batch_driver():
+    """examples/cvo_batch_multi_gpu.cpp: cvo_b200_align_multi over every visible GPU (here: however many the box has)."""
+    from cvo_rgbd_b200 import build
+    build.build_library()
+    exe = build.build_multi_gpu_example()
+    out = subprocess.run([exe, "24", "2000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
