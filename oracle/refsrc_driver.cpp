@@ -15,7 +15,7 @@
 //   * NOT compiled: src/pcd_generator.cpp and thirdparty/PixelSelector2.cpp (the image front end needs the real
 //     OpenCV).  This file supplies stand-ins for the four pcd_generator members set_pcd() calls; they hand the test
 //     case's prepared cloud (N x 3 positions, N x 5 features) through the opaque cv::Mat of oracle/shim.
-//   * The Eigen arithmetic is the shim's (oracle/shim/shim_eigen.hpp): same types, same promotion rules, scalar-type
+//   * The Eigen arithmetic is the shim's (oracle/shim/eigen/shim_eigen.hpp): same types, same promotion rules, scalar-type
 //     accumulation; summation order inside a product and the 3 x 3 eigenvalue iteration are NOT bit-identical to any
 //     particular Eigen release (the reference pins none: "Eigen3", README.md:11).
 //   * Private members are reached with -fno-access-control (this translation unit only).  The per-iteration trace

@@ -1,4 +1,4 @@
-// oracle/shim/opencv2/opencv.hpp -- TEST INFRASTRUCTURE ONLY.
+// oracle/shim/cv/opencv2/opencv.hpp -- TEST INFRASTRUCTURE ONLY.
 // The reference's hot path never touches an image: cv::Mat only appears in the signatures of set_pcd()/run_cvo()
 // (src/cvo.cpp:319,422) and as members of cvo::frame (include/data_type.h:46-49), and is handed through to
 // pcd_generator.  This stand-in carries an opaque payload pointer instead of pixels: the shim driver

@@ -1,4 +1,4 @@
-// oracle/shim/pcl/point_types.h -- TEST INFRASTRUCTURE ONLY.
+// oracle/shim/cv/pcl/point_types.h -- TEST INFRASTRUCTURE ONLY.
 // cvo::point_cloud carries two pcl clouds for visualisation / PCD export (include/data_type.h:68-69); nothing on the
 // registration path reads them.  Empty stand-ins so that the reference's headers parse.
 #ifndef CVO_ORACLE_SHIM_PCL_H

@@ -1,4 +1,4 @@
-// oracle/shim/shim_eigen.hpp -- TEST INFRASTRUCTURE ONLY (see oracle/README in DESIGN.md section 4).
+// oracle/shim/eigen/shim_eigen.hpp -- TEST INFRASTRUCTURE ONLY (see oracle/README in DESIGN.md section 4).
 //
 // A minimal, EAGER stand-in for the subset of Eigen 3.3 that the reference's FIRST-PARTY sources use
 // (cpp/rkhs_registration/src/cvo.cpp, src/adaptive_cvo.cpp, src/LieGroup.cpp and the headers they include), so that

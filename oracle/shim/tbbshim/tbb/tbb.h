@@ -1,4 +1,4 @@
-// oracle/shim/tbb/tbb.h -- TEST INFRASTRUCTURE ONLY.
+// oracle/shim/tbbshim/tbb/tbb.h -- TEST INFRASTRUCTURE ONLY.
 // Stand-in for the three Intel TBB facilities the reference's first-party sources use (src/cvo.cpp:116,170,246,
 // src/adaptive_cvo.cpp): tbb::parallel_for(first, last, body), tbb::spin_mutex, tbb::concurrent_vector and
 // tbb::task_scheduler_init::default_num_threads().  parallel_for runs the index range on OpenMP threads when the

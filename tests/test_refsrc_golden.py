@@ -196,7 +196,7 @@ def test_restatement_equals_refsrc_on_fresh_seeds(oracle, kind, seed, n, m):
 
 
 def test_shim_eigenvalues_and_log_against_numpy():
-    """The two pieces of Eigen the shim has to re-derive numerically (oracle/shim/shim_eigen.hpp): the cubic's roots
+    """The two pieces of Eigen the shim has to re-derive numerically (oracle/shim/eigen/shim_eigen.hpp): the cubic's roots
     (MatrixXf::eigenvalues through poly_solver) and the 4x4 matrix logarithm inside dist_se3 (through a converging
     align: checked above).  Roots against numpy.roots on well-conditioned cubics."""
     Rs = _refsrc()
