@@ -363,18 +363,22 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
                     if (have && lane == __ffs(m) - 1) qb.rowCur[t * kTile + r] = cur + __popc(m);
                     __syncwarp();
                     if (have) {
+                        // SLOT-MAJOR inside the row: candidate `pos` of a row with n quads is slot pos / n of quad pos % n, so
+                        // that the lanes holding consecutive quads of a row read consecutive candidates -- consecutive
+                        // columns, different shared-memory banks -- in each of their four slots
                         const int pos = cur + __popc(m & ((1u << lane) - 1u));
-                        const int q = tile_q + qb.rowQ[t * kTile + r] + (pos >> 2), slot = pos & 3;
+                        const int nqr = (qb.rowCnt[t * kTile + r] + 3) >> 2;
+                        const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
                         ntc[q * 4 + slot] = -__uint_as_float(e.y);
                         cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
                         if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
                     }
                 }
             }
-            // the tail of every row's last quad
-            const int cnt = qb.rowCnt[t * kTile + lane];
-            for (int pos = cnt; pos < ((cnt + 3) & ~3); ++pos) {
-                const int q = tile_q + qb.rowQ[t * kTile + lane] + (pos >> 2), slot = pos & 3;
+            // the unused slots of every row's quads
+            const int cnt = qb.rowCnt[t * kTile + lane], nqr = (cnt + 3) >> 2;
+            for (int pos = cnt; pos < 4 * nqr; ++pos) {
+                const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + lane] + (pos - slot * nqr);
                 ntc[q * 4 + slot] = ninf;
                 cols[q * 4 + slot] = 0;
             }

@@ -131,14 +131,16 @@ def test_second_set_pcd_without_align_only_replaces_the_moving_cloud(oracle, kin
         op = oracle.default_params(kind)
         o = oracle.align(a["x_pos"], a["x_feat"], b["y_pos"], b["y_feat"], op)
         rot, tr = pose_diff(reg.transform, o["transform"])
-        assert rot < POSE_TOL_FLOOR and tr < POSE_TOL_FLOOR, (rot, tr)
+        # (a functional test on a small 900-point pair, whose converged pose is noisier than the 3000-point configs': the
+        #  wrong fixed cloud would be off by more than 1e-2)
+        assert rot < 1e-3 and tr < 1e-3, (rot, tr)
         # after the align the promotion has happened: the next set_pcd pairs (b.moving, new cloud)
         reg.set_pcd(a["y_pos"], a["y_feat"])
         reg.align()
         ell = o["ell"] if kind == "cvo" else float(op.ell_init)
         o2 = oracle.align(b["y_pos"], b["y_feat"], a["y_pos"], a["y_feat"], op, R=o["R"], T=o["T"], ell=ell)
         rot, tr = pose_diff(reg.transform, o2["transform"])
-        assert rot < 2 * POSE_TOL_FLOOR and tr < 2 * POSE_TOL_FLOOR, (rot, tr)
+        assert rot < 2e-3 and tr < 2e-3, (rot, tr)
     finally:
         reg.close()
 
