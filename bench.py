@@ -427,7 +427,7 @@ def main():
     barrier()
     sampler.start()
     launches0 = ctx.kernel_launches
-    kernel_ms, total_iters, list_builds = [], 0, 0
+    kernel_ms, total_iters, list_builds, list_fill = [], 0, 0, (0, 0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations
@@ -436,6 +436,7 @@ def main():
         kernel_ms.append(ctx.last_kernel_ms)
         total_iters += ctx.last_total_iterations
         list_builds += ctx.last_list_builds
+        list_fill = ctx.last_list_fill
     barrier()
     wall_resident = time.perf_counter() - t0
     launches = ctx.kernel_launches - launches0
@@ -498,7 +499,9 @@ def main():
             "config": CONFIG,
             "launch": {"pairs_per_gpu_per_step": P, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "ctas_per_pair": ctx.last_cluster_size, "clusters": ctx.last_num_clusters,
-                       "neighbour_list_builds_per_pair": list_builds / (args.steps * P)},
+                       "neighbour_list_builds_per_pair": list_builds / (args.steps * P),
+                       "list_candidates_per_build": list_fill[0] / max(ctx.last_list_builds, 1),
+                       "list_slots_per_build": list_fill[1] / max(ctx.last_list_builds, 1)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "launches_per_step": e2e_launches / args.steps},
             "gpu_launches": int(launches),

@@ -27,7 +27,7 @@ EXPORTS = [
     "cvo_b200_set_neighbor_lists", "cvo_b200_last_list_builds", "cvo_b200_last_list_refines",
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
-    "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes", "cvo_b200_align_multi",
+    "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes", "cvo_b200_align_multi", "cvo_b200_last_list_fill",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.cvo_b200_replace_moving_images.argtypes = lib.cvo_b200_push_frame_images.argtypes
     lib.cvo_b200_align_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, fp, fp, ip, fp, fp, ip, C.c_int, C.POINTER(Params), fp, ip,
                                          ip, fp]
+    lib.cvo_b200_last_list_fill.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.cvo_b200_neighbor_lists_active.argtypes = [vp]
     lib.cvo_b200_list_scratch_bytes.argtypes = [vp]
     lib.cvo_b200_list_scratch_bytes.restype = C.c_longlong
@@ -348,6 +349,13 @@ class Context:
         self._check(self._lib.cvo_b200_selftest_exp_sek3(self._h, rows.ctypes.data_as(C.POINTER(C.c_float)), len(rows),
                                                          out.ctypes.data_as(C.POINTER(C.c_float))))
         return out[:, :9].reshape(-1, 3, 3), out[:, 9:]
+
+    @property
+    def last_list_fill(self):
+        """(candidates kept, quad slots holding them) of the (x, y) lists built by the last align call."""
+        e, sl = C.c_longlong(0), C.c_longlong(0)
+        self._check(self._lib.cvo_b200_last_list_fill(self._h, C.byref(e), C.byref(sl)))
+        return e.value, sl.value
 
     @property
     def neighbor_lists_active(self):

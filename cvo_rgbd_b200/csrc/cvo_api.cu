@@ -95,7 +95,7 @@ struct cvo_b200_ctx {
     float list_skin = 0.08f;
     float list_shrink = 0.7f;
     float list_refine_min = 1.0f;
-    long long last_list_builds = 0, last_list_refines = 0;
+    long long last_list_builds = 0, last_list_refines = 0, last_xy_entries = 0, last_xy_slots = 0;
 
     float last_ms = 0.f;
     long long launches = 0;
@@ -527,12 +527,14 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_G = G;
     ctx->last_nclusters = ncl;
-    long long total = 0, builds = 0, refines = 0;
+    long long total = 0, builds = 0, refines = 0, xy_entries = 0, xy_slots = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const PairState& st = ctx->h_states[i];
         total += st.n_run;
         builds += st.n_builds;
         refines += st.n_refines;
+        xy_entries += st.xy_entries;
+        xy_slots += st.xy_slots;
         if (RT_io) {
             memcpy(RT_io + (size_t)i * 12, st.R, sizeof(float) * 9);
             memcpy(RT_io + (size_t)i * 12 + 9, st.T, sizeof(float) * 3);
@@ -546,6 +548,8 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     ctx->last_total_iters = total;
     ctx->last_list_builds = builds;
     ctx->last_list_refines = refines;
+    ctx->last_xy_entries = xy_entries;
+    ctx->last_xy_slots = xy_slots;
     if (args.trace) {
         const int n = ctx->h_states[0].n_run < args.trace_cap ? ctx->h_states[0].n_run : args.trace_cap;
         memcpy(trace, ctx->h_trace, sizeof(cvo_b200_iter_rec) * n);
@@ -1228,6 +1232,12 @@ int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_total_iters : 0; }
 long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_builds : 0; }
 long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_refines : 0; }
+int cvo_b200_last_list_fill(const cvo_b200_ctx* ctx, long long* entries, long long* slots) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (entries) *entries = ctx->last_xy_entries;
+    if (slots) *slots = ctx->last_xy_slots;
+    return CVO_B200_OK;
+}
 int cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (!(skin >= 0.f && skin <= 1.f)) return fail_arg(ctx, "skin must be in [0, 1]");

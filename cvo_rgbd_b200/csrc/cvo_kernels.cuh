@@ -113,6 +113,8 @@ struct PairState {
     int n_run;
     int n_builds;  // neighbour-list (re)builds of the (x, y) list during this align()
     int n_refines;  // ... and how often one of the pair's lists was narrowed in place instead (refine_list)
+    int xy_entries;  // summed over this CTA's (x, y) list builds (rank 0 of the cluster): candidates kept ...
+    int xy_slots;    // ... and the slots of the quads that hold them (4 per quad, padding included)
     float tf[16];
     float prev_tf[16];
 };
@@ -160,7 +162,6 @@ struct WarpScratch {
 // Row-sorted compaction of a freshly built (x, y) list (build_list<0>, "quads"): per row of the round how many entries
 // it has, where its first quad sits inside its row tile, and a running cursor; per row tile the first quad.
 struct QuadBuild {
-    int rowCnt[kColChunk];
     int rowQ[kColChunk];
     int rowCur[kColChunk];
     int tileQ[kColTiles + 1];
@@ -183,7 +184,9 @@ struct BuildUnits {  // neighbour-list build, per unit of the round:
     int off[kMaxUnits];  // where its entries sit in the staging area
     int act[kMaxUnits];  // how many it has
     int pos[kMaxUnits];  // their position in the round's flat list
+    int rowCnt[kColChunk];  // (x, y) list: candidates kept per row of the round, counted while the units are evaluated
 };
+static_assert(sizeof(BuildUnits) <= sizeof(double) * kMaxUnits * kUnitAcc, "BuildUnits shares the memory of the on-the-fly unit slots");
 struct OnTheFlyStage {
     FeatStage fs;
     WarpScratch ws[kWorkWarps];
@@ -446,14 +449,22 @@ __device__ void prepare_iter(Smem& sm, const KParams& kp, float d2c_thres) {
             nRt[i * 3 + j] = -R[j * 3 + i];
         }
     mat3_vec(nRt, T, &ic.tf[9]);
-    const double l = (double)sm.st.ell;
-    ic.d2_thres = (float)(-2.0 * l * l * (double)kp.log_ratio);
     ic.d2c_thres = d2c_thres;
-    ic.inv2l2 = (float)(1.0 / (2.0 * l * l));
-    ic.c1 = (float)(1.4426950408889634 / (2.0 * l * l));
-    ic.ell = sm.st.ell;
-    const float ell3 = __fmul_rn(__fmul_rn(sm.st.ell, sm.st.ell), sm.st.ell);  // src/adaptive_cvo.cpp:171
-    ic.inv_ell3 = 1.0f / ell3;
+    // Everything below depends on the length-scale only: f64 divisions on one thread, recomputed when ell has changed
+    // (never in the fixed-ell benchmark schedule, three times in the stock cvo schedule).  ic.ell < 0: a new pair.
+    if (ic.ell != sm.st.ell) {
+        const double l = (double)sm.st.ell;
+        const double inv = 1.0 / (2.0 * l * l);
+        ic.d2_thres = (float)(-2.0 * l * l * (double)kp.log_ratio);
+        ic.inv2l2 = (float)inv;
+        ic.c1 = (float)(1.4426950408889634 / (2.0 * l * l));
+        ic.ell = sm.st.ell;
+        const float ell3 = __fmul_rn(__fmul_rn(sm.st.ell, sm.st.ell), sm.st.ell);  // src/adaptive_cvo.cpp:171
+        ic.inv_ell3 = 1.0f / ell3;
+        ic.temp_coef = (float)inv;  // src/cvo.cpp:241
+        ic.m2t = (float)(-2.0 * (double)ic.temp_coef);
+        ic.p2t = (float)(2.0 * (double)ic.temp_coef);
+    }
 }
 
 // tail of compute_flow (src/cvo.cpp:208-209) + the per-iteration constants of compute_step_size (:215-241)
@@ -464,10 +475,7 @@ __device__ void finalize_flow(Smem& sm) {
         ic.omega[t] = (float)sm.sum[kFlowOff + ACC_W0 + t];
         ic.v[t] = (float)sm.sum[kFlowOff + ACC_V0 + t];
     }
-    const double l = (double)sm.st.ell;
-    ic.temp_coef = (float)(1.0 / (2.0 * l * l));  // src/cvo.cpp:241
-    ic.m2t = (float)(-2.0 * (double)ic.temp_coef);
-    ic.p2t = (float)(2.0 * (double)ic.temp_coef);
+    // (temp_coef = 1 / (2 l^2), src/cvo.cpp:241, and its multiples: prepare_iter, with the other functions of ell)
 }
 
 // poly_solver + root selection (src/cvo.cpp:53-69,291-307): smallest positive real root of
@@ -533,7 +541,11 @@ __device__ float step_from_coeffs(double B, double C, double D, double E, float 
                 const double f = ((x + a2) * x + a1) * x + a0;
                 const double fp = (3.0 * x + 2.0 * a2) * x + a1;
                 if (fp == 0.0 || !isfinite(f)) break;
-                const double dx = f / fp;
+                // f / fp through an f32 reciprocal refined once in f64 (relative error ~1e-14; Newton corrects itself): the
+                // IEEE f64 division is the longest dependent chain of this loop
+                double inv = (double)__frcp_rn((float)fp);
+                inv = inv * (2.0 - fp * inv);
+                const double dx = isfinite(inv) ? f * inv : f / fp;
                 const double xn = x - dx;
                 if (!isfinite(xn)) break;
                 x = xn;
@@ -587,7 +599,13 @@ __device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_r
     const float ell_used = st.ell;
     bool stop = false;
     int status = CVO_B200_STATUS_MAX_ITER;
-    const float w2 = dot3f(ic.omega, ic.omega), v2 = dot3f(ic.v, ic.v);
+    // the twist and the pose in registers: one round of shared-memory loads instead of one per use
+    float om[3], vv[3], Rc[9], Tc[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { om[t] = ic.omega[t]; vv[t] = ic.v[t]; Tc[t] = st.T[t]; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) Rc[t] = st.R[t];
+    const float w2 = dot3f(om, om), v2 = dot3f(vv, vv);
     if (!(isfinite(w2) && isfinite(v2))) {
         stop = true;
         status = CVO_B200_STATUS_NAN;
@@ -595,9 +613,8 @@ __device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_r
     if (!stop && stops) {
         bool small;
         if (kp.mode == CVO_B200_MODE_ACVO) {  // src/adaptive_cvo.cpp:509, norms in f64
-            const double dw = sqrt((double)ic.omega[0] * ic.omega[0] + (double)ic.omega[1] * ic.omega[1] +
-                                   (double)ic.omega[2] * ic.omega[2]);
-            const double dv = sqrt((double)ic.v[0] * ic.v[0] + (double)ic.v[1] * ic.v[1] + (double)ic.v[2] * ic.v[2]);
+            const double dw = sqrt((double)om[0] * om[0] + (double)om[1] * om[1] + (double)om[2] * om[2]);
+            const double dv = sqrt((double)vv[0] * vv[0] + (double)vv[1] * vv[1] + (double)vv[2] * vv[2]);
             small = dw < (double)kp.eps && dv < (double)kp.eps;
         } else {  // src/cvo.cpp:380
             small = sqrtf(w2) < kp.eps && sqrtf(v2) < kp.eps;
@@ -609,11 +626,11 @@ __device__ void update_state(Smem& sm, const KParams& kp, int k, cvo_b200_iter_r
     }
     if (!stop) {
         float dR[9], dT[3], RdT[3], Rn[9];
-        exp_sek3(ic.omega, ic.v, step, dR, dT);  // src/cvo.cpp:391
-        mat3_vec(st.R, dT, RdT);
+        exp_sek3(om, vv, step, dR, dT);  // src/cvo.cpp:391
+        mat3_vec(Rc, dT, RdT);
 #pragma unroll
-        for (int t = 0; t < 3; ++t) st.T[t] = __fadd_rn(RdT[t], st.T[t]);  // :398
-        mat3_mul(st.R, dR, Rn);                                             // :399
+        for (int t = 0; t < 3; ++t) st.T[t] = __fadd_rn(RdT[t], Tc[t]);  // :398
+        mat3_mul(Rc, dR, Rn);                                           // :399
 #pragma unroll
         for (int t = 0; t < 9; ++t) st.R[t] = Rn[t];
         if (stops) {
@@ -1494,34 +1511,40 @@ __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws
 }
 // appends the kept candidates of one warp-wide batch in lane order
 // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
-__device__ __forceinline__ void build_append(bool keep, const uint2& e, uint2* out, int limit, int& cursor) {
+template <int SELF>
+__device__ __forceinline__ void build_append(Smem& sm, bool keep, const uint2& e, uint2* out, int limit, int& cursor) {
     const int lane = threadIdx.x & 31;
+    if (SELF == 0) {  // per-row counts for the row-sorted compaction: one shared atomic per distinct row of the batch
+        const int r = keep ? (int)(e.x >> 18) : -1 - lane;
+        const unsigned m = __match_any_sync(0xffffffffu, r);
+        if (keep && lane == __ffs(m) - 1) atomicAdd(&sm.u.of.bu.rowCnt[r], __popc(m));
+    }
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
     if (keep && cursor + kTile <= limit) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
     cursor += __popc(b);
 }
 template <int SELF>
-__device__ __forceinline__ void build_eval(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+__device__ __forceinline__ void build_eval(Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
                                            uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2* out, int limit,
                                            int& cursor) {
     uint2 e;
     const bool keep = build_test<SELF>(sm, ws, kp, L, ent, live, row_off, yy_row_min, e);
-    build_append(keep, e, out, limit, cursor);
+    build_append<SELF>(sm, keep, e, out, limit, cursor);
 }
 // two batches at once: their loads and arithmetic interleave (the evaluation is latency-bound on one batch)
 template <int SELF>
-__device__ __forceinline__ void build_eval2(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
+__device__ __forceinline__ void build_eval2(Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
                                             uint32_t ent0, uint32_t ent1, uint32_t row_off, int yy_row_min, uint2* out,
                                             int limit, int& cursor) {
     uint2 e0, e1;
     const bool k0 = build_test<SELF>(sm, ws, kp, L, ent0, true, row_off, yy_row_min, e0);
     const bool k1 = build_test<SELF>(sm, ws, kp, L, ent1, true, row_off, yy_row_min, e1);
-    build_append(k0, e0, out, limit, cursor);
-    build_append(k1, e1, out, limit, cursor);
+    build_append<SELF>(sm, k0, e0, out, limit, cursor);
+    build_append<SELF>(sm, k1, e1, out, limit, cursor);
 }
 
 template <int SELF>
-__device__ __forceinline__ int build_unit_write(const Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
+__device__ __forceinline__ int build_unit_write(Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
                                                 const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int yy_row_min,
                                                 int ct_begin, int ct_end, uint2* out, int limit) {
     const int lane = threadIdx.x & 31;
@@ -1607,6 +1630,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             }
             stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
             if (threadIdx.x == 0) sm.next_unit = 0;
+            if (SELF == 0)
+                for (int i = threadIdx.x; i < ntile * kTile; i += kThreads) sm.u.of.bu.rowCnt[i] = 0;
             __syncthreads();
             CVO_PHASE(6)
             int wcur = 0;  // entries this warp has staged in this round
@@ -2099,6 +2124,11 @@ template <int NV>
 __device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& cluster, const double* src, int buf,
                                                   int dst_off) {
     const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    if (G == 1) {  // one CTA per pair (the batch benchmark): the CTA's totals ARE the pair's totals (0.0 + x == x)
+        if (threadIdx.x < NV) sm.sum[dst_off + threadIdx.x] = src[threadIdx.x];
+        __syncthreads();
+        return;
+    }
     if (threadIdx.x < NV) {
         const double v = src[threadIdx.x];
         for (int r = 0; r < G; ++r) {
@@ -2106,8 +2136,7 @@ __device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& c
             *dst = v;
         }
     }
-    if (G == 1) __syncthreads();  // one CTA per pair: no need for the (slower) hardware cluster barrier
-    else cluster.sync();
+    cluster.sync();
     if (threadIdx.x < NV) {
         double t = 0.0;
         for (int r = 0; r < G; ++r) t += sm.xchg[buf][r][threadIdx.x];
@@ -2162,7 +2191,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             sm.st.n_run = 0;
             sm.st.n_builds = 0;
             sm.st.n_refines = 0;
+            sm.st.xy_entries = sm.st.xy_slots = 0;
             sm.done = 0;
+            sm.ic.ell = -1.f;  // the constants cached by length-scale (prepare_iter) belong to the previous pair
             sm.colTag.serial = sm.rowTag.serial = -2;
 #pragma unroll
             for (int i = 0; i < LIST_KINDS; ++i) sm.lst[i].valid = sm.lst[i].need = 0;
@@ -2294,6 +2325,7 @@ __global__ void __launch_bounds__(kThreads, 1) inner_product_kernel(const InnerA
         for (int i = 0; i < 9; ++i) sm.st.R[i] = (i % 4 == 0) ? 1.f : 0.f;
         sm.st.T[0] = sm.st.T[1] = sm.st.T[2] = 0.f;
         sm.st.ell = args.ell;
+        sm.ic.ell = -1.f;
         prepare_iter(sm, args.kp, args.kp.d2c_thres);
     }
     cluster.sync();  // (also: every CTA of the cluster runs before the all-reduce writes into its shared memory)

@@ -266,11 +266,11 @@ __device__ __forceinline__ void stage_row_step_terms(Smem& sm, int n) {
 
 // Row-sorted compaction of the round that build_list<0> has just evaluated: the units' staged candidates
 // ((row, col) byte offsets, t_c), unit by unit, become the round's quads.
-//   count    every row tile is taken by ONE warp, which walks the tile's units in unit order and counts the candidates of
-//            each of its 32 rows (the lanes of a batch that hold the same row are found with match.any);
+//   count    (done while the units were evaluated, build_append: one shared atomic per distinct row of a batch, found
+//            with match.any; the counts do not depend on the order)
 //   place    quads per row -> exclusive scan inside the tile -> exclusive scan over the tiles -> the round's region in
 //            the list area (ntc | cols | row arrays, padded to a whole trip with quads that can never pass);
-//   scatter  the same warp walks the same units in the same order: a candidate's slot is its row's cursor plus its rank
+//   scatter  every row tile is taken by ONE warp, which walks the tile's units in unit order: a candidate's slot is its row's cursor plus its rank
 //            among the batch's lanes with that row.  Rows are private to the warp, so no atomics are involved and the
 //            list is a pure function of the inputs, whichever warp evaluated which unit.
 // Returns false (and sets sm.lst_ovf) if the region does not fit the list area.
@@ -281,22 +281,9 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
     const BuildUnits& bu = sm.u.of.bu;
     const float ninf = -__int_as_float(0x7f800000);
     if (sm.lst_ovf) return false;  // a unit outgrew its staging segment: its tail was never stored (stable since the barrier)
-    // ---- count
+    // ---- quads per row (the rows were counted while the units were evaluated, build_append) -> offsets inside the tile
     for (int t = warp; t < ntile; t += kWarps) {
-        qb.rowCnt[t * kTile + lane] = 0;
-        __syncwarp();
-        for (int sg = 0; sg < Sb; ++sg) {
-            const int u = t * Sb + sg, c = bu.act[u];
-            const uint2* src = lr.staging + bu.off[u];
-            for (int i0 = 0; i0 < c; i0 += 32) {
-                const bool have = i0 + lane < c;
-                const int r = have ? (int)(__ldcg(src + i0 + lane).x >> 18) - t * kTile : kTile + lane;  // idle lanes: singletons
-                const unsigned m = __match_any_sync(0xffffffffu, r);
-                if (have && lane == __ffs(m) - 1) qb.rowCnt[t * kTile + r] += __popc(m);
-                __syncwarp();
-            }
-        }
-        const int q = (qb.rowCnt[t * kTile + lane] + 3) >> 2;
+        const int q = (bu.rowCnt[t * kTile + lane] + 3) >> 2;
         int excl, total;
         warp_scan_count(q, lane, excl, total);
         qb.rowQ[t * kTile + lane] = excl;
@@ -332,6 +319,10 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
                 sm.lround[kind][round] = make_uint2(at, (unsigned)nq);
                 sm.lst_base = (int)at;
                 sm.lst_used = (int)(at + units16);
+                int kept = 0;  // work accounting (cvo_b200_last_list_fill)
+                for (int u = 0; u < ntile * Sb; ++u) kept += bu.act[u];
+                sm.st.xy_entries += kept;
+                sm.st.xy_slots += 4 * nq;
             } else {
                 sm.lst_ovf = 1;
             }
@@ -353,30 +344,38 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
             for (int sg = 0; sg < Sb; ++sg) {
                 const int u = t * Sb + sg, c = bu.act[u];
                 const uint2* src = lr.staging + bu.off[u];
-                for (int i0 = 0; i0 < c; i0 += 32) {
-                    const bool have = i0 + lane < c;
-                    const uint2 e = have ? __ldcg(src + i0 + lane) : make_uint2(0u, 0u);
-                    const int r = have ? (int)(e.x >> 18) - t * kTile : kTile + lane;
-                    const unsigned m = __match_any_sync(0xffffffffu, r);
-                    const int cur = have ? qb.rowCur[t * kTile + r] : 0;
-                    __syncwarp();
-                    if (have && lane == __ffs(m) - 1) qb.rowCur[t * kTile + r] = cur + __popc(m);
-                    __syncwarp();
-                    if (have) {
-                        // SLOT-MAJOR inside the row: candidate `pos` of a row with n quads is slot pos / n of quad pos % n, so
-                        // that the lanes holding consecutive quads of a row read consecutive candidates -- consecutive
-                        // columns, different shared-memory banks -- in each of their four slots
-                        const int pos = cur + __popc(m & ((1u << lane) - 1u));
-                        const int nqr = (qb.rowCnt[t * kTile + r] + 3) >> 2;
-                        const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
-                        ntc[q * 4 + slot] = -__uint_as_float(e.y);
-                        cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
-                        if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
+                for (int i1 = 0; i1 < c; i1 += 128) {  // four batches of loads in flight: the walk is latency-bound
+                    uint2 ev[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ev[j] = (i1 + 32 * j + lane < c) ? __ldcg(src + i1 + 32 * j + lane) : make_uint2(0u, 0u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i0 = i1 + 32 * j;
+                        if (i0 >= c) break;
+                        const bool have = i0 + lane < c;
+                        const uint2 e = ev[j];
+                        const int r = have ? (int)(e.x >> 18) - t * kTile : kTile + lane;  // idle lanes: singletons
+                        const unsigned m = __match_any_sync(0xffffffffu, r);
+                        const int cur = have ? qb.rowCur[t * kTile + r] : 0;
+                        __syncwarp();
+                        if (have && lane == __ffs(m) - 1) qb.rowCur[t * kTile + r] = cur + __popc(m);
+                        __syncwarp();
+                        if (have) {
+                            // SLOT-MAJOR inside the row: candidate `pos` of a row with n quads is slot pos / n of quad pos % n,
+                            // so that the lanes holding consecutive quads of a row read consecutive candidates --
+                            // consecutive columns, different shared-memory banks -- in each of their four slots
+                            const int pos = cur + __popc(m & ((1u << lane) - 1u));
+                            const int nqr = (bu.rowCnt[t * kTile + r] + 3) >> 2;
+                            const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
+                            ntc[q * 4 + slot] = -__uint_as_float(e.y);
+                            cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
+                            if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
+                        }
                     }
                 }
             }
             // the unused slots of every row's quads
-            const int cnt = qb.rowCnt[t * kTile + lane], nqr = (cnt + 3) >> 2;
+            const int cnt = bu.rowCnt[t * kTile + lane], nqr = (cnt + 3) >> 2;
             for (int pos = cnt; pos < 4 * nqr; ++pos) {
                 const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + lane] + (pos - slot * nqr);
                 ntc[q * 4 + slot] = ninf;

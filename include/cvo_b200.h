@@ -235,6 +235,9 @@ long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx);
 /* ... and of the times one of the pair's lists ((x, y), or acvo's (x, x) / (y, y)) was narrowed in place after ell
  * shrank: a filter of the old list instead of an all-pairs sweep. */
 long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx);
+/* Work accounting of the (x, y) lists of the last align call, summed over its pairs and their list builds (rank-0 CTA
+ * of every cluster): candidates kept, and the quad slots that hold them (four per quad, padding included). */
+int       cvo_b200_last_list_fill(const cvo_b200_ctx* ctx, long long* entries, long long* slots);
 int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
 /* 1 if the last align used (or the next will use) neighbour lists; 0 if they are disabled or their scratch could not
  * be allocated (every pass then runs on the fly: same results, several times slower). */

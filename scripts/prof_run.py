@@ -12,4 +12,4 @@ gp = capi.default_params('cvo'); gp.ell_policy = capi.ELL_FIXED; gp.ell_init = 0
 ctx.set_cluster_size(G)
 for rep in range(2):
     ctx.align(list(range(P)), gp)
-print('kernel_ms', ctx.last_kernel_ms)
+print('kernel_ms', ctx.last_kernel_ms, 'list builds', ctx.last_list_builds, 'fill (entries, slots)', ctx.last_list_fill)
