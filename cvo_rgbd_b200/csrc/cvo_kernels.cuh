@@ -45,6 +45,9 @@ namespace cg = cooperative_groups;
 #ifndef CVO_BUILD_SEGMENTS
 #define CVO_BUILD_SEGMENTS 4
 #endif
+#ifndef CVO_QUADS_PER_LANE
+#define CVO_QUADS_PER_LANE 2
+#endif
 constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;
 // The on-the-fly passes and the list builds keep per-warp queues and row tiles in shared memory: at most 16 warps

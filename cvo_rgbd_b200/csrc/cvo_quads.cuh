@@ -136,16 +136,20 @@ __device__ __noinline__ float quad_exact1(const Smem& sm, const KParams& kp, con
     if (!(d2 < ic.d2_thres)) a = 0.f;  // thirdparty/nanoflann.hpp:249-253
     return a;
 }
-__device__ __forceinline__ void redecide(const Smem& sm, const KParams& kp, const ListSrc& src, const Quad& q, bool near, QuadGeom& g) {
-    if (__any_sync(0xffffffffu, near)) {
-        if (near) {  // padding candidates (-t_c = -inf) stay at a = 0
-            const float ninf = -__int_as_float(0x7f800000);
-            g.aa.x = q.ntc.x > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.x & 0xffffu, g.d2a.x) : 0.f;
-            g.aa.y = q.ntc.y > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.x >> 16, g.d2a.y) : 0.f;
-            g.ab.x = q.ntc.z > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.y & 0xffffu, g.d2b.x) : 0.f;
-            g.ab.y = q.ntc.w > ninf ? quad_exact1(sm, kp, src, q.row, q.cols.y >> 16, g.d2b.y) : 0.f;
-        }
+// Called (warp-uniformly) when some lane of the warp saw a candidate inside the band: every lane re-decides the candidates
+// of ITS quad that sit inside the band.  Padding candidates (-t_c = -inf, a = 0) are far outside it.
+__device__ __forceinline__ void redecide(const Smem& sm, const HotConsts& hc, const KParams& kp, const ListSrc& src, const Quad& q, QuadGeom& g) {
+    const float nt[4] = {q.ntc.x, q.ntc.y, q.ntc.z, q.ntc.w};
+    const float d2[4] = {g.d2a.x, g.d2a.y, g.d2b.x, g.d2b.y};
+    const uint32_t cb[4] = {q.cols.x & 0xffffu, q.cols.x >> 16, q.cols.y & 0xffffu, q.cols.y >> 16};
+    float a[4] = {g.aa.x, g.aa.y, g.ab.x, g.ab.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float fast = __fmul_rn(kp.s2cs2, exp2f_approx(fmaf(d2[e], -hc.c1, nt[e])));
+        if (fabsf(fast - kp.sp_thres) < kp.sp_band) a[e] = quad_exact1(sm, kp, src, q.row, cb[e], d2[e]);
     }
+    g.aa = make_float2(a[0], a[1]);
+    g.ab = make_float2(a[2], a[3]);
 }
 
 // ---- FLOW (src/cvo.cpp:164-210; acvo: + the (x, y) term of the length-scale gradient, src/adaptive_cvo.cpp:202,228) ----
@@ -430,39 +434,48 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             src.row_base = row_first;
             src.col_base = col_first;
             const quads::Round rd = quads::round_ref(lr, sm.lround[LIST_XY][round], lane);
-            int t = warp;
-            if (t < rd.ntrip) {
-                // three register sets rotate between "being processed" and "being loaded" (never copied): the loads run two
-                // trips ahead of the arithmetic, the L2 prefetch a few trips ahead of the loads
-                quads::Quad qa = quads::load_quad(rd, t, lane), qb2 = quads::load_quad(rd, t + kWarps, lane), qc;
-#define CVO_QUAD_TRIP(q)                                                                     \
-    {                                                                                        \
-        quads::QuadGeom g;                                                                   \
-        const bool near = quads::quad_geom(sm, hc, kp, q, g);                                \
-        quads::redecide(sm, kp, src, q, near, g);                                            \
-        if (KIND == PASS_STEP) quads::step_quad(sm, sc, q.row, g, acc);                      \
-        else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                   \
-    }
+            // A warp takes CVO_QUADS_PER_LANE consecutive trips of its share at a time (the bodies of a step are independent:
+            // more instruction-level parallelism for the dependent chains of a quad), with the next step's quads already
+            // in registers and the lines of the step after in flight to L2.
+            constexpr int QPL = CVO_QUADS_PER_LANE;
+            const int nstep = (rd.ntrip + QPL - 1) / QPL;  // steps of QPL trips; a warp takes steps warp, warp + kWarps, ...
+            int st = warp;
+            if (st < nstep) {
+                quads::Quad cur[QPL], nxt[QPL];
+#pragma unroll
+                for (int j = 0; j < QPL; ++j) cur[j] = quads::load_quad(rd, st * QPL + j, lane);
 #pragma unroll 1
                 while (true) {
-                    qc = quads::load_quad(rd, t + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
-                    CVO_QUAD_TRIP(qa)
-                    t += kWarps;
-                    if (t >= rd.ntrip) break;
-                    qa = quads::load_quad(rd, t + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
-                    CVO_QUAD_TRIP(qb2)
-                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 2 quads (one or two rows) per f32 partial
-                    t += kWarps;
-                    if (t >= rd.ntrip) break;
-                    qb2 = quads::load_quad(rd, t + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, t + (2 + kPrefetchTrips) * kWarps, lane);
-                    CVO_QUAD_TRIP(qc)
-                    t += kWarps;
-                    if (t >= rd.ntrip) break;
+                    const int sn = st + kWarps;
+#pragma unroll
+                    for (int j = 0; j < QPL; ++j) {
+                        nxt[j] = quads::load_quad(rd, sn * QPL + j, lane);
+                        quads::prefetch_trip(rd, (sn + kPrefetchTrips * kWarps) * QPL + j, lane);
+                    }
+                    quads::QuadGeom g[QPL];
+                    bool near = false;
+#pragma unroll
+                    for (int j = 0; j < QPL; ++j) {
+                        const bool live = st * QPL + j < rd.ntrip;  // the last step of a round may be short
+                        const bool nj = quads::quad_geom(sm, hc, kp, cur[j], g[j]);
+                        if (!live) g[j].aa = g[j].ab = make_float2(0.f, 0.f);
+                        near |= nj && live;
+                    }
+                    if (__any_sync(0xffffffffu, near)) {
+#pragma unroll
+                        for (int j = 0; j < QPL; ++j) quads::redecide(sm, hc, kp, src, cur[j], g[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < QPL; ++j) {
+                        if (KIND == PASS_STEP) quads::step_quad(sm, sc, cur[j].row, g[j], acc);
+                        else quads::flow_quad<KIND, STATS>(hc, kp, g[j], fp);
+                    }
+                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= QPL quads per f32 partial
+                    st = sn;
+                    if (st >= nstep) break;
+#pragma unroll
+                    for (int j = 0; j < QPL; ++j) cur[j] = nxt[j];
                 }
-#undef CVO_QUAD_TRIP
             }
             if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
         }

@@ -40,6 +40,14 @@ def pose_diff(Ta, Tb):
     return rot_angle(Ta[:3, :3], Tb[:3, :3]), float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
 
 
+def iters_comparable(a, b):
+    """Exit iterations of two correct executions: the stop tests fire on 1e-5-sized quantities (eps, eps_2), so the exit
+    iteration is chaotic -- the reference's own align() and its restatement differ by up to 2x on the same pair (59 vs
+    45, tests/golden) while their poses agree to 1e-5.  Bounded here to a factor of two plus a slack of 15."""
+    a, b = int(a), int(b)
+    return abs(a - b) <= max(15, max(a, b) // 2)
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

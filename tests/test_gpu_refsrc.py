@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import POSE_TOL_FLOOR, POSE_TOL_NORTH_STAR, pose_diff
+from conftest import POSE_TOL_FLOOR, POSE_TOL_NORTH_STAR, pose_diff, iters_comparable
 from cvo_rgbd_b200 import capi, frontend, synth
 from test_refsrc_golden import GOLD, R0, T0, _clouds, _pair, check_eval_against_reference
 
@@ -44,7 +44,7 @@ def test_device_align_equals_reference_align(gpu_ctx, name):
     tol = POSE_TOL_NORTH_STAR if name in ("cfg1", "cfg2_stock", "cfg3") else POSE_TOL_FLOOR
     assert rot < tol and tr < tol, (name, rot, tr, g["iters"], case["iters"])
     assert g["status"] in (capi.STATUS_CONVERGED_TWIST, capi.STATUS_CONVERGED_UPDATE)
-    assert abs(g["iters"] - case["iters"]) <= max(15, case["iters"] // 3)
+    assert iters_comparable(g["iters"], case["iters"])
     want0 = case["first_iterations"][0]  # iteration 0: identical inputs on both sides
     got0 = g["trace"][0]
     assert abs(got0["nnz"] - want0["nnz"]) <= 2 and abs(got0["ell"] - want0["ell"]) < 1e-7
@@ -89,7 +89,7 @@ def test_frontend_sequence_equals_reference_driver_loop(kind):
             if k:
                 rot, tr = pose_diff(reg.transform, np.array(case["transform"][k]))
                 assert rot < 2 * POSE_TOL_NORTH_STAR * k and tr < 2 * POSE_TOL_NORTH_STAR * k, (k, rot, tr)
-                assert abs(reg.iter - case["iter"][k]) <= max(15, case["iter"][k] // 2)
+                assert iters_comparable(reg.iter, case["iter"][k])
     finally:
         reg.close()
 
