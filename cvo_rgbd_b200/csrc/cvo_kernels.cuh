@@ -792,12 +792,23 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
         tma_bulk_g2s(sm.u.of.fs.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
     }
     const float* tf12 = sm.ic.tf;
-    for (int i = threadIdx.x; i < ntiles * kTile; i += kThreads) {
+    // all of a thread's points are requested before the first is used: one memory latency per chunk instead of one per point
+    constexpr int kPerThread = (kColChunk + kThreads - 1) / kThreads;
+    float4 pre[kPerThread];
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+        const int i = threadIdx.x + u * kThreads;
+        pre[u] = (i < ntiles * kTile && base + i < c.n) ? __ldg(c.g + base + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+        const int i = threadIdx.x + u * kThreads;
+        if (i >= ntiles * kTile) break;
         const int p = base + i;
         bool valid = p < c.n;
         float4 g;
         if (valid) {
-            g = __ldg(c.g + p);
+            g = pre[u];
             if (tf) apply_tf(tf12, g.x, g.y, g.z);
             // a point with a NaN / Inf coordinate is nobody's neighbour (d2 < thr is false): move it far away so that
             // the branch-free bodies only ever multiply their zero weights with finite numbers
