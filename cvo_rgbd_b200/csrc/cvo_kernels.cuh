@@ -46,7 +46,7 @@ namespace cg = cooperative_groups;
 #define CVO_BUILD_SEGMENTS 4
 #endif
 #ifndef CVO_QUADS_PER_LANE
-#define CVO_QUADS_PER_LANE 2
+#define CVO_QUADS_PER_LANE 1
 #endif
 constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;

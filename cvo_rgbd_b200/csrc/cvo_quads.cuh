@@ -79,6 +79,9 @@ struct Quad {
     uint32_t row;
 };
 __device__ __forceinline__ Quad load_quad(const Round& r, int trip, int lane) {
+#ifdef CVO_EXP_SAMETRIP  // timing experiment only (wrong results): every trip re-reads the round's first trips (cache hits)
+    trip &= 15;
+#endif
     const int q = min(trip, r.ntrip - 1) * kQuadTrip + lane;  // loads past the warp's last trip are clamped to it
     Quad v;
     v.ntc = __ldcg(r.ntc + q);
@@ -431,6 +434,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
                 sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = sm.serial;
                 sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = -1;
             }
+            CVO_PHASE(15)  // instrumented variant: staging of both passes
             src.row_base = row_first;
             src.col_base = col_first;
             const quads::Round rd = quads::round_ref(lr, sm.lround[LIST_XY][round], lane);
@@ -480,6 +484,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
         }
     }
+    CVO_PHASE(KIND == PASS_STEP ? 4 : 2)  // instrumented variant: warp 0's trips; what follows is the wait for the slowest warp
     warp_sum_multi<NV>(acc, lane);
     if (NV >= 8) {
         if ((lane & 3) == 0) sm.u.ls.warpTot[warp][multi_value_index(lane)] = acc[0];
@@ -499,4 +504,5 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
         sm.blockTot[threadIdx.x] = tt;
     }
     __syncthreads();
+    CVO_PHASE(8)  // instrumented variant: reduction tail of both passes (incl. waiting for the slowest warp)
 }

@@ -14,8 +14,8 @@ out = (C.c_ulonglong * 16)()
 lib.cvo_b200_phase_clocks(out, 1)
 ctx.align(list(range(296)), gp)
 lib.cvo_b200_phase_clocks(out, 1)
-v = np.array(out[:15], float)
-names = ["(loop top)", "list build: rest", "FLOW pass", "allreduce + finalize_flow", "STEP pass", "barrier after the serial section", "build: stage", "build: evaluate sweep", "build: scan", "build: compaction copy", "serial: all-reduce of B..E", "serial: update_state after the step", "serial: prepare_iter", "serial: list_policy", "serial: step_from_coeffs"]
+v = np.array(out[:16], float)
+names = ["(loop top)", "list build: rest", "FLOW pass (trips of warp 0)", "allreduce + finalize_flow", "STEP pass (trips of warp 0)", "barrier after the serial section", "build: stage", "build: evaluate sweep", "list passes: tail (slowest warp + reduction)", "build: compaction copy", "serial: all-reduce of B..E", "serial: update_state after the step", "serial: prepare_iter", "serial: list_policy", "serial: step_from_coeffs", "list passes: staging"]
 print("kernel_ms", ctx.last_kernel_ms, "total Mcycles on CTA 0:", v.sum() / 1e6)
 for n, x in zip(names, v):
     print("%-45s %8.2f Mcycles  %5.1f %%" % (n, x / 1e6, 100 * x / v.sum()))
