@@ -795,10 +795,22 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
     // all of a thread's points are requested before the first is used: one memory latency per chunk instead of one per point
     constexpr int kPerThread = (kColChunk + kThreads - 1) / kThreads;
     float4 pre[kPerThread];
+#ifdef CVO_CLOUD_EVICT_LAST
+    unsigned long long l2_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
+#endif
 #pragma unroll
     for (int u = 0; u < kPerThread; ++u) {
         const int i = threadIdx.x + u * kThreads;
-        pre[u] = (i < ntiles * kTile && base + i < c.n) ? __ldg(c.g + base + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < ntiles * kTile && base + i < c.n) {
+#ifdef CVO_CLOUD_EVICT_LAST  // the clouds are re-read every iteration while the lists stream through L2 between two uses
+            asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(pre[u].x), "=f"(pre[u].y), "=f"(pre[u].z), "=f"(pre[u].w) : "l"(c.g + base + i), "l"(l2_keep));
+#else
+            pre[u] = __ldg(c.g + base + i);
+#endif
+        }
     }
 #pragma unroll
     for (int u = 0; u < kPerThread; ++u) {

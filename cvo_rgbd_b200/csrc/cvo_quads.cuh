@@ -84,8 +84,15 @@ __device__ __forceinline__ Quad load_quad(const Round& r, int trip, int lane) {
 #endif
     const int q = min(trip, r.ntrip - 1) * kQuadTrip + lane;  // loads past the warp's last trip are clamped to it
     Quad v;
+#ifdef CVO_LIST_EVICT_FIRST
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.ntc.x), "=f"(v.ntc.y), "=f"(v.ntc.z), "=f"(v.ntc.w) : "l"(r.ntc + q), "l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.cols.x), "=r"(v.cols.y) : "l"(r.cols + q), "l"(pol));
+#else
     v.ntc = __ldcg(r.ntc + q);
     v.cols = __ldcg(r.cols + q);
+#endif
     v.row = (uint32_t)__ldcg(r.row + q);
     return v;
 }
@@ -373,7 +380,8 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
                             // consecutive columns, different shared-memory banks -- in each of their four slots
                             const int pos = cur + __popc(m & ((1u << lane) - 1u));
                             const int nqr = (bu.rowCnt[t * kTile + r] + 3) >> 2;
-                            const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
+                            const int slot = (pos >= nqr) + (pos >= 2 * nqr) + (pos >= 3 * nqr);  // pos / nqr, pos < 4 nqr
+                            const int q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
                             ntc[q * 4 + slot] = -__uint_as_float(e.y);
                             cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
                             if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
@@ -444,7 +452,40 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             constexpr int QPL = CVO_QUADS_PER_LANE;
             const int nstep = (rd.ntrip + QPL - 1) / QPL;  // steps of QPL trips; a warp takes steps warp, warp + kWarps, ...
             int st = warp;
-            if (st < nstep) {
+            if (QPL == 1 && st < nstep) {
+                // one quad per lane per trip: three register sets rotate between "being processed" and "being loaded" (never
+                // copied), so the loads run TWO trips ahead of the arithmetic and the L2 prefetch a few trips ahead of them
+                quads::Quad qa = quads::load_quad(rd, st, lane), qb2 = quads::load_quad(rd, st + kWarps, lane), qc;
+#define CVO_QUAD_TRIP(q)                                                                       \
+    {                                                                                          \
+        quads::QuadGeom g;                                                                     \
+        const bool near = quads::quad_geom(sm, hc, kp, q, g);                                  \
+        if (__any_sync(0xffffffffu, near)) quads::redecide(sm, hc, kp, src, q, g);             \
+        if (KIND == PASS_STEP) quads::step_quad(sm, sc, q.row, g, acc);                        \
+        else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                     \
+    }
+#pragma unroll 1
+                while (true) {
+                    qc = quads::load_quad(rd, st + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qa)
+                    st += kWarps;
+                    if (st >= nstep) break;
+                    qa = quads::load_quad(rd, st + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qb2)
+                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 2 quads (one or two rows) per f32 partial
+                    st += kWarps;
+                    if (st >= nstep) break;
+                    qb2 = quads::load_quad(rd, st + 2 * kWarps, lane);
+                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    CVO_QUAD_TRIP(qc)
+                    st += kWarps;
+                    if (st >= nstep) break;
+                }
+#undef CVO_QUAD_TRIP
+                if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
+            } else if (st < nstep) {
                 quads::Quad cur[QPL], nxt[QPL];
 #pragma unroll
                 for (int j = 0; j < QPL; ++j) cur[j] = quads::load_quad(rd, st * QPL + j, lane);
