@@ -1072,9 +1072,9 @@ int cvo_b200_reset_slot(cvo_b200_ctx* ctx, int slot) {
 
 #ifdef CVO_PHASE_CLOCKS
 int cvo_b200_phase_clocks(unsigned long long* out16, int reset) {
-    cudaMemcpyFromSymbol(out16, g_phase_clocks, sizeof(unsigned long long) * 16);
+    cudaMemcpyFromSymbol(out16, g_phase_clocks, sizeof(unsigned long long) * 24);  // (the caller passes 24 slots)
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[24] = {0};
         cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z));
     }
     return 0;

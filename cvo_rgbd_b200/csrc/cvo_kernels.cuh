@@ -48,6 +48,15 @@ namespace cg = cooperative_groups;
 #ifndef CVO_QUADS_PER_LANE
 #define CVO_QUADS_PER_LANE 1
 #endif
+// L2 policies (measured, profiles/r02_variants.txt): the clouds are re-read every iteration while 148 lists stream through
+// L2 between two uses, so cloud lines are loaded evict_last and list lines evict_first: cfg2 17.04k -> 17.50k pairs/s.
+#ifndef CVO_L2_POLICIES
+#define CVO_L2_POLICIES 1
+#endif
+#if CVO_L2_POLICIES
+#define CVO_CLOUD_EVICT_LAST
+#define CVO_LIST_EVICT_FIRST
+#endif
 constexpr int kThreads = CVO_THREADS;
 constexpr int kWarps = kThreads / 32;
 // The on-the-fly passes and the list builds keep per-warp queues and row tiles in shared memory: at most 16 warps
@@ -422,7 +431,7 @@ __device__ __forceinline__ float dot3f(const float* a, const float* b) {
 }
 
 #ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles CTA 0
-__device__ unsigned long long g_phase_clocks[16];  // spends per phase
+__device__ unsigned long long g_phase_clocks[24];  // spends per phase
 __device__ long long g_phase_t0;
 #define CVO_PHASE(i)                                                         \
     if (blockIdx.x == 0 && threadIdx.x == 0) {                               \

@@ -426,6 +426,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
         for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
             __syncthreads();  // everyone is done with the previous round's stage (and its tags are written)
+            CVO_PHASE(KIND == PASS_STEP ? 18 : 16)
             // Stage only what is not there already: the fixed cloud's rows survive from pass to pass and from iteration to
             // iteration, the STEP pass finds the columns the FLOW pass transformed and adds the per-row step-size terms.
             const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
@@ -437,6 +438,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
                 if (!have_rows) __syncthreads();
                 stage_row_step_terms(sm, ntile * kTile);
             }
+            CVO_PHASE(KIND == PASS_STEP ? 19 : 17)
             __syncthreads();
             if (threadIdx.x == 0) {  // read again only after the next barrier
                 sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = sm.serial;

@@ -10,12 +10,12 @@ for s in range(296):
     ctx.set_pair(s, pr['x_pos'], pr['x_feat'], pr['y_pos'], pr['y_feat'])
 gp = capi.default_params('cvo'); gp.ell_policy = capi.ELL_FIXED; gp.ell_init = 0.10; gp.fixed_iters = 100
 ctx.align(list(range(296)), gp)
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 24)()
 lib.cvo_b200_phase_clocks(out, 1)
 ctx.align(list(range(296)), gp)
 lib.cvo_b200_phase_clocks(out, 1)
-v = np.array(out[:16], float)
-names = ["(loop top)", "list build: rest", "FLOW pass (trips of warp 0)", "allreduce + finalize_flow", "STEP pass (trips of warp 0)", "barrier after the serial section", "build: stage", "build: evaluate sweep", "list passes: tail (slowest warp + reduction)", "build: compaction copy", "serial: all-reduce of B..E", "serial: update_state after the step", "serial: prepare_iter", "serial: list_policy", "serial: step_from_coeffs", "list passes: staging"]
+v = np.array(out[:20], float)
+names = ["(loop top)", "list build: rest", "FLOW pass (trips of warp 0)", "allreduce + finalize_flow", "STEP pass (trips of warp 0)", "barrier after the serial section", "build: stage", "build: evaluate sweep", "list passes: tail (slowest warp + reduction)", "build: compaction copy", "serial: all-reduce of B..E", "serial: update_state after the step", "serial: prepare_iter", "serial: list_policy", "serial: step_from_coeffs", "list passes: staging barrier + tags", "FLOW: entry (setup + barrier)", "FLOW: column staging (thread 0)", "STEP: entry (setup + barrier)", "STEP: row terms (thread 0)"]
 print("kernel_ms", ctx.last_kernel_ms, "total Mcycles on CTA 0:", v.sum() / 1e6)
 for n, x in zip(names, v):
     print("%-45s %8.2f Mcycles  %5.1f %%" % (n, x / 1e6, 100 * x / v.sum()))
