@@ -26,8 +26,9 @@
 //                                                          f32 rounding noise around 0; its effect on D is < 1e-9 relative)
 //     |z2|^2 + 2 z1 . z3 = -|z2|^2                        (z3 = omega x z2: the reference's epsil_const, :237)
 //   with Q := 3 S - 4 w_i . d:
-//     beta = 2t u_i . d     gamma = -t (|u_i|^2 + Q)     delta = 2t ((omega . v)(omega . d) - |omega|^2 u_i . d)
+//     beta = 2t u_i . d     gamma = -t (|u_i|^2 + Q)     delta = 2t (omega . v)(omega . d) - |omega|^2 beta
 //     epsil = t (|w_i|^2 + |omega|^2 Q)                                                            (t = 1 / (2 l^2))
+//   (the rows are staged as 2t u_i and -4 w_i, so beta and Q's last term are plain dot products with d)
 // Three dot products per candidate (u.d, w.d, omega.d), nothing per COLUMN: the eight per-column planes the STEP pass
 // used to stage and gather (nine shared loads per candidate) are gone; eight per-ROW terms are staged instead and read
 // once per quad.
@@ -201,80 +202,84 @@ __device__ __forceinline__ void flush_flow(FlowPartial& fp, double* acc) {
 
 // ---- STEP (src/cvo.cpp:213-289): this quad's terms of B, C, D, E ----
 struct StepRow {  // the row's staged terms, see stage_row_step_terms
-    float ux, uy, uz, wx, wy, wz, guu, ew2;
+    float bx, by, bz;   // 2t u_i           (beta  = b_i . d)
+    float qx, qy, qz;   // -4 w_i           (Q     = 3 S + q_i . d)
+    float guu, ew2;     // -t |u_i|^2, t |w_i|^2
 };
 struct StepConsts {  // per-iteration scalars of the row-factored form
     float w0, w1, w2;   // omega
-    float ww;           // |omega|^2
-    float b2t;          // 2t                     beta  = b2t u.d
-    float mt;           // -t                     gamma = guu + mt Q            (guu = -t |u|^2)
-    float dk1, dk2;     // 2t (omega.v), -2t |omega|^2      delta = dk1 omega.d + dk2 u.d
-    float etw;          // t |omega|^2            epsil = ew2 + etw Q           (ew2 = t |w|^2)
+    float ww3;          // 3 |omega|^2      Q = 3 S - 4 w.d = ww3 |d|^2 - 3 (omega.d)^2 + q_i . d
+    float mt;           // -t               gamma = guu + mt Q
+    float dk1, nww;     // 2t (omega.v), -|omega|^2      delta = dk1 omega.d + nww beta
+    float etw;          // t |omega|^2      epsil = ew2 + etw Q
 };
 __device__ __forceinline__ StepConsts step_consts(const HotConsts& hc) {
     StepConsts s;
     s.w0 = hc.omega[0]; s.w1 = hc.omega[1]; s.w2 = hc.omega[2];
-    s.ww = (s.w0 * s.w0 + s.w1 * s.w1) + s.w2 * s.w2;
+    const float ww = (s.w0 * s.w0 + s.w1 * s.w1) + s.w2 * s.w2;
     const float wv = (s.w0 * hc.v[0] + s.w1 * hc.v[1]) + s.w2 * hc.v[2];
-    s.b2t = hc.p2t;
+    s.ww3 = 3.f * ww;
     s.mt = -hc.temp_coef;
     s.dk1 = hc.p2t * wv;
-    s.dk2 = -hc.p2t * s.ww;
-    s.etw = hc.temp_coef * s.ww;
+    s.nww = -ww;
+    s.etw = hc.temp_coef * ww;
     return s;
 }
-__device__ __forceinline__ float2 step_pair(const StepConsts& sc, const StepRow& r, float2 dx, float2 dy, float2 dz, float2 d2, float2 a,
-                                            float2& tC, float2& tD, float2& tE) {
-    const float2 pu = __ffma2_rn(bc(r.uz), dz, __ffma2_rn(bc(r.uy), dy, __fmul2_rn(bc(r.ux), dx)));  // u_i . d
-    const float2 pw = __ffma2_rn(bc(r.wz), dz, __ffma2_rn(bc(r.wy), dy, __fmul2_rn(bc(r.wx), dx)));  // w_i . d
+// One pair of candidates: beta .. epsil (src/cvo.cpp:260-271) from three dot products, then this pair's UNWEIGHTED
+// polynomial terms (the brackets of :275-279); the caller weights them with a and sums.
+//   C:  gamma + beta^2/2 =: c
+//   D:  delta + beta gamma + beta^3/6        = delta + beta (gamma + beta^2/6)
+//   E:  epsil + beta delta + beta^2 gamma/2 + gamma^2/2 + beta^4/24  = epsil + beta delta + c^2/2 - beta^4/12
+__device__ __forceinline__ void step_pair(const StepConsts& sc, const StepRow& r, float2 dx, float2 dy, float2 dz, float2 d2,
+                                          float2& beta, float2& tC, float2& tD, float2& tE) {
+    beta = __ffma2_rn(bc(r.bz), dz, __ffma2_rn(bc(r.by), dy, __fmul2_rn(bc(r.bx), dx)));                 // :262
+    const float2 qd = __ffma2_rn(bc(r.qz), dz, __ffma2_rn(bc(r.qy), dy, __fmul2_rn(bc(r.qx), dx)));      // -4 w_i . d
     const float2 po = __ffma2_rn(bc(sc.w2), dz, __ffma2_rn(bc(sc.w1), dy, __fmul2_rn(bc(sc.w0), dx)));  // omega . d
-    const float2 S = __ffma2_rn(make_float2(-po.x, -po.y), po, __fmul2_rn(bc(sc.ww), d2));           // |omega x d|^2
-    const float2 Q = __ffma2_rn(bc(3.f), S, __fmul2_rn(bc(-4.f), pw));
-    const float2 beta = __fmul2_rn(bc(sc.b2t), pu);                                   // src/cvo.cpp:262
-    const float2 gamma = __ffma2_rn(bc(sc.mt), Q, bc(r.guu));                         // :264
-    const float2 delta = __ffma2_rn(bc(sc.dk1), po, __fmul2_rn(bc(sc.dk2), pu));     // :267
-    const float2 epsil = __ffma2_rn(bc(sc.etw), Q, bc(r.ew2));                       // :270
+    const float2 Q = __ffma2_rn(__fmul2_rn(bc(-3.f), po), po, __ffma2_rn(bc(sc.ww3), d2, qd));           // 3 |omega x d|^2 - 4 w.d
+    const float2 gamma = __ffma2_rn(bc(sc.mt), Q, bc(r.guu));                                             // :264
+    const float2 delta = __ffma2_rn(bc(sc.dk1), po, __fmul2_rn(bc(sc.nww), beta));                        // :267
+    const float2 epsil = __ffma2_rn(bc(sc.etw), Q, bc(r.ew2));                                            // :270
     const float2 b2 = __fmul2_rn(beta, beta);
-    const float2 tB = __fmul2_rn(a, beta);                                            // :275
-    tC = __fmul2_rn(a, __ffma2_rn(bc(0.5f), b2, gamma));                              // :276
-    tD = __fmul2_rn(a, __ffma2_rn(__fmul2_rn(b2, beta), bc(1.f / 6.f), __ffma2_rn(beta, gamma, delta)));  // :277
-    tE = __fmul2_rn(a, __ffma2_rn(__fmul2_rn(b2, b2), bc(1.f / 24.f),
-                                  __ffma2_rn(bc(0.5f), __fmul2_rn(gamma, __fadd2_rn(b2, gamma)), __ffma2_rn(beta, delta, epsil))));  // :278-279
-    return tB;
+    tC = __ffma2_rn(bc(0.5f), b2, gamma);
+    tD = __ffma2_rn(beta, __ffma2_rn(b2, bc(1.f / 6.f), gamma), delta);
+    tE = __ffma2_rn(__fmul2_rn(b2, b2), bc(-1.f / 12.f), __ffma2_rn(__fmul2_rn(bc(0.5f), tC), tC, __ffma2_rn(beta, delta, epsil)));
 }
 __device__ __forceinline__ void step_quad(const Smem& sm, const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {
-    const void* z1 = sm.u.ls.ss.colZ1;  // the step stage holds the ROW terms here: planes ux, uy, uz, guu | wx, wy, wz, ew2
+    const void* z1 = sm.u.ls.ss.colZ1;  // the step stage holds the ROW terms here: planes bx, by, bz, guu | qx, qy, qz, ew2
     const void* z2 = sm.u.ls.ss.colZ2;
     StepRow r;
-    r.ux = plane_ld<0>(z1, rowb); r.uy = plane_ld<1>(z1, rowb); r.uz = plane_ld<2>(z1, rowb); r.guu = plane_ld<3>(z1, rowb);
-    r.wx = plane_ld<0>(z2, rowb); r.wy = plane_ld<1>(z2, rowb); r.wz = plane_ld<2>(z2, rowb); r.ew2 = plane_ld<3>(z2, rowb);
-    float2 cA, dA, eA, cB, dB, eB;
-    const float2 bA = step_pair(sc, r, g.dxa, g.dya, g.dza, g.d2a, g.aa, cA, dA, eA);
-    const float2 bB = step_pair(sc, r, g.dxb, g.dyb, g.dzb, g.d2b, g.ab, cB, dB, eB);
-    // the quad's four terms are summed in f32, then promoted (the reference promotes every term, src/cvo.cpp:275-279)
-    acc[0] += (double)hsum(__fadd2_rn(bA, bB));
-    acc[1] += (double)hsum(__fadd2_rn(cA, cB));
-    acc[2] += (double)hsum(__fadd2_rn(dA, dB));
-    acc[3] += (double)hsum(__fadd2_rn(eA, eB));
+    r.bx = plane_ld<0>(z1, rowb); r.by = plane_ld<1>(z1, rowb); r.bz = plane_ld<2>(z1, rowb); r.guu = plane_ld<3>(z1, rowb);
+    r.qx = plane_ld<0>(z2, rowb); r.qy = plane_ld<1>(z2, rowb); r.qz = plane_ld<2>(z2, rowb); r.ew2 = plane_ld<3>(z2, rowb);
+    float2 bA, cA, dA, eA, bB, cB, dB, eB;
+    step_pair(sc, r, g.dxa, g.dya, g.dza, g.d2a, bA, cA, dA, eA);
+    step_pair(sc, r, g.dxb, g.dyb, g.dzb, g.d2b, bB, cB, dB, eB);
+    // A_ij times the brackets (:275-279); the quad's four terms are summed in f32, then promoted (the reference promotes
+    // every term)
+    acc[0] += (double)hsum(__ffma2_rn(g.ab, bB, __fmul2_rn(g.aa, bA)));
+    acc[1] += (double)hsum(__ffma2_rn(g.ab, cB, __fmul2_rn(g.aa, cA)));
+    acc[2] += (double)hsum(__ffma2_rn(g.ab, dB, __fmul2_rn(g.aa, dA)));
+    acc[3] += (double)hsum(__ffma2_rn(g.ab, eB, __fmul2_rn(g.aa, eA)));
 }
 
 }  // namespace quads
 
-// Per-ROW step-size terms of the round's staged rows (untransformed fixed cloud): u = omega x x + v, w = omega x u,
-// -t |u|^2, t |w|^2 (t = 1 / (2 l^2)); see the header of this file.  Runs once per iteration, n <= kColChunk rows.
+// Per-ROW step-size terms of the round's staged rows (untransformed fixed cloud): with u = omega x x + v, w = omega x u
+// and t = 1 / (2 l^2) the planes hold 2t u, -t |u|^2 | -4 w, t |w|^2 (the factors the quads' polynomial needs, see
+// step_pair).  Runs once per iteration, n <= kColChunk rows.
 __device__ __forceinline__ void stage_row_step_terms(Smem& sm, int n) {
     const IterConsts& ic = sm.ic;
-    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2];
+    const float w0 = ic.omega[0], w1 = ic.omega[1], w2 = ic.omega[2], v0 = ic.v[0], v1 = ic.v[1], v2 = ic.v[2];
+    const float t = ic.temp_coef, t2 = ic.p2t;
     float* z1 = plane_of(sm.u.ls.ss.colZ1, 0);
     float* z2 = plane_of(sm.u.ls.ss.colZ2, 0);
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const float x = plane_of(sm.u.ls.rowG, 0)[i], y = plane_of(sm.u.ls.rowG, 1)[i], z = plane_of(sm.u.ls.rowG, 2)[i];
-        const float ux = (w1 * z - w2 * y) + ic.v[0], uy = (w2 * x - w0 * z) + ic.v[1], uz = (w0 * y - w1 * x) + ic.v[2];
+        const float ux = (w1 * z - w2 * y) + v0, uy = (w2 * x - w0 * z) + v1, uz = (w0 * y - w1 * x) + v2;
         const float wx = w1 * uz - w2 * uy, wy = w2 * ux - w0 * uz, wz = w0 * uy - w1 * ux;
-        z1[i] = ux; z1[i + kColChunk] = uy; z1[i + 2 * kColChunk] = uz;
-        z1[i + 3 * kColChunk] = -ic.temp_coef * ((ux * ux + uy * uy) + uz * uz);
-        z2[i] = wx; z2[i + kColChunk] = wy; z2[i + 2 * kColChunk] = wz;
-        z2[i + 3 * kColChunk] = ic.temp_coef * ((wx * wx + wy * wy) + wz * wz);
+        z1[i] = t2 * ux; z1[i + kColChunk] = t2 * uy; z1[i + 2 * kColChunk] = t2 * uz;
+        z1[i + 3 * kColChunk] = -t * ((ux * ux + uy * uy) + uz * uz);
+        z2[i] = -4.f * wx; z2[i + kColChunk] = -4.f * wy; z2[i + 2 * kColChunk] = -4.f * wz;
+        z2[i + 3 * kColChunk] = t * ((wx * wx + wy * wy) + wz * wz);
     }
 }
 
