@@ -326,7 +326,7 @@ class Context:
     def set_cluster_size(self, g):
         self._check(self._lib.cvo_b200_set_cluster_size(self._h, g))
 
-    def set_neighbor_lists(self, enable=True, skin=0.08):
+    def set_neighbor_lists(self, enable=True, skin=0.10):
         self._check(self._lib.cvo_b200_set_neighbor_lists(self._h, int(bool(enable)), C.c_float(skin)))
 
     @property

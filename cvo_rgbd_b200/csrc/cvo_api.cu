@@ -92,7 +92,7 @@ struct cvo_b200_ctx {
     int list_ctas = 0;  // CTAs the scratch currently has areas for
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
-    float list_skin = 0.08f;
+    float list_skin = 0.10f;  // measured optimum (cfg2 and the stock schedules, profiles/r02_skin_sweep.txt)
     float list_shrink = 0.7f;
     float list_refine_min = 1.0f;
     long long last_list_builds = 0, last_list_refines = 0, last_xy_entries = 0, last_xy_slots = 0;
@@ -338,7 +338,7 @@ void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
         if (ctx->list_ctas > n_ctas) n_ctas = ctx->list_ctas;
     }
     const size_t areas = (size_t)n_ctas * (LIST_KINDS + 1);
-    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2) + kListSlackBytes) != cudaSuccess) {
         cudaGetLastError();
         ctx->d_list_entries = nullptr;
         ctx->lists_alloc_failed = true;

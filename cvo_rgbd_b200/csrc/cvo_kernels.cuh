@@ -45,9 +45,6 @@ namespace cg = cooperative_groups;
 #ifndef CVO_BUILD_SEGMENTS
 #define CVO_BUILD_SEGMENTS 4
 #endif
-#ifndef CVO_QUADS_PER_LANE
-#define CVO_QUADS_PER_LANE 1
-#endif
 // L2 policies (measured, profiles/r02_variants.txt): the clouds are re-read every iteration while 148 lists stream through
 // L2 between two uses, so cloud lines are loaded evict_last and list lines evict_first: cfg2 17.04k -> 17.50k pairs/s.
 #ifndef CVO_L2_POLICIES
@@ -95,6 +92,9 @@ constexpr int kListTrip = 128;      // entries one warp handles per trip of a li
 #define CVO_PREFETCH_TRIPS 4
 #endif
 constexpr int kPrefetchTrips = CVO_PREFETCH_TRIPS;  // how many of its own trips ahead a warp prefetches the list into L2
+// The quad passes neither clamp their look-ahead loads nor their prefetches to the end of a list (cvo_quads.cuh): the
+// scratch allocation ends in this much slack, so they stay inside mapped memory whichever area comes last.
+constexpr size_t kListSlackBytes = 64 * 1024;
 
 // accumulator slots of the flow exchange
 enum { ACC_W0 = 0, ACC_V0 = 3, ACC_SUMA = 6, ACC_NNZ = 7, ACC_DLXY = 8, ACC_NNZXX = 9, ACC_SXX = 10,
@@ -172,10 +172,9 @@ struct WarpScratch {
 // features, the warps' survivor queues and row tiles, and the per-unit partial sums; a pass over a neighbour list
 // needs this CTA's rows (geometry only) and, for the STEP pass, the per-column step-size terms.
 // Row-sorted compaction of a freshly built (x, y) list (build_list<0>, "quads"): per row of the round how many entries
-// it has, where its first quad sits inside its row tile, and a running cursor; per row tile the first quad.
+// it has and where its first quad sits inside its row tile; per row tile the first quad.
 struct QuadBuild {
     int rowQ[kColChunk];
-    int rowCur[kColChunk];
     int tileQ[kColTiles + 1];
 };
 struct FeatStage {
@@ -196,7 +195,7 @@ struct BuildUnits {  // neighbour-list build, per unit of the round:
     int off[kMaxUnits];  // where its entries sit in the staging area
     int act[kMaxUnits];  // how many it has
     int pos[kMaxUnits];  // their position in the round's flat list
-    int rowCnt[kColChunk];  // (x, y) list: candidates kept per row of the round, counted while the units are evaluated
+    int rowCnt[kColChunk];  // (x, y) list: candidates kept per row of the round, counted by the warp that owns the row's tile
 };
 static_assert(sizeof(BuildUnits) <= sizeof(double) * kMaxUnits * kUnitAcc, "BuildUnits shares the memory of the on-the-fly unit slots");
 struct OnTheFlyStage {
@@ -281,6 +280,9 @@ struct Smem {
     IterConsts ic;
     PairState st;
     unsigned long long tma_bar;  // mbarrier the TMA bulk copies of a column chunk complete on
+#ifdef CVO_PHASE_CLOCKS
+    long long phase_t0;
+#endif
 };
 
 #ifdef CVO_PRINT_SMEM
@@ -430,14 +432,13 @@ __device__ __forceinline__ float dot3f(const float* a, const float* b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
 }
 
-#ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles CTA 0
-__device__ unsigned long long g_phase_clocks[24];  // spends per phase
-__device__ long long g_phase_t0;
-#define CVO_PHASE(i)                                                         \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
-        const long long now = clock64();                                     \
-        g_phase_clocks[i] += (unsigned long long)(now - g_phase_t0);         \
-        g_phase_t0 = now;                                                    \
+#ifdef CVO_PHASE_CLOCKS  // tuning aid (scripts/build_variants.py clk:CVO_PHASE_CLOCKS, scripts/gpu_phase_clocks.py): cycles
+__device__ unsigned long long g_phase_clocks[24];  // thread 0 of every CTA spends per phase, summed over the CTAs
+#define CVO_PHASE(i)                                                                        \
+    if (threadIdx.x == 0) {                                                                 \
+        const long long now = clock64();                                                    \
+        atomicAdd(&g_phase_clocks[i], (unsigned long long)(now - sm.phase_t0));             \
+        sm.phase_t0 = now;                                                                  \
     }
 #else
 #define CVO_PHASE(i)
@@ -1536,8 +1537,8 @@ __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws
     const float t_c = __fmul_rn(d2c, kp.c2);
     const float re2 = (kp.t_lim - t_c) * L.inv_c1;  // the pair's own squared ball radius (rounded up)
     const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + L.s_build;
-    if (SELF == 0) {  // the flat list addresses its stages in bytes within a plane: (row * 4) << 16 | col * 4
-        e = make_uint2((((uint32_t)row + row_off) << 18) | ((uint32_t)col << 2), __float_as_uint(t_c));
+    if (SELF == 0) {  // staged candidate of an (x, y) build: col | row within the tile << 12 (build_append adds rank << 17)
+        e = make_uint2(((uint32_t)row << 12) | (uint32_t)col, __float_as_uint(t_c));
     } else {
         const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
         e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
@@ -1546,13 +1547,22 @@ __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws
 }
 // appends the kept candidates of one warp-wide batch in lane order
 // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
+// SELF == 0: a row tile of an (x, y) build belongs to ONE warp for the whole column range, so the rows' candidate counts
+// are private to the warp (no atomics) and every kept candidate gets its RANK within its row here -- count so far plus
+// its position among the batch's lanes with the same row (match.any).  The rank is stored with the candidate, which
+// makes the row-sorted compaction (compact_quads) a scatter of independent entries.
 template <int SELF>
-__device__ __forceinline__ void build_append(Smem& sm, bool keep, const uint2& e, uint2* out, int limit, int& cursor) {
+__device__ __forceinline__ void build_append(Smem& sm, bool keep, uint2 e, uint2* out, int limit, int& cursor, int row_off) {
     const int lane = threadIdx.x & 31;
-    if (SELF == 0) {  // per-row counts for the row-sorted compaction: one shared atomic per distinct row of the batch
-        const int r = keep ? (int)(e.x >> 18) : -1 - lane;
+    if (SELF == 0) {
+        const int r = keep ? row_off + (int)((e.x >> 12) & 31u) : -1 - lane;
         const unsigned m = __match_any_sync(0xffffffffu, r);
-        if (keep && lane == __ffs(m) - 1) atomicAdd(&sm.u.of.bu.rowCnt[r], __popc(m));
+        int* cnt = sm.u.of.bu.rowCnt;
+        const int base = keep ? cnt[r] : 0;
+        __syncwarp();
+        if (keep && lane == __ffs(m) - 1) cnt[r] = base + __popc(m);
+        __syncwarp();
+        e.x |= (uint32_t)(base + __popc(m & ((1u << lane) - 1u))) << 17;
     }
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
     if (keep && cursor + kTile <= limit) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
@@ -1564,7 +1574,7 @@ __device__ __forceinline__ void build_eval(Smem& sm, const WarpScratch& ws, cons
                                            int& cursor) {
     uint2 e;
     const bool keep = build_test<SELF>(sm, ws, kp, L, ent, live, row_off, yy_row_min, e);
-    build_append<SELF>(sm, keep, e, out, limit, cursor);
+    build_append<SELF>(sm, keep, e, out, limit, cursor, (int)row_off);
 }
 // two batches at once: their loads and arithmetic interleave (the evaluation is latency-bound on one batch)
 template <int SELF>
@@ -1574,8 +1584,8 @@ __device__ __forceinline__ void build_eval2(Smem& sm, const WarpScratch& ws, con
     uint2 e0, e1;
     const bool k0 = build_test<SELF>(sm, ws, kp, L, ent0, true, row_off, yy_row_min, e0);
     const bool k1 = build_test<SELF>(sm, ws, kp, L, ent1, true, row_off, yy_row_min, e1);
-    build_append<SELF>(sm, k0, e0, out, limit, cursor);
-    build_append<SELF>(sm, k1, e1, out, limit, cursor);
+    build_append<SELF>(sm, k0, e0, out, limit, cursor, (int)row_off);
+    build_append<SELF>(sm, k1, e1, out, limit, cursor, (int)row_off);
 }
 
 template <int SELF>
@@ -1655,7 +1665,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             const int nct = min(kColTiles, pg.total_ct - cb);
             // the build's own unit decomposition (the list passes do not use units): enough column segments per row
             // tile that the 16 warps end together -- the evaluation cost per unit varies a lot
-            const int Sb = max(1, min(min(kMaxUnits / ntile, CVO_BUILD_SEGMENTS), nct / 8));
+            // ((x, y) list: one unit per row tile -- the warp that owns a tile ranks its candidates row by row, build_append)
+            const int Sb = SELF == 0 ? 1 : max(1, min(min(kMaxUnits / ntile, CVO_BUILD_SEGMENTS), nct / 8));
             const int nunits = ntile * Sb;
             __syncthreads();
             if (round >= kMaxListRounds) {  // uniform: every thread counts the rounds itself.  (sm.lst_ovf is only ever READ
@@ -1684,6 +1695,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 }
                 wcur = min(wcur + c, seg);
             }
+            CVO_PHASE(20)  // instrumented variant: warp 0's units; what follows is the wait for the slowest warp
             __syncthreads();
             CVO_PHASE(7)
             if (SELF == 0) {  // the (x, y) list: row-sorted quads (see compact_quads)
@@ -2271,7 +2283,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
         }
         __syncthreads();
 #ifdef CVO_PHASE_CLOCKS
-        if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_t0 = clock64();
+        if (threadIdx.x == 0) sm.phase_t0 = clock64();
 #endif
         for (int k = 0; k < max_iter; ++k) {
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)

@@ -5,8 +5,9 @@
 // multiple of four, so the list is a sequence of QUADS: four candidates of ONE row.  A quad is stored as three
 // parallel arrays (structure of arrays, 26 B per quad = 6.5 B per candidate; 8 B before):
 //     ntc  float4   the four NEGATED colour exponents -t_c (padding: -inf  =>  a = 0)
-//     cols 4 x u16  byte offsets of the four columns inside a plane of the staged column chunk
-//     row  u16      byte offset of the row inside a plane of the staged row chunk
+//     cols 4 x u16  shared-memory byte addresses of the four columns' x inside the staged column planes
+//     row  u16      shared-memory byte address of the row's x inside the staged row planes
+// (absolute shared::cta addresses: the operands of the hot loop are LDS [field + plane offset], see lds_at)
 // and a round is padded to a whole TRIP of 32 quads: lane l of a warp takes quad l of the trip with one LDG.128, one
 // LDG.64 and one LDG.U16, all three coalesced.
 //
@@ -48,29 +49,42 @@ namespace quads {
 
 constexpr int kQuadTrip = 32;            // quads per trip (one per lane)
 constexpr int kQuadBytes = 26;           // 16 (ntc) + 8 (cols) + 2 (row)
+#ifdef CVO_TRIPS_CONTIGUOUS              // tuning: every warp takes a contiguous sixteenth of a round's trips
+constexpr int kTripStride = 1;           // (measured: cfg2 +0.4 %, stock cvo -4 %)
+#else
+constexpr int kTripStride = kWarps;      // the warps take the trips w, w + 16, ...
+#endif
 
 __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float hsum(float2 a) { return a.x + a.y; }
+
+// Shared-memory operands of the hot loop.  A quad's row / column fields are ABSOLUTE shared-memory (shared::cta) byte
+// addresses of the point's x inside the staged row / column planes (written by compact_quads of the same kernel, so the
+// layout can never disagree): one LDS with an immediate plane offset per operand, no base-address arithmetic per trip.
+template <uint32_t OFF>
+__device__ __forceinline__ float lds_at(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+// plane offsets relative to a row's x: the row geometry planes, then the STEP pass's row terms (ListStage layout)
+constexpr uint32_t kRowZ1 = (uint32_t)sizeof(float4) * kColChunk;      // ls.ss.colZ1 - ls.rowG
+constexpr uint32_t kRowZ2 = 2u * (uint32_t)sizeof(float4) * kColChunk;  // ls.ss.colZ2 - ls.rowG
+static_assert(offsetof(ListStage, ss) == kRowZ1 && offsetof(StepStage, colZ2) == kRowZ1, "row-term planes follow the row planes");
 
 struct Round {  // one round's arrays inside the CTA's list area
     const float4* ntc;
     const uint2* cols;
     const unsigned short* row;
     int ntrip;
-    const char* pf_base;  // this lane's share of the L2 prefetch of a trip: first line and bytes per trip (lanes 0..6)
-    int pf_stride;
 };
-__device__ __forceinline__ Round round_ref(const ListRef& lr, uint2 rd, int lane) {
+__device__ __forceinline__ Round round_ref(const ListRef& lr, uint2 rd) {
     const char* base = reinterpret_cast<const char*>(lr.entries) + (size_t)rd.x * 16u;
     Round r;
     r.ntc = reinterpret_cast<const float4*>(base);
     r.cols = reinterpret_cast<const uint2*>(base + (size_t)rd.y * 16u);
     r.row = reinterpret_cast<const unsigned short*>(base + (size_t)rd.y * 24u);
     r.ntrip = (int)rd.y / kQuadTrip;
-    // a trip is 512 B of ntc (4 lines), 256 B of cols (2 lines), 64 B of rows (half a line)
-    r.pf_base = lane < 4 ? reinterpret_cast<const char*>(r.ntc) + lane * 128
-                : lane < 6 ? reinterpret_cast<const char*>(r.cols) + (lane - 4) * 128 : reinterpret_cast<const char*>(r.row);
-    r.pf_stride = lane < 4 ? 512 : lane < 6 ? 256 : 64;
     return r;
 }
 
@@ -79,27 +93,37 @@ struct Quad {
     uint2 cols;
     uint32_t row;
 };
-__device__ __forceinline__ Quad load_quad(const Round& r, int trip, int lane) {
+// Quad `qi` of the round (lane l of a warp: its trip's first quad + l) and, with the same address registers, the L2
+// prefetch of the lines kPrefetchTrips of the warp's trips further down the round (one instruction per array with an
+// immediate offset: no address arithmetic, no predicate; the eight lanes of a line coalesce into one request).  Neither the loads
+// two trips ahead nor the prefetches are clamped to the round: the list scratch ends in a slack region that keeps them
+// inside mapped memory (kListSlackBytes), and what is loaded past the warp's share is never used.
+__device__ __forceinline__ Quad load_quad(const Round& r, uint32_t qi, bool pf_lane) {
 #ifdef CVO_EXP_SAMETRIP  // timing experiment only (wrong results): every trip re-reads the round's first trips (cache hits)
-    trip &= 15;
+    qi &= 511u;
 #endif
-    const int q = min(trip, r.ntrip - 1) * kQuadTrip + lane;  // loads past the warp's last trip are clamped to it
     Quad v;
+    const float4* pn = r.ntc + qi;
+    const uint2* pc = r.cols + qi;
+    const unsigned short* pr = r.row + qi;
 #ifdef CVO_LIST_EVICT_FIRST
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.ntc.x), "=f"(v.ntc.y), "=f"(v.ntc.z), "=f"(v.ntc.w) : "l"(r.ntc + q), "l"(pol));
-    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.cols.x), "=r"(v.cols.y) : "l"(r.cols + q), "l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.ntc.x), "=f"(v.ntc.y), "=f"(v.ntc.z), "=f"(v.ntc.w) : "l"(pn), "l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.cols.x), "=r"(v.cols.y) : "l"(pc), "l"(pol));
 #else
-    v.ntc = __ldcg(r.ntc + q);
-    v.cols = __ldcg(r.cols + q);
+    v.ntc = __ldcg(pn);
+    v.cols = __ldcg(pc);
 #endif
-    v.row = (uint32_t)__ldcg(r.row + q);
+    v.row = (uint32_t)__ldcg(pr);
+#ifndef CVO_NO_LIST_PREFETCH
+    if (pf_lane) {  // (all lanes: the eight lanes of a line coalesce)
+        asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(pn), "n"(kPrefetchTrips * kTripStride * kQuadTrip * 16));
+        asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(pc), "n"(kPrefetchTrips * kTripStride * kQuadTrip * 8));
+        asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(pr), "n"(kPrefetchTrips * kTripStride * kQuadTrip * 2));
+    }
+#endif
     return v;
-}
-// the lines of a trip a few trips ahead -> L2
-__device__ __forceinline__ void prefetch_trip(const Round& r, int trip, int lane) {
-    if (lane < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(r.pf_base + (size_t)min(trip, r.ntrip - 1) * r.pf_stride));
 }
 
 // Geometry and gated kernel values of one quad.
@@ -111,17 +135,16 @@ struct QuadGeom {
 };
 
 // `near`: some candidate of the quad has its fast kernel value inside the re-decision band around sp_thres.
-__device__ __forceinline__ bool quad_geom(const Smem& sm, const HotConsts& hc, const KParams& kp, const Quad& q, QuadGeom& g) {
-    const void* rp = sm.u.ls.rowG;
-    const void* cp = sm.colG;
-    g.xr = plane_ld<0>(rp, q.row); g.yr = plane_ld<1>(rp, q.row); g.zr = plane_ld<2>(rp, q.row);
+__device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp, const Quad& q, QuadGeom& g) {
+    constexpr uint32_t P = kPlaneBytes;
+    g.xr = lds_at<0>(q.row); g.yr = lds_at<P>(q.row); g.zr = lds_at<2 * P>(q.row);
     const uint32_t c0 = q.cols.x & 0xffffu, c1 = q.cols.x >> 16, c2 = q.cols.y & 0xffffu, c3 = q.cols.y >> 16;
-    g.dxa = __fadd2_rn(make_float2(plane_ld<0>(cp, c0), plane_ld<0>(cp, c1)), bc(-g.xr));
-    g.dya = __fadd2_rn(make_float2(plane_ld<1>(cp, c0), plane_ld<1>(cp, c1)), bc(-g.yr));
-    g.dza = __fadd2_rn(make_float2(plane_ld<2>(cp, c0), plane_ld<2>(cp, c1)), bc(-g.zr));
-    g.dxb = __fadd2_rn(make_float2(plane_ld<0>(cp, c2), plane_ld<0>(cp, c3)), bc(-g.xr));
-    g.dyb = __fadd2_rn(make_float2(plane_ld<1>(cp, c2), plane_ld<1>(cp, c3)), bc(-g.yr));
-    g.dzb = __fadd2_rn(make_float2(plane_ld<2>(cp, c2), plane_ld<2>(cp, c3)), bc(-g.zr));
+    g.dxa = __fadd2_rn(make_float2(lds_at<0>(c0), lds_at<0>(c1)), bc(-g.xr));
+    g.dya = __fadd2_rn(make_float2(lds_at<P>(c0), lds_at<P>(c1)), bc(-g.yr));
+    g.dza = __fadd2_rn(make_float2(lds_at<2 * P>(c0), lds_at<2 * P>(c1)), bc(-g.zr));
+    g.dxb = __fadd2_rn(make_float2(lds_at<0>(c2), lds_at<0>(c3)), bc(-g.xr));
+    g.dyb = __fadd2_rn(make_float2(lds_at<P>(c2), lds_at<P>(c3)), bc(-g.yr));
+    g.dzb = __fadd2_rn(make_float2(lds_at<2 * P>(c2), lds_at<2 * P>(c3)), bc(-g.zr));
     g.d2a = __ffma2_rn(g.dza, g.dza, __ffma2_rn(g.dya, g.dya, __fmul2_rn(g.dxa, g.dxa)));
     g.d2b = __ffma2_rn(g.dzb, g.dzb, __ffma2_rn(g.dyb, g.dyb, __fmul2_rn(g.dxb, g.dxb)));
     // a = s2 c_sigma^2 2^-(d2 c1 + t_c)  (kernel_a; -(d2 c1 + t_c) = fma(d2, -c1, -t_c) bit for bit)
@@ -141,7 +164,7 @@ __device__ __forceinline__ bool quad_geom(const Smem& sm, const HotConsts& hc, c
 // ten thousand gets here; not inlined so that it costs the hot loop no registers.
 __device__ __noinline__ float quad_exact1(const Smem& sm, const KParams& kp, const ListSrc& src, uint32_t rowb, uint32_t colb, float d2) {
     const IterConsts& ic = sm.ic;
-    const int ri = src.row_base + (int)(rowb >> 2), ci = src.col_base + (int)(colb >> 2);
+    const int ri = src.row_base + (int)((rowb - smem_u32(sm.u.ls.rowG)) >> 2), ci = src.col_base + (int)((colb - smem_u32(sm.colG)) >> 2);
     float a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri), __ldg(src.rows->f4 + ri),
                                  __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     if (!(d2 < ic.d2_thres)) a = 0.f;  // thirdparty/nanoflann.hpp:249-253
@@ -244,12 +267,11 @@ __device__ __forceinline__ void step_pair(const StepConsts& sc, const StepRow& r
     tD = __ffma2_rn(beta, __ffma2_rn(b2, bc(1.f / 6.f), gamma), delta);
     tE = __ffma2_rn(__fmul2_rn(b2, b2), bc(-1.f / 12.f), __ffma2_rn(__fmul2_rn(bc(0.5f), tC), tC, __ffma2_rn(beta, delta, epsil)));
 }
-__device__ __forceinline__ void step_quad(const Smem& sm, const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {
-    const void* z1 = sm.u.ls.ss.colZ1;  // the step stage holds the ROW terms here: planes bx, by, bz, guu | qx, qy, qz, ew2
-    const void* z2 = sm.u.ls.ss.colZ2;
+__device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {
+    constexpr uint32_t P = kPlaneBytes;  // the step stage holds the ROW terms: planes bx, by, bz, guu | qx, qy, qz, ew2
     StepRow r;
-    r.bx = plane_ld<0>(z1, rowb); r.by = plane_ld<1>(z1, rowb); r.bz = plane_ld<2>(z1, rowb); r.guu = plane_ld<3>(z1, rowb);
-    r.qx = plane_ld<0>(z2, rowb); r.qy = plane_ld<1>(z2, rowb); r.qz = plane_ld<2>(z2, rowb); r.ew2 = plane_ld<3>(z2, rowb);
+    r.bx = lds_at<kRowZ1>(rowb); r.by = lds_at<kRowZ1 + P>(rowb); r.bz = lds_at<kRowZ1 + 2 * P>(rowb); r.guu = lds_at<kRowZ1 + 3 * P>(rowb);
+    r.qx = lds_at<kRowZ2>(rowb); r.qy = lds_at<kRowZ2 + P>(rowb); r.qz = lds_at<kRowZ2 + 2 * P>(rowb); r.ew2 = lds_at<kRowZ2 + 3 * P>(rowb);
     float2 bA, cA, dA, eA, bB, cB, dB, eB;
     step_pair(sc, r, g.dxa, g.dya, g.dza, g.d2a, bA, cA, dA, eA);
     step_pair(sc, r, g.dxb, g.dyb, g.dzb, g.d2b, bB, cB, dB, eB);
@@ -283,15 +305,26 @@ __device__ __forceinline__ void stage_row_step_terms(Smem& sm, int n) {
     }
 }
 
-// Row-sorted compaction of the round that build_list<0> has just evaluated: the units' staged candidates
-// ((row, col) byte offsets, t_c), unit by unit, become the round's quads.
-//   count    (done while the units were evaluated, build_append: one shared atomic per distinct row of a batch, found
-//            with match.any; the counts do not depend on the order)
+// Shared memory of the scatter (compact_quads): per warp kScatterQuads quads -- the ntc part (16 B per quad) in the memory
+// of the column geometry / feature stages at the start of Smem, the cols + row part (10 B per quad) behind the
+// compaction's counters in the memory of the queues and the warps' row tiles.
+constexpr int kScatterQuads = 416;
+constexpr size_t kScatterRegB = (sizeof(QuadBuild) + 15) & ~size_t(15);
+static_assert(offsetof(Smem, colG) == 0 && offsetof(Smem, u) == sizeof(float4) * kColChunk && offsetof(OnTheFlyStage, fs) == 0 &&
+              offsetof(FeatStage, colF) == 0, "the scatter's first region starts at the start of Smem");
+static_assert((size_t)kWarps * kScatterQuads * 16 <= sizeof(float4) * kColChunk + offsetof(FeatStage, queue), "scatter region A");
+static_assert(offsetof(OnTheFlyStage, ws) == sizeof(FeatStage) &&
+              kScatterRegB + (size_t)kWarps * kScatterQuads * 10 <= sizeof(uint32_t) * kWorkWarps * kQueueCap + sizeof(WarpScratch) * kWorkWarps,
+              "scatter region B");
+
+// Row-sorted compaction of the round that build_list<0> has just evaluated: the staged candidates (column, row within
+// the tile, rank within the row, t_c; one unit per row tile) become the round's quads.
+//   count    done while the tiles were evaluated (build_append: the warp that owns a tile counts its rows and ranks
+//            every kept candidate within its row, in evaluation order -- a pure function of the inputs);
 //   place    quads per row -> exclusive scan inside the tile -> exclusive scan over the tiles -> the round's region in
 //            the list area (ntc | cols | row arrays, padded to a whole trip with quads that can never pass);
-//   scatter  every row tile is taken by ONE warp, which walks the tile's units in unit order: a candidate's slot is its row's cursor plus its rank
-//            among the batch's lanes with that row.  Rows are private to the warp, so no atomics are involved and the
-//            list is a pure function of the inputs, whichever warp evaluated which unit.
+//   scatter  (row, rank) fixes a candidate's quad and slot, so the staged entries are scattered independently of one
+//            another by all warps, with many loads in flight.
 // Returns false (and sets sm.lst_ovf) if the region does not fit the list area.
 template <int SELF>
 __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int kind, int round, int ntile, int Sb) {
@@ -299,6 +332,12 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
     QuadBuild& qb = sm.u.of.fs.qb;
     const BuildUnits& bu = sm.u.of.bu;
     const float ninf = -__int_as_float(0x7f800000);
+    // a quad addresses its operands by their absolute shared-memory byte address inside the list passes' planes (lds_at)
+    const uint32_t col_addr0 = smem_u32(sm.colG), row_addr0 = smem_u32(sm.u.ls.rowG);
+    if (row_addr0 + kPlaneBytes > 0x10000u || col_addr0 + kPlaneBytes > 0x10000u) {  // (cannot happen with this Smem layout)
+        if (threadIdx.x == 0) sm.lst_ovf = 1;
+        return false;
+    }
     if (sm.lst_ovf) return false;  // a unit outgrew its staging segment: its tail was never stored (stable since the barrier)
     // ---- quads per row (the rows were counted while the units were evaluated, build_append) -> offsets inside the tile
     for (int t = warp; t < ntile; t += kWarps) {
@@ -320,6 +359,7 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
             if (i0 + lane < ntile) qb.tileQ[i0 + lane] = base + excl;
             base += total;
         }
+        if (lane == 0) qb.tileQ[ntile] = base;  // (the scatter reads a tile's quad count as a difference)
         const int nq = (base + quads::kQuadTrip - 1) / quads::kQuadTrip * quads::kQuadTrip;
         const unsigned units16 = ((unsigned)nq * quads::kQuadBytes + 15u) / 16u;  // the region, in 16-byte units
         const unsigned at = (unsigned)sm.lst_used;
@@ -328,8 +368,8 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
             char* rb = reinterpret_cast<char*>(lr.entries) + (size_t)at * 16u;
             for (int q = base + lane; q < nq; q += 32) {
                 __stcg(reinterpret_cast<float4*>(rb) + q, make_float4(ninf, ninf, ninf, ninf));
-                __stcg(reinterpret_cast<uint2*>(rb + (size_t)nq * 16u) + q, make_uint2(0u, 0u));
-                reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u)[q] = 0;
+                __stcg(reinterpret_cast<uint2*>(rb + (size_t)nq * 16u) + q, make_uint2(col_addr0 * 0x10001u, col_addr0 * 0x10001u));
+                reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u)[q] = (unsigned short)row_addr0;
             }
         }
         __syncwarp();
@@ -348,61 +388,66 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
         }
     }
     __syncthreads();
+    CVO_PHASE(21)  // instrumented variant: count + place
     if (sm.lst_ovf) return false;
-    // ---- scatter
+    // ---- scatter, through shared memory: (row, rank) fixes a candidate's quad and slot -- SLOT-MAJOR inside the row:
+    // candidate `rank` of a row with n quads is slot rank / n of quad rank % n, so that the lanes holding consecutive
+    // quads of a row read consecutive candidates (consecutive columns, different shared-memory banks) in each of their
+    // four slots.  Scattering 4- and 2-byte fields straight into the list costs one 32-byte store transaction per field
+    // (measured: 120 k cycles per build).  Instead every warp assembles the quads of a row tile, kScatterQuads at a time,
+    // in its own piece of the shared memory the evaluation has finished with (column geometry and features, the tail
+    // of the queues, the row tiles) and copies them out with coalesced 16 / 8 / 2-byte stores.
     {
         const unsigned nq = sm.lround[kind][round].y;
         char* rb = reinterpret_cast<char*>(lr.entries) + (size_t)sm.lst_base * 16u;
-        float* ntc = reinterpret_cast<float*>(rb);
-        unsigned short* cols = reinterpret_cast<unsigned short*>(rb + (size_t)nq * 16u);
-        unsigned short* rowq = reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u);
+        float4* g_ntc = reinterpret_cast<float4*>(rb);
+        uint2* g_cols = reinterpret_cast<uint2*>(rb + (size_t)nq * 16u);
+        unsigned short* g_row = reinterpret_cast<unsigned short*>(rb + (size_t)nq * 24u);
+        float* s_ntc = reinterpret_cast<float*>(reinterpret_cast<char*>(&sm) + (size_t)warp * kScatterQuads * 16);
+        char* regB = reinterpret_cast<char*>(sm.u.of.fs.queue) + kScatterRegB + (size_t)warp * kScatterQuads * 10;
+        unsigned short* s_cols = reinterpret_cast<unsigned short*>(regB);
+        unsigned short* s_row = reinterpret_cast<unsigned short*>(regB + kScatterQuads * 8);
+        const float4 ninf4 = make_float4(ninf, ninf, ninf, ninf);
+        const uint2 col00 = make_uint2(col_addr0 * 0x10001u, col_addr0 * 0x10001u);
         for (int t = warp; t < ntile; t += kWarps) {
-            qb.rowCur[t * kTile + lane] = 0;
-            __syncwarp();
-            const int tile_q = qb.tileQ[t];
-            for (int sg = 0; sg < Sb; ++sg) {
-                const int u = t * Sb + sg, c = bu.act[u];
-                const uint2* src = lr.staging + bu.off[u];
-                for (int i1 = 0; i1 < c; i1 += 128) {  // four batches of loads in flight: the walk is latency-bound
-                    uint2 ev[4];
+            const int c = bu.act[t], tile_q = qb.tileQ[t], tile_nq = qb.tileQ[t + 1] - tile_q;
+            const uint2* src = lr.staging + bu.off[t];
+            for (int q0 = 0; q0 < tile_nq; q0 += kScatterQuads) {  // (one chunk for all but very dense tiles)
+                const int nqc = min(kScatterQuads, tile_nq - q0);
+                __syncwarp();  // the previous chunk has been copied out
+                for (int i = lane; i < nqc; i += 32) {  // unused slots: never pass, address column 0
+                    reinterpret_cast<float4*>(s_ntc)[i] = ninf4;
+                    reinterpret_cast<uint2*>(s_cols)[i] = col00;
+                }
+                __syncwarp();
+                for (int i1 = 0; i1 < c; i1 += 256) {
+                    uint2 ev[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ev[j] = (i1 + 32 * j + lane < c) ? __ldcg(src + i1 + 32 * j + lane) : make_uint2(0u, 0u);
+                    for (int j = 0; j < 8; ++j) ev[j] = (i1 + 32 * j + lane < c) ? __ldcg(src + i1 + 32 * j + lane) : make_uint2(0xffffffffu, 0u);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i0 = i1 + 32 * j;
-                        if (i0 >= c) break;
-                        const bool have = i0 + lane < c;
+                    for (int j = 0; j < 8; ++j) {
                         const uint2 e = ev[j];
-                        const int r = have ? (int)(e.x >> 18) - t * kTile : kTile + lane;  // idle lanes: singletons
-                        const unsigned m = __match_any_sync(0xffffffffu, r);
-                        const int cur = have ? qb.rowCur[t * kTile + r] : 0;
-                        __syncwarp();
-                        if (have && lane == __ffs(m) - 1) qb.rowCur[t * kTile + r] = cur + __popc(m);
-                        __syncwarp();
-                        if (have) {
-                            // SLOT-MAJOR inside the row: candidate `pos` of a row with n quads is slot pos / n of quad pos % n,
-                            // so that the lanes holding consecutive quads of a row read consecutive candidates --
-                            // consecutive columns, different shared-memory banks -- in each of their four slots
-                            const int pos = cur + __popc(m & ((1u << lane) - 1u));
-                            const int nqr = (bu.rowCnt[t * kTile + r] + 3) >> 2;
-                            const int slot = (pos >= nqr) + (pos >= 2 * nqr) + (pos >= 3 * nqr);  // pos / nqr, pos < 4 nqr
-                            const int q = tile_q + qb.rowQ[t * kTile + r] + (pos - slot * nqr);
-                            ntc[q * 4 + slot] = -__uint_as_float(e.y);
-                            cols[q * 4 + slot] = (unsigned short)(e.x & 0xffffu);
-                            if (slot == 0) rowq[q] = (unsigned short)(e.x >> 16);
-                        }
+                        if (e.x == 0xffffffffu) continue;  // (no candidate has rank 32767)
+                        const int r = t * kTile + (int)((e.x >> 12) & 31u), rank = (int)(e.x >> 17);
+                        const int nqr = (bu.rowCnt[r] + 3) >> 2;
+                        const int slot = (rank >= nqr) + (rank >= 2 * nqr) + (rank >= 3 * nqr);  // rank / nqr, rank < 4 nqr
+                        const int q = qb.rowQ[r] + (rank - slot * nqr) - q0;
+                        if ((unsigned)q >= (unsigned)nqc) continue;  // another chunk's quad
+                        s_ntc[q * 4 + slot] = -__uint_as_float(e.y);
+                        s_cols[q * 4 + slot] = (unsigned short)(col_addr0 + ((e.x & 0xfffu) << 2));
+                        if (slot == 0) s_row[q] = (unsigned short)(row_addr0 + ((uint32_t)r << 2));
                     }
                 }
-            }
-            // the unused slots of every row's quads
-            const int cnt = bu.rowCnt[t * kTile + lane], nqr = (cnt + 3) >> 2;
-            for (int pos = cnt; pos < 4 * nqr; ++pos) {
-                const int slot = pos / nqr, q = tile_q + qb.rowQ[t * kTile + lane] + (pos - slot * nqr);
-                ntc[q * 4 + slot] = ninf;
-                cols[q * 4 + slot] = 0;
+                __syncwarp();
+                for (int i = lane; i < nqc; i += 32) {
+                    __stcg(g_ntc + tile_q + q0 + i, reinterpret_cast<const float4*>(s_ntc)[i]);
+                    __stcg(g_cols + tile_q + q0 + i, reinterpret_cast<const uint2*>(s_cols)[i]);
+                    g_row[tile_q + q0 + i] = s_row[i];
+                }
             }
         }
     }
+    CVO_PHASE(22)  // instrumented variant: warp 0's tiles of the scatter; the wait for the slowest warp follows
     return true;
 }
 
@@ -452,82 +497,45 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             CVO_PHASE(15)  // instrumented variant: staging of both passes
             src.row_base = row_first;
             src.col_base = col_first;
-            const quads::Round rd = quads::round_ref(lr, sm.lround[LIST_XY][round], lane);
-            // A warp takes CVO_QUADS_PER_LANE consecutive trips of its share at a time (the bodies of a step are independent:
-            // more instruction-level parallelism for the dependent chains of a quad), with the next step's quads already
-            // in registers and the lines of the step after in flight to L2.
-            constexpr int QPL = CVO_QUADS_PER_LANE;
-            const int nstep = (rd.ntrip + QPL - 1) / QPL;  // steps of QPL trips; a warp takes steps warp, warp + kWarps, ...
-            int st = warp;
-            if (QPL == 1 && st < nstep) {
-                // one quad per lane per trip: three register sets rotate between "being processed" and "being loaded" (never
-                // copied), so the loads run TWO trips ahead of the arithmetic and the L2 prefetch a few trips ahead of them
-                quads::Quad qa = quads::load_quad(rd, st, lane), qb2 = quads::load_quad(rd, st + kWarps, lane), qc;
+            // The warps take the round's trips round-robin (one quad per lane per trip).  Three register sets rotate between "being processed" and "being loaded" (never copied), so
+            // the loads run TWO trips ahead of the arithmetic and the L2 prefetch kPrefetchTrips trips ahead of them.
+            const quads::Round rd = quads::round_ref(lr, sm.lround[LIST_XY][round]);
+            constexpr uint32_t kStep = quads::kTripStride * quads::kQuadTrip;  // quads between two trips of a warp
+            const int t0 = quads::kTripStride > 1 ? warp : (rd.ntrip * warp) / kWarps;
+            int left = quads::kTripStride > 1 ? (rd.ntrip - warp + kWarps - 1) / kWarps : (rd.ntrip * (warp + 1)) / kWarps - t0;
+            if (left > 0) {
+#ifdef CVO_PF_LANE_PREDICATE  // tuning: one prefetching lane per line (measured: 2 % SLOWER than all lanes)
+                const bool pf_lane = (lane & 7) == 0;
+#else
+                const bool pf_lane = true;
+#endif
+                uint32_t qi = (uint32_t)(t0 * quads::kQuadTrip + lane);
+                quads::Quad qa = quads::load_quad(rd, qi, pf_lane), qb2 = quads::load_quad(rd, qi + kStep, pf_lane), qc;
 #define CVO_QUAD_TRIP(q)                                                                       \
     {                                                                                          \
         quads::QuadGeom g;                                                                     \
-        const bool near = quads::quad_geom(sm, hc, kp, q, g);                                  \
+        const bool near = quads::quad_geom(hc, kp, q, g);                                      \
         if (__any_sync(0xffffffffu, near)) quads::redecide(sm, hc, kp, src, q, g);             \
-        if (KIND == PASS_STEP) quads::step_quad(sm, sc, q.row, g, acc);                        \
+        if (KIND == PASS_STEP) quads::step_quad(sc, q.row, g, acc);                            \
         else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                     \
     }
 #pragma unroll 1
                 while (true) {
-                    qc = quads::load_quad(rd, st + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    qc = quads::load_quad(rd, qi + 2 * kStep, pf_lane);
                     CVO_QUAD_TRIP(qa)
-                    st += kWarps;
-                    if (st >= nstep) break;
-                    qa = quads::load_quad(rd, st + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    qi += kStep;
+                    if (--left == 0) break;
+                    qa = quads::load_quad(rd, qi + 2 * kStep, pf_lane);
                     CVO_QUAD_TRIP(qb2)
                     if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 2 quads (one or two rows) per f32 partial
-                    st += kWarps;
-                    if (st >= nstep) break;
-                    qb2 = quads::load_quad(rd, st + 2 * kWarps, lane);
-                    quads::prefetch_trip(rd, st + (2 + kPrefetchTrips) * kWarps, lane);
+                    qi += kStep;
+                    if (--left == 0) break;
+                    qb2 = quads::load_quad(rd, qi + 2 * kStep, pf_lane);
                     CVO_QUAD_TRIP(qc)
-                    st += kWarps;
-                    if (st >= nstep) break;
+                    qi += kStep;
+                    if (--left == 0) break;
                 }
 #undef CVO_QUAD_TRIP
-                if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
-            } else if (st < nstep) {
-                quads::Quad cur[QPL], nxt[QPL];
-#pragma unroll
-                for (int j = 0; j < QPL; ++j) cur[j] = quads::load_quad(rd, st * QPL + j, lane);
-#pragma unroll 1
-                while (true) {
-                    const int sn = st + kWarps;
-#pragma unroll
-                    for (int j = 0; j < QPL; ++j) {
-                        nxt[j] = quads::load_quad(rd, sn * QPL + j, lane);
-                        quads::prefetch_trip(rd, (sn + kPrefetchTrips * kWarps) * QPL + j, lane);
-                    }
-                    quads::QuadGeom g[QPL];
-                    bool near = false;
-#pragma unroll
-                    for (int j = 0; j < QPL; ++j) {
-                        const bool live = st * QPL + j < rd.ntrip;  // the last step of a round may be short
-                        const bool nj = quads::quad_geom(sm, hc, kp, cur[j], g[j]);
-                        if (!live) g[j].aa = g[j].ab = make_float2(0.f, 0.f);
-                        near |= nj && live;
-                    }
-                    if (__any_sync(0xffffffffu, near)) {
-#pragma unroll
-                        for (int j = 0; j < QPL; ++j) quads::redecide(sm, hc, kp, src, cur[j], g[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < QPL; ++j) {
-                        if (KIND == PASS_STEP) quads::step_quad(sm, sc, cur[j].row, g[j], acc);
-                        else quads::flow_quad<KIND, STATS>(hc, kp, g[j], fp);
-                    }
-                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= QPL quads per f32 partial
-                    st = sn;
-                    if (st >= nstep) break;
-#pragma unroll
-                    for (int j = 0; j < QPL; ++j) cur[j] = nxt[j];
-                }
             }
             if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
         }

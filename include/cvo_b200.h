@@ -228,7 +228,7 @@ long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
  * following iterations until the pose has moved the moving cloud by more than skin * r (or ell changed r);
  * the strict ell-ball test and the kernel values are still evaluated on the fly, A is never stored.
  * enable = 0: every pass tests all tile pairs on the fly (also the automatic fallback if a list overflows
- * its scratch).  Default: enabled, skin = 0.08.  Results agree between the two modes up to f32 summation order. */
+ * its scratch).  Default: enabled, skin = 0.10.  Results agree between the two modes up to f32 summation order. */
 int       cvo_b200_set_neighbor_lists(cvo_b200_ctx* ctx, int enable, float skin);
 /* Sum over the pairs of the last align call of (x, y) list builds. */
 long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx);
