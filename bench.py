@@ -174,7 +174,7 @@ def pose_error(Ta, Tb):
     return rot, float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
 
 
-def parity_report(gpu_poses, cpu_poses, tol=POSE_TOL):
+def parity_report(gpu_poses, cpu_poses, tol=POSE_TOL, min_frac=0.9, med_frac=0.5):
     """GPU poses against the oracle's on the same pairs.
 
     north_star's bound is 1e-4 rad / 1e-4 m per pair.  The reference algorithm itself does not reproduce its final pose
@@ -183,18 +183,22 @@ def parity_report(gpu_poses, cpu_poses, tol=POSE_TOL):
     200 pairs per mode (profiles/r02_parity_distribution.json): the SAME CPU restatement compiled two ways agrees with
     itself within 1e-4 on 98 % (cfg2) / 92 % (stock cvo) of the pairs, worst pair 1.7e-4 .. 2.3e-4 -- and the GPU agrees
     with it within 1e-4 on 98.5 % / 92.5 %, quantile by quantile the same distribution.  So `ok` means: every pose
-    finite, median error under tol / 2, at least 90 % of the pairs within tol, no pair beyond 10 x tol (a gross error:
-    wrong schedule, wrong cloud, a dropped iteration batch).  `frac_within_tol` and the maxima are reported as measured."""
+    finite, median error under `med_frac` x tol, at least `min_frac` of the pairs within tol, no pair beyond 10 x tol (a
+    gross error: wrong schedule, wrong cloud, a dropped iteration batch).  (Oracle-vs-itself medians: 1.1e-5 m on cfg2,
+    4.1e-5 m under the stock schedule -- hence med_frac 0.5 and 0.75.)  `min_frac` sits a sampling margin below the
+    oracle-vs-itself fraction of the schedule: 0.90 for cfg2 (0.98 measured; 96 pairs), 0.80 for the stock cvo schedule
+    with its stop tests (0.92 measured; with 48 pairs a correct implementation falls below 0.80 about once in 300 runs).
+    `frac_within_tol` and the maxima are reported as measured."""
     errs = np.array([pose_error(g, c) for g, c in zip(gpu_poses, cpu_poses)]).reshape(-1, 2)
     within = (errs[:, 0] < tol) & (errs[:, 1] < tol)
     finite = bool(np.isfinite(np.asarray(gpu_poses)).all())
     med = np.median(errs, axis=0)
-    ok = finite and within.mean() >= 0.9 and med.max() < tol / 2 and errs.max() < 10 * tol
+    ok = finite and within.mean() >= min_frac and med.max() < med_frac * tol and errs.max() < 10 * tol
     return {"pairs": int(len(errs)), "max_rot": float(errs[:, 0].max()), "max_trans": float(errs[:, 1].max()),
             "median_rot": float(med[0]), "median_trans": float(med[1]),
             "tol": tol, "frac_within_tol": float(within.mean()),
             "oracle_vs_itself_frac_within_tol": {"cfg2": 0.98, "stock_cvo": 0.92, "source": "profiles/r02_parity_distribution.json"},
-            "criterion": "finite, median < tol/2, >= 90% of pairs within tol, max < 10 tol", "ok": bool(ok)}
+            "criterion": "finite, median < %.2f tol, >= %d%% of pairs within tol, max < 10 tol" % (med_frac, round(100 * min_frac)), "ok": bool(ok)}
 
 
 def level1_report(ctx, capi, pairs, slots):
@@ -317,10 +321,10 @@ def run_cfg4(args, torch, dist, capi, sharding, synth, rank, world, local_rank):
     G, ncl, num_sms = ctx.last_cluster_size, ctx.last_num_clusters, ctx.num_sms
     out = None
     if rank == 0:
-        # parity on this workload too: 16 pairs spread over the job against the oracle
-        sample = np.linspace(0, CFG4_PAIRS - 1, 16).astype(int)
+        # parity on this workload too: 48 pairs spread over the job against the oracle
+        sample = np.linspace(0, CFG4_PAIRS - 1, 48).astype(int)
         cpu = cpu_reference_run(sample, cfg=4)
-        par = parity_report(np.asarray(poses)[sample], cpu["poses"], POSE_TOL)
+        par = parity_report(np.asarray(poses)[sample], cpu["poses"], POSE_TOL, min_frac=0.8, med_frac=0.75)
         out = {"workload": "cfg4: %d independent ragged pairs (N, M ~ U{2700..3300}), stock cvo schedule, identity init, "
                            "pair p -> rank p mod W, one all-gather of the poses" % CFG4_PAIRS,
                "scaling": "strong", "pairs_total": CFG4_PAIRS, "pairs_per_gpu": int(P), "steps": steps,

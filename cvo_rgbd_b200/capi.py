@@ -28,6 +28,7 @@ EXPORTS = [
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
     "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes", "cvo_b200_align_multi", "cvo_b200_last_list_fill",
+    "cvo_b200_set_group_clusters", "cvo_b200_last_group_clusters",
 ]
 
 
@@ -105,6 +106,8 @@ def load():
     lib.cvo_b200_last_cluster_size.argtypes = [vp]
     lib.cvo_b200_last_num_clusters.argtypes = [vp]
     lib.cvo_b200_set_cluster_size.argtypes = [vp, C.c_int]
+    lib.cvo_b200_set_group_clusters.argtypes = [vp, C.c_int]
+    lib.cvo_b200_last_group_clusters.argtypes = [vp]
     lib.cvo_b200_last_total_iterations.argtypes = [vp]
     lib.cvo_b200_last_total_iterations.restype = C.c_longlong
     lib.cvo_b200_num_sms.argtypes = [vp]
@@ -326,6 +329,10 @@ class Context:
     def set_cluster_size(self, g):
         self._check(self._lib.cvo_b200_set_cluster_size(self._h, g))
 
+    def set_group_clusters(self, n):
+        """Whole-GPU mode: clusters per pair (0 automatic, 1 off, n > 1 forced); see include/cvo_b200.h."""
+        self._check(self._lib.cvo_b200_set_group_clusters(self._h, n))
+
     def set_neighbor_lists(self, enable=True, skin=0.10):
         self._check(self._lib.cvo_b200_set_neighbor_lists(self._h, int(bool(enable)), C.c_float(skin)))
 
@@ -381,6 +388,10 @@ class Context:
     @property
     def last_cluster_size(self):
         return int(self._lib.cvo_b200_last_cluster_size(self._h))
+
+    @property
+    def last_group_clusters(self):
+        return int(self._lib.cvo_b200_last_group_clusters(self._h))
 
     @property
     def last_num_clusters(self):

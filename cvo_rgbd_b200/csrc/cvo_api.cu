@@ -43,6 +43,7 @@ struct cvo_b200_ctx {
     PairDev* h_pairs_dev = nullptr;     // the device's view of the two
     PairState* h_states_dev = nullptr;
     int* d_counter = nullptr;
+    double* d_group_xchg = nullptr;  // whole-GPU mode (group_allreduce): cluster records, and d_counter[1] counts the arrivals
     cvo_b200_iter_rec* d_trace = nullptr;
     cvo_b200_iter_rec* h_trace = nullptr;  // pinned
     int trace_cap = 0;
@@ -100,6 +101,7 @@ struct cvo_b200_ctx {
     float last_ms = 0.f;
     long long launches = 0;
     int last_G = 0, last_nclusters = 0, force_G = 0;
+    int force_group = 0, last_group = 1;  // clusters per pair: 0 = automatic, 1 = one cluster per pair, n = whole-GPU mode
     int max_clusters[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // per cluster size, -1 = not asked yet
     long long last_total_iters = 0;
     int sort_points = 1;
@@ -483,6 +485,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     }
     args.kp = make_kparams(p, false);
     int G = choose_cluster(ctx, n_pairs);
+    int group = 1;
     {
         int fit = max_resident_clusters(ctx, G);
         if (fit < 1 && G > 8 && ctx->force_G == 0) {  // 16-CTA clusters are opt-in; fall back to portable 8
@@ -498,8 +501,21 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
             max_n = ctx->h_pairs[i].x.n > max_n ? ctx->h_pairs[i].x.n : max_n;
             max_n = ctx->h_pairs[i].y.n > max_n ? ctx->h_pairs[i].y.n : max_n;
         }
-        ensure_list_scratch(ctx, (n_pairs < fit ? n_pairs : fit) * G, max_n);
+        // Whole-GPU mode (group_allreduce in cvo_kernels.cuh): a single pair whose clouds give every CTA of one cluster
+        // eight or more row tiles is spread over every cluster the device holds.  Below that the iteration is dominated
+        // by what does not split -- the serial section, the column staging every CTA repeats, the barriers -- and the
+        // two extra global-memory barriers cost more than the shorter passes save (measured, profiles/r02_group_mode.txt:
+        // 3000 points 20.5 -> 21.8 us per iteration, 10000 points 75.9 -> 46.2).
+        if (ctx->force_group > 1) group = ctx->force_group;
+        else if (ctx->force_group == 0 && n_pairs == 1 && max_n / kTile >= 8 * G) group = fit;
+        if (group > fit) group = fit;
+        if (group > kMaxGroupClusters) group = kMaxGroupClusters;
+        if (group < 1) group = 1;
+        ensure_list_scratch(ctx, (group > 1 ? group : (n_pairs < fit ? n_pairs : fit)) * G, max_n);
     }
+    args.group_clusters = group;
+    args.group_xchg = ctx->d_group_xchg;
+    args.group_count = reinterpret_cast<unsigned*>(ctx->d_counter + 1);
     // the list passes rely on a > sp_thres implying the ell-ball test, which holds for c_sigma^2 <= 1 (cvo_quads.cuh)
     const bool lists = ctx->lists_enabled && ctx->d_list_entries != nullptr && args.kp.cs2 <= 1.0f;
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
@@ -510,10 +526,10 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     // The pair descriptors and states live in pinned host memory that the kernel reads and writes directly (unified
     // addressing: 272 B per pair, once at its start and once at its end).  No host->device copy sits in the launch
     // path: a small copy would queue behind the upload of the NEXT batch on the copy engine (measured: 0.8 ms).
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, 2 * sizeof(int), ctx->stream));
     int ncl = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = launch_cluster_kernel(ctx, align_kernel, args, G, n_pairs, &ncl);
+    int rc = launch_cluster_kernel(ctx, align_kernel, args, G, group > 1 ? group : n_pairs, &ncl);
     if (rc != CVO_B200_OK) return rc;
     if (lists && ncl * G > ctx->list_ctas) {  // cannot happen: both sides use the same occupancy query
         ctx->err = "internal: launch larger than the neighbour-list scratch";
@@ -527,6 +543,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_G = G;
     ctx->last_nclusters = ncl;
+    ctx->last_group = group;
     long long total = 0, builds = 0, refines = 0, xy_entries = 0, xy_slots = 0;
     for (int i = 0; i < n_pairs; ++i) {
         const PairState& st = ctx->h_states[i];
@@ -641,7 +658,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     CKC(cudaHostAlloc(&ctx->h_states, sizeof(PairState) * max_slots, cudaHostAllocMapped));
     CKC(cudaHostGetDevicePointer(&ctx->h_pairs_dev, ctx->h_pairs, 0));
     CKC(cudaHostGetDevicePointer(&ctx->h_states_dev, ctx->h_states, 0));
-    CKC(cudaMalloc(&ctx->d_counter, sizeof(int)));
+    CKC(cudaMalloc(&ctx->d_counter, 2 * sizeof(int)));
+    CKC(cudaMalloc(&ctx->d_group_xchg, sizeof(double) * 2 * kMaxGroupClusters * kNumAcc));
     CKC(cudaMalloc(&ctx->d_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMallocHost(&ctx->h_trace, sizeof(cvo_b200_iter_rec) * kTraceCap));
     CKC(cudaMalloc(&ctx->d_inner, sizeof(double) * 2));
@@ -688,6 +706,7 @@ void cvo_b200_destroy(cvo_b200_ctx* ctx) {
     cudaFreeHost(ctx->h_pairs);
     cudaFreeHost(ctx->h_states);
     cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_group_xchg);
     cudaFree(ctx->d_trace);
     cudaFreeHost(ctx->h_trace);
     cudaFree(ctx->d_inner);
@@ -1229,6 +1248,13 @@ int cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int g) {
     ctx->force_G = g;
     return CVO_B200_OK;
 }
+int cvo_b200_set_group_clusters(cvo_b200_ctx* ctx, int clusters_per_pair) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (clusters_per_pair < 0 || clusters_per_pair > kMaxGroupClusters) return fail_arg(ctx, "clusters per pair must be 0 (automatic) or 1..160");
+    ctx->force_group = clusters_per_pair;
+    return CVO_B200_OK;
+}
+int cvo_b200_last_group_clusters(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_group : 0; }
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_total_iters : 0; }
 long long cvo_b200_last_list_builds(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_builds : 0; }
 long long cvo_b200_last_list_refines(const cvo_b200_ctx* ctx) { return ctx ? ctx->last_list_refines : 0; }

@@ -63,6 +63,7 @@ constexpr int kTile = 32;
 constexpr int kColChunk = 3072;                 // moving-cloud points resident in shared memory per pass
 constexpr int kColTiles = kColChunk / kTile;
 constexpr int kMaxCluster = 16;
+constexpr int kMaxGroupClusters = 160;           // whole-GPU mode: clusters that can work on one pair
 constexpr int kNumAcc = 16;
 constexpr int kMaxUnits = 256;                  // work units (row tile x column segment) per scheduling round
 static_assert(kThreads >= 32 + kMaxUnits, "build_list ranks one unit per thread beside the scanning warp");
@@ -305,6 +306,11 @@ struct AlignArgs {
     float list_skin;
     float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius
     float list_refine_min;  // ... by filtering the old list if it has at least this fraction of a fresh skin to spare
+    // Whole-GPU mode for a few large pairs: ALL `group_clusters` clusters of the launch work on the same pair (the pairs
+    // are taken one after the other); the cluster totals meet in global memory, see group_allreduce.  <= 1: off.
+    int group_clusters;
+    double* group_xchg;     // [2][kMaxGroupClusters][kNumAcc]
+    unsigned* group_count;  // arrivals of the clusters' rank-0 CTAs, zeroed before the launch
 };
 
 struct InnerArgs {
@@ -2192,6 +2198,40 @@ __device__ __forceinline__ void cluster_allreduce(Smem& sm, cg::cluster_group& c
     __syncthreads();
 }
 
+// Whole-GPU mode: the H clusters of the launch work on one pair.  After the cluster all-reduce every CTA holds its
+// cluster's totals in sm.sum[dst_off ...]; rank 0 of every cluster publishes them in global memory and arrives on a
+// counter, every CTA waits for the H arrivals of this round and sums the H records in cluster order -- identical
+// totals everywhere, bit-deterministic.  Two record buffers alternate: a cluster can only reach round r + 2 after
+// every CTA has contributed to round r + 1, i.e. has finished reading round r.  All CTAs of the launch are resident
+// (the host launches no more clusters than the device holds), so the wait cannot deadlock.
+template <int NV>
+__device__ __forceinline__ void group_allreduce(Smem& sm, const AlignArgs& args, int H, int cid, int crank, int dst_off,
+                                                unsigned& round) {
+    if (H <= 1) return;
+    round += 1;
+    double* rec = args.group_xchg + (size_t)(round & 1u) * kMaxGroupClusters * kNumAcc;
+    if (crank == 0 && threadIdx.x < NV) __stcg(rec + cid * kNumAcc + threadIdx.x, sm.sum[dst_off + threadIdx.x]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (crank == 0) {
+            __threadfence();  // the CTA's records (ordered before this thread by the barrier) before the arrival
+            atomicAdd(args.group_count, 1u);
+        }
+        const unsigned target = round * (unsigned)H;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(args.group_count) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (int c = 0; c < H; ++c) t += __ldcg(rec + c * kNumAcc + threadIdx.x);
+        sm.sum[dst_off + threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 // --------------------------------------------------------------------------------------------
 // the persistent align kernel
 // --------------------------------------------------------------------------------------------
@@ -2200,7 +2240,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+    // rank / G: this CTA's place among the CTAs that share a pair -- the cluster, or in whole-GPU mode all H clusters
+    const int crank = (int)cluster.block_rank(), cG = (int)cluster.num_blocks();
+    const int H = args.group_clusters > 1 ? args.group_clusters : 1, cid = (int)blockIdx.x / cG;
+    const int rank = H > 1 ? cid * cG + crank : crank, G = H * cG;
+    unsigned group_round = 0;
     const KParams& kp = args.kp;
     const bool acvo = kp.mode == CVO_B200_MODE_ACVO;
     const int max_iter = kp.fixed_iters > 0 ? kp.fixed_iters : kp.max_iter;
@@ -2222,13 +2266,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
 
     cluster.sync();  // every CTA of the cluster runs before anyone writes into its shared memory
 
-    while (true) {
-        if (rank == 0 && threadIdx.x == 0) {
-            const int idx = atomicAdd(args.counter, 1);
-            for (int r = 0; r < G; ++r) *cluster.map_shared_rank(&sm.next_pair, r) = idx;
+    for (int group_pi = 0;; ++group_pi) {
+        if (H == 1) {  // a free cluster pulls the next pair
+            if (crank == 0 && threadIdx.x == 0) {
+                const int idx = atomicAdd(args.counter, 1);
+                for (int r = 0; r < cG; ++r) *cluster.map_shared_rank(&sm.next_pair, r) = idx;
+            }
+            cluster.sync();
         }
-        cluster.sync();
-        const int pi = sm.next_pair;
+        const int pi = H == 1 ? sm.next_pair : group_pi;  // whole-GPU mode: every cluster takes every pair, in order
         if (pi >= args.n_pairs) break;
         const PairDev pair = args.pairs[pi];
         if (threadIdx.x == 0) {
@@ -2317,6 +2363,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             }
             __syncthreads();
             cluster_allreduce<ACC_FLOW_COUNT>(sm, cluster, sm.flowTot, 0, kFlowOff);
+            group_allreduce<ACC_FLOW_COUNT>(sm, args, H, cid, crank, kFlowOff, group_round);
             if (threadIdx.x == 0) finalize_flow(sm);
             __syncthreads();
             CVO_PHASE(3)
@@ -2325,6 +2372,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             else run_pass<PASS_STEP>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase);
             CVO_PHASE(4)
             cluster_allreduce<4>(sm, cluster, sm.blockTot, 1, 0);
+            group_allreduce<4>(sm, args, H, cid, crank, 0, group_round);
             CVO_PHASE(10)
             if (threadIdx.x < 32) {  // the serial section of the iteration, on warp 0 (its parallel parts use the lanes)
                 // remember the transform used by this iteration: it is what the reference multiplies

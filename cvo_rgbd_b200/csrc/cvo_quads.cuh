@@ -7,7 +7,8 @@
 //     ntc  float4   the four NEGATED colour exponents -t_c (padding: -inf  =>  a = 0)
 //     cols 4 x u16  shared-memory byte addresses of the four columns' x inside the staged column planes
 //     row  u16      shared-memory byte address of the row's x inside the staged row planes
-// (absolute shared::cta addresses: the operands of the hot loop are LDS [field + plane offset], see lds_at)
+// (addresses relative to the CTA's shared-memory window: the operands of the hot loop are LDS [field + window + plane
+// offset], see lds_at)
 // and a round is padded to a whole TRIP of 32 quads: lane l of a warp takes quad l of the trip with one LDG.128, one
 // LDG.64 and one LDG.U16, all three coalesced.
 //
@@ -58,9 +59,17 @@ constexpr int kTripStride = kWarps;      // the warps take the trips w, w + 16, 
 __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float hsum(float2 a) { return a.x + a.y; }
 
-// Shared-memory operands of the hot loop.  A quad's row / column fields are ABSOLUTE shared-memory (shared::cta) byte
-// addresses of the point's x inside the staged row / column planes (written by compact_quads of the same kernel, so the
-// layout can never disagree): one LDS with an immediate plane offset per operand, no base-address arithmetic per trip.
+// Shared-memory operands of the hot loop.  A quad's row / column fields are the shared-memory byte addresses of the
+// point's x inside the staged row / column planes, relative to the CTA's shared-memory WINDOW (written by compact_quads
+// of the same kernel, so the layout can never disagree): one LDS [field + window + plane offset] per operand, the
+// window base in a uniform register, no address arithmetic per operand.  (In a cluster launch the shared::cta window
+// of CTA rank r starts at r << 24: a bare offset would address rank 0's shared memory.)
+__device__ __forceinline__ uint32_t smem_window(const void* p) {  // (volatile: kept in a register, not re-derived per trip)
+    uint32_t w;
+    asm volatile("and.b32 %0, %1, 0xff000000;" : "=r"(w) : "r"(smem_u32(p)));
+    return w;
+}
+__device__ __forceinline__ uint32_t smem_offset(const void* p) { return smem_u32(p) & 0x00ffffffu; }
 template <uint32_t OFF>
 __device__ __forceinline__ float lds_at(uint32_t addr) {
     float v;
@@ -102,6 +111,9 @@ __device__ __forceinline__ Quad load_quad(const Round& r, uint32_t qi, bool pf_l
 #ifdef CVO_EXP_SAMETRIP  // timing experiment only (wrong results): every trip re-reads the round's first trips (cache hits)
     qi &= 511u;
 #endif
+#ifdef CVO_CLAMP_LOADS
+    qi = min(qi, (uint32_t)(r.ntrip * kQuadTrip - 1));
+#endif
     Quad v;
     const float4* pn = r.ntc + qi;
     const uint2* pc = r.cols + qi;
@@ -115,7 +127,7 @@ __device__ __forceinline__ Quad load_quad(const Round& r, uint32_t qi, bool pf_l
     v.ntc = __ldcg(pn);
     v.cols = __ldcg(pc);
 #endif
-    v.row = (uint32_t)__ldcg(pr);
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=r"(v.row) : "l"(pr));  // (zero-extended into the 32-bit register)
 #ifndef CVO_NO_LIST_PREFETCH
     if (pf_lane) {  // (all lanes: the eight lanes of a line coalesce)
         asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(pn), "n"(kPrefetchTrips * kTripStride * kQuadTrip * 16));
@@ -135,10 +147,13 @@ struct QuadGeom {
 };
 
 // `near`: some candidate of the quad has its fast kernel value inside the re-decision band around sp_thres.
-__device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp, const Quad& q, QuadGeom& g) {
+__device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp, uint32_t win, const Quad& q, QuadGeom& g) {
     constexpr uint32_t P = kPlaneBytes;
-    g.xr = lds_at<0>(q.row); g.yr = lds_at<P>(q.row); g.zr = lds_at<2 * P>(q.row);
-    const uint32_t c0 = q.cols.x & 0xffffu, c1 = q.cols.x >> 16, c2 = q.cols.y & 0xffffu, c3 = q.cols.y >> 16;
+    // field | window in one byte permute each: bytes {f0, f1, w2, w3}
+    const uint32_t rw = __byte_perm(q.row, win, 0x7610);
+    g.xr = lds_at<0>(rw); g.yr = lds_at<P>(rw); g.zr = lds_at<2 * P>(rw);
+    const uint32_t c0 = __byte_perm(q.cols.x, win, 0x7610), c1 = __byte_perm(q.cols.x, win, 0x7632);
+    const uint32_t c2 = __byte_perm(q.cols.y, win, 0x7610), c3 = __byte_perm(q.cols.y, win, 0x7632);
     g.dxa = __fadd2_rn(make_float2(lds_at<0>(c0), lds_at<0>(c1)), bc(-g.xr));
     g.dya = __fadd2_rn(make_float2(lds_at<P>(c0), lds_at<P>(c1)), bc(-g.yr));
     g.dza = __fadd2_rn(make_float2(lds_at<2 * P>(c0), lds_at<2 * P>(c1)), bc(-g.zr));
@@ -164,7 +179,7 @@ __device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp
 // ten thousand gets here; not inlined so that it costs the hot loop no registers.
 __device__ __noinline__ float quad_exact1(const Smem& sm, const KParams& kp, const ListSrc& src, uint32_t rowb, uint32_t colb, float d2) {
     const IterConsts& ic = sm.ic;
-    const int ri = src.row_base + (int)((rowb - smem_u32(sm.u.ls.rowG)) >> 2), ci = src.col_base + (int)((colb - smem_u32(sm.colG)) >> 2);
+    const int ri = src.row_base + (int)((rowb - quads::smem_offset(sm.u.ls.rowG)) >> 2), ci = src.col_base + (int)((colb - quads::smem_offset(sm.colG)) >> 2);
     float a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri), __ldg(src.rows->f4 + ri),
                                  __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     if (!(d2 < ic.d2_thres)) a = 0.f;  // thirdparty/nanoflann.hpp:249-253
@@ -267,7 +282,7 @@ __device__ __forceinline__ void step_pair(const StepConsts& sc, const StepRow& r
     tD = __ffma2_rn(beta, __ffma2_rn(b2, bc(1.f / 6.f), gamma), delta);
     tE = __ffma2_rn(__fmul2_rn(b2, b2), bc(-1.f / 12.f), __ffma2_rn(__fmul2_rn(bc(0.5f), tC), tC, __ffma2_rn(beta, delta, epsil)));
 }
-__device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {
+__device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {  // rowb: window included
     constexpr uint32_t P = kPlaneBytes;  // the step stage holds the ROW terms: planes bx, by, bz, guu | qx, qy, qz, ew2
     StepRow r;
     r.bx = lds_at<kRowZ1>(rowb); r.by = lds_at<kRowZ1 + P>(rowb); r.bz = lds_at<kRowZ1 + 2 * P>(rowb); r.guu = lds_at<kRowZ1 + 3 * P>(rowb);
@@ -333,7 +348,7 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
     const BuildUnits& bu = sm.u.of.bu;
     const float ninf = -__int_as_float(0x7f800000);
     // a quad addresses its operands by their absolute shared-memory byte address inside the list passes' planes (lds_at)
-    const uint32_t col_addr0 = smem_u32(sm.colG), row_addr0 = smem_u32(sm.u.ls.rowG);
+    const uint32_t col_addr0 = quads::smem_offset(sm.colG), row_addr0 = quads::smem_offset(sm.u.ls.rowG);
     if (row_addr0 + kPlaneBytes > 0x10000u || col_addr0 + kPlaneBytes > 0x10000u) {  // (cannot happen with this Smem layout)
         if (threadIdx.x == 0) sm.lst_ovf = 1;
         return false;
@@ -464,6 +479,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
     src.cols = &cols;
     const HotConsts hc = hot_consts(sm.ic);
     const quads::StepConsts sc = quads::step_consts(hc);
+    const uint32_t win = quads::smem_window(&sm);  // this CTA's shared-memory window (cluster rank << 24)
     FlowPartial fp;
     fp.po0 = fp.po1 = fp.po2 = fp.pv0 = fp.pv1 = fp.pv2 = fp.psum = fp.pdl = 0.f;
     fp.cnt = 0;
@@ -514,9 +530,9 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
 #define CVO_QUAD_TRIP(q)                                                                       \
     {                                                                                          \
         quads::QuadGeom g;                                                                     \
-        const bool near = quads::quad_geom(hc, kp, q, g);                                      \
+        const bool near = quads::quad_geom(hc, kp, win, q, g);                                     \
         if (__any_sync(0xffffffffu, near)) quads::redecide(sm, hc, kp, src, q, g);             \
-        if (KIND == PASS_STEP) quads::step_quad(sc, q.row, g, acc);                            \
+        if (KIND == PASS_STEP) quads::step_quad(sc, q.row | win, g, acc);                        \
         else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                     \
     }
 #pragma unroll 1

@@ -220,6 +220,15 @@ int       cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx);
 /* Overrides the CTAs-per-pair choice (1..16); 0 = automatic: the size that minimises waves x per-pair time for
  * the batch at hand (a single pair: 16 CTAs; 63 pairs: 2; 2 x #SMs pairs: 1). */
 int       cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int ctas_per_pair);
+/* Whole-GPU mode for one large pair (the reference's own use: one warm-started pair at a time, src/cvo_main.cpp:36-52;
+ * BASELINE config 5): the pairs of an align call are taken one after the other and EVERY cluster of the launch works
+ * on the current one; the clusters' partial sums meet in global memory (two grid-wide barriers per iteration).
+ * clusters_per_pair: 0 = automatic (a single-pair call with at least eight row tiles per CTA of one cluster, i.e.
+ * more than 4096 points at 16 CTAs, takes every cluster the device holds; smaller pairs stay on one cluster: their
+ * iteration is dominated by the part that does not split), 1 = off (one cluster per pair), n > 1 = n clusters
+ * (clamped to what the device holds).  Results are bit-deterministic for a given (ctas_per_pair, clusters_per_pair). */
+int       cvo_b200_set_group_clusters(cvo_b200_ctx* ctx, int clusters_per_pair);
+int       cvo_b200_last_group_clusters(const cvo_b200_ctx* ctx);
 /* Sum over the pairs of the last align call of iterations executed (work accounting for the roofline). */
 long long cvo_b200_last_total_iterations(const cvo_b200_ctx* ctx);
 /* Neighbour candidate lists: the device-side replacement of the kd-tree the reference rebuilds in every

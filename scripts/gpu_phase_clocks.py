@@ -11,10 +11,13 @@ for s in range(296):
 gp = capi.default_params('cvo')
 if "stock" not in sys.argv:
     gp.ell_policy = capi.ELL_FIXED; gp.ell_init = 0.10; gp.fixed_iters = 100
-ctx.align(list(range(296)), gp)
+P = 1 if "single" in sys.argv else 296  # `single`: one pair on one 16-CTA cluster (latency mode)
+if P == 1:
+    ctx.set_cluster_size(16); ctx.set_group_clusters(1)
+ctx.align(list(range(P)), gp)
 out = (C.c_ulonglong * 24)()
 lib.cvo_b200_phase_clocks(out, 1)
-ctx.align(list(range(296)), gp)
+ctx.align(list(range(P)), gp)
 lib.cvo_b200_phase_clocks(out, 1)
 v = np.array(out[:23], float)
 names = ["(loop top)", "list build: rest", "FLOW pass (trips of warp 0)", "allreduce + finalize_flow", "STEP pass (trips of warp 0)", "barrier after the serial section", "build: stage", "build: evaluate: wait for the slowest warp", "list passes: tail (slowest warp + reduction)", "build: scatter: wait for the slowest warp", "serial: all-reduce of B..E", "serial: update_state after the step", "serial: prepare_iter", "serial: list_policy", "serial: step_from_coeffs", "list passes: staging barrier + tags", "FLOW: entry (setup + barrier)", "FLOW: column staging (thread 0)", "STEP: entry (setup + barrier)", "STEP: row terms (thread 0)", "build: evaluate (warp 0's units)", "build: count + place", "build: scatter (warp 0's tiles)"]

@@ -66,7 +66,11 @@ def test_device_benchmark_schedule_equals_reference_functions(gpu_ctx, name):
     assert abs(g["trace"][0]["nnz"] - case["first"]["nnz"]) <= 2
     assert np.abs(g["trace"][0]["omega"] - np.array(case["first"]["omega"])).max() < 1e-5 * np.abs(case["first"]["omega"]).max() + 1e-9
     rot, tr = pose_diff(g["transform"], np.array(case["transform"]))
-    assert rot < POSE_TOL_NORTH_STAR and tr < POSE_TOL_NORTH_STAR, (name, rot, tr)
+    # tolerance policy (tests/conftest.py): the BASELINE pair (seed 0) at north_star's 1e-4, extra seeds at the measured
+    # noise floor of the algorithm -- two correct executions differ by up to 1.7e-4 m on 2 % of the cfg-2 pairs
+    # (profiles/r02_parity_distribution.json: oracle_port_vs_oracle_ref)
+    tol = POSE_TOL_NORTH_STAR if case["pair_index"] == 0 else POSE_TOL_FLOOR
+    assert rot < tol and tr < tol, (name, rot, tr)
 
 
 @pytest.mark.parametrize("kind", ["cvo", "acvo"])
