@@ -75,3 +75,18 @@ def test_group_mode_is_automatic_for_a_large_pair_and_takes_pairs_in_order(ctx, 
     for s in (0, 1):
         one = ctx.align(np.array([s]), gp)
         assert np.array_equal(one["transform"][0], both["transform"][s])
+
+
+def test_every_cluster_rank_runs_on_its_lists(ctx):
+    """Guard against a silent fallback: a CTA whose neighbour list fails falls back to on-the-fly passes with identical
+    results, five times slower (this happened to every cluster rank > 0 when the quads' shared-memory addresses ignored
+    the cluster's shared-memory window).  cfg2 on one 16-CTA cluster takes 2.05 ms with lists, 10.5 ms without; the
+    budget sits between the two with a factor of two either side."""
+    pr = synth.config_pair(2)
+    ctx.set_pair(0, pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"])
+    ctx.set_cluster_size(16)
+    ctx.set_group_clusters(1)
+    gp = _fixed(capi.default_params("cvo"), capi, 100)
+    best = min(ctx.align(np.array([0]), gp) and ctx.last_kernel_ms for _ in range(3))
+    ctx.set_cluster_size(0)
+    assert best < 4.5, best
