@@ -94,6 +94,7 @@ struct cvo_b200_ctx {
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
     float list_skin = 0.10f;  // measured optimum (cfg2 and the stock schedules, profiles/r02_skin_sweep.txt)
+    float list_skin_min = 0.003f;  // absolute floor of the skin [m]: stock cvo +4 % (short lists at small ell, fewer rebuilds)
     float list_shrink = 0.7f;
     float list_refine_min = 1.0f;
     long long last_list_builds = 0, last_list_refines = 0, last_xy_entries = 0, last_xy_slots = 0;
@@ -521,6 +522,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     args.list_entries = lists ? ctx->d_list_entries : nullptr;
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
+    args.list_skin_min = ctx->list_skin_min;
     args.list_shrink = ctx->list_shrink;
     args.list_refine_min = ctx->list_refine_min;
     // The pair descriptors and states live in pinned host memory that the kernel reads and writes directly (unified
@@ -687,6 +689,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     if (env && atof(env) > 0.0 && atof(env) <= 1.0) ctx->list_shrink = (float)atof(env);
     env = getenv("CVO_B200_LIST_REFINE_MIN");
     if (env && atof(env) > 0.0) ctx->list_refine_min = (float)atof(env);
+    env = getenv("CVO_B200_LIST_SKIN_MIN");
+    if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin_min = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN");
     if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin = (float)atof(env);
 #undef CKC

@@ -304,6 +304,7 @@ struct AlignArgs {
     uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
     unsigned list_cap;
     float list_skin;
+    float list_skin_min;  // absolute floor of the skin [m]: at small length-scales the lists are short and rebuilds dominate
     float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius
     float list_refine_min;  // ... by filtering the old list if it has at least this fraction of a fresh skin to spare
     // Whole-GPU mode for a few large pairs: ALL `group_clusters` clusters of the launch work on the same pair (the pairs
@@ -1397,7 +1398,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
 // Called by all lanes of warp 0 (after lane 0 ran prepare_iter and a __syncwarp): the 8 box corners go to 8 lanes.
-__device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink, float refine_min) {
+__device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, float shrink, float refine_min) {
     const int lane = threadIdx.x & 31;
     double disp_xy = 0.0;
     if (sm.lst[LIST_XY].valid > 0) {
@@ -1438,7 +1439,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float shrink, float
         }
         L.need = need ? 1 : 0;
         if (need) {
-            double s = (double)skin * r_now;
+            double s = fmax((double)skin * r_now, (double)skin_min);
             if (kind != LIST_XY && L.valid > 0 && r_now <= (double)L.r0) {  // (the (x, y) list is rebuilt: its quads are row-sorted)
                 // The ball has shrunk and the old list still covers the pose with room to spare: everything the new
                 // list must hold (|x_i - T1 y_j| < r_e1 + s1, r_e1 <= r_e0) is in the old one as long as
@@ -2325,7 +2326,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 prepare_iter(sm, kp, kp.d2c_thres);
             }
             __syncwarp();
-            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink, args.list_refine_min);
+            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min);
         }
         __syncthreads();
 #ifdef CVO_PHASE_CLOCKS
@@ -2390,7 +2391,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                     }
                     __syncwarp();
                     CVO_PHASE(12)
-                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_shrink, args.list_refine_min);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min);
                     CVO_PHASE(13)
                 }
             }

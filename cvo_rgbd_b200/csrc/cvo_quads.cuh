@@ -144,13 +144,14 @@ struct QuadGeom {
     float2 dxa, dya, dza, d2a;     // candidates 0, 1: d = y - x, |d|^2 (nanoflann's accumulation order, see dist2)
     float2 dxb, dyb, dzb, d2b;     // candidates 2, 3
     float2 aa, ab;                 // a (0 where a gate failed)
+    uint32_t rw;                   // the row's shared-memory address, window included
 };
 
 // `near`: some candidate of the quad has its fast kernel value inside the re-decision band around sp_thres.
 __device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp, uint32_t win, const Quad& q, QuadGeom& g) {
     constexpr uint32_t P = kPlaneBytes;
     // field | window in one byte permute each: bytes {f0, f1, w2, w3}
-    const uint32_t rw = __byte_perm(q.row, win, 0x7610);
+    const uint32_t rw = g.rw = __byte_perm(q.row, win, 0x7610);
     g.xr = lds_at<0>(rw); g.yr = lds_at<P>(rw); g.zr = lds_at<2 * P>(rw);
     const uint32_t c0 = __byte_perm(q.cols.x, win, 0x7610), c1 = __byte_perm(q.cols.x, win, 0x7632);
     const uint32_t c2 = __byte_perm(q.cols.y, win, 0x7610), c3 = __byte_perm(q.cols.y, win, 0x7632);
@@ -194,7 +195,9 @@ __device__ __forceinline__ void redecide(const Smem& sm, const HotConsts& hc, co
     float a[4] = {g.aa.x, g.aa.y, g.ab.x, g.ab.y};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float fast = __fmul_rn(kp.s2cs2, exp2f_approx(fmaf(d2[e], -hc.c1, nt[e])));
+        float d2e = d2[e];
+        asm volatile("" : "+f"(d2e));  // pins this arithmetic to the cold path (the compiler hoisted it above the vote otherwise)
+        const float fast = __fmul_rn(kp.s2cs2, exp2f_approx(fmaf(d2e, -hc.c1, nt[e])));
         if (fabsf(fast - kp.sp_thres) < kp.sp_band) a[e] = quad_exact1(sm, kp, src, q.row, cb[e], d2[e]);
     }
     g.aa = make_float2(a[0], a[1]);
@@ -532,7 +535,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
         quads::QuadGeom g;                                                                     \
         const bool near = quads::quad_geom(hc, kp, win, q, g);                                     \
         if (__any_sync(0xffffffffu, near)) quads::redecide(sm, hc, kp, src, q, g);             \
-        if (KIND == PASS_STEP) quads::step_quad(sc, q.row | win, g, acc);                        \
+        if (KIND == PASS_STEP) quads::step_quad(sc, g.rw, g, acc);                               \
         else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                     \
     }
 #pragma unroll 1
