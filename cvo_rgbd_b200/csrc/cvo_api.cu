@@ -94,6 +94,10 @@ struct cvo_b200_ctx {
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
     float list_skin = 0.10f;  // measured optimum (cfg2 and the stock schedules, profiles/r02_skin_sweep.txt)
+    // Extra slack W / r of the WIDE (x, y) list (WideState in cvo_kernels.cuh); 0 = off, < 0 = automatic: 0.5 for acvo, whose
+    // length-scale moves every iteration (12.8 rebuilds per pair: stock acvo +5 %), off for cvo (a filter of the wide list costs
+    // 0.6 of a sweep and the wide sweep 1.6: cfg 2 -2 %, stock cvo -8 %; profiles/r02_wide_list.txt)
+    float list_wide = -1.0f;
     float list_skin_min = 0.003f;  // absolute floor of the skin [m]: stock cvo +4 % (short lists at small ell, fewer rebuilds)
     float list_shrink = 0.7f;
     float list_refine_min = 1.0f;
@@ -340,7 +344,7 @@ void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
         if (ctx->list_cap > cap) cap = ctx->list_cap;
         if (ctx->list_ctas > n_ctas) n_ctas = ctx->list_ctas;
     }
-    const size_t areas = (size_t)n_ctas * (LIST_KINDS + 1);
+    const size_t areas = (size_t)n_ctas * kListAreas;
     if (cudaMalloc(&ctx->d_list_entries, areas * cap * sizeof(uint2) + kListSlackBytes) != cudaSuccess) {
         cudaGetLastError();
         ctx->d_list_entries = nullptr;
@@ -523,6 +527,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
     args.list_skin_min = ctx->list_skin_min;
+    args.list_wide = ctx->list_wide >= 0.f ? ctx->list_wide : (args.kp.mode == CVO_B200_MODE_ACVO ? 0.5f : 0.f);
     args.list_shrink = ctx->list_shrink;
     args.list_refine_min = ctx->list_refine_min;
     // The pair descriptors and states live in pinned host memory that the kernel reads and writes directly (unified
@@ -689,6 +694,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     if (env && atof(env) > 0.0 && atof(env) <= 1.0) ctx->list_shrink = (float)atof(env);
     env = getenv("CVO_B200_LIST_REFINE_MIN");
     if (env && atof(env) > 0.0) ctx->list_refine_min = (float)atof(env);
+    env = getenv("CVO_B200_LIST_WIDE");
+    if (env && atof(env) >= 0.0 && atof(env) <= 4.0) ctx->list_wide = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN_MIN");
     if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin_min = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN");
@@ -1281,7 +1288,7 @@ int cvo_b200_neighbor_lists_active(const cvo_b200_ctx* ctx) {
 }
 long long cvo_b200_list_scratch_bytes(const cvo_b200_ctx* ctx) {
     if (!ctx || !ctx->d_list_entries) return 0;
-    return (long long)ctx->list_ctas * (LIST_KINDS + 1) * (long long)ctx->list_cap * (long long)sizeof(uint2);
+    return (long long)ctx->list_ctas * kListAreas * (long long)ctx->list_cap * (long long)sizeof(uint2);
 }
 
 }  // extern "C"

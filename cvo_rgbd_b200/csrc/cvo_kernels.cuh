@@ -87,6 +87,7 @@ enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INN
 // column cloud by more than the skin (or ell changed the radius).  Only INDICES are stored: the strict ell-ball
 // test, the colour gate and the kernel value are still evaluated on the fly in every pass, A never exists.
 enum ListKind { LIST_XY = 0, LIST_XX = 1, LIST_YY = 2, LIST_KINDS = 3 };
+constexpr int kListAreas = LIST_KINDS + 2;  // per CTA: the three lists, the build staging, the wide (x, y) list
 constexpr int kMaxListRounds = 36;  // (row round, column chunk) combinations of one pass: 6 x 6 chunks of 3072 points
 constexpr int kListTrip = 128;      // entries one warp handles per trip of a list pass; rounds are padded to it
 #ifndef CVO_PREFETCH_TRIPS
@@ -224,6 +225,22 @@ struct ListState {
     int need;         // (re)build before this iteration's passes
 };
 
+// The WIDE (x, y) candidate list: what an all-pairs sweep found within r_e + s + W of the sweep's pose, kept per row tile in
+// the staged format (column, row within the tile, t_c).  While it covers the current pose and length-scale, a rebuild of
+// the quads is a FILTER of it (one streaming pass, ~45 instructions per 32 entries) instead of another all-pairs sweep.
+// Coverage: a pair can only be wanted by a new list (|x_i - T1 y_j| < r_e1 + s1) if it is in the wide one
+// (|x_i - Tw y_j| < r_e_w + s_w + W), i.e. as long as  max(0, r1 - r_w) + disp(Tw -> T1) + s1 <= s_w + W  (r_e scales
+// with the length-scale and never exceeds r: the pair-specific radii only make the left side smaller).
+struct WideState {
+    float tf[12];      // transform of the sweep
+    float r0;          // ell-ball radius of the sweep
+    float slack;       // s_w + W, rounded down: what the coverage test may assume
+    float s_build;     // s_w + W + rounding margin, rounded up: what the sweep adds to a pair's own radius
+    float thr_build;   // (r0 + s_build)^2: the sweep's prefilter ball
+    int valid;         // 1: covers what `slack` says; 0: none (never built, overflowed its area, other pair)
+    int make;          // this iteration's sweep also writes the wide list
+};
+
 // Identity of the points a shared-memory stage holds: (cloud, first point, count, pose).  `serial` is the iteration
 // whose transform was applied, -1 for untransformed points, -2 for "nothing usable".
 struct StageTag {
@@ -247,10 +264,12 @@ __device__ __forceinline__ float plane_ld(const void* base, uint32_t byte_off) {
 __device__ __forceinline__ float* plane_of(void* base, int plane) { return reinterpret_cast<float*>(base) + plane * kColChunk; }
 
 struct ListRef {
-    uint2* entries;  // the flat list: (row * 4 << 16 | col * 4 within the round's chunks, bits of the colour exponent t_c)
+    uint2* entries;  // the list area: quads ((x, y) list, cvo_quads.cuh) or flat 8-byte entries (self lists)
     uint2* staging;  // build scratch of the CTA (shared by its three lists): per-unit regions before compaction
+    uint2* wide;     // the CTA's WIDE (x, y) candidate list (see WideState): [kWideTable (offset, count) records][entries]
     unsigned cap;
 };
+constexpr int kWideTable = kMaxListRounds * kColTiles;  // one record per (round, row tile) of the CTA
 
 struct Smem {
     float4 colG[kColChunk];   // on-the-fly passes / list builds: {x, y, z, |c|^2} records of the staged (transformed) columns;
@@ -271,6 +290,8 @@ struct Smem {
     float wred[kWarps][6];    // per-warp partial bounding boxes (pair start)
     float ybox[6];            // bounding box of the moving cloud, original coordinates
     ListState lst[LIST_KINDS];
+    WideState wide;
+    int wide_ovf;  // a warp's share of the wide area overflowed during this sweep
     int lst_used, lst_ovf;
     int next_unit;
     int next_pair;
@@ -304,6 +325,7 @@ struct AlignArgs {
     uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
     unsigned list_cap;
     float list_skin;
+    float list_wide;      // W / r: extra slack of the wide list, 0 = no wide list (every rebuild is a sweep)
     float list_skin_min;  // absolute floor of the skin [m]: at small length-scales the lists are short and rebuilds dominate
     float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius
     float list_refine_min;  // ... by filtering the old list if it has at least this fraction of a fresh skin to spare
@@ -1398,32 +1420,36 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
 // Called by all lanes of warp 0 (after lane 0 ran prepare_iter and a __syncwarp): the 8 box corners go to 8 lanes.
-__device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, float shrink, float refine_min) {
+__device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, float shrink, float refine_min, float wide_factor) {
     const int lane = threadIdx.x & 31;
-    double disp_xy = 0.0;
-    if (sm.lst[LIST_XY].valid > 0) {
-        // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is attained at
-        // one of the 8 corners
-        const ListState& L = sm.lst[LIST_XY];
+    // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is attained at one of
+    // the 8 corners.  Lanes 0..7: against the pose the (x, y) list was built at; lanes 8..15: against the wide list's.
+    double disp_xy = 0.0, disp_wide = 0.0;
+    {
+        const bool wide_half = (lane & 8) != 0;
+        const float* tf0 = wide_half ? sm.wide.tf : sm.lst[LIST_XY].tf;
+        const bool have = wide_half ? sm.wide.valid > 0 : sm.lst[LIST_XY].valid > 0;
         const int c = lane & 7;
         double dm[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)L.tf[i];
+        for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)tf0[i];
         const double px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
         const double ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
         const double ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
         const double ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
         double d = sqrt(ex * ex + ey * ey + ez * ez);
-        if (!(d == d)) d = 1.0e30;  // NaN state: never trust an old list
+        if (!(d == d) || !have) d = 1.0e30;  // NaN state / no such list: never trust it
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
-        disp_xy = d;
+        disp_xy = __shfl_sync(0xffffffffu, d, 0);
+        disp_wide = __shfl_sync(0xffffffffu, d, 8);
     }
-    __syncwarp();  // every lane has read the build transform before lane 0 may replace it
+    __syncwarp();  // every lane has read the build transforms before lane 0 may replace them
     if (lane != 0) return;
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
     const int nk = acvo ? LIST_KINDS : 1;
+    sm.wide.make = 0;
     for (int kind = 0; kind < nk; ++kind) {
         ListState& L = sm.lst[kind];
         if (L.valid < 0) {  // overflowed earlier for this pair: stay on the fly
@@ -1444,11 +1470,30 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
                 // The ball has shrunk and the old list still covers the pose with room to spare: everything the new
                 // list must hold (|x_i - T1 y_j| < r_e1 + s1, r_e1 <= r_e0) is in the old one as long as
                 // s1 + disp <= s0, so the new list is a FILTER of the old one (refine_list) -- no all-pairs sweep.
-                const double disp = kind == LIST_XY ? disp_xy : 0.0;
-                const double left = (double)L.slack - disp - margin;
+                const double left = (double)L.slack - margin;
                 if (left >= (double)refine_min * s) {
                     s = fmin(s, left);
                     L.need = 2;
+                }
+            }
+            if (kind == LIST_XY && wide_factor > 0.f) {
+                // the quads as a filter of the wide list (need = 3) while it covers them -- and is not much too wide itself
+                WideState& Wd = sm.wide;
+                const bool covers = Wd.valid > 0 && fmax(0.0, r_now - (double)Wd.r0) + disp_wide + s + margin <= (double)Wd.slack &&
+                                    r_now >= 0.6 * (double)Wd.r0;
+                if (covers) {
+                    L.need = 3;
+                } else {  // this sweep writes a new wide list as well
+                    const double sw = s + (double)wide_factor * r_now;
+                    const double rbw = r_now + sw + margin;
+                    Wd.make = 1;
+                    Wd.valid = 0;
+                    Wd.r0 = (float)r_now;
+                    Wd.slack = (float)(sw * (1.0 - 1.0e-6));
+                    Wd.s_build = (float)((sw + margin) * (1.0 + 1.0e-6));
+                    Wd.thr_build = (float)(rbw * rbw * (1.0 + 1.0e-6));
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) Wd.tf[i] = sm.ic.tf[i];
                 }
             }
             const double rb = r_now + s + margin;
@@ -1460,7 +1505,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
             L.inv_c1 = (float)(2.0 * (double)sm.st.ell * (double)sm.st.ell / 1.4426950408889634 * (1.0 + 1.0e-6));
 #pragma unroll
             for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i];
-            if (L.need == 2) sm.st.n_refines += 1;
+            if (L.need >= 2) sm.st.n_refines += 1;
             else if (kind == LIST_XY) sm.st.n_builds += 1;
         }
     }
@@ -1530,9 +1575,16 @@ __device__ __forceinline__ uint32_t live_col_tiles(const Smem& sm, const RowTile
 // pair of invariants (d2, colour d2), and a pass over it touches no point data at all.  For (y, y) the sign bit of the
 // colour distance marks the rows that contribute to the length-scale gradient (always for (x, x); for (y, y) quirk Q1:
 // original index >= num_fixed).
+// Where a sweep writes the WIDE (x, y) list (WideState): this warp's share of the wide area.
+struct WideOut {
+    uint2* out;
+    int limit, cursor;
+    float s_build;  // 0 = this sweep writes no wide list
+};
 template <int SELF>
 __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
-                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2& e) {
+                                           uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2& e,
+                                           float wide_s_build, bool& keep_wide) {
     const int row = (int)(ent >> 12), col = (int)(ent & 0xfffu);
     const float4 xg = ws.rowG[row];
     const float4 xf = ws.rowF[row];
@@ -1550,66 +1602,90 @@ __device__ __forceinline__ bool build_test(const Smem& sm, const WarpScratch& ws
         const bool q1 = SELF == 1 || ws.rowOrig[row] >= yy_row_min;  // (x, x): every row counts
         e = make_uint2(__float_as_uint(d2), __float_as_uint(d2c) | (q1 ? 0x80000000u : 0u));
     }
-    return live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
+    const bool gates = live && (d2c < sm.ic.d2c_thres) && (re2 > 0.f);
+    if (SELF == 0) {  // the wide list's ball around the same pair (wide_s_build = 0: not asked for)
+        const float limw = lim - L.s_build + wide_s_build;
+        keep_wide = gates && (d2 < limw * limw * 1.000001f);
+    }
+    return gates && (d2 < lim * lim * 1.000001f);
 }
 // appends the kept candidates of one warp-wide batch in lane order
 // (a unit that outgrows the warp's staging segment keeps counting without storing: the build then reports overflow)
-// SELF == 0: a row tile of an (x, y) build belongs to ONE warp for the whole column range, so the rows' candidate counts
-// are private to the warp (no atomics) and every kept candidate gets its RANK within its row here -- count so far plus
-// its position among the batch's lanes with the same row (match.any).  The rank is stored with the candidate, which
-// makes the row-sorted compaction (compact_quads) a scatter of independent entries.
+// SELF == 0: a row tile of an (x, y) build belongs to ONE warp for the whole column range, and its 32 rows map onto the
+// warp's 32 lanes: lane r keeps row r's candidate count in a REGISTER (`row_cnt`).  Every kept candidate gets its RANK
+// within its row here -- the row's count so far (one shuffle) plus its position among the batch's lanes with the same
+// row.  Those lane sets come from six ballots (keep + the five bits of the row), combined per lane with a few logic
+// operations: no shared memory, no warp barrier, nothing the compiler cannot interleave with the next batch.  The rank
+// is stored with the candidate, which makes the row-sorted compaction (compact_quads) a scatter of independent entries.
 template <int SELF>
-__device__ __forceinline__ void build_append(Smem& sm, bool keep, uint2 e, uint2* out, int limit, int& cursor, int row_off) {
-    const int lane = threadIdx.x & 31;
-    if (SELF == 0) {
-        const int r = keep ? row_off + (int)((e.x >> 12) & 31u) : -1 - lane;
-        const unsigned m = __match_any_sync(0xffffffffu, r);
-        int* cnt = sm.u.of.bu.rowCnt;
-        const int base = keep ? cnt[r] : 0;
-        __syncwarp();
-        if (keep && lane == __ffs(m) - 1) cnt[r] = base + __popc(m);
-        __syncwarp();
-        e.x |= (uint32_t)(base + __popc(m & ((1u << lane) - 1u))) << 17;
-    }
+__device__ __forceinline__ void build_append(bool keep, uint2 e, uint2* out, int limit, int& cursor, int& row_cnt) {
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (SELF == 0) {
+        const uint32_t row = (e.x >> 12) & 31u;
+        uint32_t same = b, mine = b;  // kept lanes whose row is this lane's candidate's row / whose row is this LANE
+#pragma unroll
+        for (int bit = 0; bit < 5; ++bit) {
+            const uint32_t bb = __ballot_sync(0xffffffffu, (row >> bit) & 1u);
+            same &= ((row >> bit) & 1u) ? bb : ~bb;
+            mine &= ((lane >> bit) & 1u) ? bb : ~bb;
+        }
+        const int base = __shfl_sync(0xffffffffu, row_cnt, (int)row);
+        e.x |= (uint32_t)(base + __popc(same & ((1u << lane) - 1u))) << 17;
+        row_cnt += __popc(mine);
+    }
     if (keep && cursor + kTile <= limit) __stcg(out + cursor + __popc(b & ((1u << lane) - 1u)), e);
     cursor += __popc(b);
+}
+// appends the batch's candidates inside the wide list's ball to the warp's share of the wide area (lane order, no ranks)
+__device__ __forceinline__ void wide_append(bool keep, const uint2& e, WideOut& wo) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (keep && wo.cursor + kTile <= wo.limit) __stcg(wo.out + wo.cursor + __popc(b & ((1u << lane) - 1u)), e);
+    wo.cursor += __popc(b);
 }
 template <int SELF>
 __device__ __forceinline__ void build_eval(Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
                                            uint32_t ent, bool live, uint32_t row_off, int yy_row_min, uint2* out, int limit,
-                                           int& cursor) {
+                                           int& cursor, WideOut& wo, int& row_cnt) {
     uint2 e;
-    const bool keep = build_test<SELF>(sm, ws, kp, L, ent, live, row_off, yy_row_min, e);
-    build_append<SELF>(sm, keep, e, out, limit, cursor, (int)row_off);
+    bool kw = false;
+    const bool keep = build_test<SELF>(sm, ws, kp, L, ent, live, row_off, yy_row_min, e, wo.s_build, kw);
+    if (SELF == 0 && wo.s_build > 0.f) wide_append(kw, e, wo);
+    build_append<SELF>(keep, e, out, limit, cursor, row_cnt);
 }
 // two batches at once: their loads and arithmetic interleave (the evaluation is latency-bound on one batch)
 template <int SELF>
 __device__ __forceinline__ void build_eval2(Smem& sm, const WarpScratch& ws, const KParams& kp, const ListState& L,
                                             uint32_t ent0, uint32_t ent1, uint32_t row_off, int yy_row_min, uint2* out,
-                                            int limit, int& cursor) {
+                                            int limit, int& cursor, WideOut& wo, int& row_cnt) {
     uint2 e0, e1;
-    const bool k0 = build_test<SELF>(sm, ws, kp, L, ent0, true, row_off, yy_row_min, e0);
-    const bool k1 = build_test<SELF>(sm, ws, kp, L, ent1, true, row_off, yy_row_min, e1);
-    build_append<SELF>(sm, k0, e0, out, limit, cursor, (int)row_off);
-    build_append<SELF>(sm, k1, e1, out, limit, cursor, (int)row_off);
+    bool kw0 = false, kw1 = false;
+    const bool k0 = build_test<SELF>(sm, ws, kp, L, ent0, true, row_off, yy_row_min, e0, wo.s_build, kw0);
+    const bool k1 = build_test<SELF>(sm, ws, kp, L, ent1, true, row_off, yy_row_min, e1, wo.s_build, kw1);
+    if (SELF == 0 && wo.s_build > 0.f) {
+        wide_append(kw0, e0, wo);
+        wide_append(kw1, e1, wo);
+    }
+    build_append<SELF>(k0, e0, out, limit, cursor, row_cnt);
+    build_append<SELF>(k1, e1, out, limit, cursor, row_cnt);
 }
 
 template <int SELF>
 __device__ __forceinline__ int build_unit_write(Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
                                                 const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int yy_row_min,
-                                                int ct_begin, int ct_end, uint2* out, int limit) {
+                                                int ct_begin, int ct_end, uint2* out, int limit, float thr_build, WideOut& wo) {
     const int lane = threadIdx.x & 31;
     const RowTile rt = load_row_tile<true, SELF == 2, true>(sm, ws, rows, row_tf, tile);
-    const float thr_box = L.thr_build * 1.0001f;
+    const float thr_box = thr_build * 1.0001f;
     uint32_t* q = sm_queue(sm);
-    int qn = 0, cursor = 0;
+    int qn = 0, cursor = 0, row_cnt = 0;
     for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
         uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
         while (lm) {
             const int j = __ffs(lm) - 1;
             lm &= lm - 1;
-            const uint32_t mask = prefilter_tile(sm, rt.rr, c0 + j, L.thr_build);
+            const uint32_t mask = prefilter_tile(sm, rt.rr, c0 + j, thr_build);
             if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
             int excl, total;
             warp_scan_count(__popc(mask), lane, excl, total);
@@ -1618,16 +1694,51 @@ __device__ __forceinline__ int build_unit_write(Smem& sm, WarpScratch& ws, const
             __syncwarp();
             while (qn >= 64) {
                 qn -= 64;
-                build_eval2<SELF>(sm, ws, kp, L, q[qn + 32 + lane], q[qn + lane], row_off, yy_row_min, out, limit, cursor);
+                build_eval2<SELF>(sm, ws, kp, L, q[qn + 32 + lane], q[qn + lane], row_off, yy_row_min, out, limit, cursor, wo, row_cnt);
             }
             if (qn >= 32) {
                 qn -= 32;
-                build_eval<SELF>(sm, ws, kp, L, q[qn + lane], true, row_off, yy_row_min, out, limit, cursor);
+                build_eval<SELF>(sm, ws, kp, L, q[qn + lane], true, row_off, yy_row_min, out, limit, cursor, wo, row_cnt);
             }
             __syncwarp();
         }
     }
-    if (qn > 0) build_eval<SELF>(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, yy_row_min, out, limit, cursor);
+    if (qn > 0) build_eval<SELF>(sm, ws, kp, L, lane < qn ? q[lane] : 0u, lane < qn, row_off, yy_row_min, out, limit, cursor, wo, row_cnt);
+    if (SELF == 0) sm.u.of.bu.rowCnt[row_off + lane] = row_cnt;  // lane r: candidates kept for row r of the tile
+    __syncwarp();
+    return cursor;
+}
+
+// A row tile of the (x, y) list as a FILTER of the wide list (WideState): the tile's wide candidates stream past, those
+// inside r_e + s of the current pose and length-scale (build_test's criterion; the colour gate was applied by the sweep)
+// are ranked and staged exactly like a sweep's.
+__device__ __forceinline__ int filter_unit_write(Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
+                                                 const CloudDev& rows, int tile, uint32_t row_off, const uint2* src, int n,
+                                                 uint2* out, int limit) {
+    const int lane = threadIdx.x & 31;
+    load_row_tile<false, false, false>(sm, ws, rows, false, tile);
+    int cursor = 0, row_cnt = 0;
+    for (int i1 = 0; i1 < n; i1 += 128) {  // four batches per step: loads, then tests, then appends
+        uint2 ev[4];
+        bool keep[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ev[j] = (i1 + 32 * j + lane < n) ? __ldcg(src + i1 + 32 * j + lane) : make_uint2(0u, 0x7f800000u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // (idle lanes: row 0, column 0, t_c = +inf: never kept)
+            const float4 xg = ws.rowG[(ev[j].x >> 12) & 31u];
+            const float4 yg = sm.colG[ev[j].x & 0xfffu];
+            const float d2 = dist2(yg.x - xg.x, yg.y - xg.y, yg.z - xg.z);
+            const float re2 = (kp.t_lim - __uint_as_float(ev[j].y)) * L.inv_c1;
+            const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + L.s_build;
+            keep[j] = (re2 > 0.f) && (d2 < lim * lim * 1.000001f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i1 + 32 * j >= n) break;
+            build_append<0>(keep[j], ev[j], out, limit, cursor, row_cnt);
+        }
+    }
+    sm.u.of.bu.rowCnt[row_off + lane] = row_cnt;
     __syncwarp();
     return cursor;
 }
@@ -1650,18 +1761,31 @@ __device__ __forceinline__ int next_unit(Smem& sm) {
 template <int SELF>
 __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int kind, int round, int ntile, int Sb);
 
+// (x, y) list only -- `from_wide`: the round's candidates come from the wide list (filter_unit_write) instead of the
+// all-pairs sweep; otherwise, if sm.wide.make is set, the sweep also writes a new wide list (per warp a share of the wide
+// area that runs on from round to round; per (round, row tile) an (offset, count) record at the head of the area).
 template <int SELF>
 __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bool row_tf, const CloudDev& cols, bool col_tf,
-                           int rank, int G, int yy_row_min, uint32_t& tma_phase, int kind, const ListRef& lr) {
+                           int rank, int G, int yy_row_min, uint32_t& tma_phase, int kind, const ListRef& lr,
+                           bool from_wide = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
     const ListState& L = sm.lst[kind];
     WarpScratch& ws = sm.u.of.ws[warp < kWorkWarps ? warp : 0];
     const int seg = (int)(lr.cap / kWorkWarps) & ~3;  // this warp's staging segment
     uint2* const stage = lr.staging + (size_t)warp * seg;
+    const bool make_wide = SELF == 0 && !from_wide && sm.wide.make != 0;
+    const int wseg = (int)((lr.cap - kWideTable) / kWorkWarps) & ~3;  // this warp's share of the wide area
+    WideOut wo;
+    wo.out = lr.wide + kWideTable + (size_t)warp * wseg;
+    wo.limit = wseg;
+    wo.cursor = 0;
+    wo.s_build = make_wide ? sm.wide.s_build : 0.f;
+    const float thr_build = make_wide ? sm.wide.thr_build : L.thr_build;
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
+        sm.wide_ovf = 0;
         sm.colTag.serial = sm.rowTag.serial = -2;  // the build's stage overwrites the list passes' stages
     }
     int round = 0;
@@ -1693,8 +1817,27 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 if (u >= nunits) break;
                 const int t = u / Sb, sg = u - t * Sb;
                 const int c_begin = (nct * sg) / Sb, c_end = (nct * (sg + 1)) / Sb;
-                const int c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile),
-                                                     yy_row_min, c_begin, c_end, stage + wcur, seg - wcur);
+                int c;
+                if (SELF == 0 && from_wide) {
+                    uint2 rec = make_uint2(0u, 0u);
+                    if (lane == 0) rec = __ldcg(lr.wide + round * kColTiles + t);
+                    rec.x = __shfl_sync(0xffffffffu, rec.x, 0);
+                    rec.y = __shfl_sync(0xffffffffu, rec.y, 0);
+                    c = filter_unit_write(sm, ws, kp, L, rows, pg.t_begin + rb + t, (uint32_t)(t * kTile),
+                                          lr.wide + kWideTable + rec.x, (int)rec.y, stage + wcur, seg - wcur);
+                } else {
+                    const int w0 = wo.cursor;
+                    wo.out = lr.wide + kWideTable + (size_t)warp * wseg + w0;
+                    wo.limit = wseg - w0;
+                    wo.cursor = 0;
+                    c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile),
+                                               yy_row_min, c_begin, c_end, stage + wcur, seg - wcur, thr_build, wo);
+                    if (make_wide && lane == 0) {
+                        __stcg(lr.wide + round * kColTiles + t, make_uint2((unsigned)(warp * wseg + w0), (unsigned)wo.cursor));
+                        if (w0 + wo.cursor > wseg) sm.wide_ovf = 1;
+                    }
+                    wo.cursor = min(w0 + wo.cursor, wseg);
+                }
                 if (lane == 0) {
                     sm.u.of.bu.off[u] = warp * seg + wcur;
                     sm.u.of.bu.act[u] = c;
@@ -1769,7 +1912,10 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     }
     __syncthreads();  // the list (global memory) is complete and visible to the whole CTA
     CVO_PHASE(9)
-    if (threadIdx.x == 0) sm.lst[kind].valid = sm.lst_ovf ? -1 : 1;
+    if (threadIdx.x == 0) {
+        sm.lst[kind].valid = sm.lst_ovf ? -1 : 1;
+        if (make_wide) sm.wide.valid = sm.wide_ovf ? 0 : 1;  // (an overflowed wide list is simply not used: sweeps go on)
+    }
     __syncthreads();
 }
 
@@ -2259,9 +2405,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
     ListRef lref[LIST_KINDS];
 #pragma unroll
     for (int i = 0; i < LIST_KINDS; ++i) {
-        const size_t area = (size_t)blockIdx.x * (LIST_KINDS + 1);
+        const size_t area = (size_t)blockIdx.x * kListAreas;
         lref[i].entries = args.list_entries + (area + i) * args.list_cap;
         lref[i].staging = args.list_entries + (area + LIST_KINDS) * args.list_cap;
+        lref[i].wide = args.list_entries + (area + LIST_KINDS + 1) * args.list_cap;
         lref[i].cap = args.list_cap;
     }
 
@@ -2291,6 +2438,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             sm.colTag.serial = sm.rowTag.serial = -2;
 #pragma unroll
             for (int i = 0; i < LIST_KINDS; ++i) sm.lst[i].valid = sm.lst[i].need = 0;
+            sm.wide.valid = sm.wide.make = 0;
         }
         __syncthreads();
         if (use_lists) {  // bounding box of the moving cloud (original coordinates), for list_policy
@@ -2326,7 +2474,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 prepare_iter(sm, kp, kp.d2c_thres);
             }
             __syncwarp();
-            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min);
+            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide);
         }
         __syncthreads();
 #ifdef CVO_PHASE_CLOCKS
@@ -2336,6 +2484,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
             // transform_pcd + se_kernel + compute_flow (src/cvo.cpp:371-374)
             CVO_PHASE(0)
             if (use_lists && sm.lst[LIST_XY].need == 1) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY]);
+            else if (use_lists && sm.lst[LIST_XY].need == 3) build_list<0>(sm, kp, pair.x, false, pair.y, true, rank, G, 0, tma_phase, LIST_XY, lref[LIST_XY], true);
             if (use_lists && acvo) {  // all builds come before the first pass: the stages the FLOW pass fills survive to the STEP pass
                 if (sm.lst[LIST_XX].need == 1) build_list<1>(sm, kp, pair.x, false, pair.x, false, rank, G, 0, tma_phase, LIST_XX, lref[LIST_XX]);
                 else if (sm.lst[LIST_XX].need == 2) refine_list<1>(sm, kp, pair.x, pair.x, rank, G, tma_phase, LIST_XX, lref[LIST_XX]);
@@ -2391,7 +2540,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                     }
                     __syncwarp();
                     CVO_PHASE(12)
-                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide);
                     CVO_PHASE(13)
                 }
             }

@@ -15,12 +15,12 @@ best = 1e9
 for rep in range(4):
     r = ctx.align(list(range(P)), gp)
     best = min(best, ctx.last_kernel_ms)
-print("%-28s cfg2 %.3f ms = %.0f pairs/s" % (tag, best, P / best * 1e3), flush=True)
+print("%-28s cfg2 %.3f ms = %.0f pairs/s  (sweeps %.2f, filters %.2f per pair)" % (tag, best, P / best * 1e3, ctx.last_list_builds / P, ctx.last_list_refines / P), flush=True)
 if "--all" in sys.argv:
     gp = capi.default_params('cvo')
     for rep in range(3):
         r = ctx.align(list(range(P)), gp)
-    print("%-28s stock cvo %.3f ms = %.0f pairs/s (iters %.1f)" % (tag, ctx.last_kernel_ms, P / ctx.last_kernel_ms * 1e3, r['iters'].mean()), flush=True)
+    print("%-28s stock cvo %.3f ms = %.0f pairs/s (iters %.1f; sweeps %.2f, filters %.2f per pair)" % (tag, ctx.last_kernel_ms, P / ctx.last_kernel_ms * 1e3, r['iters'].mean(), ctx.last_list_builds / P, ctx.last_list_refines / P), flush=True)
     for s in range(P):
         pr = synth.config_pair(3, s)
         ctx.set_pair(s, pr['x_pos'], pr['x_feat'], pr['y_pos'], pr['y_feat'])
