@@ -6,7 +6,9 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- synthetic 3000 x 3000-point RGB-D pairs, fixed
 ell = 0.10, exactly 100 inner iterations per pair (stop tests off) -- as a batch of `--pairs` independent
-pairs per GPU per step (default 2 x #SMs).  One step = align() of the whole batch.
+pairs per GPU per step (default 4 x #SMs: the CTAs pull pairs from a queue and a pair's cost varies with its
+list rebuilds, so a deeper queue amortises the last wave -- 2 x #SMs 19.1 k, 4 x 19.8 k, 8 x 20.4 k pairs/s,
+profiles/r02_batch_size.txt).  One step = align() of the whole batch.
   value  = pairs / device time of the align kernel (CUDA events on the library's stream), clouds resident in HBM
   e2e    = pairs / wall time of: upload of every pair from pinned host memory (cvo_b200_set_pairs: H2D + on-device
            Morton sort/pack) + cvo_b200_align + the poses coming back to the host (+ NCCL all-gather of the poses
@@ -349,7 +351,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (default 2 x #SMs)")
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU per step (default 4 x #SMs)")
     ap.add_argument("--cpu-pairs", type=int, default=0,
                     help="pairs in the bounded CPU sample (default: 96 for cpu_baseline ~ 12 s, 32 per step for --impl reference)")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per pair (0 = automatic)")
@@ -383,7 +385,7 @@ def main():
     probe = capi.Context(local_rank, 64, 1)
     num_sms = probe.num_sms
     probe.close()
-    P = args.pairs if args.pairs > 0 else 2 * num_sms
+    P = args.pairs if args.pairs > 0 else 4 * num_sms
     ctx = capi.Context(local_rank, max_points=N_POINTS + 72, max_slots=2 * P)
     if args.cluster:
         ctx.set_cluster_size(args.cluster)

@@ -1430,19 +1430,22 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
         const float* tf0 = wide_half ? sm.wide.tf : sm.lst[LIST_XY].tf;
         const bool have = wide_half ? sm.wide.valid > 0 : sm.lst[LIST_XY].valid > 0;
         const int c = lane & 7;
-        double dm[12];
+        // f32 throughout: the differences of the transform entries are exact or nearly so (neighbouring poses), the
+        // rounding of the rest (~1e-7 relative of a displacement of centimetres) is five orders below `margin`; the
+        // result is rounded UP by 1e-5 relative before it is trusted
+        float dm[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) dm[i] = (double)sm.ic.tf[i] - (double)tf0[i];
-        const double px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
-        const double ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
-        const double ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
-        const double ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
-        double d = sqrt(ex * ex + ey * ey + ez * ez);
-        if (!(d == d) || !have) d = 1.0e30;  // NaN state / no such list: never trust it
+        for (int i = 0; i < 12; ++i) dm[i] = sm.ic.tf[i] - tf0[i];
+        const float px = sm.ybox[(c & 1) ? 3 : 0], py = sm.ybox[(c & 2) ? 4 : 1], pz = sm.ybox[(c & 4) ? 5 : 2];
+        const float ex = dm[0] * px + dm[1] * py + dm[2] * pz + dm[9];
+        const float ey = dm[3] * px + dm[4] * py + dm[5] * pz + dm[10];
+        const float ez = dm[6] * px + dm[7] * py + dm[8] * pz + dm[11];
+        float d = sqrtf(ex * ex + ey * ey + ez * ez) * 1.00001f;
+        if (!(d == d) || !have) d = 1.0e30f;  // NaN state / no such list: never trust it
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
-        disp_xy = __shfl_sync(0xffffffffu, d, 0);
-        disp_wide = __shfl_sync(0xffffffffu, d, 8);
+        for (int o = 4; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+        disp_xy = (double)__shfl_sync(0xffffffffu, d, 0);
+        disp_wide = (double)__shfl_sync(0xffffffffu, d, 8);
     }
     __syncwarp();  // every lane has read the build transforms before lane 0 may replace them
     if (lane != 0) return;

@@ -285,7 +285,7 @@ __device__ __forceinline__ void step_pair(const StepConsts& sc, const StepRow& r
     tD = __ffma2_rn(beta, __ffma2_rn(b2, bc(1.f / 6.f), gamma), delta);
     tE = __ffma2_rn(__fmul2_rn(b2, b2), bc(-1.f / 12.f), __ffma2_rn(__fmul2_rn(bc(0.5f), tC), tC, __ffma2_rn(beta, delta, epsil)));
 }
-__device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, const QuadGeom& g, double* acc) {  // rowb: window included
+__device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, const QuadGeom& g, FlowPartial& fp) {  // rowb: window included
     constexpr uint32_t P = kPlaneBytes;  // the step stage holds the ROW terms: planes bx, by, bz, guu | qx, qy, qz, ew2
     StepRow r;
     r.bx = lds_at<kRowZ1>(rowb); r.by = lds_at<kRowZ1 + P>(rowb); r.bz = lds_at<kRowZ1 + 2 * P>(rowb); r.guu = lds_at<kRowZ1 + 3 * P>(rowb);
@@ -293,12 +293,16 @@ __device__ __forceinline__ void step_quad(const StepConsts& sc, uint32_t rowb, c
     float2 bA, cA, dA, eA, bB, cB, dB, eB;
     step_pair(sc, r, g.dxa, g.dya, g.dza, g.d2a, bA, cA, dA, eA);
     step_pair(sc, r, g.dxb, g.dyb, g.dzb, g.d2b, bB, cB, dB, eB);
-    // A_ij times the brackets (:275-279); the quad's four terms are summed in f32, then promoted (the reference promotes
-    // every term)
-    acc[0] += (double)hsum(__ffma2_rn(g.ab, bB, __fmul2_rn(g.aa, bA)));
-    acc[1] += (double)hsum(__ffma2_rn(g.ab, cB, __fmul2_rn(g.aa, cA)));
-    acc[2] += (double)hsum(__ffma2_rn(g.ab, dB, __fmul2_rn(g.aa, dA)));
-    acc[3] += (double)hsum(__ffma2_rn(g.ab, eB, __fmul2_rn(g.aa, eA)));
+    // A_ij times the brackets (:275-279); the terms of up to three quads are summed in f32 (each is an f32 value already),
+    // then promoted (flush_step; the reference promotes every term)
+    fp.po0 += hsum(__ffma2_rn(g.ab, bB, __fmul2_rn(g.aa, bA)));
+    fp.po1 += hsum(__ffma2_rn(g.ab, cB, __fmul2_rn(g.aa, cA)));
+    fp.po2 += hsum(__ffma2_rn(g.ab, dB, __fmul2_rn(g.aa, dA)));
+    fp.pv0 += hsum(__ffma2_rn(g.ab, eB, __fmul2_rn(g.aa, eA)));
+}
+__device__ __forceinline__ void flush_step(FlowPartial& fp, double* acc) {
+    acc[0] += (double)fp.po0; acc[1] += (double)fp.po1; acc[2] += (double)fp.po2; acc[3] += (double)fp.pv0;
+    fp.po0 = fp.po1 = fp.po2 = fp.pv0 = 0.f;
 }
 
 }  // namespace quads
@@ -535,7 +539,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
         quads::QuadGeom g;                                                                     \
         const bool near = quads::quad_geom(hc, kp, win, q, g);                                     \
         if (__any_sync(0xffffffffu, near)) quads::redecide(sm, hc, kp, src, q, g);             \
-        if (KIND == PASS_STEP) quads::step_quad(sc, g.rw, g, acc);                               \
+        if (KIND == PASS_STEP) quads::step_quad(sc, g.rw, g, fp);                                \
         else quads::flow_quad<KIND, STATS>(hc, kp, g, fp);                                     \
     }
 #pragma unroll 1
@@ -546,7 +550,8 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
                     if (--left == 0) break;
                     qa = quads::load_quad(rd, qi + 2 * kStep, pf_lane);
                     CVO_QUAD_TRIP(qb2)
-                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 2 quads (one or two rows) per f32 partial
+                    if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);  // <= 3 quads (a few rows) per f32 partial
+                    else quads::flush_step(fp, acc);
                     qi += kStep;
                     if (--left == 0) break;
                     qb2 = quads::load_quad(rd, qi + 2 * kStep, pf_lane);
@@ -557,6 +562,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
 #undef CVO_QUAD_TRIP
             }
             if (KIND != PASS_STEP) quads::flush_flow<KIND, STATS>(fp, acc);
+            else quads::flush_step(fp, acc);
         }
     }
     CVO_PHASE(KIND == PASS_STEP ? 4 : 2)  // instrumented variant: warp 0's trips; what follows is the wait for the slowest warp

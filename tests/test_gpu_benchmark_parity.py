@@ -2,7 +2,7 @@
 (1e-4 rad / 1e-4 m per pair, written below):
 
   cfg2  BASELINE.json configs[1]: 3000 x 3000 points, ELL_FIXED 0.10, exactly 100 iterations, stop tests off --
-        as a single pair on a whole-machine cluster AND as pairs inside the 2 x #SMs batch the benchmark launches
+        as a single pair on a 16-CTA cluster AND as pairs inside the k x #SMs batch the benchmark launches
         (one CTA per pair), i.e. the exact launch geometry of the headline number;
   cfg4  BASELINE.json configs[3]: ragged pairs N, M ~ U{2700..3300}, stock cvo schedule, identity init, aligned to
         convergence in ONE batch (reference loop: src/cvo_main.cpp:36-66 with cvo::align, src/cvo.cpp:361-420).
@@ -89,7 +89,7 @@ def test_cfg2_exact_single_pair_on_a_cluster(gpu_ctx, oracle):
 
 
 def test_cfg2_exact_pairs_inside_the_benchmark_batch(oracle):
-    """bench.py's launch: 2 x #SMs distinct cfg-2 pairs, one CTA per pair (G = 1), batched upload.  Sixteen pairs spread
+    """bench.py's launch geometry: a multiple of #SMs distinct cfg-2 pairs (here 2 x, bench.py 4 x), one CTA per pair (G = 1), batched upload.  Sixteen pairs spread
     over the batch (first and last CTA wave included) are checked against the oracle (module docstring); the whole batch must
     have run exactly 100 iterations and be finite; pair 0 must agree with the single-pair cluster run."""
     probe = capi.Context(0, 64, 1)
