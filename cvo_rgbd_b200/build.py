@@ -4,8 +4,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "cvo_api.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "cvo_kernels.cuh"), os.path.join(_HERE, "csrc", "cvo_quads.cuh"), os.path.join(_HERE, "csrc", "pcd_kernels.cuh"),
-        os.path.join(_HERE, "..", "include", "cvo_b200.h")]
+DEPS = [SRC, os.path.join(_HERE, "..", "include", "cvo_b200.h")] + sorted(
+    os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc")) if f.endswith(".cuh"))
 OUT = os.path.join(_HERE, "libcvo_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

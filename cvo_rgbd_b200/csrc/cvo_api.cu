@@ -94,7 +94,7 @@ struct cvo_b200_ctx {
     bool lists_enabled = true;
     bool lists_alloc_failed = false;
     float list_skin = 0.10f;  // measured optimum (cfg2 and the stock schedules, profiles/r02_skin_sweep.txt)
-    // Extra slack W / r of the WIDE (x, y) list (WideState in cvo_kernels.cuh); 0 = off, < 0 = automatic: 0.5 for acvo, whose
+    // Extra slack W / r of the WIDE (x, y) list (WideState in cvo_common.cuh); 0 = off, < 0 = automatic: 0.5 for acvo, whose
     // length-scale moves every iteration (12.8 rebuilds per pair: stock acvo +5 %), off for cvo (a filter of the wide list costs
     // 0.6 of a sweep and the wide sweep 1.6: cfg 2 -2 %, stock cvo -8 %; profiles/r02_wide_list.txt)
     float list_wide = -1.0f;

@@ -1,5 +1,5 @@
 """Host-side property checks of the neighbour-list validity rules the kernel applies (list_policy / build_list /
-refine_list in cvo_rgbd_b200/csrc/cvo_kernels.cuh), in f64 on random clouds and poses.
+refine_list in cvo_rgbd_b200/csrc/cvo_lists.cuh), in f64 on random clouds and poses.
 
 The lists replace the kd-tree radius search of the reference (src/cvo.cpp:106-125): they must hold a SUPERSET of
 the pairs that can pass the strict gates at every pose they are used for, otherwise a nonzero of A would be lost."""

@@ -1,4 +1,4 @@
-"""Host-side check of the algebra behind the STEP pass (cvo_rgbd_b200/csrc/cvo_kernels.cuh: step_col, step_terms).
+"""Host-side check of the algebra behind the STEP pass (cvo_rgbd_b200/csrc/cvo_onthefly.cuh: step_col, step_terms; the row-factored form of cvo_quads.cuh is checked against the same expressions).
 
 The reference forms xi^k z as matrix powers of Omega = skew(omega) (src/cvo.cpp:229-234) and takes four dot products
 with diff_xy per nonzero (:262-271).  The kernel takes three (z1.r, z2.r, omega.r) and uses
