@@ -424,14 +424,14 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                     if (lane == 0) rec = __ldcg(lr.wide + round * kColTiles + t);
                     rec.x = __shfl_sync(0xffffffffu, rec.x, 0);
                     rec.y = __shfl_sync(0xffffffffu, rec.y, 0);
-                    c = filter_unit_write(sm, ws, kp, L, rows, pg.t_begin + rb + t, (uint32_t)(t * kTile),
+                    c = filter_unit_write(sm, ws, kp, L, rows, pg.t_begin + (rb + t) * pg.t_stride, (uint32_t)(t * kTile),
                                           lr.wide + kWideTable + rec.x, (int)rec.y, stage + wcur, seg - wcur);
                 } else {
                     const int w0 = wo.cursor;
                     wo.out = lr.wide + kWideTable + (size_t)warp * wseg + w0;
                     wo.limit = wseg - w0;
                     wo.cursor = 0;
-                    c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + rb + t, (uint32_t)(t * kTile),
+                    c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + (rb + t) * pg.t_stride, (uint32_t)(t * kTile),
                                                yy_row_min, c_begin, c_end, stage + wcur, seg - wcur, thr_build, wo);
                     if (make_wide && lane == 0) {
                         __stcg(lr.wide + round * kColTiles + t, make_uint2((unsigned)(warp * wseg + w0), (unsigned)wo.cursor));
@@ -470,7 +470,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 const bool fits = !sm.lst_ovf && (unsigned)(at + padded) <= lr.cap;
                 if (fits)  // padding: t_c = +inf (pair list) / d2 = 1e30, colour d2 = +inf (self lists) => a = 0, finite terms
                     for (int i = base + lane; i < padded; i += 32)
-                        __stcg(lr.entries + at + i, make_uint2(SELF ? __float_as_uint(1.0e30f) : 0u, 0x7f800000u));
+                        __stcg(lr.entries + at + i, make_uint2(__float_as_uint(1.0e30f), 0x7f800000u));
                 __syncwarp();
                 if (lane == 0) {
                     if (fits) {
@@ -520,11 +520,11 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     __syncthreads();
 }
 
-// Stages this CTA's rows [first, first + n) of a packed cloud for a pass over a list: geometry only (transformed
-// if the rows are the moving cloud), the original index in the w lane; rows past the cloud's end are far away.
-__device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int first, int n, bool tf) {
+// Stages n rows of this CTA -- its row tiles tile0, tile0 + stride, ... of a packed cloud -- for a pass over a list:
+// geometry only (transformed if the rows are the moving cloud); rows past the cloud's end are far away.
+__device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int tile0, int stride, int n, bool tf) {
     for (int i = threadIdx.x; i < n; i += kThreads) {
-        const int p = first + i;
+        const int p = (tile0 + (i >> 5) * stride) * kTile + (i & 31);
         float4 g = make_float4(kRowSentinel, kRowSentinel, kRowSentinel, __int_as_float(-1));
         if (p < c.n) {
             float4 q = __ldg(c.g + p);
@@ -541,8 +541,8 @@ __device__ __forceinline__ void stage_rows(Smem& sm, const CloudDev& c, int firs
 // same range of the staging area (order kept, so the list stays a pure function of the inputs), the 16 counts are
 // scanned, the ranges are copied back behind one another and the round is padded to a whole trip.  The narrowed
 // rounds only ever move towards the front of the list area, behind the read position.
-//   SELF == 0: entries (row, col, t_c); the distance is measured on the staged rows / transformed columns.
-//   SELF != 0: entries (d2, colour d2 | Q1 flag): d2 is pose-independent, nothing is staged.
+// Self lists only (SELF = 1, 2; the row-sorted (x, y) list is rebuilt or filtered from the wide list instead): the
+// entries are (d2, colour d2 | Q1 flag), d2 is pose-independent, nothing is staged.
 template <int SELF>
 __device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const CloudDev& rows, const CloudDev& cols, int rank, int G,
                             uint32_t& tma_phase, int kind, const ListRef& lr) {
@@ -557,18 +557,6 @@ __device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const Clou
         for (int cb = 0; cb < pg.total_ct; cb += kColTiles, ++round) {
             const int nct = min(kColTiles, pg.total_ct - cb);
             __syncthreads();
-            if (SELF == 0) {  // the stages of a list pass (run_pass_list finds them afterwards)
-                const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
-                const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, sm.serial);
-                const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, -1);
-                if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase);
-                if (!have_rows) stage_rows(sm, rows, row_first, ntile * kTile, false);
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    sm.colTag.g = cols.g; sm.colTag.first = col_first; sm.colTag.n = nct * kTile; sm.colTag.serial = sm.serial;
-                    sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = -1;
-                }
-            }
             const uint2 rd = sm.lround[kind][round];
             const int ntrip = (int)rd.y / kListTrip;
             const int t_begin = (ntrip * warp) / kWarps, t_end = (ntrip * (warp + 1)) / kWarps;
@@ -582,17 +570,8 @@ __device__ __noinline__ void refine_list(Smem& sm, const KParams& kp, const Clou
                 for (int j = 0; j < 4; ++j) v[j] = __ldcg(q + j * kTile);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float d2, t_c;
-                    if (SELF == 0) {
-                        const uint32_t rowb = v[j].x >> 16, colb = v[j].x & 0xffffu;
-                        d2 = dist2(plane_ld<0>(sm.colG, colb) - plane_ld<0>(sm.u.ls.rowG, rowb),
-                                   plane_ld<1>(sm.colG, colb) - plane_ld<1>(sm.u.ls.rowG, rowb),
-                                   plane_ld<2>(sm.colG, colb) - plane_ld<2>(sm.u.ls.rowG, rowb));
-                        t_c = __uint_as_float(v[j].y);
-                    } else {
-                        d2 = __uint_as_float(v[j].x);
-                        t_c = __fmul_rn(__uint_as_float(v[j].y & 0x7fffffffu), c2);
-                    }
+                    const float d2 = __uint_as_float(v[j].x);
+                    const float t_c = __fmul_rn(__uint_as_float(v[j].y & 0x7fffffffu), c2);
                     const float re2 = (t_lim - t_c) * inv_c1;  // (padding: t_c = +inf, never kept)
                     const float lim = sqrtf_approx(fmaxf(re2, 0.f)) * 1.000002f + s_build;
                     const bool keep = (re2 > 0.f) && (d2 < lim * lim * 1.000001f);

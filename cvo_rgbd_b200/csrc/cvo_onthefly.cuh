@@ -176,7 +176,8 @@ __device__ __forceinline__ void survivor_body(const Smem& sm, const WarpScratch&
 struct ListSrc {
     const CloudDev* rows;
     const CloudDev* cols;
-    int row_base, col_base;  // global index of the unit's row 0 / of the staged chunk's column 0
+    int row_tile0, row_stride;  // the round's l-th staged row tile is tile row_tile0 + l * row_stride of the cloud
+    int col_base;               // global index of the staged chunk's column 0
 };
 // The per-iteration constants a list body reads, held in registers for the whole pass (IterConsts lives in shared memory).
 struct HotConsts {
@@ -402,15 +403,19 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
 
 // How one all-pairs pass of rows x cols is cut into work units for the CTA of rank `rank` in a cluster of G:
 // a pure function of the sizes, so that the neighbour-list build and every later pass over the list agree.
+// The row tiles are dealt to the CTAs that share a pair ROUND-ROBIN (tile t -> CTA t mod G): Morton neighbours have
+// similar candidate densities, so every CTA gets its share of the dense and of the sparse regions (contiguous ranges
+// left the slowest CTA of a 16-CTA cluster with 2.5 x the mean list: the others waited at the cluster barriers).
 struct PassGeom {
-    int t_begin, my_tiles, total_ct, S, tiles_per_round;
+    int t_begin, t_stride;  // this CTA's l-th row tile is tile t_begin + l * t_stride of the cloud
+    int my_tiles, total_ct, S, tiles_per_round;
 };
 __device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, int G) {
     PassGeom pg;
     const int total_rt = (rows_n + kTile - 1) / kTile;
-    pg.t_begin = (total_rt * rank) / G;  // total_rt <= 512, G <= 16
-    const int t_end = (total_rt * (rank + 1)) / G;
-    pg.my_tiles = t_end - pg.t_begin;
+    pg.t_begin = rank;
+    pg.t_stride = G;
+    pg.my_tiles = rank < total_rt ? (total_rt - rank + G - 1) / G : 0;
     pg.total_ct = (cols_n + kTile - 1) / kTile;
     // split every row tile's column range into S segments so that there are >= ~4 units per warp
     int S = 1;
@@ -433,7 +438,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
     constexpr int NV = PassTraits<KIND>::NV;
     const int lane = threadIdx.x & 31;
     const PassGeom pg = pass_geom(rows.n, cols.n, rank, G);
-    const int t_begin = pg.t_begin, my_tiles = pg.my_tiles, total_ct = pg.total_ct, S = pg.S;
+    const int t_begin = pg.t_begin, t_stride = pg.t_stride, my_tiles = pg.my_tiles, total_ct = pg.total_ct, S = pg.S;
     const int tiles_per_round = pg.tiles_per_round;
     if (threadIdx.x < kNumAcc) sm.blockTot[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) sm.colTag.serial = sm.rowTag.serial = -2;  // this pass overwrites the list passes' stages
@@ -453,7 +458,7 @@ __device__ void run_pass(Smem& sm, const KParams& kp, const CloudDev& rows, bool
                 if (u >= nunits) break;
                 const int t = u / S, seg = u - t * S;
                 const int c_begin = (int)(((long long)nct * seg) / S), c_end = (int)(((long long)nct * (seg + 1)) / S);
-                process_unit<KIND>(sm, kp, rows, row_tf, t_begin + rb + t, c_begin, c_end, u, cb == 0, yy_row_min);
+                process_unit<KIND>(sm, kp, rows, row_tf, t_begin + (rb + t) * t_stride, c_begin, c_end, u, cb == 0, yy_row_min);
             }
         }
         __syncthreads();

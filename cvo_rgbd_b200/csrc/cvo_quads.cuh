@@ -180,7 +180,8 @@ __device__ __forceinline__ bool quad_geom(const HotConsts& hc, const KParams& kp
 // ten thousand gets here; not inlined so that it costs the hot loop no registers.
 __device__ __noinline__ float quad_exact1(const Smem& sm, const KParams& kp, const ListSrc& src, uint32_t rowb, uint32_t colb, float d2) {
     const IterConsts& ic = sm.ic;
-    const int ri = src.row_base + (int)((rowb - quads::smem_offset(sm.u.ls.rowG)) >> 2), ci = src.col_base + (int)((colb - quads::smem_offset(sm.colG)) >> 2);
+    const int rl = (int)((rowb - quads::smem_offset(sm.u.ls.rowG)) >> 2);  // row within the round's staged rows
+    const int ri = (src.row_tile0 + (rl >> 5) * src.row_stride) * kTile + (rl & 31), ci = src.col_base + (int)((colb - quads::smem_offset(sm.colG)) >> 2);
     float a = kernel_value_exact(ic.ell, ic.d2c_thres, kp.s2, kp.cs2, kp.c_ell, kp.sp_thres, __ldg(src.rows->f + ri), __ldg(src.rows->f4 + ri),
                                  __ldg(src.cols->f + ci), __ldg(src.cols->f4 + ci), d2);
     if (!(d2 < ic.d2_thres)) a = 0.f;  // thirdparty/nanoflann.hpp:249-253
@@ -502,11 +503,11 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             CVO_PHASE(KIND == PASS_STEP ? 18 : 16)
             // Stage only what is not there already: the fixed cloud's rows survive from pass to pass and from iteration to
             // iteration, the STEP pass finds the columns the FLOW pass transformed and adds the per-row step-size terms.
-            const int row_first = (pg.t_begin + rb) * kTile, col_first = cb * kTile;
+            const int row_tile0 = pg.t_begin + rb * pg.t_stride, row_first = row_tile0 * kTile, col_first = cb * kTile;
             const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, sm.serial);
             const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, -1);
             if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase);
-            if (!have_rows) stage_rows(sm, rows, row_first, ntile * kTile, false);
+            if (!have_rows) stage_rows(sm, rows, row_tile0, pg.t_stride, ntile * kTile, false);
             if (KIND == PASS_STEP) {
                 if (!have_rows) __syncthreads();
                 stage_row_step_terms(sm, ntile * kTile);
@@ -518,7 +519,8 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
                 sm.rowTag.g = rows.g; sm.rowTag.first = row_first; sm.rowTag.n = ntile * kTile; sm.rowTag.serial = -1;
             }
             CVO_PHASE(15)  // instrumented variant: staging of both passes
-            src.row_base = row_first;
+            src.row_tile0 = row_tile0;
+            src.row_stride = pg.t_stride;
             src.col_base = col_first;
             // The warps take the round's trips round-robin (one quad per lane per trip).  Three register sets rotate between "being processed" and "being loaded" (never copied), so
             // the loads run TWO trips ahead of the arithmetic and the L2 prefetch kPrefetchTrips trips ahead of them.
