@@ -98,6 +98,7 @@ struct cvo_b200_ctx {
     // length-scale moves every iteration (12.8 rebuilds per pair: stock acvo +5 %), off for cvo (a filter of the wide list costs
     // 0.6 of a sweep and the wide sweep 1.6: cfg 2 -2 %, stock cvo -8 %; profiles/r02_wide_list.txt)
     float list_wide = -1.0f;
+    float list_ahead = 0.5f;  // the (x, y) list is built this many skins ahead of the motion (list_policy; measured optimum)
     float list_skin_min = 0.003f;  // absolute floor of the skin [m]: stock cvo +4 % (short lists at small ell, fewer rebuilds)
     float list_shrink = 0.7f;
     float list_refine_min = 1.0f;
@@ -353,6 +354,9 @@ void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
         ctx->list_ctas = 0;
         return;
     }
+    // The quad passes load two trips ahead without clamping to the end of a list (cvo_quads.cuh): what they read past it
+    // is never used, but it should be defined memory (compute-sanitizer initcheck stays meaningful).  Once per allocation.
+    cudaMemsetAsync(ctx->d_list_entries, 0, areas * cap * sizeof(uint2) + kListSlackBytes, ctx->stream);
     ctx->list_cap = (unsigned)cap;
     ctx->list_ctas = n_ctas;
 }
@@ -527,6 +531,7 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     args.list_cap = ctx->list_cap;
     args.list_skin = ctx->list_skin;
     args.list_skin_min = ctx->list_skin_min;
+    args.list_ahead = ctx->list_ahead;
     args.list_wide = ctx->list_wide >= 0.f ? ctx->list_wide : (args.kp.mode == CVO_B200_MODE_ACVO ? 0.5f : 0.f);
     args.list_shrink = ctx->list_shrink;
     args.list_refine_min = ctx->list_refine_min;
@@ -696,6 +701,8 @@ int cvo_b200_create(cvo_b200_ctx** out, int device, int max_points, int max_slot
     if (env && atof(env) > 0.0) ctx->list_refine_min = (float)atof(env);
     env = getenv("CVO_B200_LIST_WIDE");
     if (env && atof(env) >= 0.0 && atof(env) <= 4.0) ctx->list_wide = (float)atof(env);
+    env = getenv("CVO_B200_LIST_AHEAD");
+    if (env && atof(env) >= 0.0 && atof(env) < 1.0) ctx->list_ahead = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN_MIN");
     if (env && atof(env) >= 0.0 && atof(env) <= 1.0) ctx->list_skin_min = (float)atof(env);
     env = getenv("CVO_B200_LIST_SKIN");

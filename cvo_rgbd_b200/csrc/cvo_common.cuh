@@ -274,6 +274,7 @@ struct Smem {
     float ybox[6];            // bounding box of the moving cloud, original coordinates
     ListState lst[LIST_KINDS];
     WideState wide;
+    float tf_prev[12];  // the transform of the previous iteration (IterConsts::tf layout): the direction the pose is moving in
     int wide_ovf;  // a warp's share of the wide area overflowed during this sweep
     int lst_used, lst_ovf;
     int next_unit;
@@ -308,6 +309,7 @@ struct AlignArgs {
     uint2* list_entries;     // nullptr: lists disabled, every pass is on the fly
     unsigned list_cap;
     float list_skin;
+    float list_ahead;     // build the (x, y) list this many skins ahead of the motion (0 = at the current pose)
     float list_wide;      // W / r: extra slack of the wide list, 0 = no wide list (every rebuild is a sweep)
     float list_skin_min;  // absolute floor of the skin [m]: at small length-scales the lists are short and rebuilds dominate
     float list_shrink;  // rebuild a list when ell has shrunk the ball below this fraction of its build radius

@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 prepare_iter(sm, kp, kp.d2c_thres);
             }
             __syncwarp();
-            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide);
+            if (threadIdx.x < 12) sm.tf_prev[threadIdx.x] = sm.ic.tf[threadIdx.x];  // iteration 0: no motion known yet
+            __syncwarp();
+            if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide, args.list_ahead);
         }
         __syncthreads();
 #ifdef CVO_PHASE_CLOCKS
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                 // remember the transform used by this iteration: it is what the reference multiplies
                 // into accum_transform when the loop exits here (quirk Q3, src/cvo.cpp:413-414)
                 if (threadIdx.x == 0) write_tf44(sm.ic.tf, sm.st.prev_tf);
+                if (threadIdx.x < 12) sm.tf_prev[threadIdx.x] = sm.ic.tf[threadIdx.x];
                 cvo_b200_iter_rec* rec = nullptr;
                 if (args.trace && pi == 0 && rank == 0 && k < args.trace_cap) rec = args.trace + k;
                 update_state(sm, kp, k, rec);
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_kernel(const AlignArgs args
                     }
                     __syncwarp();
                     CVO_PHASE(12)
-                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide);
+                    if (use_lists) list_policy(sm, acvo, args.list_skin, args.list_skin_min, args.list_shrink, args.list_refine_min, args.list_wide, args.list_ahead);
                     CVO_PHASE(13)
                 }
             }

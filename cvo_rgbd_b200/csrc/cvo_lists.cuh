@@ -18,15 +18,18 @@
 // max(0, r1 - r0) + disp <= s.  The (x, x) list never moves and rigid motion preserves the (y, y) distances (up to
 // the f32 rounding of the transformed coordinates, covered by the margin): those two only follow ell.
 // Called by all lanes of warp 0 (after lane 0 ran prepare_iter and a __syncwarp): the 8 box corners go to 8 lanes.
-__device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, float shrink, float refine_min, float wide_factor) {
+__device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, float shrink, float refine_min, float wide_factor, float ahead) {
     const int lane = threadIdx.x & 31;
     // |(M1 - M0) p + (t1 - t0)| is convex in p: its maximum over the moving cloud's bounding box is attained at one of
     // the 8 corners.  Lanes 0..7: against the pose the (x, y) list was built at; lanes 8..15: against the wide list's.
-    double disp_xy = 0.0, disp_wide = 0.0;
+    // Lanes 16..23: against the previous iteration's pose -- how far, and which way, the cloud has just moved.
+    double disp_xy = 0.0, disp_wide = 0.0, disp_last = 0.0;
     {
-        const bool wide_half = (lane & 8) != 0;
-        const float* tf0 = wide_half ? sm.wide.tf : sm.lst[LIST_XY].tf;
-        const bool have = wide_half ? sm.wide.valid > 0 : sm.lst[LIST_XY].valid > 0;
+        const int grp = (lane >> 3) & 3;
+        const bool wide_half = grp == 1;
+        const float* tf0 = grp == 0 ? sm.lst[LIST_XY].tf : grp == 1 ? sm.wide.tf : sm.tf_prev;
+        const bool have = grp == 0 ? sm.lst[LIST_XY].valid > 0 : grp == 1 ? sm.wide.valid > 0 : true;
+        (void)wide_half;
         const int c = lane & 7;
         // f32 throughout: the differences of the transform entries are exact or nearly so (neighbouring poses), the
         // rounding of the rest (~1e-7 relative of a displacement of centimetres) is five orders below `margin`; the
@@ -44,6 +47,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
         for (int o = 4; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
         disp_xy = (double)__shfl_sync(0xffffffffu, d, 0);
         disp_wide = (double)__shfl_sync(0xffffffffu, d, 8);
+        disp_last = (double)__shfl_sync(0xffffffffu, d, 16);
     }
     __syncwarp();  // every lane has read the build transforms before lane 0 may replace them
     if (lane != 0) return;
@@ -77,10 +81,14 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
                     L.need = 2;
                 }
             }
+            double alpha = 0.0;  // (see below: the (x, y) list is built `ahead` skins ahead of the motion)
+            if (kind == LIST_XY && ahead > 0.f && disp_last > 1.0e-7 && disp_last < 1.0e29)
+                alpha = fmin((double)ahead * s * (1.0 - 1.0e-6) / disp_last, 8.0);
+            const double lead = alpha * disp_last;  // distance between the current pose and the build pose
             if (kind == LIST_XY && wide_factor > 0.f) {
                 // the quads as a filter of the wide list (need = 3) while it covers them -- and is not much too wide itself
                 WideState& Wd = sm.wide;
-                const bool covers = Wd.valid > 0 && fmax(0.0, r_now - (double)Wd.r0) + disp_wide + s + margin <= (double)Wd.slack &&
+                const bool covers = Wd.valid > 0 && fmax(0.0, r_now - (double)Wd.r0) + disp_wide + lead + s + margin <= (double)Wd.slack &&
                                     r_now >= 0.6 * (double)Wd.r0;
                 if (covers) {
                     L.need = 3;
@@ -94,7 +102,7 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
                     Wd.s_build = (float)((sw + margin) * (1.0 + 1.0e-6));
                     Wd.thr_build = (float)(rbw * rbw * (1.0 + 1.0e-6));
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) Wd.tf[i] = sm.ic.tf[i];
+                    for (int i = 0; i < 12; ++i) Wd.tf[i] = sm.ic.tf[i] + (float)alpha * (sm.ic.tf[i] - sm.tf_prev[i]);  // = L.tf
                 }
             }
             const double rb = r_now + s + margin;
@@ -104,8 +112,13 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
             L.s_build = (float)((s + margin) * (1.0 + 1.0e-6));  // rounded UP: what the build adds to r_e
             L.thr_build = (float)(rb * rb * (1.0 + 1.0e-6));  // rounded UP: the build prefilter's ball
             L.inv_c1 = (float)(2.0 * (double)sm.st.ell * (double)sm.st.ell / 1.4426950408889634 * (1.0 + 1.0e-6));
+            // The (x, y) list is built AHEAD of the motion: at the pose extrapolated along the last iteration's change by
+            // alpha steps, alpha chosen so that the current pose sits `ahead` (0.5) skins behind the build pose.  The displacement
+            // is linear along that line (the corner bound holds for any affine map), so while the pose keeps moving the
+            // same way it first approaches the build pose and then leaves it: the list lives for up to 1.5 skins of
+            // travel instead of 1.  A wrong guess costs nothing but the lifetime: coverage is tested against L.tf as ever.
 #pragma unroll
-            for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i];
+            for (int i = 0; i < 12; ++i) L.tf[i] = sm.ic.tf[i] + (float)alpha * (sm.ic.tf[i] - sm.tf_prev[i]);
             if (L.need >= 2) sm.st.n_refines += 1;
             else if (kind == LIST_XY) sm.st.n_builds += 1;
         }
@@ -406,7 +419,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                 stop = true;
                 break;
             }
-            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase);
+            stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase, SELF == 0 ? L.tf : nullptr);
             if (threadIdx.x == 0) sm.next_unit = 0;
             if (SELF == 0)
                 for (int i = threadIdx.x; i < ntile * kTile; i += kThreads) sm.u.of.bu.rowCnt[i] = 0;

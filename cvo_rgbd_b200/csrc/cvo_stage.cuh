@@ -74,7 +74,7 @@ __device__ __forceinline__ StepCol step_col(const IC& ic, float yx, float yy, fl
 enum StageMode { STAGE_FULL = 0, STAGE_GEOM = 1, STAGE_STEP = 2 };
 template <int MODE>
 __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int base, int ntiles, bool tf,
-                                            float sentinel, uint32_t& tma_phase) {
+                                            float sentinel, uint32_t& tma_phase, const float* tf_override = nullptr) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
     if (MODE == STAGE_FULL) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
         tma_bulk_g2s(sm.u.of.fs.colF, c.f + base, bytes_f, &sm.tma_bar);
         tma_bulk_g2s(sm.u.of.fs.colF4, c.f4 + base, bytes_f4, &sm.tma_bar);
     }
-    const float* tf12 = sm.ic.tf;
+    const float* tf12 = tf_override ? tf_override : sm.ic.tf;  // (a list sweep stages the columns at the list's own pose)
     // all of a thread's points are requested before the first is used: one memory latency per chunk instead of one per point
     constexpr int kPerThread = (kColChunk + kThreads - 1) / kThreads;
     float4 pre[kPerThread];
