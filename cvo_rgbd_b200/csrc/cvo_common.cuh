@@ -265,6 +265,7 @@ struct Smem {
     float colBox[kColTiles][8];  // [0..2] lo, [3..5] hi, [6] max |c|^2
     double blockTot[kNumAcc];
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
+    uint32_t colMask[kMaxListRounds][kColTiles / 32];  // per round of the (x, y) list: the column tiles its sweep found live
     uint2 lround[LIST_KINDS][kMaxListRounds];  // (offset, entries) of every round of a list; entries % kListTrip == 0
     int lst_base;
     int refineCnt[kWarps], refinePos[kWarps];  // refine_list: entries every warp kept / where they go

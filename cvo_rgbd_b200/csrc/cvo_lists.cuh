@@ -288,7 +288,8 @@ __device__ __forceinline__ void build_eval2(Smem& sm, const WarpScratch& ws, con
 template <int SELF>
 __device__ __forceinline__ int build_unit_write(Smem& sm, WarpScratch& ws, const KParams& kp, const ListState& L,
                                                 const CloudDev& rows, bool row_tf, int tile, uint32_t row_off, int yy_row_min,
-                                                int ct_begin, int ct_end, uint2* out, int limit, float thr_build, WideOut& wo) {
+                                                int ct_begin, int ct_end, uint2* out, int limit, float thr_build, WideOut& wo,
+                                                uint32_t* col_mask) {
     const int lane = threadIdx.x & 31;
     const RowTile rt = load_row_tile<true, SELF == 2, true>(sm, ws, rows, row_tf, tile);
     const float thr_box = thr_build * 1.0001f;
@@ -296,6 +297,7 @@ __device__ __forceinline__ int build_unit_write(Smem& sm, WarpScratch& ws, const
     int qn = 0, cursor = 0, row_cnt = 0;
     for (int c0 = ct_begin; c0 < ct_end; c0 += 32) {
         uint32_t lm = live_col_tiles(sm, rt, c0, ct_end, thr_box);
+        if (SELF == 0 && lm != 0u && lane == 0) atomicOr(col_mask + (c0 >> 5), lm);  // (the quad passes stage only these)
         while (lm) {
             const int j = __ffs(lm) - 1;
             lm &= lm - 1;
@@ -421,8 +423,12 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             }
             stage_tiles<STAGE_FULL>(sm, cols, cb * kTile, nct, col_tf, kColSentinel, tma_phase, SELF == 0 ? L.tf : nullptr);
             if (threadIdx.x == 0) sm.next_unit = 0;
-            if (SELF == 0)
+            if (SELF == 0) {
                 for (int i = threadIdx.x; i < ntile * kTile; i += kThreads) sm.u.of.bu.rowCnt[i] = 0;
+                // a sweep finds the round's live column tiles anew (a filter keeps its wide sweep's, a superset); tile 0
+                // always: the padding slots of the quads address column 0 and must read finite coordinates
+                if (!from_wide && threadIdx.x < kColTiles / 32) sm.colMask[round][threadIdx.x] = threadIdx.x == 0 ? 1u : 0u;
+            }
             __syncthreads();
             CVO_PHASE(6)
             int wcur = 0;  // entries this warp has staged in this round
@@ -445,7 +451,8 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                     wo.limit = wseg - w0;
                     wo.cursor = 0;
                     c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + (rb + t) * pg.t_stride, (uint32_t)(t * kTile),
-                                               yy_row_min, c_begin, c_end, stage + wcur, seg - wcur, thr_build, wo);
+                                               yy_row_min, c_begin, c_end, stage + wcur, seg - wcur, thr_build, wo,
+                                               sm.colMask[round]);
                     if (make_wide && lane == 0) {
                         __stcg(lr.wide + round * kColTiles + t, make_uint2((unsigned)(warp * wseg + w0), (unsigned)wo.cursor));
                         if (w0 + wo.cursor > wseg) sm.wide_ovf = 1;

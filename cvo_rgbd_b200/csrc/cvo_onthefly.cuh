@@ -403,9 +403,12 @@ __device__ __forceinline__ void process_unit(Smem& sm, const KParams& kp, const 
 
 // How one all-pairs pass of rows x cols is cut into work units for the CTA of rank `rank` in a cluster of G:
 // a pure function of the sizes, so that the neighbour-list build and every later pass over the list agree.
-// The row tiles are dealt to the CTAs that share a pair ROUND-ROBIN (tile t -> CTA t mod G): Morton neighbours have
-// similar candidate densities, so every CTA gets its share of the dense and of the sparse regions (contiguous ranges
-// left the slowest CTA of a 16-CTA cluster with 2.5 x the mean list: the others waited at the cluster barriers).
+// How the row tiles are dealt to the CTAs that share a pair.  ROUND-ROBIN (tile t -> CTA t mod G) when the moving cloud
+// fits one column chunk: Morton neighbours have similar candidate densities, so every CTA gets its share of the dense and
+// of the sparse regions (3000 points on 16 CTAs: -5 % against contiguous ranges, whose slowest CTA keeps the others
+// waiting at the cluster barriers).  CONTIGUOUS ranges when there are several column chunks: a CTA's rows then
+// reference few column tiles, and the quad passes stage only those (Smem::colMask) -- 10 000 points on 112 CTAs: 43.6 us
+// per iteration against 52.0 round-robin (profiles/r02_group_mode.txt).
 struct PassGeom {
     int t_begin, t_stride;  // this CTA's l-th row tile is tile t_begin + l * t_stride of the cloud
     int my_tiles, total_ct, S, tiles_per_round;
@@ -413,10 +416,16 @@ struct PassGeom {
 __device__ __forceinline__ PassGeom pass_geom(int rows_n, int cols_n, int rank, int G) {
     PassGeom pg;
     const int total_rt = (rows_n + kTile - 1) / kTile;
-    pg.t_begin = rank;
-    pg.t_stride = G;
-    pg.my_tiles = rank < total_rt ? (total_rt - rank + G - 1) / G : 0;
     pg.total_ct = (cols_n + kTile - 1) / kTile;
+    if (pg.total_ct <= kColTiles) {  // the moving cloud is one column chunk: balance wins
+        pg.t_begin = rank;
+        pg.t_stride = G;
+        pg.my_tiles = rank < total_rt ? (total_rt - rank + G - 1) / G : 0;
+    } else {  // several column chunks: locality wins (see above)
+        pg.t_begin = (total_rt * rank) / G;
+        pg.t_stride = 1;
+        pg.my_tiles = (total_rt * (rank + 1)) / G - pg.t_begin;
+    }
     // split every row tile's column range into S segments so that there are >= ~4 units per warp
     int S = 1;
     if (pg.my_tiles > 0) {

@@ -74,7 +74,8 @@ __device__ __forceinline__ StepCol step_col(const IC& ic, float yx, float yy, fl
 enum StageMode { STAGE_FULL = 0, STAGE_GEOM = 1, STAGE_STEP = 2 };
 template <int MODE>
 __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int base, int ntiles, bool tf,
-                                            float sentinel, uint32_t& tma_phase, const float* tf_override = nullptr) {
+                                            float sentinel, uint32_t& tma_phase, const float* tf_override = nullptr,
+                                            const uint32_t* tile_mask = nullptr) {
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
     if (MODE == STAGE_FULL) {
@@ -101,6 +102,9 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
     for (int u = 0; u < kPerThread; ++u) {
         const int i = threadIdx.x + u * kThreads;
         pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // (tile_mask: a quad pass only stages the column tiles its list references -- a CTA that holds a few row tiles of
+        // a large pair touches a small part of the moving cloud; warp-uniform: a warp stages whole tiles)
+        if (tile_mask && !((tile_mask[i >> 10] >> ((i >> 5) & 31)) & 1u)) continue;
         if (i < ntiles * kTile && base + i < c.n) {
 #ifdef CVO_CLOUD_EVICT_LAST  // the clouds are re-read every iteration while the lists stream through L2 between two uses
             asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -114,6 +118,7 @@ __device__ __forceinline__ void stage_tiles(Smem& sm, const CloudDev& c, int bas
     for (int u = 0; u < kPerThread; ++u) {
         const int i = threadIdx.x + u * kThreads;
         if (i >= ntiles * kTile) break;
+        if (tile_mask && !((tile_mask[i >> 10] >> ((i >> 5) & 31)) & 1u)) continue;
         const int p = base + i;
         bool valid = p < c.n;
         float4 g;
