@@ -489,10 +489,14 @@ def main():
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             traffic = tj.get("dram_bytes_per_launch")
+            cap_pairs = tj.get("pairs_per_launch") or 296
+            if traffic is not None and cap_pairs != P:  # per launch like `achieved`: the capture's bytes per pair x this launch's pairs
+                traffic = traffic * P / cap_pairs
             fp_now = source_fingerprint()
             traffic_meta = {"source": "profiles/align_kernel_traffic.json (one ncu --set full capture of this workload's launch)",
                             "capture_source_fingerprint": tj.get("source_fingerprint"), "current_source_fingerprint": fp_now,
                             "stale": tj.get("source_fingerprint") != fp_now, "capture_kernel_ms": tj.get("kernel_ms"),
+                            "capture_pairs_per_launch": cap_pairs,
                             "capture_commit": tj.get("git_commit")}
         list_cap = ctx.list_capacity if hasattr(ctx, "list_capacity") else None
         sm_mhz = clocks["sm_mhz"] or 1965.0

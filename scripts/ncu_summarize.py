@@ -1,5 +1,6 @@
 """Turns the ncu outputs a gpurun call brought back into the small summaries committed under profiles/.
-usage: ncu_summarize.py <launches.csv> <full.ncu-rep> <tag>      (run here; needs `ncu` on PATH, no GPU)"""
+usage: ncu_summarize.py <launches.csv> <full.ncu-rep> <tag> [pairs per launch]   (run here; needs `ncu` on PATH, no GPU;
+run it at the commit the capture was taken at: the source fingerprint bench.py compares is computed from the tree)"""
 import collections
 import csv
 import json
@@ -9,6 +10,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches_csv, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+pairs = int(sys.argv[4]) if len(sys.argv) > 4 else 592
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (source_fingerprint, algorithmic bytes)
 
 # 1. launch list -> per-kernel totals and shares
 rows = [r for r in csv.reader(open(launches_csv, errors="replace")) if r]
@@ -53,10 +57,15 @@ rd, wr = out["dram__bytes_read.sum"], out["dram__bytes_write.sum"]
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
 rd *= scale.get(units["dram__bytes_read.sum"], 1.0)
 wr *= scale.get(units["dram__bytes_write.sum"], 1.0)
-traffic = {"kernel": "cvo_b200::align_kernel", "source": "ncu --set full --clock-control none -k regex:align_kernel -s 1 -c 1 python bench.py --steps 1 --warmup 1 --no-cpu-baseline (%s)" % os.path.basename(rep),
-           "workload": "296 cfg-2 pairs (3000x3000, fixed ell 0.10, 100 iterations) in one launch",
-           "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "metrics": out,
-           "note": "algorithmic bytes by SURVEY 8d (64(N+M)+96 per iteration) are 11.37 GB per launch; the measured DRAM traffic is dominated by the neighbour candidate lists (about 100 k entries x 8 B per pair, read by both passes of every iteration; 148 of them exceed the 126 MB L2, so they stream from HBM): about 0.74 MB x 2 passes x 29 600 iterations = 44 GB if nothing hit L2"}
+alg = pairs * 100 * bench.algorithmic_bytes_per_iteration(3000, 3000)
+commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+traffic = {"kernel": "cvo_b200::align_kernel", "source": "ncu --set full --clock-control none -k regex:align_kernel -s 1 -c 1 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-cfg4 (%s)" % os.path.basename(rep),
+           "workload": "%d cfg-2 pairs (3000x3000, fixed ell 0.10, 100 iterations) in one launch" % pairs,
+           "pairs_per_launch": pairs, "source_fingerprint": bench.source_fingerprint(), "git_commit": commit,
+           "kernel_ms": out["gpu__time_duration.sum"],
+           "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+           "algorithmic_bytes_per_launch": alg, "traffic_over_algorithmic": (rd + wr) / alg, "metrics": out,
+           "note": "algorithmic bytes by SURVEY 8d (64(N+M)+96 per iteration); the measured DRAM traffic is dominated by the neighbour candidate lists (quads: 6.5 B per candidate slot, about 0.61 MB per pair, read by both passes of every iteration; 148 of them plus the clouds exceed the 126 MB L2, so part of the stream comes from HBM)"}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "align_kernel_traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))
 
@@ -64,6 +73,6 @@ print(json.dumps(traffic, indent=1))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 tmp = "/tmp/_src_%s.csv" % tag
 open(tmp, "w").write(src)
-txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), tmp, "40"], capture_output=True, text=True).stdout
-open(os.path.join(ROOT, "profiles", "%s_align_kernel_hot_lines.txt" % tag), "w").write(txt)
-print(txt[:1500])
+txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_funcs.py"), tmp, "--lines", "40"], capture_output=True, text=True).stdout
+open(os.path.join(ROOT, "profiles", "%s_align_kernel_by_function.txt" % tag), "w").write(txt)
+print(txt[:2500])
