@@ -329,6 +329,9 @@ int launch_cluster_kernel(cvo_b200_ctx* ctx, KernelT kernel, const ArgT& args, i
 // (cvo_b200_neighbor_lists_active reports it).
 void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
     if (ctx->lists_alloc_failed || !ctx->lists_enabled) return;
+    // (the cloud size in steps of 512 points: a sequence whose frames differ by a few points must not re-allocate -- a
+    // re-allocation of the scratch costs about 17 ms, twenty alignments)
+    max_n = (max_n + 511) & ~511;
     unsigned long long cap = (unsigned long long)max_n * max_n / 8;
     if (cap < (1ull << 18)) cap = 1ull << 18;
     if (cap > (1ull << 21)) cap = 1ull << 21;
