@@ -51,6 +51,22 @@ __device__ void list_policy(Smem& sm, bool acvo, float skin, float skin_min, flo
     }
     __syncwarp();  // every lane has read the build transforms before lane 0 may replace them
     if (lane != 0) return;
+    {   // Fast path, f32: nothing to do while every list covers the pose (the common iteration).  The same inequalities as
+        // below; f32 rounding (1e-8 m) is three orders below the margin the builds add to their radii.
+        const float r_f = sqrtf(sm.ic.d2_thres);
+        bool all_fine = true;
+        for (int kind = 0; kind < (acvo ? LIST_KINDS : 1); ++kind) {
+            const ListState& L = sm.lst[kind];
+            if (L.valid < 0) continue;
+            const float disp = kind == LIST_XY ? (float)disp_xy : 0.f;
+            all_fine = all_fine && L.valid > 0 && (fmaxf(0.f, r_f - L.r0) + disp) * 1.000001f <= L.slack && r_f >= shrink * L.r0 * 1.000001f;
+        }
+        if (all_fine) {
+            for (int kind = 0; kind < LIST_KINDS; ++kind) sm.lst[kind].need = 0;
+            sm.wide.make = 0;
+            return;
+        }
+    }
     const double r_now = sqrt((double)sm.ic.d2_thres);
     const double margin = 2.0e-5 + 1.0e-5 * r_now;  // f32 rounding of the transformed coordinates, generously
     const int nk = acvo ? LIST_KINDS : 1;
