@@ -28,7 +28,8 @@ EXPORTS = [
     "cvo_b200_push_frame_images", "cvo_b200_last_generated_cloud", "cvo_b200_reset_slot", "cvo_b200_selftest_rand_bytes",
     "cvo_b200_last_frame_used_canny", "cvo_b200_selftest_step_size", "cvo_b200_selftest_exp_sek3",
     "cvo_b200_neighbor_lists_active", "cvo_b200_list_scratch_bytes", "cvo_b200_align_multi", "cvo_b200_last_list_fill",
-    "cvo_b200_set_group_clusters", "cvo_b200_last_group_clusters",
+    "cvo_b200_set_group_clusters", "cvo_b200_last_group_clusters", "cvo_b200_prefetch_frame_images",
+    "cvo_b200_push_prefetched_frame", "cvo_b200_align_begin", "cvo_b200_align_finish",
 ]
 
 
@@ -94,6 +95,8 @@ def load():
     lib.cvo_b200_replace_moving.argtypes = [vp, C.c_int, fp, fp, C.c_int]
     lib.cvo_b200_eval.argtypes = [vp, C.c_int, fp, fp, C.c_float, C.POINTER(Params), C.POINTER(IterRec)]
     lib.cvo_b200_align.argtypes = [vp, ip, C.c_int, C.POINTER(Params), fp, fp, fp, fp, ip, ip]
+    lib.cvo_b200_align_begin.argtypes = [vp, ip, C.c_int, C.POINTER(Params), fp, fp]
+    lib.cvo_b200_align_finish.argtypes = [vp, fp, fp, fp, fp, ip, ip]
     lib.cvo_b200_align_trace.argtypes = [vp, C.c_int, C.POINTER(Params), fp, fp, fp, fp, ip, ip,
                                          C.POINTER(IterRec), C.c_int, ip]
     lib.cvo_b200_inner_product.argtypes = [vp, C.c_int, C.c_float, C.POINTER(Params), fp,
@@ -114,6 +117,8 @@ def load():
     lib.cvo_b200_push_frame_images.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ushort), C.c_int, C.c_int,
                                                C.c_int, C.c_int, ip]
     lib.cvo_b200_replace_moving_images.argtypes = lib.cvo_b200_push_frame_images.argtypes
+    lib.cvo_b200_prefetch_frame_images.argtypes = [vp, C.POINTER(C.c_ubyte), C.POINTER(C.c_ushort), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.cvo_b200_push_prefetched_frame.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.cvo_b200_align_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, fp, fp, ip, fp, fp, ip, C.c_int, C.POINTER(Params), fp, ip,
                                          ip, fp]
     lib.cvo_b200_last_list_fill.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -261,6 +266,23 @@ class Context:
             img3.shape[1], img3.shape[0], dataset_seq, feature_type, C.byref(n)))
         return n.value
 
+    def prefetch_frame_images(self, img3, depth, dataset_seq=1, feature_type=1):
+        """Starts the front end for the NEXT frame on the copy stream (overlaps a running align()); the arrays are kept
+        alive until push_prefetched_frame."""
+        img3 = np.ascontiguousarray(img3, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        assert img3.ndim == 3 and img3.shape[2] == 3 and depth.shape == img3.shape[:2]
+        self._prefetched = (img3, depth)
+        self._check(self._lib.cvo_b200_prefetch_frame_images(
+            self._h, img3.ctypes.data_as(C.POINTER(C.c_ubyte)), depth.ctypes.data_as(C.POINTER(C.c_ushort)),
+            img3.shape[1], img3.shape[0], dataset_seq, feature_type))
+
+    def push_prefetched_frame(self, slot, promote=True):
+        n = C.c_int(0)
+        self._check(self._lib.cvo_b200_push_prefetched_frame(self._h, slot, int(bool(promote)), C.byref(n)))
+        self._prefetched = None
+        return n.value
+
     def last_generated_cloud(self):
         """(xyz[n,3], feat[n,5]) of the last push_frame_images, in the reference's raster order."""
         n = C.c_int(0)
@@ -297,6 +319,31 @@ class Context:
                                              None if RT_io is None else _fp(RT_io),
                                              None if ell_io is None else _fp(ell_io),
                                              _fp(tf), _fp(ptf), _ipt(iters), _ipt(status)))
+        return dict(RT=RT_io, ell=ell_io, transform=tf, prev_transform=ptf, iters=iters, status=status)
+
+    def align_begin(self, slots, params, RT=None, ell=None):
+        """Launches the align and returns; align_finish() collects it.  In between: prefetch_frame_images."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        P = slots.shape[0]
+        RT_io = None if RT is None else _f32(RT).reshape(P, 12).copy()
+        ell_io = None if ell is None else _f32(ell).reshape(P).copy()
+        self._check(self._lib.cvo_b200_align_begin(self._h, _ipt(slots), P, C.byref(params),
+                                                   None if RT_io is None else _fp(RT_io),
+                                                   None if ell_io is None else _fp(ell_io)))
+        self._in_flight = (P, RT_io, ell_io)
+
+    def align_finish(self):
+        P, RT_io, ell_io = self._in_flight
+        self._in_flight = None
+        tf = np.zeros((P, 4, 4), np.float32)
+        ptf = np.zeros((P, 4, 4), np.float32)
+        iters = np.zeros(P, np.int32)
+        status = np.zeros(P, np.int32)
+        if RT_io is None:
+            RT_io = np.zeros((P, 12), np.float32)
+        if ell_io is None:
+            ell_io = np.zeros(P, np.float32)
+        self._check(self._lib.cvo_b200_align_finish(self._h, _fp(RT_io), _fp(ell_io), _fp(tf), _fp(ptf), _ipt(iters), _ipt(status)))
         return dict(RT=RT_io, ell=ell_io, transform=tf, prev_transform=ptf, iters=iters, status=status)
 
     def align_trace(self, slot, params, R=None, T=None, ell=None, trace_cap=2048):

@@ -82,6 +82,17 @@ struct cvo_b200_ctx {
         SelCtl* d_ctl = nullptr;
         SelCtl* h_ctl = nullptr;     // pinned
         bool tables = false;
+        // cvo_b200_prefetch_frame_images: the NEXT frame's cloud, generated on copy_stream while an align() runs
+        float* d_next_raw_xyz = nullptr;
+        float* d_next_raw_feat = nullptr;
+        float4* d_next_g = nullptr;
+        float4* d_next_f = nullptr;
+        float* d_next_f4 = nullptr;
+        PackJob* d_next_job = nullptr;
+        SelCtl* h_ctl_next = nullptr;    // pinned
+        cudaEvent_t ev_next = nullptr;   // recorded on copy_stream behind the prefetched frame
+        cudaEvent_t ev_taken = nullptr;  // recorded on stream behind the copy of a prefetched cloud into its slot
+        bool next_pending = false;
     } pipe;
     int last_gen_n = 0;
     int last_gen_canny = 0;
@@ -107,7 +118,9 @@ struct cvo_b200_ctx {
     float last_ms = 0.f;
     long long launches = 0;
     int last_G = 0, last_nclusters = 0, force_G = 0;
-    int force_group = 0, last_group = 1;  // clusters per pair: 0 = automatic, 1 = one cluster per pair, n = whole-GPU mode
+    int force_group = 0, last_group = 1;
+    // an align launched by cvo_b200_align_begin and not yet collected by cvo_b200_align_finish
+    struct PendingAlign { bool active = false; int n_pairs = 0, G = 0, ncl = 0, group = 1, trace_cap = 0; bool trace = false; } pending;  // clusters per pair: 0 = automatic, 1 = one cluster per pair, n = whole-GPU mode
     int max_clusters[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // per cluster size, -1 = not asked yet
     long long last_total_iters = 0;
     int sort_points = 1;
@@ -331,11 +344,20 @@ void ensure_list_scratch(cvo_b200_ctx* ctx, int n_ctas, int max_n) {
     if (ctx->lists_alloc_failed || !ctx->lists_enabled) return;
     // (the cloud size in steps of 512 points: a sequence whose frames differ by a few points must not re-allocate -- a
     // re-allocation of the scratch costs about 17 ms, twenty alignments)
+    auto cap_for = [](int n) {
+        unsigned long long c = (unsigned long long)n * n / 8;
+        if (c < (1ull << 18)) c = 1ull << 18;
+        if (c > (1ull << 21)) c = 1ull << 21;
+        return (c + 1023ull) & ~1023ull;
+    };
     max_n = (max_n + 511) & ~511;
-    unsigned long long cap = (unsigned long long)max_n * max_n / 8;
-    if (cap < (1ull << 18)) cap = 1ull << 18;
-    if (cap > (1ull << 21)) cap = 1ull << 21;
-    cap = (cap + 1023ull) & ~1023ull;
+    unsigned long long cap = cap_for(max_n);
+    if (!(ctx->d_list_entries && ctx->list_cap >= cap)) {  // (re)allocating: with a quarter of headroom, within max_points
+        int roomy = (max_n + max_n / 4 + 511) & ~511;
+        const int limit = (ctx->max_points + 511) & ~511;
+        if (roomy > limit) roomy = limit > max_n ? limit : max_n;
+        cap = cap_for(roomy);
+    }
     if (const char* env = getenv("CVO_B200_LIST_CAP")) {  // test hook: a small area forces the overflow fallback
         const long long v = atoll(env);
         if (v >= 1024) cap = (unsigned long long)v & ~1023ull;
@@ -398,6 +420,11 @@ void free_image_pipe(cvo_b200_ctx* ctx) {
     cudaFree(P.d_img3); cudaFree(P.d_depth); cudaFree(P.d_pyr); cudaFree(P.d_ths); cudaFree(P.d_map); cudaFree(P.d_rnd); cudaFree(P.d_blockcnt);
     cudaFree(P.d_ctl);
     if (P.h_ctl) cudaFreeHost(P.h_ctl);
+    cudaFree(P.d_next_raw_xyz); cudaFree(P.d_next_raw_feat); cudaFree(P.d_next_g); cudaFree(P.d_next_f); cudaFree(P.d_next_f4);
+    cudaFree(P.d_next_job);
+    if (P.h_ctl_next) cudaFreeHost(P.h_ctl_next);
+    if (P.ev_next) cudaEventDestroy(P.ev_next);
+    if (P.ev_taken) cudaEventDestroy(P.ev_taken);
     P = cvo_b200_ctx::ImagePipe();
 }
 
@@ -415,8 +442,19 @@ int ensure_image_pipe(cvo_b200_ctx* ctx, int w, int h) {
     cvo_b200_ctx::ImagePipe& P = ctx->pipe;
     if (P.w == w && P.h == h) return CVO_B200_OK;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     free_image_pipe(ctx);
     const size_t wh = (size_t)w * h;
+    const size_t mp = (size_t)ctx->max_points;
+    CK(cudaMalloc(&P.d_next_raw_xyz, mp * 3 * sizeof(float)));
+    CK(cudaMalloc(&P.d_next_raw_feat, mp * 5 * sizeof(float)));
+    CK(cudaMalloc(&P.d_next_g, mp * sizeof(float4)));
+    CK(cudaMalloc(&P.d_next_f, mp * sizeof(float4)));
+    CK(cudaMalloc(&P.d_next_f4, mp * sizeof(float)));
+    CK(cudaMalloc(&P.d_next_job, sizeof(PackJob)));
+    CK(cudaMallocHost(&P.h_ctl_next, sizeof(SelCtl)));
+    CK(cudaEventCreateWithFlags(&P.ev_next, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&P.ev_taken, cudaEventDisableTiming));
     CK(cudaMalloc(&P.d_img3, wh * 3));
     CK(cudaMalloc(&P.d_depth, wh * sizeof(uint16_t)));
     CK(cudaMalloc(&P.d_pyr, pyr_floats(w, h) * 4 * sizeof(float)));
@@ -459,10 +497,11 @@ PairDev make_pair_dev(cvo_b200_ctx* ctx, int slot) {
     return pd;
 }
 
-int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, float* RT_io,
-              float* ell_io, float* transform, float* prev_transform, int* iters, int* status,
-              cvo_b200_iter_rec* trace, int trace_cap, int* trace_len) {
+// The launch half of an align: pair descriptors and states into the pinned arrays the kernel reads, scratch, launch.
+int run_align_begin(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, const float* RT_io,
+                    const float* ell_io, bool trace, int trace_cap) {
     if (!ctx) return CVO_B200_ERR_ARG;
+    if (ctx->pending.active) return fail_arg(ctx, "an align is in flight (cvo_b200_align_finish first)");
     if (!slots || !p || n_pairs <= 0 || n_pairs > ctx->max_slots) return fail_arg(ctx, "bad align arguments");
     CK(cudaSetDevice(ctx->device));
     for (int i = 0; i < n_pairs; ++i) {
@@ -554,6 +593,24 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     if (args.trace)
         CK(cudaMemcpyAsync(ctx->h_trace, ctx->d_trace, sizeof(cvo_b200_iter_rec) * args.trace_cap,
                            cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending.active = true;
+    ctx->pending.n_pairs = n_pairs;
+    ctx->pending.G = G;
+    ctx->pending.ncl = ncl;
+    ctx->pending.group = group;
+    ctx->pending.trace = args.trace != nullptr;
+    ctx->pending.trace_cap = args.trace_cap;
+    return CVO_B200_OK;
+}
+
+// The collecting half: waits for the kernel, hands the results out.
+int run_align_finish(cvo_b200_ctx* ctx, float* RT_io, float* ell_io, float* transform, float* prev_transform, int* iters,
+                     int* status, cvo_b200_iter_rec* trace, int* trace_len) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (!ctx->pending.active) return fail_arg(ctx, "no align in flight (cvo_b200_align_begin)");
+    CK(cudaSetDevice(ctx->device));
+    const int n_pairs = ctx->pending.n_pairs, G = ctx->pending.G, ncl = ctx->pending.ncl, group = ctx->pending.group;
+    ctx->pending.active = false;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     ctx->last_G = G;
@@ -582,12 +639,20 @@ int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_p
     ctx->last_list_refines = refines;
     ctx->last_xy_entries = xy_entries;
     ctx->last_xy_slots = xy_slots;
-    if (args.trace) {
-        const int n = ctx->h_states[0].n_run < args.trace_cap ? ctx->h_states[0].n_run : args.trace_cap;
+    if (ctx->pending.trace && trace) {
+        const int n = ctx->h_states[0].n_run < ctx->pending.trace_cap ? ctx->h_states[0].n_run : ctx->pending.trace_cap;
         memcpy(trace, ctx->h_trace, sizeof(cvo_b200_iter_rec) * n);
     }
     if (trace_len) *trace_len = ctx->h_states[0].n_run;
     return CVO_B200_OK;
+}
+
+int run_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, float* RT_io,
+              float* ell_io, float* transform, float* prev_transform, int* iters, int* status,
+              cvo_b200_iter_rec* trace, int trace_cap, int* trace_len) {
+    const int rc = run_align_begin(ctx, slots, n_pairs, p, RT_io, ell_io, trace != nullptr, trace_cap);
+    if (rc) return rc;
+    return run_align_finish(ctx, RT_io, ell_io, transform, prev_transform, iters, status, trace, trace_len);
 }
 
 }  // namespace
@@ -970,17 +1035,20 @@ int cvo_b200_replace_moving(cvo_b200_ctx* ctx, int slot, const float* xyz, const
     return push_cloud(ctx, slot, xyz, feat, n, false);
 }
 
+static int check_image_args(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width, int height,
+                            int feature_type);
+static int enqueue_frontend(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width, int height,
+                            int dataset_seq, int feature_type, float* raw_xyz, float* raw_feat, PackJob* d_job, float4* out_g,
+                            float4* out_f, float* out_f4, cudaStream_t st, SelCtl* h_ctl);
+
 static int push_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth, int width,
                        int height, int dataset_seq, int feature_type, int* num_points, bool promote) {
     if (!ctx) return CVO_B200_ERR_ARG;
     if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
-    if (!img3 || !depth) return fail_arg(ctx, "null image pointer");
-    if (width < 64 || height < 64 || width % 32 || height % 32 || (long long)width * height > (1 << 24))
-        return fail_arg(ctx, "image size must be a multiple of 32 in both directions (the selector's block thresholds, "
-                             "thirdparty/PixelSelector2.cpp:367, are only defined then)");
-    if (feature_type != 0 && feature_type != 1) return fail_arg(ctx, "feature_type must be 0 (acvo) or 1 (cvo)");
+    int rc = check_image_args(ctx, img3, depth, width, height, feature_type);
+    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    int rc = flush_all_batches(ctx);
+    rc = flush_all_batches(ctx);
     if (rc) return rc;
     rc = ensure_image_pipe(ctx, width, height);
     if (rc) return rc;
@@ -993,8 +1061,37 @@ static int push_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, c
     else if (!s.bound) target = 1 - fixed_buf;
     else if (promote) { fixed_buf = 1 - fixed_buf; target = 1 - fixed_buf; }
     else target = 1 - fixed_buf;  // no align() since the last frame: the moving cloud is replaced (src/cvo.cpp:336-351)
+    if (P.next_pending) {  // a prefetched frame is still in flight through the pipe's scratch: this frame replaces it
+        CK(cudaEventSynchronize(P.ev_next));
+        P.next_pending = false;
+    }
+    rc = enqueue_frontend(ctx, img3, depth, width, height, dataset_seq, feature_type, ctx->d_raw_xyz, ctx->d_raw_feat, ctx->d_jobs,
+                          slot_g(ctx, slot, target), slot_f(ctx, slot, target), slot_f4(ctx, slot, target), ctx->stream, P.h_ctl);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const SelCtl& c = *P.h_ctl;
+    ctx->last_gen_n = c.num_points < ctx->max_points ? c.num_points : ctx->max_points;
+    if (num_points) *num_points = c.num_points;
+    ctx->last_gen_canny = c.canny_used;
+    if (c.status == PCD_STATUS_TOO_MANY_POINTS) return fail_arg(ctx, "the frame yields more points than max_points");
+    if (c.num_points <= 0) {
+        ctx->err = "empty cloud";
+        return CVO_B200_ERR_EMPTY;
+    }
+    s.fixed_buf = fixed_buf;
+    s.n[target] = c.num_points;
+    if (!s.have_fixed) s.have_fixed = true;
+    else s.bound = true;
+    return CVO_B200_OK;
+}
+
+// The device image front end (pcd_kernels.cuh) for one frame, enqueued on `st`: image + depth up, 23 launches, the packed
+// cloud into (out_g, out_f, out_f4), the selector's control block back into the pinned `h_ctl`.  No synchronisation.
+static int enqueue_frontend(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width, int height,
+                            int dataset_seq, int feature_type, float* raw_xyz, float* raw_feat, PackJob* d_job, float4* out_g,
+                            float4* out_f, float* out_f4, cudaStream_t st, SelCtl* h_ctl) {
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
     const int w = width, h = height, wh = w * h;
-    cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(P.d_img3, img3, (size_t)wh * 3, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(P.d_depth, depth, (size_t)wh * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     PcdBuffers B;
@@ -1050,19 +1147,58 @@ static int push_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, c
         pcd_topup_kernel<<<((w / 8) * (h / 8) + T - 1) / T, T, 0, st>>>(B, cs);
         pcd_topup_done_kernel<<<1, 1, 0, st>>>(B);
     }
-    PackJob job = {ctx->d_raw_xyz, ctx->d_raw_feat, slot_g(ctx, slot, target), slot_f(ctx, slot, target),
-                   slot_f4(ctx, slot, target), 0, 0};
-    CK(cudaMemcpyAsync(ctx->d_jobs, &job, sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    PackJob job = {raw_xyz, raw_feat, out_g, out_f, out_f4, 0, 0};
+    CK(cudaMemcpyAsync(d_job, &job, sizeof(PackJob), cudaMemcpyHostToDevice, st));
     pcd_count_kernel<FLAG_POINT><<<nblk, 1024, 0, st>>>(B, P.d_blockcnt);
-    pcd_points_kernel<<<nblk, 1024, 0, st>>>(B, P.d_blockcnt, camera_info(dataset_seq), feature_type, ctx->d_raw_xyz,
-                                            ctx->d_raw_feat, ctx->max_points, &ctx->d_jobs->n);
-    pack_sort_kernel<<<1, kPackThreads, ctx->pack_smem_max, st>>>(ctx->d_jobs, ctx->sort_points);
+    pcd_points_kernel<<<nblk, 1024, 0, st>>>(B, P.d_blockcnt, camera_info(dataset_seq), feature_type, raw_xyz, raw_feat,
+                                            ctx->max_points, &d_job->n);
+    pack_sort_kernel<<<1, kPackThreads, ctx->pack_smem_max, st>>>(d_job, ctx->sort_points);
     CK(cudaGetLastError());
     ctx->launches += 23;
-    CK(cudaMemcpyAsync(P.h_ctl, P.d_ctl, sizeof(SelCtl), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const SelCtl& c = *P.h_ctl;
-    ctx->last_gen_n = c.num_points < ctx->max_points ? c.num_points : ctx->max_points;
+    CK(cudaMemcpyAsync(h_ctl, P.d_ctl, sizeof(SelCtl), cudaMemcpyDeviceToHost, st));
+    return CVO_B200_OK;
+}
+
+static int check_image_args(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width, int height,
+                            int feature_type) {
+    if (!img3 || !depth) return fail_arg(ctx, "null image pointer");
+    if (width < 64 || height < 64 || width % 32 || height % 32 || (long long)width * height > (1 << 24))
+        return fail_arg(ctx, "image size must be a multiple of 32 in both directions (the selector's block thresholds, "
+                             "thirdparty/PixelSelector2.cpp:367, are only defined then)");
+    if (feature_type != 0 && feature_type != 1) return fail_arg(ctx, "feature_type must be 0 (acvo) or 1 (cvo)");
+    return CVO_B200_OK;
+}
+
+int cvo_b200_prefetch_frame_images(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width,
+                                   int height, int dataset_seq, int feature_type) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    int rc = check_image_args(ctx, img3, depth, width, height, feature_type);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    rc = flush_all_batches(ctx);
+    if (rc) return rc;
+    rc = ensure_image_pipe(ctx, width, height);
+    if (rc) return rc;
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
+    // the previous prefetched cloud must have left the `next` buffers (cvo_b200_push_prefetched_frame copies it on `stream`)
+    CK(cudaStreamWaitEvent(ctx->copy_stream, P.ev_taken, 0));
+    rc = enqueue_frontend(ctx, img3, depth, width, height, dataset_seq, feature_type, P.d_next_raw_xyz, P.d_next_raw_feat,
+                          P.d_next_job, P.d_next_g, P.d_next_f, P.d_next_f4, ctx->copy_stream, P.h_ctl_next);
+    if (rc) return rc;
+    CK(cudaEventRecord(P.ev_next, ctx->copy_stream));
+    P.next_pending = true;
+    return CVO_B200_OK;
+}
+
+int cvo_b200_push_prefetched_frame(cvo_b200_ctx* ctx, int slot, int promote, int* num_points) {
+    if (!ctx) return CVO_B200_ERR_ARG;
+    if (slot < 0 || slot >= ctx->max_slots) return fail_arg(ctx, "slot out of range");
+    cvo_b200_ctx::ImagePipe& P = ctx->pipe;
+    if (!P.next_pending) return fail_arg(ctx, "no prefetched frame (cvo_b200_prefetch_frame_images)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(P.ev_next));
+    P.next_pending = false;
+    const SelCtl& c = *P.h_ctl_next;
     if (num_points) *num_points = c.num_points;
     ctx->last_gen_canny = c.canny_used;
     if (c.status == PCD_STATUS_TOO_MANY_POINTS) return fail_arg(ctx, "the frame yields more points than max_points");
@@ -1070,6 +1206,17 @@ static int push_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, c
         ctx->err = "empty cloud";
         return CVO_B200_ERR_EMPTY;
     }
+    cvo_b200_ctx::Slot& s = ctx->slots[slot];
+    int fixed_buf = s.fixed_buf, target;  // as in push_images
+    if (!s.have_fixed) { fixed_buf = 0; target = 0; }
+    else if (!s.bound) target = 1 - fixed_buf;
+    else if (promote) { fixed_buf = 1 - fixed_buf; target = 1 - fixed_buf; }
+    else target = 1 - fixed_buf;
+    const size_t n = (size_t)c.num_points;
+    CK(cudaMemcpyAsync(slot_g(ctx, slot, target), P.d_next_g, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(slot_f(ctx, slot, target), P.d_next_f, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(slot_f4(ctx, slot, target), P.d_next_f4, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(P.ev_taken, ctx->stream));
     s.fixed_buf = fixed_buf;
     s.n[target] = c.num_points;
     if (!s.have_fixed) s.have_fixed = true;
@@ -1194,6 +1341,16 @@ int cvo_b200_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b
                    float* ell_io, float* transform, float* prev_transform, int* iters, int* status) {
     return run_align(ctx, slots, n_pairs, p, RT_io, ell_io, transform, prev_transform, iters, status, nullptr, 0,
                      nullptr);
+}
+
+int cvo_b200_align_begin(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p, const float* RT_in,
+                         const float* ell_in) {
+    return run_align_begin(ctx, slots, n_pairs, p, RT_in, ell_in, false, 0);
+}
+
+int cvo_b200_align_finish(cvo_b200_ctx* ctx, float* RT_out, float* ell_out, float* transform, float* prev_transform,
+                          int* iters, int* status) {
+    return run_align_finish(ctx, RT_out, ell_out, transform, prev_transform, iters, status, nullptr, nullptr);
 }
 
 int cvo_b200_align_trace(cvo_b200_ctx* ctx, int slot, const cvo_b200_params* p, float* RT_io, float* ell_io,

@@ -31,6 +31,7 @@ class _Registration:
         self._bound = False
         self._have_moving = False
         self._aligned = False  # an align() has run since the last set_pcd: the next set_pcd promotes moving -> fixed
+        self._prefetched_key = None
         self.status = 0
 
     def close(self):
@@ -68,8 +69,12 @@ class _Registration:
         if self._first is not None or (self.init and not self._images):
             raise RuntimeError("one frontend object takes either arrays or images, not both")
         self._images = True
-        n = self._ctx.push_frame_images(self._slot, img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1,
-                                        promote=(not self._bound) or self._aligned)
+        promote = (not self._bound) or self._aligned
+        if self._prefetched_key is not None and self._prefetched_key == (id(img3), id(depth)):
+            n = self._ctx.push_prefetched_frame(self._slot, promote=promote)  # the look-ahead of prefetch_images
+        else:
+            n = self._ctx.push_frame_images(self._slot, img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1, promote=promote)
+        self._prefetched_key = None
         self._aligned = False
         if not self.init:
             self.init = True
@@ -80,6 +85,13 @@ class _Registration:
         self._have_moving = True
         return n
 
+    def prefetch_images(self, dataset_seq, img3, depth):
+        """Look-ahead for a sequence loop (the reference's driver has frame k + 1 on disk while it aligns frame k,
+        src/cvo_main.cpp:36-66): starts the front end for the frame that the NEXT set_pcd_images / run_cvo_images will be
+        given (the same array objects) so that it overlaps the align() in between."""
+        self._ctx.prefetch_frame_images(img3, depth, dataset_seq, 0 if self._KIND == "acvo" else 1)
+        self._prefetched_key = (id(img3), id(depth))
+
     def run_cvo_images(self, dataset_seq, img3, depth):
         """run_cvo(dataset_seq, RGB, depth, ...) (src/cvo.cpp:422-435)."""
         first = not self.init
@@ -87,11 +99,18 @@ class _Registration:
         if not first:
             self.align()
 
-    def align(self):
-        """align (src/cvo.cpp:361-420)."""
+    def align(self, next_frame=None):
+        """align (src/cvo.cpp:361-420).  next_frame = (dataset_seq, img3, depth): the look-ahead of a sequence loop -- the
+        kernel is launched, the front end of the next frame is enqueued while it runs (prefetch_images), then the
+        result is collected."""
         if not self._have_moving:
             raise RuntimeError("align() called before a moving cloud was set")
-        r = self._ctx.align([self._slot], self.params, RT=self._RT[None], ell=np.array([self._ell], np.float32))
+        if next_frame is None:
+            r = self._ctx.align([self._slot], self.params, RT=self._RT[None], ell=np.array([self._ell], np.float32))
+        else:
+            self._ctx.align_begin([self._slot], self.params, RT=self._RT[None], ell=np.array([self._ell], np.float32))
+            self.prefetch_images(*next_frame)
+            r = self._ctx.align_finish()
         self._RT, self._ell = r["RT"][0], float(r["ell"][0])
         self.status = int(r["status"][0])
         if self.status != capi.STATUS_MAX_ITER:  # Q5: iter only assigned on early exit

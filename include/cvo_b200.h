@@ -159,6 +159,25 @@ int cvo_b200_push_frame_images(cvo_b200_ctx* ctx, int slot, const unsigned char*
  * cvo_b200_replace_moving).  On a slot without a bound pair it behaves like cvo_b200_push_frame_images. */
 int cvo_b200_replace_moving_images(cvo_b200_ctx* ctx, int slot, const unsigned char* img3, const unsigned short* depth,
                                    int width, int height, int dataset_seq, int feature_type, int* num_points);
+/* cvo_b200_align in two halves, for a driver that has something else to enqueue while the kernel runs (the front end of
+ * the next frame: cvo_b200_prefetch_frame_images).  _begin validates, writes the pair records and launches; _finish waits
+ * and hands the results out exactly as cvo_b200_align does.  One align in flight per context: a second _begin, or any
+ * other align / eval call, before _finish is an error.  Uploads enqueued in between are ordered behind the kernel. */
+int cvo_b200_align_begin(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* params,
+                         const float* RT_in, const float* ell_in);
+int cvo_b200_align_finish(cvo_b200_ctx* ctx, float* RT_out, float* ell_out, float* transform, float* prev_transform,
+                          int* iters, int* status);
+/* Look-ahead for a sequence driver (src/cvo_main.cpp:36-66 reads frame k + 1 from disk before it needs it): starts the
+ * image front end for the NEXT frame on the context's copy stream and returns at once -- image upload, the 23 launches
+ * and the packed cloud (into a context-level buffer) overlap the cvo_b200_align() of the current pair, which occupies a
+ * fraction of the SMs.  cvo_b200_push_prefetched_frame then gives the cloud to a slot exactly as
+ * cvo_b200_push_frame_images (promote != 0) / cvo_b200_replace_moving_images (promote == 0) would have: it waits for the
+ * prefetch (normally long finished), checks the point count and copies the cloud device-to-device.  The image buffers
+ * must stay valid until cvo_b200_push_prefetched_frame returns.  One prefetched frame per context; a
+ * cvo_b200_push_frame_images in between discards it.  The resulting cloud is bit-identical to the synchronous path's. */
+int cvo_b200_prefetch_frame_images(cvo_b200_ctx* ctx, const unsigned char* img3, const unsigned short* depth, int width,
+                                   int height, int dataset_seq, int feature_type);
+int cvo_b200_push_prefetched_frame(cvo_b200_ctx* ctx, int slot, int promote, int* num_points);
 /* The cloud the last cvo_b200_push_frame_images generated, in the reference's (raster) order: xyz n x 3,
  * feat n x 5 row-major (parity hook; valid until the next upload of any kind). */
 int cvo_b200_last_generated_cloud(cvo_b200_ctx* ctx, float* xyz, float* feat, int capacity, int* n);

@@ -115,10 +115,13 @@ class registration {
     // continuous CV_8UC3), depth: height x width 16-bit (CV_16UC1).  Returns the number of points.
     int set_pcd(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
         int n = 0;
-        if (!pair_bound_ || aligned_since_set_)
+        if (prefetched_ == img3 && img3 != nullptr)  // the look-ahead of prefetch(): the cloud is (being) generated already
+            check(cvo_b200_push_prefetched_frame(ctx_, 0, (!pair_bound_ || aligned_since_set_) ? 1 : 0, &n));
+        else if (!pair_bound_ || aligned_since_set_)
             check(cvo_b200_push_frame_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
         else  // no align() since the last frame: only the moving cloud is replaced (src/cvo.cpp:336-351)
             check(cvo_b200_replace_moving_images(ctx_, 0, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1, &n));
+        prefetched_ = nullptr;
         aligned_since_set_ = false;
         if (!init) {
             init = true;
@@ -128,6 +131,13 @@ class registration {
         if (adaptive_) ell_ = params_.ell_init;  // src/adaptive_cvo.cpp:476-478
         have_moving_ = true;
         return n;
+    }
+    // Look-ahead for a sequence loop (src/cvo_main.cpp:36-66 has frame k + 1 on disk while it aligns frame k): starts the
+    // front end for the frame the NEXT set_pcd / run_cvo will be given (the same pointers, valid until then), so that
+    // it overlaps the align() in between (cvo_b200_prefetch_frame_images).
+    void prefetch(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
+        check(cvo_b200_prefetch_frame_images(ctx_, img3, depth, width, height, dataset_seq, adaptive_ ? 0 : 1));
+        prefetched_ = img3;
     }
     void run_cvo(int dataset_seq, const unsigned char* img3, const unsigned short* depth, int width, int height) {
         const bool first = !init;  // src/cvo.cpp:422-435
@@ -146,6 +156,23 @@ class registration {
         last_status_ = status;
         have_moving_ = false;
         aligned_since_set_ = true;  // ptr_fixed_pcd = std::move(ptr_moving_pcd) (src/cvo.cpp:417): the next set_pcd promotes
+    }
+
+    // align() with the reference driver's look-ahead (src/cvo_main.cpp:36-66 has frame k + 1 on disk while frame k is
+    // aligned): the kernel is launched, the front end of the NEXT frame is enqueued while it runs (prefetch), then the
+    // result is collected.  The next set_pcd / run_cvo must be given the same image pointers.
+    void align(int next_dataset_seq, const unsigned char* next_img3, const unsigned short* next_depth, int width, int height) {
+        if (!have_moving_) throw std::runtime_error("align() called before a moving cloud was set");
+        const int slot = 0;
+        int iters = 0, status = 0;
+        check(cvo_b200_align_begin(ctx_, &slot, 1, &params_, RT_, &ell_));
+        prefetch(next_dataset_seq, next_img3, next_depth, width, height);
+        check(cvo_b200_align_finish(ctx_, RT_, &ell_, transform.m, prev_transform.m, &iters, &status));
+        if (status != CVO_B200_STATUS_MAX_ITER) iter = iters;      // Q5
+        accum_transform = accum_transform * prev_transform;        // Q3 (src/cvo.cpp:413-414)
+        last_status_ = status;
+        have_moving_ = false;
+        aligned_since_set_ = true;
     }
 
     void run_cvo(const float* xyz, const float* feat, int n) {  // src/cvo.cpp:422-435
@@ -173,6 +200,7 @@ class registration {
     std::vector<float> first_xyz_, first_feat_;
     int first_n_ = 0;
     bool pair_bound_ = false, have_moving_ = false, aligned_since_set_ = false;
+    const unsigned char* prefetched_ = nullptr;  // image of the frame whose front end was started by prefetch()
     int last_status_ = 0;
 };
 

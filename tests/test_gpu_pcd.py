@@ -130,3 +130,37 @@ def test_image_sequence_through_the_frontend_equals_the_array_path(kind):
     finally:
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("kind", ["cvo", "acvo"])
+def test_prefetched_frames_equal_the_synchronous_front_end(kind):
+    """cvo_b200_prefetch_frame_images + cvo_b200_push_prefetched_frame (the front end of frame k + 1 overlapping the align of
+    frame k, the look-ahead of src/cvo_main.cpp:36-66) give bit-identical clouds, hence bit-identical trajectories."""
+    base_img, base_dep = synth.make_frame(43)
+    frames = [(np.roll(base_img, 3 * k, axis=1).copy(), np.roll(base_dep, 3 * k, axis=1).copy()) for k in range(5)]
+    cls = frontend.cvo if kind == "cvo" else frontend.acvo
+    a, b = cls(max_points=4096), cls(max_points=4096)
+    try:
+        for k, (img, dep) in enumerate(frames):
+            a.run_cvo_images(1, img, dep)
+            if k == 0:
+                b.set_pcd_images(1, img, dep)
+            else:
+                b.set_pcd_images(1, img, dep)  # (prefetched during the previous align, see below)
+                if k + 1 < len(frames) and k % 2:  # both look-ahead styles: prefetch, then a blocking align ...
+                    b.prefetch_images(1, *frames[k + 1])
+                    b.align()
+                else:  # ... and align_begin / prefetch / align_finish
+                    b.align(next_frame=(1,) + frames[k + 1] if k + 1 < len(frames) else None)
+            if k == 0 and len(frames) > 1:
+                b.prefetch_images(1, *frames[1])
+            assert np.array_equal(a.transform, b.transform) and np.array_equal(a.accum_transform, b.accum_transform), k
+        assert np.linalg.norm(a.accum_transform[:3, 3]) > 1e-4
+        # a synchronous frame in between discards a pending prefetch; pushing without one is an error
+        b.prefetch_images(1, *frames[0])
+        b.set_pcd_images(1, *frames[1])
+        with pytest.raises(capi.CvoB200Error):
+            b._ctx.push_prefetched_frame(0)
+    finally:
+        a.close()
+        b.close()
