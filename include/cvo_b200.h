@@ -270,7 +270,7 @@ int       cvo_b200_num_sms(const cvo_b200_ctx* ctx);
 /* 1 if the last align used (or the next will use) neighbour lists; 0 if they are disabled or their scratch could not
  * be allocated (every pass then runs on the fly: same results, several times slower). */
 int       cvo_b200_neighbor_lists_active(const cvo_b200_ctx* ctx);
-/* Bytes of HBM scratch the neighbour lists currently occupy: CTAs of the largest launch so far x 4 areas x capacity,
+/* Bytes of HBM scratch the neighbour lists currently occupy: CTAs of the largest launch so far x 5 areas x capacity,
  * the capacity following the largest cloud aligned so far (not max_points). */
 long long cvo_b200_list_scratch_bytes(const cvo_b200_ctx* ctx);
 
