@@ -71,6 +71,7 @@ enum PassKind { PASS_FLOW = 0, PASS_XX = 1, PASS_YY = 2, PASS_STEP = 3, PASS_INN
 // test, the colour gate and the kernel value are still evaluated on the fly in every pass, A never exists.
 enum ListKind { LIST_XY = 0, LIST_XX = 1, LIST_YY = 2, LIST_KINDS = 3 };
 constexpr int kListAreas = LIST_KINDS + 2;  // per CTA: the three lists, the build staging, the wide (x, y) list
+constexpr int kMaxColChunks = 6;    // column chunks of a pass: 6 x 3072 = 18 432 points (> the 16 384 a context can hold)
 constexpr int kMaxListRounds = 36;  // (row round, column chunk) combinations of one pass: 6 x 6 chunks of 3072 points
 constexpr int kListTrip = 128;      // entries one warp handles per trip of a list pass; rounds are padded to it
 #ifndef CVO_PREFETCH_TRIPS
@@ -265,7 +266,9 @@ struct Smem {
     float colBox[kColTiles][8];  // [0..2] lo, [3..5] hi, [6] max |c|^2
     double blockTot[kNumAcc];
     double flowTot[kNumAcc];  // this CTA's flow-exchange vector (ACC_* layout)
-    uint32_t colMask[kMaxListRounds][kColTiles / 32];  // per round of the (x, y) list: the column tiles its sweep found live
+    // per column chunk of the (x, y) list: the column tiles its sweep found live in ANY of the row rounds that share the chunk
+    // (the quad passes stage a chunk once for all of them, and only these tiles)
+    uint32_t colMask[kMaxColChunks][kColTiles / 32];
     uint2 lround[LIST_KINDS][kMaxListRounds];  // (offset, entries) of every round of a list; entries % kListTrip == 0
     int lst_base;
     int refineCnt[kWarps], refinePos[kWarps];  // refine_list: entries every warp kept / where they go

@@ -414,6 +414,10 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
     wo.cursor = 0;
     wo.s_build = make_wide ? sm.wide.s_build : 0.f;
     const float thr_build = make_wide ? sm.wide.thr_build : L.thr_build;
+    // a sweep finds the live column tiles anew (a filter keeps its wide sweep's, a superset); tile 0 of every chunk always:
+    // the padding slots of the quads address column 0 and must read finite coordinates
+    if (SELF == 0 && !from_wide && threadIdx.x < kMaxColChunks * (kColTiles / 32))
+        sm.colMask[threadIdx.x / (kColTiles / 32)][threadIdx.x % (kColTiles / 32)] = (threadIdx.x % (kColTiles / 32)) == 0 ? 1u : 0u;
     if (threadIdx.x == 0) {
         sm.lst_used = 0;
         sm.lst_ovf = 0;
@@ -441,9 +445,6 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
             if (threadIdx.x == 0) sm.next_unit = 0;
             if (SELF == 0) {
                 for (int i = threadIdx.x; i < ntile * kTile; i += kThreads) sm.u.of.bu.rowCnt[i] = 0;
-                // a sweep finds the round's live column tiles anew (a filter keeps its wide sweep's, a superset); tile 0
-                // always: the padding slots of the quads address column 0 and must read finite coordinates
-                if (!from_wide && threadIdx.x < kColTiles / 32) sm.colMask[round][threadIdx.x] = threadIdx.x == 0 ? 1u : 0u;
             }
             __syncthreads();
             CVO_PHASE(6)
@@ -468,7 +469,7 @@ __device__ void build_list(Smem& sm, const KParams& kp, const CloudDev& rows, bo
                     wo.cursor = 0;
                     c = build_unit_write<SELF>(sm, ws, kp, L, rows, row_tf, pg.t_begin + (rb + t) * pg.t_stride, (uint32_t)(t * kTile),
                                                yy_row_min, c_begin, c_end, stage + wcur, seg - wcur, thr_build, wo,
-                                               sm.colMask[round]);
+                                               sm.colMask[cb / kColTiles]);
                     if (make_wide && lane == 0) {
                         __stcg(lr.wide + round * kColTiles + t, make_uint2((unsigned)(warp * wseg + w0), (unsigned)wo.cursor));
                         if (w0 + wo.cursor > wseg) sm.wide_ovf = 1;

@@ -506,7 +506,7 @@ __device__ void run_pass_quads(Smem& sm, const KParams& kp, const CloudDev& rows
             const int row_tile0 = pg.t_begin + rb * pg.t_stride, row_first = row_tile0 * kTile, col_first = cb * kTile;
             const bool have_cols = tag_is(sm.colTag, cols.g, col_first, nct * kTile, sm.serial);
             const bool have_rows = tag_is(sm.rowTag, rows.g, row_first, ntile * kTile, -1);
-            if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase, nullptr, sm.colMask[round]);
+            if (!have_cols) stage_tiles<STAGE_GEOM>(sm, cols, col_first, nct, true, kColSentinel, tma_phase, nullptr, sm.colMask[cb / kColTiles]);
             if (!have_rows) stage_rows(sm, rows, row_tile0, pg.t_stride, ntile * kTile, false);
             if (KIND == PASS_STEP) {
                 if (!have_rows) __syncthreads();

@@ -562,3 +562,38 @@ def test_device_exp_sek3_matches_the_oracle_including_the_small_angle_quirk(gpu_
         assert np.abs(gT - wT).max() <= 3e-7 * max(1.0, np.abs(wT).max()) + 1e-6 * np.abs(wT).max(), r
     small = rows[-4]  # theta = 1e-8: dR = I, dT = v (not dt * v)
     assert np.array_equal(dR[-4], np.eye(3, dtype=np.float32)) and np.allclose(dT[-4], small[3:6], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("seed,kind,n,m,wide", [(11, "cvo", 333, 2111, None), (12, "cvo", 2500, 40, "0.5"), (13, "acvo", 900, 700, None),
+                                                (14, "acvo", 65, 3100, "0"), (15, "cvo", 31, 33, "0.8"), (16, "cvo", 3300, 2700, "0.3")])
+def test_ragged_pairs_lists_wide_lists_and_clusters_agree_with_on_the_fly_passes(seed, kind, n, m, wide, monkeypatch):
+    """Ragged and tiny clouds (fewer points than a tile, one cloud forty times the other), the wide-list filter forced on
+    and off for both classes, lists built ahead of the motion, on 1, 3 and 16 CTAs per pair and on two clusters: the lists
+    only change which index pairs a pass looks at, so the first iteration's counts equal the on-the-fly passes' exactly,
+    the next ones within boundary flips, and the run ends at the same fixed point."""
+    if wide is not None:
+        monkeypatch.setenv("CVO_B200_LIST_WIDE", wide)
+    pr = synth.make_pair(seed, n, m, kind, motion_scale=1.5)
+    gp = capi.default_params(kind)
+    gp.max_iter = 150
+    with capi.Context(0, max_points=4096, max_slots=1) as ctx:
+        _set(ctx, 0, pr)
+        ctx.set_neighbor_lists(False)
+        ref = ctx.align_trace(0, gp, trace_cap=60)
+        ctx.set_neighbor_lists(True)
+        for g, clusters in ((1, 1), (3, 1), (16, 1), (4, 2)):
+            ctx.set_cluster_size(g)
+            ctx.set_group_clusters(clusters)
+            got = ctx.align_trace(0, gp, trace_cap=60)
+            assert ctx.neighbor_lists_active and ctx.last_list_builds >= 1
+            a, b = got["trace"][0], ref["trace"][0]
+            assert (a["nnz"], a["nnz_xx"], a["nnz_yy"]) == (b["nnz"], b["nnz_xx"], b["nnz_yy"]), (g, clusters)
+            for key in ("omega", "v", "B", "E"):
+                assert rel_err(a[key], b[key]) < 5e-6, (g, clusters, key)
+            for k in range(1, min(6, got["n_iterations_run"], ref["n_iterations_run"])):
+                a, b = got["trace"][k], ref["trace"][k]
+                assert abs(a["nnz"] - b["nnz"]) <= 3 + b["nnz"] // 20000, (g, clusters, k)
+            rot, tr = pose_diff(got["transform"], ref["transform"])
+            converged = got["status"] != capi.STATUS_MAX_ITER and ref["status"] != capi.STATUS_MAX_ITER
+            tol = POSE_TOL_FLOOR if converged else 1e-3  # (cut off mid-trajectory: rounding differences still amplified, level 2)
+            assert rot < tol and tr < tol, (g, clusters, rot, tr, got["status"], ref["status"])
