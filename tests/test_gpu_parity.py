@@ -565,10 +565,12 @@ def test_device_exp_sek3_matches_the_oracle_including_the_small_angle_quirk(gpu_
 
 
 @pytest.mark.parametrize("seed,kind,n,m,wide", [(11, "cvo", 333, 2111, None), (12, "cvo", 2500, 40, "0.5"), (13, "acvo", 900, 700, None),
-                                                (14, "acvo", 65, 3100, "0"), (15, "cvo", 31, 33, "0.8"), (16, "cvo", 3300, 2700, "0.3")])
+                                                (14, "acvo", 65, 3100, "0"), (15, "cvo", 31, 33, "0.8"), (16, "cvo", 3300, 2700, "0.3"),
+                                                (17, "cvo", 4000, 5000, None), (18, "acvo", 3500, 3300, None), (19, "cvo", 7000, 3100, "0.5")])
 def test_ragged_pairs_lists_wide_lists_and_clusters_agree_with_on_the_fly_passes(seed, kind, n, m, wide, monkeypatch):
     """Ragged and tiny clouds (fewer points than a tile, one cloud forty times the other), the wide-list filter forced on
-    and off for both classes, lists built ahead of the motion, on 1, 3 and 16 CTAs per pair and on two clusters: the lists
+    and off for both classes, several row rounds and column chunks (more than 3072 points on either side), lists built ahead
+    of the motion, on 1, 3 and 16 CTAs per pair and on two clusters: the lists
     only change which index pairs a pass looks at, so the first iteration's counts equal the on-the-fly passes' exactly,
     the next ones within boundary flips, and the run ends at the same fixed point."""
     if wide is not None:
@@ -576,7 +578,7 @@ def test_ragged_pairs_lists_wide_lists_and_clusters_agree_with_on_the_fly_passes
     pr = synth.make_pair(seed, n, m, kind, motion_scale=1.5)
     gp = capi.default_params(kind)
     gp.max_iter = 150
-    with capi.Context(0, max_points=4096, max_slots=1) as ctx:
+    with capi.Context(0, max_points=8192, max_slots=1) as ctx:
         _set(ctx, 0, pr)
         ctx.set_neighbor_lists(False)
         ref = ctx.align_trace(0, gp, trace_cap=60)
