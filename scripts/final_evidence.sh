@@ -15,4 +15,5 @@ timeout 300 python scripts/gpu_other_configs.py all > gpurun_out/ev/other_config
 for m in cfg2 stock single; do echo "== $m"; CVO_B200_LIB=build/variants/libcvo_b200_clk.so timeout 200 python scripts/gpu_phase_clocks.py $m; done > gpurun_out/ev/phase.txt 2>&1
 timeout 300 python scripts/gpu_sequence_perf.py > gpurun_out/ev/sequence.txt 2>&1
 timeout 300 python scripts/gpu_pcd_perf.py > gpurun_out/ev/pcd.txt 2>&1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/ev/smoke.txt 2>&1
 tail -3 gpurun_out/ev/pytest_gpu.txt; cat gpurun_out/ev/other_configs.txt; tail -c 600 gpurun_out/ev/bench_ref.json

@@ -7,24 +7,23 @@ from cvo_rgbd_b200 import frontend, synth
 from oracle import pcd_oracle as P, cvo_oracle as O
 base_img, base_dep = synth.make_frame(41)
 frames = [(np.roll(base_img, 2 * k, axis=1), np.roll(base_dep, 2 * k, axis=1)) for k in range(41)]
+WARM = 3  # frames before the clock starts: the context's first align allocates the list scratch (about 17 ms)
 for kind in ("cvo", "acvo"):
     cls = frontend.cvo if kind == "cvo" else frontend.acvo
     reg = cls(max_points=4096)
-    for img, dep in frames[:3]:
-        reg.run_cvo_images(1, img, dep)
-    reg.close()
-    reg = cls(max_points=4096)
-    t0 = time.perf_counter()
     iters = []
-    for img, dep in frames:
+    for k, (img, dep) in enumerate(frames):
+        if k == WARM:
+            t0 = time.perf_counter()
         reg.run_cvo_images(1, img, dep)
         iters.append(reg.iter)
     dt = time.perf_counter() - t0
     reg.close()
     # the same loop with the reference driver's look-ahead: the front end of frame k + 1 overlaps the align of frame k
     reg = cls(max_points=4096)
-    t0 = time.perf_counter()
     for k, (img, dep) in enumerate(frames):
+        if k == WARM:
+            t0 = time.perf_counter()
         reg.set_pcd_images(1, img, dep)
         nxt = (1,) + frames[k + 1] if k + 1 < len(frames) else None
         if k > 0:
@@ -33,7 +32,8 @@ for kind in ("cvo", "acvo"):
             reg.prefetch_images(*nxt)
     dt_ahead = time.perf_counter() - t0
     reg.close()
-    print("%s: with look-ahead (cvo_b200_align_begin / prefetch_frame_images / align_finish): %d frames in %.1f ms -> %.1f frames/s" % (kind, len(frames), 1e3 * dt_ahead, len(frames) / dt_ahead), flush=True)
+    nt = len(frames) - WARM
+    print("%s: with look-ahead (cvo_b200_align_begin / prefetch_frame_images / align_finish): %d frames in %.1f ms -> %.1f frames/s" % (kind, nt, 1e3 * dt_ahead, nt / dt_ahead), flush=True)
     # CPU: 6 frames are enough for a rate
     n_cpu = 6
     op = O.default_params(kind)
@@ -48,4 +48,4 @@ for kind in ("cvo", "acvo"):
         prev = c
     dc = time.perf_counter() - t0
     print("%s: %d frames in %.1f ms -> %.1f frames/s on the device (mean %.1f iterations per pair); CPU restatement %.2f frames/s (%d threads)"
-          % (kind, len(frames), dt * 1e3, (len(frames) - 1) / dt, float(np.mean(iters[1:])), (n_cpu - 1) / dc, O.num_threads()))
+          % (kind, len(frames) - WARM, dt * 1e3, (len(frames) - WARM) / dt, float(np.mean(iters[1:])), (n_cpu - 1) / dc, O.num_threads()))
