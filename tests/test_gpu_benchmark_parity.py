@@ -12,7 +12,7 @@ positive root of a cubic (src/cvo.cpp:291-307), which jumps when two roots merge
 drift apart along the weakly constrained directions.  Measured over 200 pairs per mode
 (profiles/r02_parity_distribution.json): the same CPU restatement compiled two ways agrees with itself within 1e-4 on
 98 % (cfg2) / 92 % (stock cvo) / 97.5 % (stock acvo) of the pairs, worst pair 1.7e-4 .. 2.3e-4; GPU-vs-oracle shows the
-same distribution quantile by quantile (98.5 % / 92.5 % / 95.5 %).  The tests therefore assert, per workload:
+same distribution (98.5 % / 92.5 % / 95.5 % at the round's first build, 96.5 % / 87 % / 95.5 % at its last).  The tests therefore assert, per workload:
   * 1e-4 on the single BASELINE pairs (seed 0 of cfg 1, 2, 3), as north_star states it;
   * in batches: 1e-4 on the bulk (>= 75 % of the sampled pairs, median), every pair inside 5e-4, and for every cfg2
     pair beyond 1e-4 that the two end states sit on the same flat top of the objective (the oracle's own objective
