@@ -106,9 +106,15 @@ def stale_yy(n_runs):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     out = {"what": __doc__.split("\n\n")[0], "modes": {}}
-    out["modes"]["cfg2_fixed_ell_0.10_100_iters"] = run_mode("cfg2", "cvo", 2, n, True)
-    out["modes"]["stock_cvo"] = run_mode("cvo", "cvo", 2, n, False)
-    out["modes"]["stock_acvo"] = run_mode("acvo", "acvo", 3, n, False)
+    only = sys.argv[2] if len(sys.argv) > 2 else None  # one mode only (tuning experiments)
+    if only in (None, "cfg2"):
+        out["modes"]["cfg2_fixed_ell_0.10_100_iters"] = run_mode("cfg2", "cvo", 2, n, True)
+    if only in (None, "cvo"):
+        out["modes"]["stock_cvo"] = run_mode("cvo", "cvo", 2, n, False)
+    if only in (None, "acvo"):
+        out["modes"]["stock_acvo"] = run_mode("acvo", "acvo", 3, n, False)
+    if only is not None:
+        return
     out["stale_yy_list"] = stale_yy(8)
     print(json.dumps(out["stale_yy_list"]))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
