@@ -53,7 +53,10 @@ struct cvo_b200_ctx {
     // Batched upload (cvo_b200_set_pairs): two staging areas so that the host->device copies of one batch run on
     // `copy_stream` while the align kernel of the previous batch runs on `stream`.  The pack launch of a batch is
     // deferred until something needs its slots (it could not overlap the persistent align kernel anyway and must
-    // not be queued in front of it).
+    // not be queued in front of it) -- unless no align is in flight when the batch is uploaded: then the pack goes
+    // onto `copy_stream` right behind the copies (packed_eager).  In a pipelined driver (upload of batch k + 1, then
+    // align of batch k) its CTAs fill the SMs the align kernel's last wave leaves idle instead of standing in front of the
+    // next align.
     struct Batch {
         float* d_raw = nullptr;       // [fixed xyz | fixed feat | moving xyz | moving feat]
         size_t raw_floats = 0;
@@ -61,7 +64,8 @@ struct cvo_b200_ctx {
         PackJob* h_jobs = nullptr;    // pinned
         cudaEvent_t copied = nullptr; // recorded on copy_stream after the batch's copies
         cudaEvent_t packed = nullptr; // recorded on stream after the pack that read d_raw
-        bool pending = false;         // copies enqueued, pack not yet
+        bool pending = false;         // copies enqueued, pack not yet (or enqueued on copy_stream: packed_eager)
+        bool packed_eager = false;
         bool used = false;
         int njobs = 0;
         std::vector<int> slots;
@@ -219,23 +223,32 @@ int launch_pack(cvo_b200_ctx* ctx, const PackJob* jobs_host, int njobs, PackJob*
 }
 
 // Enqueues the deferred pack launch of a batched upload on the main stream (after its copies).
+int launch_pack(cvo_b200_ctx* ctx, cvo_b200_ctx::Batch& B, cudaStream_t st) {
+    int nmax = 0;
+    for (int i = 0; i < B.njobs; ++i) nmax = B.h_jobs[i].n > nmax ? B.h_jobs[i].n : nmax;
+    int npad = 1;
+    while (npad < nmax) npad <<= 1;
+    const size_t smem = (size_t)npad * sizeof(unsigned long long);
+    pack_sort_kernel<<<B.njobs, kPackThreads, smem, st>>>(B.d_jobs, ctx->sort_points);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(B.packed, st));
+    ctx->launches += 1;
+    return CVO_B200_OK;
+}
+
 int flush_batch(cvo_b200_ctx* ctx, int b) {
     cvo_b200_ctx::Batch& B = ctx->batch[b];
     if (!B.pending) return CVO_B200_OK;
     B.pending = false;
     for (int s : B.slots)
         if (ctx->slots[s].pending_batch == b) ctx->slots[s].pending_batch = -1;
-    int nmax = 0;
-    for (int i = 0; i < B.njobs; ++i) nmax = B.h_jobs[i].n > nmax ? B.h_jobs[i].n : nmax;
-    int npad = 1;
-    while (npad < nmax) npad <<= 1;
-    const size_t smem = (size_t)npad * sizeof(unsigned long long);
+    if (B.packed_eager) {  // already packed on copy_stream: whatever uses the slots next waits for that
+        B.packed_eager = false;
+        CK(cudaStreamWaitEvent(ctx->stream, B.packed, 0));
+        return CVO_B200_OK;
+    }
     CK(cudaStreamWaitEvent(ctx->stream, B.copied, 0));
-    pack_sort_kernel<<<B.njobs, kPackThreads, smem, ctx->stream>>>(B.d_jobs, ctx->sort_points);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(B.packed, ctx->stream));
-    ctx->launches += 1;
-    return CVO_B200_OK;
+    return launch_pack(ctx, B, ctx->stream);
 }
 int flush_all_batches(cvo_b200_ctx* ctx) {
     for (int b = 0; b < 2; ++b) {
@@ -937,6 +950,12 @@ static int set_pairs_strided(cvo_b200_ctx* ctx, const int* slots, int n_pairs, c
     CK(cudaEventRecord(B.copied, cs));
     B.pending = true;
     B.used = true;
+    B.packed_eager = false;
+    if (!ctx->pending.active) {  // no align in flight that could be reading these slots: pack right behind the copies
+        const int rc = launch_pack(ctx, B, cs);
+        if (rc) return rc;
+        B.packed_eager = true;
+    }
     return CVO_B200_OK;
 }
 
