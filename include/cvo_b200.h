@@ -109,10 +109,11 @@ int cvo_b200_set_pair(cvo_b200_ctx* ctx, int slot,
  * i * stride_points * 3 (xyz) or i * stride_points * 5 (feat) and holds n_fixed[i] / n_moving[i]
  * (<= stride_points) points.  Same copy / ownership rules as cvo_b200_set_pair.
  * Pipelining: the copies are enqueued on a copy stream of their own and the call returns at once; the pack
- * launch is enqueued when something first needs these slots.  A driver that binds batch k+1 to a second set
- * of slots BEFORE calling cvo_b200_align on batch k therefore overlaps the upload of k+1 with the align kernel
- * of k (two batches can be in flight; host buffers must stay untouched until the batch has been aligned or
- * cvo_b200_sync() returned). */
+ * launch follows them on that stream (or, while a cvo_b200_align_begin is in flight, is enqueued when something
+ * first needs these slots).  A driver that binds batch k+1 to a second set of slots BEFORE calling
+ * cvo_b200_align on batch k therefore overlaps the upload of k+1 with the align kernel of k, and the pack of
+ * k+1 fills the SMs that kernel's last wave leaves idle (two batches can be in flight; host buffers must stay
+ * untouched until the batch has been aligned or cvo_b200_sync() returned). */
 int cvo_b200_set_pairs(cvo_b200_ctx* ctx, const int* slots, int n_pairs,
                        const float* fixed_xyz, const float* fixed_feat, const int* n_fixed,
                        const float* moving_xyz, const float* moving_feat, const int* n_moving,
