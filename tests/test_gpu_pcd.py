@@ -164,3 +164,28 @@ def test_prefetched_frames_equal_the_synchronous_front_end(kind):
     finally:
         a.close()
         b.close()
+
+
+def test_align_begin_finish_protocol_errors():
+    """One align in flight per context: a second begin, a blocking align, or a finish without a begin are errors (and
+    leave the context usable); a refused image size does not start a prefetch."""
+    pr = synth.config_pair(1)
+    with capi.Context(0, max_points=1024, max_slots=1) as ctx:
+        ctx.set_pair(0, pr["x_pos"], pr["x_feat"], pr["y_pos"], pr["y_feat"])
+        gp = capi.default_params("cvo")
+        with pytest.raises(capi.CvoB200Error):
+            ctx._lib.cvo_b200_align_finish  # noqa: B018  (exists)
+            ctx._in_flight = (1, None, None)
+            ctx.align_finish()
+        ctx.align_begin([0], gp)
+        with pytest.raises(capi.CvoB200Error):
+            ctx.align_begin([0], gp)
+        with pytest.raises(capi.CvoB200Error):
+            ctx.align([0], gp)
+        with pytest.raises(capi.CvoB200Error):
+            ctx.prefetch_frame_images(np.zeros((100, 100, 3), np.uint8), np.zeros((100, 100), np.uint16))  # not a multiple of 32
+        a = ctx.align_finish()
+        b = ctx.align([0], gp)
+        assert np.array_equal(a["transform"], b["transform"]) and a["iters"][0] == b["iters"][0]
+        with pytest.raises(capi.CvoB200Error):
+            ctx.push_prefetched_frame(0)
