@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <algorithm>
 #include <vector>
 
 #include "cvo_kernels.cuh"
@@ -124,6 +125,7 @@ struct cvo_b200_ctx {
     int last_G = 0, last_nclusters = 0, force_G = 0;
     int force_group = 0, last_group = 1;
     // an align launched by cvo_b200_align_begin and not yet collected by cvo_b200_align_finish
+    std::vector<int> order;  // queue position -> index into the caller's arrays (largest pairs first, see run_align_begin)
     struct PendingAlign { bool active = false; int n_pairs = 0, G = 0, ncl = 0, group = 1, trace_cap = 0; bool trace = false; } pending;  // clusters per pair: 0 = automatic, 1 = one cluster per pair, n = whole-GPU mode
     int max_clusters[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};  // per cluster size, -1 = not asked yet
     long long last_total_iters = 0;
@@ -286,24 +288,29 @@ int max_resident_clusters(cvo_b200_ctx* ctx, int G) {
     return n;
 }
 
-// CTAs per pair.  One pair on a cluster of G CTAs takes about (s + (1 - s) / G) of its one-CTA time, s being the part
-// of an iteration that does not split (the serial section on one warp and the cluster barriers: measured 0.08-0.12
-// of a one-CTA iteration at 3000 points).  With `fit` clusters resident, a batch of P <= fit pairs takes one pair
-// time; a larger one is pulled from the shared counter by whichever cluster is free, i.e. P / fit pair times plus
-// about half a pair time of tail (the pairs' iteration counts differ).  The G with the smallest estimate wins, a
-// larger G only if it is at least 3 % better; any size 1..16 is allowed (the row tiles are dealt rank * tiles / G),
-// so e.g. 63 pairs -- the per-GPU share of BASELINE config 4 on 8 GPUs -- run as 63 clusters of 2 = 126 of 148 SMs
-// instead of the 63 CTAs the power-of-two rule of round 1 (2 P G <= #SMs) launched.
-int choose_cluster(cvo_b200_ctx* ctx, int n_pairs) {
+// CTAs per pair.  Measured on BASELINE config 4 (profiles/r02_cfg4_cluster_sweep.txt): a pair on a cluster of G CTAs takes
+// kPairTime[G] of its one-CTA time -- the serial section on one warp, the cluster barriers and the column staging every
+// CTA repeats do not split.  With `fit` clusters resident, a batch of P <= fit pairs lasts as long as its SLOWEST pair:
+// with the stop tests on the pairs' iteration counts differ by a factor of three (59 in the mean, 100 at the end of the
+// tail: 1.5 mean pair times for a wave of 60 - 150 pairs), with a fixed iteration count only the list rebuilds differ
+// (1.2).  A larger batch is pulled from the shared counter by whichever cluster is free: P / fit pair times plus about
+// half a pair time of tail, and never less than the single wave.  The G with the smallest estimate wins, a larger G
+// only if it is at least 3 % better; any size 1..16 is allowed (the row tiles are dealt rank * tiles / G).  E.g. the
+// per-GPU shares of config 4: 63 pairs (8 GPUs) run as 63 clusters of 2 (3.7 ms; one CTA each: 6.8), 125 pairs (4 GPUs)
+// as 74 clusters of 2 pulling from the queue (5.5 ms; one wave of 125 CTAs: 7.7), 250 and 500 pairs on one CTA each.
+int choose_cluster(cvo_b200_ctx* ctx, int n_pairs, bool stop_tests) {
     if (ctx->force_G > 0) return ctx->force_G;
-    const double serial = 0.12;
+    static const double kPairTime[kMaxCluster + 1] = {1.0,  1.0,  0.57, 0.50, 0.45, 0.41, 0.38, 0.37, 0.36,
+                                                      0.34, 0.32, 0.31, 0.29, 0.28, 0.27, 0.26, 0.25};
+    const double slowest = n_pairs < 4 ? 1.0 : (stop_tests ? 1.5 : 1.2);
     int best_G = 1;
     double best = 1.0e30;
     for (int G = 1; G <= kMaxCluster; ++G) {
         const int fit = max_resident_clusters(ctx, G);
         if (fit < 1) continue;
-        const double waves = n_pairs <= fit ? 1.0 : (double)n_pairs / fit + 0.5;
-        const double cost = waves * (serial + (1.0 - serial) / G);
+        double waves = slowest;
+        if (n_pairs > fit && (double)n_pairs / fit + 0.5 > waves) waves = (double)n_pairs / fit + 0.5;
+        const double cost = waves * kPairTime[G];
         if (cost < best * 0.97) {
             best = cost;
             best_G = G;
@@ -524,8 +531,21 @@ int run_align_begin(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_
             const int rc = flush_batch(ctx, ctx->slots[s].pending_batch);
             if (rc) return rc;
         }
-        ctx->h_pairs[i] = make_pair_dev(ctx, s);
-        PairState& st = ctx->h_states[i];
+    }
+    // The clusters pull pairs from a queue: the largest pairs go first (N x M, stable), so that a ragged batch ends on its
+    // cheap pairs -- the last wave is what a batch of a few pairs per cluster waits for.  Results go back by `order`.
+    // (A traced align keeps the caller's pair 0 at the head of the queue: the kernel traces queue position 0.)
+    ctx->order.resize(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) ctx->order[i] = i;
+    std::stable_sort(ctx->order.begin() + ((trace && trace_cap > 0) ? 1 : 0), ctx->order.end(), [&](int a, int b) {
+        const cvo_b200_ctx::Slot& sa = ctx->slots[slots[a]];
+        const cvo_b200_ctx::Slot& sb = ctx->slots[slots[b]];
+        return (long long)sa.n[0] * sa.n[1] > (long long)sb.n[0] * sb.n[1];
+    });
+    for (int q = 0; q < n_pairs; ++q) {
+        const int i = ctx->order[q];
+        ctx->h_pairs[q] = make_pair_dev(ctx, slots[i]);
+        PairState& st = ctx->h_states[q];
         memset(&st, 0, sizeof(st));
         if (RT_io) {
             memcpy(st.R, RT_io + (size_t)i * 12, sizeof(float) * 9);
@@ -548,7 +568,7 @@ int run_align_begin(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_
         args.trace_cap = trace_cap < ctx->trace_cap ? trace_cap : ctx->trace_cap;
     }
     args.kp = make_kparams(p, false);
-    int G = choose_cluster(ctx, n_pairs);
+    int G = choose_cluster(ctx, n_pairs, p->fixed_iters <= 0);
     int group = 1;
     {
         int fit = max_resident_clusters(ctx, G);
@@ -630,8 +650,9 @@ int run_align_finish(cvo_b200_ctx* ctx, float* RT_io, float* ell_io, float* tran
     ctx->last_nclusters = ncl;
     ctx->last_group = group;
     long long total = 0, builds = 0, refines = 0, xy_entries = 0, xy_slots = 0;
-    for (int i = 0; i < n_pairs; ++i) {
-        const PairState& st = ctx->h_states[i];
+    for (int q = 0; q < n_pairs; ++q) {
+        const PairState& st = ctx->h_states[q];
+        const int i = ctx->order[q];
         total += st.n_run;
         builds += st.n_builds;
         refines += st.n_refines;

@@ -342,6 +342,28 @@ def test_batched_upload_of_ragged_pairs_equals_single_uploads(gpu_ctx):
         gpu_ctx.set_pairs(slots, fx, ff, nf0, mx, mf, nm)
 
 
+def test_largest_first_queue_order_hands_results_back_in_caller_order(gpu_ctx):
+    """The library queues a batch largest pair first (cvo_api.cu: run_align_begin); poses, iteration counts, stop
+    status and the carried state come back at the caller's indices.  Sizes ascending, so the queue is the reverse."""
+    sizes = [(300, 350), (700, 650), (1200, 1100), (2000, 2100), (3000, 2900)]
+    prs = [synth.make_pair(900 + i, n, m, "cvo") for i, (n, m) in enumerate(sizes)]
+    for s, pr in enumerate(prs):
+        _set(gpu_ctx, s, pr)
+    gp = capi.default_params("cvo")  # stock schedule, stop tests on: every pair runs its own number of iterations
+    P = len(prs)
+    RT = np.tile(np.concatenate([np.eye(3).reshape(9), np.zeros(3)]).astype(np.float32), (P, 1))
+    RT[:, 9] = 1e-3 * np.arange(P)  # a different start per pair
+    ell = np.full(P, gp.ell_init, np.float32)
+    batch = gpu_ctx.align(np.arange(P), gp, RT=RT, ell=ell)
+    assert len(set(batch["iters"].tolist())) > 1
+    for s in range(P):
+        one = gpu_ctx.align(np.array([s]), gp, RT=RT[s:s + 1], ell=ell[s:s + 1])
+        assert one["iters"][0] == batch["iters"][s] and one["status"][0] == batch["status"][s]
+        assert np.array_equal(one["transform"][0], batch["transform"][s])
+        assert np.array_equal(one["prev_transform"][0], batch["prev_transform"][s])
+        assert np.array_equal(one["RT"][0], batch["RT"][s]) and one["ell"][0] == batch["ell"][s]
+
+
 def test_permutation_and_rigid_motion_properties_at_full_size(gpu_ctx):
     """Size-independent properties at BASELINE's 10 000-point stress size (config 5)."""
     pr = synth.config_pair(5)
