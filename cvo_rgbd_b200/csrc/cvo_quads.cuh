@@ -335,9 +335,9 @@ constexpr int kScatterQuads = 416;
 constexpr size_t kScatterRegB = (sizeof(QuadBuild) + 15) & ~size_t(15);
 static_assert(offsetof(Smem, colG) == 0 && offsetof(Smem, u) == sizeof(float4) * kColChunk && offsetof(OnTheFlyStage, fs) == 0 &&
               offsetof(FeatStage, colF) == 0, "the scatter's first region starts at the start of Smem");
-static_assert((size_t)kWarps * kScatterQuads * 16 <= sizeof(float4) * kColChunk + offsetof(FeatStage, queue), "scatter region A");
+static_assert((size_t)kWorkWarps * kScatterQuads * 16 <= sizeof(float4) * kColChunk + offsetof(FeatStage, queue), "scatter region A");
 static_assert(offsetof(OnTheFlyStage, ws) == sizeof(FeatStage) &&
-              kScatterRegB + (size_t)kWarps * kScatterQuads * 10 <= sizeof(uint32_t) * kWorkWarps * kQueueCap + sizeof(WarpScratch) * kWorkWarps,
+              kScatterRegB + (size_t)kWorkWarps * kScatterQuads * 10 <= sizeof(uint32_t) * kWorkWarps * kQueueCap + sizeof(WarpScratch) * kWorkWarps,
               "scatter region B");
 
 // Row-sorted compaction of the round that build_list<0> has just evaluated: the staged candidates (column, row within
@@ -432,7 +432,7 @@ __device__ __forceinline__ bool compact_quads(Smem& sm, const ListRef& lr, int k
         unsigned short* s_row = reinterpret_cast<unsigned short*>(regB + kScatterQuads * 8);
         const float4 ninf4 = make_float4(ninf, ninf, ninf, ninf);
         const uint2 col00 = make_uint2(col_addr0 * 0x10001u, col_addr0 * 0x10001u);
-        for (int t = warp; t < ntile; t += kWarps) {
+        for (int t = warp < kWorkWarps ? warp : ntile; t < ntile; t += kWorkWarps) {  // (the warps that own a staging piece)
             const int c = bu.act[t], tile_q = qb.tileQ[t], tile_nq = qb.tileQ[t + 1] - tile_q;
             const uint2* src = lr.staging + bu.off[t];
             for (int q0 = 0; q0 < tile_nq; q0 += kScatterQuads) {  // (one chunk for all but very dense tiles)
