@@ -167,6 +167,26 @@ def cpu_reference_run(pair_indices, threads=None, cfg=2):
                 backend=O.backend(variant), kind=cpu_kind(variant), poses=np.array(poses), iters=np.array(iters))
 
 
+def oracle_poses_over_ranks(pair_indices, cfg, dist, torch, rank, world):
+    """The parity sample at N > 1: every rank runs the oracle on every world-th pair of the sample with its share of
+    the host cores, one all-gather brings the poses together (every rank gets them).  With rank 0 alone on all cores
+    the other ranks' busy-waiting on the next collective oversubscribes the OpenMP team -- measured 2.5 s per pair
+    instead of 0.08.  No cpu_baseline comes from this (that is N = 1 only): just the poses."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count()
+    pair_indices = [int(i) for i in pair_indices]
+    mine = list(range(rank, len(pair_indices), world))
+    dev = "cuda" if torch.cuda.is_available() else "cpu"  # (cpu: the gloo test of this helper)
+    out = torch.zeros((len(pair_indices), 16), dtype=torch.float32, device=dev)
+    if mine:
+        r = cpu_reference_run([pair_indices[k] for k in mine], threads=max(1, cores // world), cfg=cfg)
+        out[mine] = torch.from_numpy(np.asarray(r["poses"], np.float32).reshape(-1, 16)).to(dev)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM)  # disjoint rows: the sum is the gather
+    return out.cpu().numpy().reshape(-1, 4, 4)
+
+
 def pose_error(Ta, Tb):
     """(rotation angle [rad], translation distance [m]) between two 4x4 poses."""
     Ta, Tb = np.asarray(Ta, np.float64), np.asarray(Tb, np.float64)
@@ -323,11 +343,16 @@ def run_cfg4(args, torch, dist, capi, sharding, synth, rank, world, local_rank):
         dev_s, e2e_s = [float(x) for x in t.tolist()]
     G, ncl, num_sms = ctx.last_cluster_size, ctx.last_num_clusters, ctx.num_sms
     out = None
-    if rank == 0:
-        # parity on this workload too: 48 pairs spread over the job against the oracle
-        sample = np.linspace(0, CFG4_PAIRS - 1, 48).astype(int)
+    # parity on this workload too: 48 pairs spread over the job against the oracle (N > 1: the sample is dealt over the ranks)
+    sample = np.linspace(0, CFG4_PAIRS - 1, 48).astype(int)
+    cpu = None
+    if dist is not None:
+        cpu_poses = oracle_poses_over_ranks(sample, 4, dist, torch, rank, world)
+    elif rank == 0:
         cpu = cpu_reference_run(sample, cfg=4)
-        par = parity_report(np.asarray(poses)[sample], cpu["poses"], POSE_TOL, min_frac=0.7, med_frac=0.75)
+        cpu_poses = cpu["poses"]
+    if rank == 0:
+        par = parity_report(np.asarray(poses)[sample], cpu_poses, POSE_TOL, min_frac=0.7, med_frac=0.75)
         out = {"workload": "cfg4: %d independent ragged pairs (N, M ~ U{2700..3300}), stock cvo schedule, identity init, "
                            "pair p -> rank p mod W, one all-gather of the poses" % CFG4_PAIRS,
                "scaling": "strong", "pairs_total": CFG4_PAIRS, "pairs_per_gpu": int(P), "steps": steps,
@@ -338,9 +363,10 @@ def run_cfg4(args, torch, dist, capi, sharding, synth, rank, world, local_rank):
                "iterations_mean": float(np.mean(iters)), "iterations_max": int(np.max(iters)),
                "ctas_per_pair": G, "clusters": ncl, "sms_busy_frac_first_wave": min(P, ncl) * G / num_sms,
                "list_builds_per_pair": ctx.last_list_builds / max(P, 1),
-               "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
-                                "sample": "%d cfg-4 pairs, sequential, all host threads per pair, %.1f s" % (cpu["pairs"], cpu["seconds"])},
                "parity_check": par}
+        if cpu is not None:  # N = 1 only
+            out["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                   "sample": "%d cfg-4 pairs, sequential, all host threads per pair, %.1f s" % (cpu["pairs"], cpu["seconds"])}
     ctx.close()
     del flush
     return out
@@ -358,7 +384,8 @@ def main():
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per pair (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (500 ragged pairs, strong scaling) block")
-    ap.add_argument("--parity-pairs", type=int, default=8, help="pairs of the timed batch checked against the oracle when no cpu_baseline sample runs")
+    ap.add_argument("--parity-pairs", type=int, default=0,
+                    help="pairs of the timed batch checked against the oracle when no cpu_baseline sample runs (default: 8; 32 at N > 1, dealt over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -479,6 +506,15 @@ def main():
 
     gpu_poses_rank0 = res["transform"]  # the poses of the last timed step: what the parity check looks at
     ok = True
+    # The oracle runs ONCE: its wall time is the cpu_baseline (N = 1 only), its poses are the parity check of the
+    # batch that was just timed (pair s of rank 0 is cfg-2 pair number rank + s * world = s * world).
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = min(args.cpu_pairs or 96, P)
+    else:
+        n_cpu = min(args.parity_pairs if args.parity_pairs > 0 else (32 if world > 1 else 8), P)
+    sample = np.unique(np.linspace(0, P - 1, n_cpu).astype(int))
+    sample_pairs_ids = [int(i) * world for i in sample]  # rank 0's pairs
+    cpu_poses_multi = oracle_poses_over_ranks(sample_pairs_ids, 2, dist, torch, rank, world) if dist is not None else None
     if rank == 0:
         peak, peak_src = load_peaks()
         iters_per_launch = total_iters / args.steps
@@ -528,14 +564,7 @@ def main():
                            "frac_nm_equivalent": pass_evals / launch_s / issue_roof,
                            "note": "N*M-equivalent candidate pairs per second vs 148 SM x 128 lanes x f_SM / 7 slots; neighbour lists and tile-box culling skip most of them"},
         }
-        # The oracle runs ONCE: its wall time is the cpu_baseline (N = 1 only), its poses are the parity check of the
-        # batch that was just timed (pair s of rank 0 is cfg-2 pair number rank + s * world).
-        if world == 1 and not args.no_cpu_baseline:
-            n_cpu = min(args.cpu_pairs or 96, P)
-        else:
-            n_cpu = min(max(args.parity_pairs, 1), P)
-        sample = np.unique(np.linspace(0, P - 1, n_cpu).astype(int))
-        r = cpu_reference_run([rank + int(i) * world for i in sample])
+        r = cpu_reference_run(sample_pairs_ids) if cpu_poses_multi is None else {"poses": cpu_poses_multi}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": "%d cfg-2 pairs of the timed batch, sequential, all host threads per pair, %.1f s; %s" % (

@@ -66,3 +66,45 @@ def test_gather_poses_world_size_2_gloo(n_pairs):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(2))
     assert got == [(0, True), (1, True)]
+
+
+def _oracle_worker(rank, world, port, ids, q):
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        poses = bench.oracle_poses_over_ranks(ids, 1, dist, torch, rank, world)
+        q.put((rank, poses))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parity_sample_dealt_over_ranks_world_size_2_gloo():
+    """bench.py at N > 1: the oracle runs of the parity sample are dealt over the ranks (pair k of the sample -> rank
+    k mod W) and summed into place by one all-reduce; every rank ends with every pose, in sample order."""
+    import sys
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench
+    ids = [0, 3, 5]  # BASELINE config 1 pairs (500 x 500 points, stock cvo schedule): seconds on the CPU
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oracle_worker, args=(r, 2, port, ids, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    want = bench.cpu_reference_run(ids, threads=2, cfg=1)["poses"]
+    for r in range(2):
+        assert got[r].shape == (3, 4, 4)
+        assert np.array_equal(got[r], np.asarray(want, np.float32))
