@@ -210,6 +210,8 @@ int cvo_b200_eval(cvo_b200_ctx* ctx, int slot, const float* R, const float* T, f
  *  prev_transform  n_pairs x 16 or NULL: the one-update-stale transform that the reference multiplies
  *               into accum_transform (quirk Q3, src/cvo.cpp:413-414)
  *  iters        n_pairs: k at exit (max_iter when the cap was hit);  status: CVO_B200_STATUS_*
+ * Every array is indexed like `slots`.  (Inside, the free clusters pull the pairs from a queue ordered largest
+ * N x M first, so that a ragged batch ends on its cheap pairs; a pair's result does not depend on its place.)
  * Synchronous: returns when results are in the host arrays. */
 int cvo_b200_align(cvo_b200_ctx* ctx, const int* slots, int n_pairs, const cvo_b200_params* p,
                    float* RT_io, float* ell_io, float* transform, float* prev_transform,
@@ -238,7 +240,8 @@ long long cvo_b200_kernel_launches(const cvo_b200_ctx* ctx);
 int       cvo_b200_last_cluster_size(const cvo_b200_ctx* ctx);
 int       cvo_b200_last_num_clusters(const cvo_b200_ctx* ctx);
 /* Overrides the CTAs-per-pair choice (1..16); 0 = automatic: the size that minimises waves x per-pair time for
- * the batch at hand (a single pair: 16 CTAs; 63 pairs: 2; 2 x #SMs pairs: 1). */
+ * the batch at hand, a single wave counted as its slowest pair (a single pair: 16 CTAs; 20 pairs: 6; 63 .. 160
+ * pairs: 2; 2 x #SMs pairs: 1 -- measured table: profiles/r02_cfg4_cluster_sweep.txt). */
 int       cvo_b200_set_cluster_size(cvo_b200_ctx* ctx, int ctas_per_pair);
 /* Whole-GPU mode for one large pair (the reference's own use: one warm-started pair at a time, src/cvo_main.cpp:36-52;
  * BASELINE config 5): the pairs of an align call are taken one after the other and EVERY cluster of the launch works
