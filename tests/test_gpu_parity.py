@@ -64,7 +64,7 @@ def test_level1_result_is_independent_of_cluster_size(gpu_ctx):
     gp = capi.default_params("acvo")
     base = None
     try:
-        for g in (1, 2, 4, 8, 16):
+        for g in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16):  # any size: choose_cluster picks e.g. 6 for 20 pairs, 10 for 10
             gpu_ctx.set_cluster_size(g)
             r = gpu_ctx.eval(0, R0, T0, 0.1, gp)
             assert gpu_ctx.last_cluster_size in (g, 8)
@@ -340,6 +340,29 @@ def test_batched_upload_of_ragged_pairs_equals_single_uploads(gpu_ctx):
         nf0 = nf.copy()
         nf0[2] = 0
         gpu_ctx.set_pairs(slots, fx, ff, nf0, mx, mf, nm)
+
+
+@pytest.mark.parametrize("P", [10, 20, 40])
+def test_automatic_cluster_size_of_small_batches_agrees_with_one_cta_per_pair(gpu_ctx, P):
+    """Batches of 10 / 20 / 40 pairs run on clusters of 10 / 6 / 3 CTAs (choose_cluster, cvo_api.cu): same alignments as
+    one CTA per pair up to the f32 summation order (the row tiles are dealt differently, every sum has a fixed order)."""
+    prs = [synth.make_pair(700 + i, 900 + 37 * (i % 5), 950 - 29 * (i % 4), "cvo") for i in range(P)]
+    for s, pr in enumerate(prs):
+        _set(gpu_ctx, s, pr)
+    gp = capi.default_params("cvo")
+    try:
+        gpu_ctx.set_cluster_size(0)
+        auto = gpu_ctx.align(np.arange(P), gp)
+        g_auto = gpu_ctx.last_cluster_size
+        assert g_auto > 1 and g_auto * min(P, gpu_ctx.last_num_clusters) >= 0.6 * gpu_ctx.num_sms, (g_auto, gpu_ctx.last_num_clusters)
+        gpu_ctx.set_cluster_size(1)
+        one = gpu_ctx.align(np.arange(P), gp)
+    finally:
+        gpu_ctx.set_cluster_size(0)
+    assert np.isfinite(auto["transform"]).all()
+    errs = np.array([pose_diff(auto["transform"][s], one["transform"][s]) for s in range(P)])
+    assert errs.max() < 1e-3, (g_auto, errs.max(0))  # (the line search amplifies rounding differences on some pairs, conftest.py)
+    assert np.mean(errs.max(1) < POSE_TOL_FLOOR) >= 0.9, (g_auto, np.sort(errs.max(1))[-4:])
 
 
 def test_largest_first_queue_order_hands_results_back_in_caller_order(gpu_ctx):
